@@ -1,0 +1,188 @@
+/* kgdet_b200 -- C ABI of the B200-native KGDet point-set head operators.
+ *
+ * One shared library (kgdet_b200/_lib/libkgdet_b200.so), plain pointers and
+ * sizes, no torch / ATen types.  Every entry point below replaces one pybind
+ * entry point of the reference (cited as file:line under
+ * mmdetection/mmdet/ops/); the Python binding that calls it is
+ * kgdet_b200/ops/_capi.py (ctypes), and INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers unless the name ends in _host.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *    the reference launches on the legacy default stream
+ *    (dcn/src/deform_conv_cuda_kernel.cu:264) and, for NMS, blocks on a D2H
+ *    copy (nms/src/nms_kernel.cu:100) -- this library never synchronises.
+ *  - No allocation inside: scratch is passed in as (workspace, workspace_bytes)
+ *    and sized by the matching *_workspace_bytes query (the reference allocates
+ *    `columns` / `output_buffer` / the NMS mask itself:
+ *    dcn/src/deform_conv_cuda.cpp:196-214, nms/src/nms_kernel.cu:89).
+ *  - Return value: 0 = ok, negative = error; kgdet_last_error() returns a
+ *    thread-local message (the reference raises through AT_CHECK/AT_ERROR:
+ *    dcn/src/deform_conv_cuda.cpp:61-149).
+ *  - Tensors use the reference's public layouts: activations NCHW contiguous,
+ *    offsets [N, dg*2*K, Ho, Wo] with (dy, dx) interleaved per tap
+ *    (dcn/src/deform_conv_cuda_kernel.cu:221-224), weights [Cout, Cin/g, kh, kw].
+ */
+#ifndef KGDET_B200_H_
+#define KGDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGDET_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define KGDET_API __attribute__((visibility("default")))
+#else
+#define KGDET_API
+#endif
+
+enum {
+  KGDET_OK = 0,
+  KGDET_ERR_INVALID_ARG = -1,
+  KGDET_ERR_CUDA = -2,
+  KGDET_ERR_WORKSPACE = -3,
+  KGDET_ERR_UNSUPPORTED = -4
+};
+
+/* storage type of activations / gradients at the boundary */
+enum { KGDET_F32 = 0, KGDET_BF16 = 1 };
+
+/* arithmetic of the dense contraction
+ *  FP32   : fp32 FFMA on the SIMT pipe (bit pattern of the sum order aside, the reference's SGEMM)
+ *  TF32X3 : tcgen05 kind::tf32 with hi/lo split operands, 3 MMAs per k-step (fp32-grade, ~1e-6)
+ *  BF16   : tcgen05 kind::f16 with bf16 operands, fp32 accumulation in TMEM (~1e-3)
+ *  TF32   : tcgen05 kind::tf32, single pass (~1e-3) */
+enum { KGDET_PREC_FP32 = 0, KGDET_PREC_TF32X3 = 1, KGDET_PREC_BF16 = 2, KGDET_PREC_TF32 = 3 };
+
+/* NMS comparator: the reference's two back-ends disagree at IoU == thr */
+enum { KGDET_NMS_GT = 0 /* nms_kernel.cu:60 */, KGDET_NMS_GE = 1 /* nms_cpu.cpp:55 */ };
+
+typedef struct kgdet_dcn_shape {
+  int32_t N, C, H, W;        /* input  [N, C, H, W]                                   */
+  int32_t Cout, kh, kw;      /* weight [Cout, C/groups, kh, kw]                       */
+  int32_t stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int32_t groups, deformable_groups;
+} kgdet_dcn_shape;
+
+KGDET_API const char* kgdet_last_error(void);
+KGDET_API int kgdet_abi_version(void);
+/* 1 when the fused tcgen05 path supports (shape, precision); 0 -> the exact SIMT path runs */
+KGDET_API int kgdet_dcn_fast_path_supported(const kgdet_dcn_shape* shape, int precision);
+
+/* ---- deformable convolution --------------------------------------------------------
+ * replaces deform_conv_forward_cuda            dcn/src/deform_conv_cuda.cpp:151-258
+ *          modulated_deform_conv_cuda_forward  dcn/src/deform_conv_cuda.cpp:486-564
+ * `mask` ([N, dg*K, Ho, Wo]) and `bias` ([Cout]) may be NULL (plain DeformConv).
+ * `weight_packed` comes from kgdet_dcn_pack_weight for the same (shape, precision). */
+KGDET_API size_t kgdet_dcn_packed_weight_bytes(const kgdet_dcn_shape* shape, int precision);
+KGDET_API int kgdet_dcn_pack_weight(const float* weight, void* weight_packed, const kgdet_dcn_shape* shape,
+                          int precision, void* stream);
+KGDET_API size_t kgdet_dcn_forward_workspace_bytes(const kgdet_dcn_shape* shape, int dtype, int precision);
+KGDET_API int kgdet_dcn_forward(const void* input, const float* offset, const float* mask,
+                      const void* weight_packed, const float* bias, void* output,
+                      const kgdet_dcn_shape* shape, int dtype, int precision, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* replaces deform_conv_backward_input_cuda     dcn/src/deform_conv_cuda.cpp:260-371
+ *          (+ the input/offset/mask part of modulated_deform_conv_cuda_backward :566-679)
+ * grad_input / grad_offset / grad_mask are fully overwritten (no pre-zeroing needed;
+ * the reference pre-zeroes in Python: dcn/deform_conv.py:73-74).  `weight` is the raw
+ * fp32 [Cout, C/g, kh, kw] tensor.  grad_mask may be NULL iff mask is NULL. */
+KGDET_API size_t kgdet_dcn_backward_input_workspace_bytes(const kgdet_dcn_shape* shape, int dtype,
+                                                int precision);
+KGDET_API int kgdet_dcn_backward_input(const void* input, const float* offset, const float* mask,
+                             const float* weight, const void* grad_output, void* grad_input,
+                             float* grad_offset, float* grad_mask, const kgdet_dcn_shape* shape,
+                             int dtype, int precision, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* replaces deform_conv_backward_parameters_cuda dcn/src/deform_conv_cuda.cpp:373-484
+ * grad_weight (fp32 [Cout, C/g, kh, kw]) is overwritten with scale * dL/dW
+ * (the reference accumulates into a zeroed tensor with scale = 1: dcn/deform_conv.py:84-91);
+ * grad_bias ([Cout], fp32) may be NULL. */
+KGDET_API size_t kgdet_dcn_backward_weight_workspace_bytes(const kgdet_dcn_shape* shape, int dtype,
+                                                 int precision);
+KGDET_API int kgdet_dcn_backward_weight(const void* input, const float* offset, const float* mask,
+                              const void* grad_output, float* grad_weight, float* grad_bias,
+                              float scale, const kgdet_dcn_shape* shape, int dtype, int precision,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- NMS ------------------------------------------------------------------------------
+ * replaces nms_cuda.nms   nms/src/nms_cuda.cpp:8-12 -> nms/src/nms_kernel.cu:70-131
+ *      and nms_cpu.nms    nms/src/nms_cpu.cpp:61-67
+ * dets: [n, 5] fp32 (x1, y1, x2, y2, score).  keep: [n] int64, the first *num_keep
+ * entries are the ORIGINAL indices of the kept boxes in ascending order
+ * (nms_kernel.cu:127-130); num_keep is a device int32.  Ties between equal scores
+ * are broken by ascending original index (the reference's at::sort leaves them
+ * unspecified). */
+KGDET_API size_t kgdet_nms_workspace_bytes(int32_t n);
+KGDET_API int kgdet_nms(const float* dets, int32_t n, float iou_thr, int cmp_mode, int64_t* keep,
+              int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Batched form over `nseg` independent segments (one per (image, class)) in ONE launch --
+ * replaces the per-class Python loop of multiclass_nms_kp
+ * (mmdet/core/post_processing/bbox_nms_kp.py:38-52).  Segment s owns rows
+ * [seg_offsets[s], seg_offsets[s+1]) of dets; keep_flags[row] = 1 if the row survives
+ * NMS within its segment.  seg_offsets: device int32 [nseg+1]; max_seg_len >= the
+ * longest segment (host-side bound, e.g. nms_pre). */
+KGDET_API size_t kgdet_nms_batched_workspace_bytes(int32_t total, int32_t nseg, int32_t max_seg_len);
+KGDET_API int kgdet_nms_batched(const float* dets, const int32_t* seg_offsets, int32_t nseg, int32_t total,
+                      int32_t max_seg_len, float iou_thr, int cmp_mode, uint8_t* keep_flags,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- sigmoid focal loss -----------------------------------------------------------------
+ * replaces sigmoid_focal_loss_cuda.forward / .backward
+ *   sigmoid_focal_loss/src/sigmoid_focal_loss.cpp:17-39 ->
+ *   sigmoid_focal_loss/src/sigmoid_focal_loss_cuda.cu:24-59, 62-98
+ * logits/losses/d_losses/d_logits: [M, C] (dtype), targets: [M] int64 (0 = background,
+ * t = c+1 positive for column c, t < 0 ignored). */
+KGDET_API int kgdet_sigmoid_focal_loss_forward(const void* logits, const int64_t* targets, int32_t M,
+                                     int32_t C, float gamma, float alpha, void* losses, int dtype,
+                                     void* stream);
+KGDET_API int kgdet_sigmoid_focal_loss_backward(const void* logits, const int64_t* targets,
+                                      const void* d_losses, int32_t M, int32_t C, float gamma,
+                                      float alpha, void* d_logits, int dtype, void* stream);
+/* Fused forward + row weight + sum (the reduction FocalLoss does in Python:
+ * mmdet/models/losses/focal_loss.py:28-42, losses/utils.py:41-52).
+ * *loss_sum (device fp32, must be zeroed by the caller) += sum_{m,c} loss[m,c] * weight[m];
+ * weight ([M] fp32) may be NULL.  Backward of that scalar:
+ * d_logits[m,c] = dloss/dx * weight[m] * (*grad_scale)  (grad_scale: device fp32). */
+KGDET_API int kgdet_sigmoid_focal_loss_sum_forward(const void* logits, const int64_t* targets,
+                                         const float* weight, int32_t M, int32_t C, float gamma,
+                                         float alpha, float* loss_sum, int dtype, void* stream);
+KGDET_API int kgdet_sigmoid_focal_loss_sum_backward(const void* logits, const int64_t* targets,
+                                          const float* weight, const float* grad_scale, int32_t M,
+                                          int32_t C, float gamma, float alpha, void* d_logits,
+                                          int dtype, void* stream);
+
+/* ---- point set -> bbox moment transform ------------------------------------------------------
+ * replaces the ~12 PyTorch kernels of points2bbox(..., 'moment')
+ *   mmdet/models/anchor_heads/reppoints_head_kp3rep_cas_1_assign_once.py:373-388
+ * pts: [N, 2P, S] fp32 (S = H*W for NCHW maps, S = 1 for row-major [M, 2P]); channel
+ * 2i = y_i, 2i+1 = x_i when y_first, swapped otherwise.  moment_transfer: device fp32[2]
+ * (width, height log-scales).  bbox: [N, 4, S] = (x1, y1, x2, y2). */
+KGDET_API int kgdet_points2bbox_moment_forward(const float* pts, const float* moment_transfer, int32_t N,
+                                     int32_t P, int32_t S, int y_first, float* bbox,
+                                     void* stream);
+/* grad_pts: [N, 2P, S] overwritten; grad_moment_transfer: device fp32[2], must be zeroed by
+ * the caller, receives moment_mul * dL/dt (KP3:378-379).  */
+KGDET_API int kgdet_points2bbox_moment_backward(const float* pts, const float* moment_transfer,
+                                      const float* grad_bbox, int32_t N, int32_t P, int32_t S,
+                                      int y_first, float moment_mul, float* grad_pts,
+                                      float* grad_moment_transfer, void* stream);
+
+/* ---- layout helpers used by the Python mirror ---------------------------------------------- */
+/* NCHW (dtype) -> NHWC fp32 or bf16 and back; S = H*W */
+KGDET_API int kgdet_nchw_to_nhwc(const void* src, void* dst, int32_t N, int32_t C, int32_t S, int src_dtype,
+                       int dst_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGDET_B200_H_ */

@@ -1,0 +1,62 @@
+// Internal declarations shared by the deformable-convolution translation units.
+#pragma once
+#include "common.cuh"
+
+namespace kgdet {
+
+// One record per (output position m, deformable group, tap): the four bilinear corners of
+// the sampling point (deform_conv_cuda_kernel.cu:88-110) resolved ONCE per offset tensor --
+// the reference recomputes them in every one of the C channel threads (:198-240).
+//   pix[i]  pixel index (n*H*W + h*W + w) of corner i, or 0 when the corner is unusable
+//   w[i]    bilinear weight of corner i * [corner inside the map] * [sample inside the
+//           (-1,H)x(-1,W) window] * mask (modulated DCN) -- 0 for unusable corners
+// corner order: (h_low,w_low) (h_low,w_high) (h_high,w_low) (h_high,w_high)
+struct __align__(16) SampleRec {
+  int pix[4];
+  float w[4];
+};
+// Extra per-sample data only the backward passes need.
+//   lh, lw  fractional parts;  mask  modulation value (1 for plain DCN)
+//   valid   bit i = corner i usable (inside map and sample inside window)
+struct __align__(16) SampleAux {
+  float lh, lw, mask;
+  int valid;
+};
+
+size_t plan_rows(const DcnGeom& g);                 // M rounded up to 128
+size_t plan_bytes(const DcnGeom& g);                // SampleRec array
+size_t plan_aux_bytes(const DcnGeom& g);            // SampleAux array
+int launch_plan(const DcnGeom& g, const float* offset, const float* mask, SampleRec* rec,
+                SampleAux* aux /* may be NULL */, cudaStream_t stream);
+
+// src [B, R, Cc] -> dst [B, Cc, R] with dtype conversion (NCHW <-> NHWC)
+int launch_transpose(const void* src, void* dst, int B, int R, int Cc, int src_dtype,
+                     int dst_dtype, cudaStream_t stream);
+
+// ---- exact fp32 SIMT path (any stride / dilation / groups / deformable_groups / mask) ----
+size_t simt_packed_weight_bytes(const DcnGeom& g);
+int simt_pack_weight(const DcnGeom& g, const float* weight, float* packed, cudaStream_t stream);
+int simt_forward(const DcnGeom& g, const float* in_nhwc, const SampleRec* plan,
+                 const float* packed_w, const float* bias, void* out_nchw, int out_dtype,
+                 cudaStream_t stream);
+// weight_dgrad: [groups][K][Cout/g][C/g] fp32 (built by simt_pack_weight_dgrad)
+int simt_pack_weight_dgrad(const DcnGeom& g, const float* weight, float* packed,
+                           cudaStream_t stream);
+int simt_backward_input(const DcnGeom& g, const float* in_nhwc, const float* go_nhwc,
+                        const SampleRec* plan, const SampleAux* aux, const float* w_dgrad,
+                        float* gin_nhwc /* zeroed */, float* grad_offset /* zeroed */,
+                        float* grad_mask /* zeroed or NULL */, cudaStream_t stream);
+int simt_backward_weight(const DcnGeom& g, const float* in_nhwc, const float* go_nhwc,
+                         const SampleRec* plan, float scale, float* grad_weight,
+                         float* grad_bias, cudaStream_t stream);
+
+// ---- fused tcgen05 path (groups == deformable_groups == 1, C % 64 == 0, Cout % 16 == 0) ----
+bool umma_supported(const DcnGeom& g, int precision);
+size_t umma_packed_weight_bytes(const DcnGeom& g, int precision);
+int umma_pack_weight(const DcnGeom& g, const float* weight, void* packed, int precision,
+                     cudaStream_t stream);
+int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec* plan, const void* packed_w,
+                 const float* bias, void* out_nchw, int out_dtype, int precision,
+                 cudaStream_t stream);
+
+}  // namespace kgdet

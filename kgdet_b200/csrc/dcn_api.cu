@@ -1,0 +1,190 @@
+// extern "C" entry points of the deformable convolution: validation, workspace carving,
+// path selection (fused tcgen05 vs exact SIMT).  See include/kgdet_b200.h for the contract.
+#include "dcn.cuh"
+
+using namespace kgdet;
+
+namespace {
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base((char*)p) {}
+  template <typename T> T* take(size_t bytes) {
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  }
+};
+
+bool valid_dtype(int d) { return d == KGDET_F32 || d == KGDET_BF16; }
+bool valid_prec(int p) { return p >= KGDET_PREC_FP32 && p <= KGDET_PREC_TF32; }
+bool use_umma(const DcnGeom& g, int precision) {
+  return precision != KGDET_PREC_FP32 && umma_supported(g, precision);
+}
+
+struct FwdWs { void* in_nhwc; SampleRec* plan; size_t total; };
+FwdWs carve_fwd(const DcnGeom& g, int precision, void* ws) {
+  Carver c(ws);
+  FwdWs w;
+  const size_t esz = (use_umma(g, precision) && precision == KGDET_PREC_BF16) ? 2 : 4;
+  w.in_nhwc = c.take<void>((size_t)g.N * g.H * g.W * g.C * esz);
+  w.plan = c.take<SampleRec>(plan_bytes(g));
+  w.total = c.off;
+  return w;
+}
+
+struct BwdInWs { float *in_nhwc, *go_nhwc, *gin_nhwc, *w_dgrad; SampleRec* plan; SampleAux* aux; size_t total; };
+BwdInWs carve_bwd_in(const DcnGeom& g, void* ws) {
+  Carver c(ws);
+  BwdInWs w;
+  w.in_nhwc = c.take<float>((size_t)g.N * g.H * g.W * g.C * 4);
+  w.go_nhwc = c.take<float>((size_t)g.M * g.Cout * 4);
+  w.gin_nhwc = c.take<float>((size_t)g.N * g.H * g.W * g.C * 4);
+  w.w_dgrad = c.take<float>(simt_packed_weight_bytes(g));
+  w.plan = c.take<SampleRec>(plan_bytes(g));
+  w.aux = c.take<SampleAux>(plan_aux_bytes(g));
+  w.total = c.off;
+  return w;
+}
+
+struct BwdWWs { float *in_nhwc, *go_nhwc; SampleRec* plan; size_t total; };
+BwdWWs carve_bwd_w(const DcnGeom& g, void* ws) {
+  Carver c(ws);
+  BwdWWs w;
+  w.in_nhwc = c.take<float>((size_t)g.N * g.H * g.W * g.C * 4);
+  w.go_nhwc = c.take<float>((size_t)g.M * g.Cout * 4);
+  w.plan = c.take<SampleRec>(plan_bytes(g));
+  w.total = c.off;
+  return w;
+}
+
+int check_ws(const char* name, void* ws, size_t have, size_t need) {
+  if (!ws || have < need) {
+    set_error("%s: workspace too small (%zu < %zu)", name, have, need);
+    return KGDET_ERR_WORKSPACE;
+  }
+  if (((uintptr_t)ws & 255) != 0) {
+    set_error("%s: workspace must be 256-byte aligned", name);
+    return KGDET_ERR_INVALID_ARG;
+  }
+  return KGDET_OK;
+}
+
+}  // namespace
+
+extern "C" int kgdet_dcn_fast_path_supported(const kgdet_dcn_shape* shape, int precision) {
+  DcnGeom g;
+  if (make_geom(shape, &g) != KGDET_OK) return 0;
+  return use_umma(g, precision) ? 1 : 0;
+}
+
+extern "C" size_t kgdet_dcn_packed_weight_bytes(const kgdet_dcn_shape* shape, int precision) {
+  DcnGeom g;
+  if (make_geom(shape, &g) != KGDET_OK) return 0;
+  return use_umma(g, precision) ? umma_packed_weight_bytes(g, precision) : simt_packed_weight_bytes(g);
+}
+
+extern "C" int kgdet_dcn_pack_weight(const float* weight, void* weight_packed,
+                                     const kgdet_dcn_shape* shape, int precision, void* stream) {
+  DcnGeom g;
+  int rc = make_geom(shape, &g);
+  if (rc != KGDET_OK) return rc;
+  KG_CHECK_ARG(valid_prec(precision), "kgdet_dcn_pack_weight: bad precision %d", precision);
+  KG_CHECK_ARG(weight && weight_packed, "kgdet_dcn_pack_weight: NULL pointer");
+  if (use_umma(g, precision)) return umma_pack_weight(g, weight, weight_packed, precision, (cudaStream_t)stream);
+  return simt_pack_weight(g, weight, (float*)weight_packed, (cudaStream_t)stream);
+}
+
+extern "C" size_t kgdet_dcn_forward_workspace_bytes(const kgdet_dcn_shape* shape, int, int precision) {
+  DcnGeom g;
+  if (make_geom(shape, &g) != KGDET_OK) return 0;
+  return carve_fwd(g, precision, nullptr).total;
+}
+
+extern "C" int kgdet_dcn_forward(const void* input, const float* offset, const float* mask,
+                                 const void* weight_packed, const float* bias, void* output,
+                                 const kgdet_dcn_shape* shape, int dtype, int precision,
+                                 void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DcnGeom g;
+  int rc = make_geom(shape, &g);
+  if (rc != KGDET_OK) return rc;
+  KG_CHECK_ARG(valid_dtype(dtype), "kgdet_dcn_forward: bad dtype %d", dtype);
+  KG_CHECK_ARG(valid_prec(precision), "kgdet_dcn_forward: bad precision %d", precision);
+  KG_CHECK_ARG(input && offset && weight_packed && output, "kgdet_dcn_forward: NULL pointer");
+  FwdWs w = carve_fwd(g, precision, workspace);
+  if ((rc = check_ws("kgdet_dcn_forward", workspace, workspace_bytes, w.total)) != KGDET_OK) return rc;
+  const bool fast = use_umma(g, precision);
+  const int cdtype = (fast && precision == KGDET_PREC_BF16) ? KGDET_BF16 : KGDET_F32;
+  if ((rc = launch_transpose(input, w.in_nhwc, g.N, g.C, g.H * g.W, dtype, cdtype, stream)) != KGDET_OK) return rc;
+  if ((rc = launch_plan(g, offset, mask, w.plan, nullptr, stream)) != KGDET_OK) return rc;
+  if (fast)
+    return umma_forward(g, w.in_nhwc, w.plan, weight_packed, bias, output, dtype, precision, stream);
+  return simt_forward(g, (const float*)w.in_nhwc, w.plan, (const float*)weight_packed, bias, output, dtype,
+                      stream);
+}
+
+extern "C" size_t kgdet_dcn_backward_input_workspace_bytes(const kgdet_dcn_shape* shape, int, int) {
+  DcnGeom g;
+  if (make_geom(shape, &g) != KGDET_OK) return 0;
+  return carve_bwd_in(g, nullptr).total;
+}
+
+extern "C" int kgdet_dcn_backward_input(const void* input, const float* offset, const float* mask,
+                                        const float* weight, const void* grad_output, void* grad_input,
+                                        float* grad_offset, float* grad_mask,
+                                        const kgdet_dcn_shape* shape, int dtype, int precision,
+                                        void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DcnGeom g;
+  int rc = make_geom(shape, &g);
+  if (rc != KGDET_OK) return rc;
+  KG_CHECK_ARG(valid_dtype(dtype), "kgdet_dcn_backward_input: bad dtype %d", dtype);
+  KG_CHECK_ARG(valid_prec(precision), "kgdet_dcn_backward_input: bad precision %d", precision);
+  KG_CHECK_ARG(input && offset && weight && grad_output && grad_input && grad_offset,
+               "kgdet_dcn_backward_input: NULL pointer");
+  KG_CHECK_ARG((mask == nullptr) == (grad_mask == nullptr),
+               "kgdet_dcn_backward_input: mask and grad_mask must both be given or both be NULL");
+  BwdInWs w = carve_bwd_in(g, workspace);
+  if ((rc = check_ws("kgdet_dcn_backward_input", workspace, workspace_bytes, w.total)) != KGDET_OK) return rc;
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  if ((rc = launch_transpose(input, w.in_nhwc, g.N, g.C, HW, dtype, KGDET_F32, stream)) != KGDET_OK) return rc;
+  if ((rc = launch_transpose(grad_output, w.go_nhwc, g.N, g.Cout, HoWo, dtype, KGDET_F32, stream)) != KGDET_OK) return rc;
+  if ((rc = launch_plan(g, offset, mask, w.plan, w.aux, stream)) != KGDET_OK) return rc;
+  if ((rc = simt_pack_weight_dgrad(g, weight, w.w_dgrad, stream)) != KGDET_OK) return rc;
+  KG_CUDA(cudaMemsetAsync(w.gin_nhwc, 0, (size_t)g.N * HW * g.C * 4, stream));
+  KG_CUDA(cudaMemsetAsync(grad_offset, 0, (size_t)g.N * g.dgroups * 2 * g.K * HoWo * 4, stream));
+  if (grad_mask) KG_CUDA(cudaMemsetAsync(grad_mask, 0, (size_t)g.N * g.dgroups * g.K * HoWo * 4, stream));
+  if ((rc = simt_backward_input(g, w.in_nhwc, w.go_nhwc, w.plan, w.aux, w.w_dgrad, w.gin_nhwc, grad_offset,
+                                grad_mask, stream)) != KGDET_OK) return rc;
+  // NHWC fp32 -> NCHW (dtype)
+  return launch_transpose(w.gin_nhwc, grad_input, g.N, HW, g.C, KGDET_F32, dtype, stream);
+}
+
+extern "C" size_t kgdet_dcn_backward_weight_workspace_bytes(const kgdet_dcn_shape* shape, int, int) {
+  DcnGeom g;
+  if (make_geom(shape, &g) != KGDET_OK) return 0;
+  return carve_bwd_w(g, nullptr).total;
+}
+
+extern "C" int kgdet_dcn_backward_weight(const void* input, const float* offset, const float* mask,
+                                         const void* grad_output, float* grad_weight, float* grad_bias,
+                                         float scale, const kgdet_dcn_shape* shape, int dtype,
+                                         int precision, void* workspace, size_t workspace_bytes,
+                                         void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DcnGeom g;
+  int rc = make_geom(shape, &g);
+  if (rc != KGDET_OK) return rc;
+  KG_CHECK_ARG(valid_dtype(dtype), "kgdet_dcn_backward_weight: bad dtype %d", dtype);
+  KG_CHECK_ARG(valid_prec(precision), "kgdet_dcn_backward_weight: bad precision %d", precision);
+  KG_CHECK_ARG(input && offset && grad_output && grad_weight, "kgdet_dcn_backward_weight: NULL pointer");
+  BwdWWs w = carve_bwd_w(g, workspace);
+  if ((rc = check_ws("kgdet_dcn_backward_weight", workspace, workspace_bytes, w.total)) != KGDET_OK) return rc;
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  if ((rc = launch_transpose(input, w.in_nhwc, g.N, g.C, HW, dtype, KGDET_F32, stream)) != KGDET_OK) return rc;
+  if ((rc = launch_transpose(grad_output, w.go_nhwc, g.N, g.Cout, HoWo, dtype, KGDET_F32, stream)) != KGDET_OK) return rc;
+  if ((rc = launch_plan(g, offset, mask, w.plan, nullptr, stream)) != KGDET_OK) return rc;
+  return simt_backward_weight(g, w.in_nhwc, w.go_nhwc, w.plan, scale, grad_weight, grad_bias, stream);
+}

@@ -1,0 +1,134 @@
+// Sampling plan + layout transforms shared by every deformable-convolution path.
+#include "dcn.cuh"
+
+namespace kgdet {
+
+size_t plan_rows(const DcnGeom& g) { return (size_t)ceil_div(g.M, 128) * 128; }
+size_t plan_bytes(const DcnGeom& g) {
+  return plan_rows(g) * g.dgroups * g.K * sizeof(SampleRec);
+}
+size_t plan_aux_bytes(const DcnGeom& g) {
+  return plan_rows(g) * g.dgroups * g.K * sizeof(SampleAux);
+}
+
+// Sampling rule of deformable_im2col_gpu_kernel (deform_conv_cuda_kernel.cu:210-236) and
+// deformable_im2col_bilinear (:83-114), evaluated once per (position, dgroup, tap).
+__global__ void dcn_plan_kernel(DcnGeom g, const float* __restrict__ offset,
+                                const float* __restrict__ mask, SampleRec* __restrict__ rec,
+                                SampleAux* __restrict__ aux, int rows_padded) {
+  const int per_row = g.dgroups * g.K;
+  const long long total = (long long)rows_padded * per_row;
+  const int HoWo = g.Ho * g.Wo;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)blockDim.x * gridDim.x) {
+    const int m = (int)(idx / per_row);
+    const int rem = (int)(idx - (long long)m * per_row);
+    SampleRec r;
+    r.pix[0] = r.pix[1] = r.pix[2] = r.pix[3] = 0;
+    r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0.f;
+    SampleAux a;
+    a.lh = a.lw = 0.f; a.mask = 0.f; a.valid = 0;
+    if (m < g.M) {
+      const int dgi = rem / g.K, tap = rem - dgi * g.K;
+      const int n = m / HoWo, p = m - n * HoWo;
+      const int y = p / g.Wo, x = p - y * g.Wo;
+      const int i = tap / g.kw, j = tap - i * g.kw;
+      const size_t obase = ((size_t)(n * g.dgroups + dgi) * 2 * g.K + 2 * tap) * HoWo + p;
+      const float off_h = offset[obase];                    // :221,223
+      const float off_w = offset[obase + HoWo];             // :222,224
+      const float mval = mask ? mask[((size_t)(n * g.dgroups + dgi) * g.K + tap) * HoWo + p] : 1.f;
+      const float h_im = (float)(y * g.sh - g.ph + i * g.dh) + off_h;   // :226
+      const float w_im = (float)(x * g.sw - g.pw + j * g.dw) + off_w;   // :227
+      a.mask = mval;
+      if (h_im > -1.f && w_im > -1.f && h_im < (float)g.H && w_im < (float)g.W) {   // :228
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int h_low = (int)hf, w_low = (int)wf;
+        const int h_high = h_low + 1, w_high = w_low + 1;
+        const float lh = h_im - hf, lw = w_im - wf;
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const bool vhl = h_low >= 0, vhh = h_high <= g.H - 1;          // :98-107
+        const bool vwl = w_low >= 0, vwh = w_high <= g.W - 1;
+        const int nbase = n * g.H * g.W;
+        a.lh = lh; a.lw = lw;
+        if (vhl && vwl) { r.pix[0] = nbase + h_low * g.W + w_low;   r.w[0] = hh * hw * mval; a.valid |= 1; }
+        if (vhl && vwh) { r.pix[1] = nbase + h_low * g.W + w_high;  r.w[1] = hh * lw * mval; a.valid |= 2; }
+        if (vhh && vwl) { r.pix[2] = nbase + h_high * g.W + w_low;  r.w[2] = lh * hw * mval; a.valid |= 4; }
+        if (vhh && vwh) { r.pix[3] = nbase + h_high * g.W + w_high; r.w[3] = lh * lw * mval; a.valid |= 8; }
+      }
+    }
+    rec[idx] = r;
+    if (aux) aux[idx] = a;
+  }
+}
+
+int launch_plan(const DcnGeom& g, const float* offset, const float* mask, SampleRec* rec,
+                SampleAux* aux, cudaStream_t stream) {
+  const int rows = (int)plan_rows(g);
+  const long long total = (long long)rows * g.dgroups * g.K;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dcn_plan_kernel<<<(int)blocks, 256, 0, stream>>>(g, offset, mask, rec, aux, rows);
+  KG_LAUNCH_CHECK("dcn_plan_kernel");
+  return KGDET_OK;
+}
+
+// ---- batched 2-D transpose with dtype conversion:  src [B, R, Cc] -> dst [B, Cc, R] ----------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+template <typename Tin, typename Tout>
+__global__ void transpose_kernel(const Tin* __restrict__ src, Tout* __restrict__ dst, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const Tin* s = src + (size_t)b * R * Cc;
+  Tout* d = dst + (size_t)b * R * Cc;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    int r = r0 + ty + k, c = c0 + tx;
+    if (r < R && c < Cc) tile[ty + k][tx] = to_f<Tin>(s[(size_t)r * Cc + c]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    int c = c0 + ty + k, r = r0 + tx;
+    if (r < R && c < Cc) d[(size_t)c * R + r] = from_f<Tout>(tile[tx][ty + k]);
+  }
+}
+
+int launch_transpose(const void* src, void* dst, int B, int R, int Cc, int src_dtype, int dst_dtype,
+                     cudaStream_t stream) {
+  if (B <= 0 || R <= 0 || Cc <= 0) return KGDET_OK;
+  KG_CHECK_ARG(B <= 65535 && ceil_div(R, 32) <= 65535, "transpose: batch/rows too large");
+  dim3 grid(ceil_div(Cc, 32), ceil_div(R, 32), B), block(32, 8);
+  if (src_dtype == KGDET_F32 && dst_dtype == KGDET_F32)
+    transpose_kernel<float, float><<<grid, block, 0, stream>>>((const float*)src, (float*)dst, R, Cc);
+  else if (src_dtype == KGDET_F32 && dst_dtype == KGDET_BF16)
+    transpose_kernel<float, __nv_bfloat16><<<grid, block, 0, stream>>>((const float*)src, (__nv_bfloat16*)dst, R, Cc);
+  else if (src_dtype == KGDET_BF16 && dst_dtype == KGDET_F32)
+    transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, stream>>>((const __nv_bfloat16*)src, (float*)dst, R, Cc);
+  else if (src_dtype == KGDET_BF16 && dst_dtype == KGDET_BF16)
+    transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, R, Cc);
+  else {
+    set_error("transpose: bad dtype %d -> %d", src_dtype, dst_dtype);
+    return KGDET_ERR_INVALID_ARG;
+  }
+  KG_LAUNCH_CHECK("transpose_kernel");
+  return KGDET_OK;
+}
+
+}  // namespace kgdet
+
+extern "C" int kgdet_nchw_to_nhwc(const void* src, void* dst, int32_t N, int32_t C, int32_t S,
+                                  int src_dtype, int dst_dtype, void* stream) {
+  KG_CHECK_ARG(N >= 0 && C >= 1 && S >= 1, "kgdet_nchw_to_nhwc: bad sizes");
+  if (N == 0) return KGDET_OK;
+  KG_CHECK_ARG(src && dst, "kgdet_nchw_to_nhwc: NULL pointer");
+  return kgdet::launch_transpose(src, dst, N, C, S, src_dtype, dst_dtype, (cudaStream_t)stream);
+}

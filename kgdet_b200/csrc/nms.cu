@@ -1,0 +1,402 @@
+// Greedy NMS on the device, bit-exact with the reference's arithmetic.
+//
+// Replaces mmdet/ops/nms/src/nms_kernel.cu:13-131 (bitmask kernel + HOST sweep after a
+// blocking D2H copy) and mmdet/ops/nms/src/nms_cpu.cpp:4-59.  Differences by design:
+//  * the greedy sweep runs on the device (no D2H of the mask, no host loop, no sync);
+//  * small problems (n <= kSmallMax, every KGDet case: n <= nms_pre = 1000 per class) run
+//    as ONE CTA per (image, class) segment: in-CTA bitonic sort, then 64-box blocks are
+//    resolved with a 64x64 diagonal bitmask and broadcast to the remaining boxes -- the
+//    n x n/64 mask never exists in memory;
+//  * large problems use upper-triangular 64x64 mask tiles in the workspace plus a
+//    single-CTA sweep that only reads the rows of kept boxes.
+// IoU uses explicitly rounded fp32 intrinsics in the reference's operation order so the
+// compiler cannot contract (Sa + Sb) - w*h into an FMA (nms_cpu.cpp:47-54).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace kgdet {
+
+static constexpr int kSmallMax = 4096;   // boxes per segment for the single-CTA path
+static constexpr int kSmallThreads = 1024;
+
+struct Box { float x1, y1, x2, y2; };
+
+__device__ __forceinline__ float box_area(const Box& b) {
+  // (x2 - x1 + 1) * (y2 - y1 + 1)            nms_cpu.cpp:18, nms_kernel.cu:18-19
+  return __fmul_rn(__fadd_rn(__fsub_rn(b.x2, b.x1), 1.f), __fadd_rn(__fsub_rn(b.y2, b.y1), 1.f));
+}
+
+// true when box b (lower score) is suppressed by box a (higher score)
+__device__ __forceinline__ bool suppresses(const Box& a, float area_a, const Box& b, float area_b,
+                                           float thr, int cmp_ge) {
+  float xx1 = fmaxf(a.x1, b.x1), yy1 = fmaxf(a.y1, b.y1);
+  float xx2 = fminf(a.x2, b.x2), yy2 = fminf(a.y2, b.y2);
+  float w = fmaxf(__fadd_rn(__fsub_rn(xx2, xx1), 1.f), 0.f);
+  float h = fmaxf(__fadd_rn(__fsub_rn(yy2, yy1), 1.f), 0.f);
+  float inter = __fmul_rn(w, h);
+  float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return cmp_ge ? (ovr >= thr) : (ovr > thr);
+}
+
+// (score desc, index asc) ordering: "a goes before b"
+__device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {
+  return (sa > sb) || (sa == sb && ia < ib);
+}
+
+// ---------------------------------------------------------------------------------------
+// Single-CTA NMS of one segment.  Dynamic smem layout (P = next pow2 >= n):
+//   float key[P]; int idx[P]; Box box[n]; float area[n]; u64 removed[ceil(n/64)];
+//   u64 diag[64]; u64 kept_word;
+// Output: flags[orig_row] = 1/0.
+__global__ void __launch_bounds__(kSmallThreads, 1)
+nms_small_kernel(const float* __restrict__ dets, const int32_t* __restrict__ seg_offsets,
+                 int single_n, float thr, int cmp_ge, uint8_t* __restrict__ flags, int P_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int row0, n;
+  if (seg_offsets) {
+    row0 = seg_offsets[blockIdx.x];
+    n = seg_offsets[blockIdx.x + 1] - row0;
+  } else {
+    row0 = 0;
+    n = single_n;
+  }
+  if (n <= 0) return;
+  int P = 1;
+  while (P < n) P <<= 1;
+  // carve
+  float* key = reinterpret_cast<float*>(smem_raw);
+  int* idx = reinterpret_cast<int*>(key + P_cap);
+  Box* box = reinterpret_cast<Box*>(idx + P_cap);
+  float* area = reinterpret_cast<float*>(box + P_cap);
+  unsigned long long* removed = reinterpret_cast<unsigned long long*>(area + P_cap);
+  unsigned long long* diag = removed + (P_cap + 63) / 64;
+  unsigned long long* kept_word = diag + 64;
+
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const float* d = dets + (size_t)row0 * 5;
+  for (int i = tid; i < P; i += nt) {
+    if (i < n) { key[i] = d[i * 5 + 4]; idx[i] = i; }
+    else { key[i] = -INFINITY; idx[i] = 0x7fffffff; }
+  }
+  __syncthreads();
+  // bitonic sort, ascending in the `before` order
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += nt) {
+        int l = i ^ j;
+        if (l > i) {
+          float si = key[i], sl = key[l];
+          int ii = idx[i], il = idx[l];
+          bool up = ((i & k) == 0);
+          bool swap = up ? before(sl, il, si, ii) : before(si, ii, sl, il);
+          if (swap) { key[i] = sl; key[l] = si; idx[i] = il; idx[l] = ii; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // gather boxes in sorted order
+  for (int i = tid; i < n; i += nt) {
+    const float* s = d + (size_t)idx[i] * 5;
+    Box b{s[0], s[1], s[2], s[3]};
+    box[i] = b;
+    area[i] = box_area(b);
+  }
+  const int nwords = (n + 63) / 64;
+  for (int i = tid; i < nwords; i += nt) removed[i] = 0ull;
+  __syncthreads();
+
+  for (int blk = 0; blk < nwords; ++blk) {
+    const int base = blk * 64;
+    const int cnt = min(64, n - base);
+    // 64x64 diagonal bitmask: thread (r) builds the word of row r (bits c > r)
+    if (tid < 64) {
+      unsigned long long wbits = 0ull;
+      if (tid < cnt) {
+        Box a = box[base + tid];
+        float aa = area[base + tid];
+        for (int c = tid + 1; c < cnt; ++c)
+          if (suppresses(a, aa, box[base + c], area[base + c], thr, cmp_ge)) wbits |= 1ull << c;
+      }
+      diag[tid] = wbits;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long rem = removed[blk];
+      unsigned long long kept = 0ull;
+      for (int r = 0; r < cnt; ++r) {
+        if (!((rem >> r) & 1ull)) { kept |= 1ull << r; rem |= diag[r]; }
+      }
+      removed[blk] = rem;
+      *kept_word = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = *kept_word;
+    // kept boxes of this block suppress every later, still-alive box
+    for (int j = base + 64 + tid; j < n; j += nt) {
+      if ((removed[j >> 6] >> (j & 63)) & 1ull) continue;
+      Box b = box[j];
+      float ab = area[j];
+      unsigned long long kk = kept;
+      bool dead = false;
+      while (kk && !dead) {
+        int r = __ffsll((long long)kk) - 1;
+        kk &= kk - 1;
+        dead = suppresses(box[base + r], area[base + r], b, ab, thr, cmp_ge);
+      }
+      if (dead) atomicOr(&removed[j >> 6], 1ull << (j & 63));
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += nt)
+    flags[row0 + idx[i]] = ((removed[i >> 6] >> (i & 63)) & 1ull) ? 0 : 1;
+}
+
+// flags[n] (0/1) -> ascending indices + count.  One CTA, chunked block scan.
+__global__ void __launch_bounds__(1024, 1)
+compact_flags_kernel(const uint8_t* __restrict__ flags, int n, int64_t* __restrict__ keep,
+                     int32_t* __restrict__ num_keep) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + tid;
+    int f = (i < n) ? flags[i] : 0;
+    unsigned bal = __ballot_sync(0xffffffffu, f);
+    int pre = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[wid] = __popc(bal);
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += warp_tot[w];
+    int c = carry;
+    if (f) keep[c + woff + pre] = i;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += warp_tot[w];
+      carry = c + t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *num_keep = carry;
+}
+
+// ---------------------------------------------------------------------------------------
+// Large-n path: CUB radix sort -> upper-triangular mask tiles -> single-CTA sweep.
+__global__ void nms_prepare_sort_kernel(const float* __restrict__ dets, int n, float* keys,
+                                        int* vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { keys[i] = dets[i * 5 + 4]; vals[i] = i; }
+}
+
+__global__ void nms_gather_sorted_kernel(const float* __restrict__ dets, const int* order, int n,
+                                         Box* box, float* area) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float* s = dets + (size_t)order[i] * 5;
+    Box b{s[0], s[1], s[2], s[3]};
+    box[i] = b;
+    area[i] = box_area(b);
+  }
+}
+
+// grid (col_blocks, col_blocks), 64 threads; tiles below the diagonal exit (never read).
+__global__ void nms_mask_kernel(const Box* __restrict__ box, const float* __restrict__ area, int n,
+                                float thr, int cmp_ge, unsigned long long* __restrict__ mask,
+                                int col_blocks) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;
+  __shared__ Box sbox[64];
+  __shared__ float sarea[64];
+  const int t = threadIdx.x;
+  const int csize = min(64, n - cb * 64), rsize = min(64, n - rb * 64);
+  if (t < csize) { sbox[t] = box[cb * 64 + t]; sarea[t] = area[cb * 64 + t]; }
+  __syncthreads();
+  if (t < rsize) {
+    const int r = rb * 64 + t;
+    Box a = box[r];
+    float aa = area[r];
+    unsigned long long bits = 0ull;
+    int start = (rb == cb) ? t + 1 : 0;
+    for (int c = start; c < csize; ++c)
+      if (suppresses(a, aa, sbox[c], sarea[c], thr, cmp_ge)) bits |= 1ull << c;
+    mask[(size_t)r * col_blocks + cb] = bits;
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order, int n,
+                 int col_blocks, uint8_t* __restrict__ flags) {
+  extern __shared__ unsigned long long remv[];  // col_blocks words
+  __shared__ unsigned long long kept_word;
+  __shared__ unsigned long long diag[64];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < col_blocks; i += nt) remv[i] = 0ull;
+  __syncthreads();
+  for (int blk = 0; blk < col_blocks; ++blk) {
+    const int base = blk * 64, cnt = min(64, n - base);
+    if (tid < cnt) diag[tid] = mask[(size_t)(base + tid) * col_blocks + blk];
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long rem = remv[blk], kept = 0ull;
+      for (int r = 0; r < cnt; ++r)
+        if (!((rem >> r) & 1ull)) {
+          kept |= 1ull << r;
+          rem |= diag[r];
+        }
+      remv[blk] = rem;
+      kept_word = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = kept_word;
+    for (int w = blk + 1 + tid; w < col_blocks; w += nt) {
+      unsigned long long acc = 0ull, kk = kept;
+      while (kk) {
+        int r = __ffsll((long long)kk) - 1;
+        kk &= kk - 1;
+        acc |= mask[(size_t)(base + r) * col_blocks + w];
+      }
+      remv[w] |= acc;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += nt)
+    flags[order[i]] = ((remv[i >> 6] >> (i & 63)) & 1ull) ? 0 : 1;
+}
+
+static size_t small_smem_bytes(int P_cap) {
+  return (size_t)P_cap * (4 + 4 + 16 + 4) + (size_t)((P_cap + 63) / 64) * 8 + 64 * 8 + 16;
+}
+static int pow2_cap(int n) {
+  int P = 64;
+  while (P < n) P <<= 1;
+  return P;
+}
+
+struct LargeWs {
+  float *keys_in, *keys_out, *area;
+  int *vals_in, *vals_out;
+  Box* box;
+  unsigned long long* mask;
+  uint8_t* flags;
+  void* cub;
+  size_t cub_bytes, total;
+};
+static LargeWs carve_large(void* ws, int n) {
+  LargeWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = ws ? (void*)((char*)ws + off) : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  int cb = (n + 63) / 64;
+  w.keys_in = (float*)take((size_t)n * 4);
+  w.keys_out = (float*)take((size_t)n * 4);
+  w.vals_in = (int*)take((size_t)n * 4);
+  w.vals_out = (int*)take((size_t)n * 4);
+  w.box = (Box*)take((size_t)n * 16);
+  w.area = (float*)take((size_t)n * 4);
+  w.flags = (uint8_t*)take((size_t)n);
+  w.mask = (unsigned long long*)take((size_t)n * cb * 8);
+  w.cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, w.cub_bytes, (float*)nullptr, (float*)nullptr,
+                                            (int*)nullptr, (int*)nullptr, n);
+  w.cub = take(w.cub_bytes);
+  w.total = off;
+  return w;
+}
+
+}  // namespace kgdet
+
+using namespace kgdet;
+
+extern "C" size_t kgdet_nms_workspace_bytes(int32_t n) {
+  if (n <= 0) return 256;
+  if (n <= kSmallMax) return align_up((size_t)n, 256);  // flags only
+  return carve_large(nullptr, n).total;
+}
+
+extern "C" int kgdet_nms(const float* dets, int32_t n, float iou_thr, int cmp_mode, int64_t* keep,
+                         int32_t* num_keep, void* workspace, size_t workspace_bytes,
+                         void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KG_CHECK_ARG(n >= 0, "kgdet_nms: n must be >= 0 (got %d)", n);
+  KG_CHECK_ARG(num_keep != nullptr, "kgdet_nms: num_keep is NULL");
+  KG_CHECK_ARG(cmp_mode == KGDET_NMS_GT || cmp_mode == KGDET_NMS_GE, "kgdet_nms: bad cmp_mode %d",
+               cmp_mode);
+  if (n == 0) {  // nms_wrapper.py:39-40 / nms_cuda.cpp:10-11: empty in, empty out
+    KG_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), stream));
+    return KGDET_OK;
+  }
+  KG_CHECK_ARG(dets && keep, "kgdet_nms: NULL dets/keep");
+  if (workspace_bytes < kgdet_nms_workspace_bytes(n) || !workspace) {
+    set_error("kgdet_nms: workspace too small (%zu < %zu)", workspace_bytes,
+              kgdet_nms_workspace_bytes(n));
+    return KGDET_ERR_WORKSPACE;
+  }
+  if (n <= kSmallMax) {
+    uint8_t* flags = (uint8_t*)workspace;
+    int P_cap = pow2_cap(n);
+    size_t smem = small_smem_bytes(P_cap);
+    KG_CUDA(cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    nms_small_kernel<<<1, kSmallThreads, smem, stream>>>(dets, nullptr, n, iou_thr,
+                                                         cmp_mode == KGDET_NMS_GE, flags, P_cap);
+    KG_LAUNCH_CHECK("nms_small_kernel");
+    compact_flags_kernel<<<1, 1024, 0, stream>>>(flags, n, keep, num_keep);
+    KG_LAUNCH_CHECK("compact_flags_kernel");
+    return KGDET_OK;
+  }
+  LargeWs w = carve_large(workspace, n);
+  const int cb = (n + 63) / 64;
+  nms_prepare_sort_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(dets, n, w.keys_in, w.vals_in);
+  KG_LAUNCH_CHECK("nms_prepare_sort_kernel");
+  size_t cub_bytes = w.cub_bytes;
+  KG_CUDA(cub::DeviceRadixSort::SortPairsDescending(w.cub, cub_bytes, w.keys_in, w.keys_out,
+                                                    w.vals_in, w.vals_out, n, 0, 32, stream));
+  nms_gather_sorted_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(dets, w.vals_out, n, w.box,
+                                                                 w.area);
+  KG_LAUNCH_CHECK("nms_gather_sorted_kernel");
+  nms_mask_kernel<<<dim3(cb, cb), 64, 0, stream>>>(w.box, w.area, n, iou_thr,
+                                                   cmp_mode == KGDET_NMS_GE, w.mask, cb);
+  KG_LAUNCH_CHECK("nms_mask_kernel");
+  size_t sweep_smem = (size_t)cb * 8;
+  KG_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sweep_smem));
+  nms_sweep_kernel<<<1, 1024, sweep_smem, stream>>>(w.mask, w.vals_out, n, cb, w.flags);
+  KG_LAUNCH_CHECK("nms_sweep_kernel");
+  compact_flags_kernel<<<1, 1024, 0, stream>>>(w.flags, n, keep, num_keep);
+  KG_LAUNCH_CHECK("compact_flags_kernel");
+  return KGDET_OK;
+}
+
+extern "C" size_t kgdet_nms_batched_workspace_bytes(int32_t, int32_t, int32_t) { return 256; }
+
+extern "C" int kgdet_nms_batched(const float* dets, const int32_t* seg_offsets, int32_t nseg,
+                                 int32_t total, int32_t max_seg_len, float iou_thr, int cmp_mode,
+                                 uint8_t* keep_flags, void*, size_t, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KG_CHECK_ARG(nseg >= 0 && total >= 0, "kgdet_nms_batched: negative sizes");
+  KG_CHECK_ARG(cmp_mode == KGDET_NMS_GT || cmp_mode == KGDET_NMS_GE,
+               "kgdet_nms_batched: bad cmp_mode %d", cmp_mode);
+  if (nseg == 0 || total == 0) return KGDET_OK;
+  KG_CHECK_ARG(dets && seg_offsets && keep_flags, "kgdet_nms_batched: NULL pointer");
+  if (max_seg_len > kSmallMax) {
+    set_error("kgdet_nms_batched: max_seg_len %d exceeds the single-CTA limit %d; call kgdet_nms "
+              "per segment", max_seg_len, kSmallMax);
+    return KGDET_ERR_UNSUPPORTED;
+  }
+  int P_cap = pow2_cap(max_seg_len < 1 ? 1 : max_seg_len);
+  size_t smem = small_smem_bytes(P_cap);
+  KG_CUDA(cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  nms_small_kernel<<<nseg, kSmallThreads, smem, stream>>>(dets, seg_offsets, 0, iou_thr,
+                                                          cmp_mode == KGDET_NMS_GE, keep_flags,
+                                                          P_cap);
+  KG_LAUNCH_CHECK("nms_small_kernel(batched)");
+  return KGDET_OK;
+}

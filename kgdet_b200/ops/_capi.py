@@ -1,0 +1,127 @@
+"""ctypes binding of include/kgdet_b200.h (the C-ABI boundary).
+
+PyTorch is only plumbing here: it owns device memory and streams; every compute call goes
+through ``libkgdet_b200.so``.  There is no CPU fallback and no alternative backend: if the
+library is missing or a call fails, a ``RuntimeError`` is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, '_lib', 'libkgdet_b200.so')
+
+# enums of include/kgdet_b200.h
+F32, BF16 = 0, 1
+PREC_FP32, PREC_TF32X3, PREC_BF16, PREC_TF32 = 0, 1, 2, 3
+NMS_GT, NMS_GE = 0, 1
+PRECISIONS = {'fp32': PREC_FP32, 'tf32x3': PREC_TF32X3, 'bf16': PREC_BF16, 'tf32': PREC_TF32}
+
+c_i32, c_f32, c_sz, c_ptr = ctypes.c_int32, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p
+
+
+class DcnShape(ctypes.Structure):
+    """struct kgdet_dcn_shape"""
+    _fields_ = [(n, c_i32) for n in (
+        'N', 'C', 'H', 'W', 'Cout', 'kh', 'kw', 'stride_h', 'stride_w', 'pad_h', 'pad_w',
+        'dil_h', 'dil_w', 'groups', 'deformable_groups')]
+
+
+_SHAPE_P = ctypes.POINTER(DcnShape)
+
+# name -> (restype, argtypes); must list every KGDET_API symbol of the header
+SIGNATURES = {
+    'kgdet_last_error': (ctypes.c_char_p, []),
+    'kgdet_abi_version': (ctypes.c_int, []),
+    'kgdet_dcn_fast_path_supported': (ctypes.c_int, [_SHAPE_P, ctypes.c_int]),
+    'kgdet_dcn_packed_weight_bytes': (c_sz, [_SHAPE_P, ctypes.c_int]),
+    'kgdet_dcn_pack_weight': (ctypes.c_int, [c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
+    'kgdet_dcn_forward_workspace_bytes': (c_sz, [_SHAPE_P, ctypes.c_int, ctypes.c_int]),
+    'kgdet_dcn_forward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, _SHAPE_P,
+                                         ctypes.c_int, ctypes.c_int, c_ptr, c_sz, c_ptr]),
+    'kgdet_dcn_backward_input_workspace_bytes': (c_sz, [_SHAPE_P, ctypes.c_int, ctypes.c_int]),
+    'kgdet_dcn_backward_input': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                                c_ptr, _SHAPE_P, ctypes.c_int, ctypes.c_int,
+                                                c_ptr, c_sz, c_ptr]),
+    'kgdet_dcn_backward_weight_workspace_bytes': (c_sz, [_SHAPE_P, ctypes.c_int, ctypes.c_int]),
+    'kgdet_dcn_backward_weight': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_f32,
+                                                 _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr, c_sz,
+                                                 c_ptr]),
+    'kgdet_nms_workspace_bytes': (c_sz, [c_i32]),
+    'kgdet_nms': (ctypes.c_int, [c_ptr, c_i32, c_f32, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_sz,
+                                 c_ptr]),
+    'kgdet_nms_batched_workspace_bytes': (c_sz, [c_i32, c_i32, c_i32]),
+    'kgdet_nms_batched': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_f32, ctypes.c_int,
+                                         c_ptr, c_ptr, c_sz, c_ptr]),
+    'kgdet_sigmoid_focal_loss_forward': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_f32, c_f32,
+                                                        c_ptr, ctypes.c_int, c_ptr]),
+    'kgdet_sigmoid_focal_loss_backward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_f32,
+                                                         c_f32, c_ptr, ctypes.c_int, c_ptr]),
+    'kgdet_sigmoid_focal_loss_sum_forward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_i32, c_i32,
+                                                            c_f32, c_f32, c_ptr, ctypes.c_int,
+                                                            c_ptr]),
+    'kgdet_sigmoid_focal_loss_sum_backward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32,
+                                                             c_i32, c_f32, c_f32, c_ptr,
+                                                             ctypes.c_int, c_ptr]),
+    'kgdet_points2bbox_moment_forward': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32,
+                                                        ctypes.c_int, c_ptr, c_ptr]),
+    'kgdet_points2bbox_moment_backward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32,
+                                                         ctypes.c_int, c_f32, c_ptr, c_ptr, c_ptr]),
+    'kgdet_nchw_to_nhwc': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, ctypes.c_int,
+                                          ctypes.c_int, c_ptr]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libkgdet_b200.so once.  Missing library is a hard error (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'kgdet_b200: %s not found. Build it with `python -m kgdet_b200.build` '
+                '(nvcc, sm_100a). There is no CPU or PyTorch fallback.' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.kgdet_abi_version() != 1:
+            raise RuntimeError('kgdet_b200: ABI version mismatch')
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().kgdet_last_error()
+        raise RuntimeError('%s failed (%d): %s' % (what, rc, msg.decode() if msg else '?'))
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError('kgdet_b200 ops support float32 and bfloat16 tensors, got %s' % t.dtype)
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def workspace(nbytes, like):
+    """Scratch from torch's caching allocator (stream-ordered reuse, no cudaMalloc in steady state)."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=like.device)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        # the reference raises NotImplementedError for CPU tensors (dcn/deform_conv.py:44-45)
+        raise NotImplementedError('%s: kgdet_b200 ops are CUDA-only (got a %s tensor)' % (name, t.device))
