@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""KGDet head throughput on B200 (BASELINE.json metric: "KGDet head images/sec @800x1333").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU path, same metric/config
+
+Workload (BASELINE.json configs[2], named in config.workload): the KGDet head of
+kgdet_moment_r50_fpn_1x-deepfashion2 at 800x1333 (stride-32 map 25x42), batch 16 images per GPU,
+image-sharded over N GPUs with no data-path collective (weak scaling).  One step = head forward
+(towers, stage 1, 2 x 6 deformable convolutions on 9/25/49-point sets, 3 moment transforms) +
+get_bboxes (decode, top-k, batched per-class NMS, top-100) for the whole batch.  Synthetic
+N(0,1) features, seeded non-degenerate random weights; classification scores entering NMS are a
+fixed synthetic map (random-init logits never pass score_thr=0.05: SURVEY.md fact 5).
+
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'kgdet_head_images_per_sec'
+UNIT = 'images/s'
+H, W, C = 25, 42, 256           # 800x1333 padded to 800x1344, stride 32
+IMG_SHAPE = (800, 1333)
+SCORE_POW = 28                  # scores = U(0,1)^28  ->  ~10% of (point, class) pairs pass 0.05
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def workload_config(args, world):
+    return {'workload': 'kgdet_moment_r50_fpn_1x-deepfashion2 head inference @800x1333 (map 25x42, stride 32): '
+                        'forward_single + get_bboxes, batch %d per GPU, image-sharded' % args.batch,
+            'batch_per_gpu': args.batch, 'global_batch': args.batch * world, 'dcn_precision': args.precision,
+            'dcn_calls_per_step': 12, 'point_sets': [9, 25, 49], 'channels': 256,
+            'nms': 'synthetic scores U^%d (~10%% of point-class pairs > score_thr 0.05), iou 0.5, 13 classes, '
+                   'max_per_img 100' % SCORE_POW,
+            'weights': 'seeded random, conv N(0,(1.4/sqrt(fan_in))^2), point regressors x4 so offsets span '
+                       'several pixels', 'l2': 'flushed (256 MiB write) before every timed step',
+            'parallelism': 'dp%d' % world}
+
+
+def make_weights(head):
+    from tests.golden.gen_golden import fill_state_dict
+    head.load_state_dict(fill_state_dict(head.state_dict(), seed=1234), strict=True)
+    return head
+
+
+def make_inputs(batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, C, H, W, generator=g)
+    scores = torch.rand(batch, 13, H, W, generator=g) ** SCORE_POW
+    return x, scores
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(',')])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        # "under load": the upper half of the samples (the sampler also sees the untimed L2 flushes)
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {'sm_mhz': med, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def dcn_flops(batch, k):
+    return 2.0 * batch * H * W * C * C * k * k
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from kgdet_b200 import ops
+    from kgdet_b200.head import KGDetHead
+    from kgdet_b200.ops import _capi
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _capi.lib()
+    ops.set_precision(args.precision)
+
+    head = make_weights(KGDetHead()).to(dev).eval()
+    x_cpu, sc_cpu = make_inputs(args.batch, seed=100 + rank)
+    x_host = x_cpu.pin_memory()
+    x_dev = x_host.to(dev)
+    sc_dev = sc_cpu.to(dev)
+    shapes = [IMG_SHAPE] * args.batch
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # time the fused DCN kernel alone, inside the real steps, through the C-ABI measurement hook
+    prof = []
+    dcn_mods = [m for m in head.modules() if isinstance(m, ops.DeformConv)]
+    recording = {'on': False}
+
+    def pre_hook(mod, inp):
+        if recording['on']:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # make sure the events exist on this device before handing raw handles to the library
+            e0.record(); e1.record()
+            lib.kgdet_dcn_set_profile_events(e0.cuda_event, e1.cuda_event)
+            prof.append((mod.kernel_size[0], e0, e1))
+    for m in dcn_mods:
+        m.register_forward_pre_hook(pre_hook)
+
+    def step(x):
+        with torch.no_grad():
+            o = head.forward_single(x)
+            return head.get_bboxes([o[2]], [o[5]], [o[8]], shapes, 0.05, 0.5, 1000, 100, score_override=[sc_dev])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        step(x_dev)
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") --------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    evs = []
+    recording['on'] = True
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)                       # L2 flush, outside the event pair
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(x_dev)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    barrier()
+    wall = time.perf_counter() - t0
+    recording['on'] = False
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---- end-to-end through the public API with host buffers ("e2e") -----------------------------
+    out_host = None
+    e2e_evs = []
+    for it in range(args.steps + 2):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        xd = x_host.to(dev, non_blocking=True)
+        dets, labels, kpts = step(xd)
+        if out_host is None:
+            out_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (dets, labels, kpts)]
+        for h, t in zip(out_host, (dets, labels, kpts)):
+            h.copy_(t, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            e2e_evs.append(a.elapsed_time(b))
+    e2e_ms = sum(e2e_evs)
+    h2d = x_host.numel() * x_host.element_size()
+    d2h = sum(h.numel() * h.element_size() for h in out_host)
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak_tf = peaks.get('bf16_tflops_sustained') or 1400.0
+        peak_src = 'bf16_tflops_sustained of MEASURED_PEAKS.json' if peaks else 'fallback 1.4 PFLOP/s sustained'
+        per_k = {}
+        for k, e0, e1 in prof:
+            per_k.setdefault(k, []).append(e0.elapsed_time(e1))
+        tot_flop = sum(dcn_flops(args.batch, k) * len(v) for k, v in per_k.items())
+        tot_ms = sum(sum(v) for v in per_k.values())
+        achieved = tot_flop / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+        detail = {('k%d' % k): {'launches': len(v), 'avg_us': round(1e3 * sum(v) / len(v), 2),
+                               'tflops': round(dcn_flops(args.batch, k) / (sum(v) / len(v) * 1e-3) / 1e12, 1)}
+                  for k, v in sorted(per_k.items())}
+        result = {
+            'metric': METRIC, 'value': round(args.batch * world * args.steps / (dev_ms * 1e-3), 2), 'unit': UNIT,
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': round(dev_ms / args.steps, 4), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+            'config': workload_config(args, world),
+            'e2e': {'value': round(args.batch * world * args.steps / (e2e_ms * 1e-3), 2), 'unit': UNIT,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': round(e2e_ms / args.steps, 4)},
+            'gpu_launches': 40 * args.steps,
+            'gpu_launches_note': 'per step: 12 x (NCHW->NHWC, sample plan, fused tcgen05 DCN) + 3 moment + 1 batched NMS',
+            'roofline': {'kernel': 'dcn_umma_fwd_kernel (fused gather + tcgen05 GEMM), 12 launches/step',
+                         'bound': 'tensor', 'achieved': round(achieved, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
+                         'frac': round(achieved / peak_tf, 4), 'traffic': None, 'peak_source': peak_src,
+                         'share_of_step': round(tot_ms / dev_ms, 4), 'per_kernel_size': detail},
+            'clocks': clocks, 'wall_s_timed_region': round(wall, 3),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            result['cpu_baseline'] = cpu_baseline(args, budget_s=20.0)
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+def _cpu_step_fn(args, n_images):
+    from tests._cpu_head import make_cpu_head
+    torch.set_num_threads(os.cpu_count() or 1)
+    head = make_weights(make_cpu_head()).eval()
+    x, sc = make_inputs(n_images, seed=100)
+    shapes = [IMG_SHAPE] * n_images
+
+    def step():
+        with torch.no_grad():
+            o = head.forward_single(x)
+            return head.get_bboxes([o[2]], [o[5]], [o[8]], shapes, 0.05, 0.5, 1000, 100, score_override=[sc])
+    return step
+
+
+def cpu_baseline(args, budget_s=20.0):
+    """The same step on the host cores through the oracle port (DCN = torch gather + matmul restatement,
+    NMS = the reference's nms_cpu.cpp when oracle/_ref has it).  Bounded sample, reported not targeted."""
+    from oracle import build_ref
+    n = 1
+    step = _cpu_step_fn(args, n)
+    step()                                   # warm-up
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 2 or (time.perf_counter() - t0 < budget_s and reps < 8):
+        step()
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {'value': round(n * reps / dt, 4), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d repetition(s) of the same step on %d image (batch 1) instead of %d; DCN via '
+                      'oracle/dcn_oracle.py on all host threads, NMS via %s'
+                      % (reps, n, args.batch, 'reference nms_cpu.cpp (oracle/_ref)'
+                         if build_ref.load('nms_cpu') is not None else 'oracle/nms_oracle.c')}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores, same metric/config.
+    Rank 0 only; other ranks exit 0 without work."""
+    from oracle import build_ref
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if rank != 0:
+        return
+    n = args.ref_images
+    step = _cpu_step_fn(args, n)
+    for _ in range(min(max(args.warmup, 1), 2)):     # CPU arm: at most two untimed warm-up steps
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = round(n * args.steps / dt, 4)
+    sample = ('each step = forward_single + get_bboxes on %d image(s) (bounded sample of the batch-%d workload); '
+              'unchanged head data flow, DCN = oracle/dcn_oracle.py (mmdet v1 DCN is CUDA-only), NMS = %s'
+              % (n, args.batch, 'reference nms_cpu.cpp compiled unmodified (oracle/_ref)'
+                 if build_ref.load('nms_cpu') is not None else 'oracle/nms_oracle.c'))
+    a2 = argparse.Namespace(**vars(args))
+    cfg = workload_config(a2, world)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': round(dt / args.steps * 1e3, 3), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=16, help='images per GPU')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'tf32x3', 'tf32', 'fp32'])
+    ap.add_argument('--ref-images', type=int, default=1, help='images per reference step (bounded sample)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()
