@@ -23,6 +23,28 @@ struct __align__(16) SampleAux {
   int valid;
 };
 
+// Compact record of the tensor-core path (deformable_groups == 1): 16 bytes per (position, tap).
+//   base   pixel index of the (h_low, w_low) corner, n*H*W + h_low*W + w_low; may point outside
+//          the image when that corner is unusable -- corners are addressed as base + {0, 1, W, W+1}
+//          and never dereferenced when their weight is 0
+//   lh, lw fractional parts; the two mantissa LSBs carry the corner-validity bits of the axis:
+//          bit0 = low index inside the map, bit1 = high index inside the map (costs < 4 ulp of lh/lw)
+//   scale  modulation mask (1 for plain DCN) * [sample inside the (-1,H)x(-1,W) window]
+struct __align__(16) SampleRec16 {
+  int base;
+  float lh, lw, scale;
+};
+// Second flavour of the same 16 bytes, used by the bf16 mode: {base, bf16x2(w0,w1), bf16x2(w2,w3), 0}
+// with the four corner weights (validity, window test and mask folded in) pre-rounded to bf16.
+// In both flavours `base` is always a safe address: the fused kernel loads all four corners
+// unconditionally (weight 0 for unusable ones) from an NHWC buffer that carries a zeroed guard band
+// of dcn_guard_pixels() pixels on each side.
+enum { PLAN16_F32 = 0, PLAN16_BF16W = 1 };
+size_t plan16_bytes(const DcnGeom& g);
+int launch_plan16(const DcnGeom& g, const float* offset, const float* mask, SampleRec16* rec, int fmt,
+                  cudaStream_t stream);
+static inline int dcn_guard_pixels(const DcnGeom& g) { return g.W + 2; }
+
 size_t plan_rows(const DcnGeom& g);                 // M rounded up to 128
 size_t plan_bytes(const DcnGeom& g);                // SampleRec array
 size_t plan_aux_bytes(const DcnGeom& g);            // SampleAux array
@@ -55,7 +77,7 @@ bool umma_supported(const DcnGeom& g, int precision);
 size_t umma_packed_weight_bytes(const DcnGeom& g, int precision);
 int umma_pack_weight(const DcnGeom& g, const float* weight, void* packed, int precision,
                      cudaStream_t stream);
-int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec* plan, const void* packed_w,
+int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec16* plan, const void* packed_w,
                  const float* bias, void* out_nchw, int out_dtype, int precision,
                  cudaStream_t stream);
 

@@ -25,13 +25,19 @@ bool use_umma(const DcnGeom& g, int precision) {
   return precision != KGDET_PREC_FP32 && umma_supported(g, precision);
 }
 
-struct FwdWs { void* in_nhwc; SampleRec* plan; size_t total; };
+// in_nhwc points past a zeroed guard band of `guard_bytes` (the fused kernel loads all four bilinear
+// corners unconditionally; see dcn.cuh); the same number of bytes follows the tensor.
+struct FwdWs { void* in_nhwc; void* plan; size_t guard_bytes, in_bytes, total; };
 FwdWs carve_fwd(const DcnGeom& g, int precision, void* ws) {
   Carver c(ws);
   FwdWs w;
-  const size_t esz = (use_umma(g, precision) && precision == KGDET_PREC_BF16) ? 2 : 4;
-  w.in_nhwc = c.take<void>((size_t)g.N * g.H * g.W * g.C * esz);
-  w.plan = c.take<SampleRec>(plan_bytes(g));
+  const bool fast = use_umma(g, precision);
+  const size_t esz = (fast && precision == KGDET_PREC_BF16) ? 2 : 4;
+  w.guard_bytes = fast ? align_up((size_t)dcn_guard_pixels(g) * g.C * esz, 1024) : 0;
+  w.in_bytes = (size_t)g.N * g.H * g.W * g.C * esz;
+  char* raw = c.take<char>(w.in_bytes + 2 * w.guard_bytes);
+  w.in_nhwc = raw ? raw + w.guard_bytes : nullptr;
+  w.plan = use_umma(g, precision) ? c.take<void>(plan16_bytes(g)) : c.take<void>(plan_bytes(g));
   w.total = c.off;
   return w;
 }
@@ -119,15 +125,22 @@ extern "C" int kgdet_dcn_forward(const void* input, const float* offset, const f
   if ((rc = check_ws("kgdet_dcn_forward", workspace, workspace_bytes, w.total)) != KGDET_OK) return rc;
   const bool fast = use_umma(g, precision);
   const int cdtype = (fast && precision == KGDET_PREC_BF16) ? KGDET_BF16 : KGDET_F32;
+  if (w.guard_bytes) {
+    KG_CUDA(cudaMemsetAsync((char*)w.in_nhwc - w.guard_bytes, 0, w.guard_bytes, stream));
+    KG_CUDA(cudaMemsetAsync((char*)w.in_nhwc + w.in_bytes, 0, w.guard_bytes, stream));
+  }
   if ((rc = launch_transpose(input, w.in_nhwc, g.N, g.C, g.H * g.W, dtype, cdtype, stream)) != KGDET_OK) return rc;
-  if ((rc = launch_plan(g, offset, mask, w.plan, nullptr, stream)) != KGDET_OK) return rc;
+  if (fast) rc = launch_plan16(g, offset, mask, (SampleRec16*)w.plan,
+                               precision == KGDET_PREC_BF16 ? PLAN16_BF16W : PLAN16_F32, stream);
+  else rc = launch_plan(g, offset, mask, (SampleRec*)w.plan, nullptr, stream);
+  if (rc != KGDET_OK) return rc;
   cudaEvent_t ev0 = g_prof_start, ev1 = g_prof_stop;
   g_prof_start = g_prof_stop = nullptr;
   if (ev0 && ev1) KG_CUDA(cudaEventRecord(ev0, stream));
   if (fast)
-    rc = umma_forward(g, w.in_nhwc, w.plan, weight_packed, bias, output, dtype, precision, stream);
+    rc = umma_forward(g, w.in_nhwc, (const SampleRec16*)w.plan, weight_packed, bias, output, dtype, precision, stream);
   else
-    rc = simt_forward(g, (const float*)w.in_nhwc, w.plan, (const float*)weight_packed, bias, output, dtype,
+    rc = simt_forward(g, (const float*)w.in_nhwc, (const SampleRec*)w.plan, (const float*)weight_packed, bias, output, dtype,
                       stream);
   if (rc == KGDET_OK && ev0 && ev1) KG_CUDA(cudaEventRecord(ev1, stream));
   return rc;

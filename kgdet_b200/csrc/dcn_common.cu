@@ -61,6 +61,81 @@ __global__ void dcn_plan_kernel(DcnGeom g, const float* __restrict__ offset,
   }
 }
 
+size_t plan16_bytes(const DcnGeom& g) { return plan_rows(g) * g.K * sizeof(SampleRec16); }
+
+// Same sampling rule as dcn_plan_kernel, compact output for the tensor-core path (dgroups == 1).
+// Threads run fastest over positions so the offset reads are coalesced (offset is [N, 2K, Ho, Wo]).
+__global__ void dcn_plan16_kernel(DcnGeom g, const float* __restrict__ offset,
+                                  const float* __restrict__ mask, SampleRec16* __restrict__ rec,
+                                  int rows_padded, int fmt) {
+  const long long total = (long long)rows_padded * g.K;
+  const int HoWo = g.Ho * g.Wo;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)blockDim.x * gridDim.x) {
+    const int tap = (int)(idx / rows_padded);
+    const int m = (int)(idx - (long long)tap * rows_padded);
+    int base = 0;
+    float lh = 0.f, lw = 0.f, scale = 0.f;
+    unsigned vh = 0u, vw = 0u;
+    if (m < g.M) {
+      const int n = m / HoWo, p = m - n * HoWo;
+      const int y = p / g.Wo, x = p - y * g.Wo;
+      const int i = tap / g.kw, j = tap - i * g.kw;
+      const size_t obase = ((size_t)n * 2 * g.K + 2 * tap) * HoWo + p;
+      const float off_h = offset[obase], off_w = offset[obase + HoWo];
+      const float mval = mask ? mask[((size_t)n * g.K + tap) * HoWo + p] : 1.f;
+      const float h_im = (float)(y * g.sh - g.ph + i * g.dh) + off_h;
+      const float w_im = (float)(x * g.sw - g.pw + j * g.dw) + off_w;
+      base = n * g.H * g.W;                         // safe address for samples outside the window
+      if (h_im > -1.f && w_im > -1.f && h_im < (float)g.H && w_im < (float)g.W) {
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int h_low = (int)hf, w_low = (int)wf;
+        lh = h_im - hf;
+        lw = w_im - wf;
+        if (h_low >= 0) vh |= 1u;
+        if (h_low + 1 <= g.H - 1) vh |= 2u;
+        if (w_low >= 0) vw |= 1u;
+        if (w_low + 1 <= g.W - 1) vw |= 2u;
+        base = n * g.H * g.W + h_low * g.W + w_low;  // within the guard band by construction
+        scale = mval;
+      }
+    }
+    SampleRec16 r;
+    r.base = base;
+    if (fmt == PLAN16_BF16W) {
+      const float hh = 1.f - lh, hw = 1.f - lw;
+      const float w0 = ((vh & 1u) && (vw & 1u)) ? hh * hw * scale : 0.f;
+      const float w1 = ((vh & 1u) && (vw & 2u)) ? hh * lw * scale : 0.f;
+      const float w2 = ((vh & 2u) && (vw & 1u)) ? lh * hw * scale : 0.f;
+      const float w3 = ((vh & 2u) && (vw & 2u)) ? lh * lw * scale : 0.f;
+      const unsigned p01 = ((unsigned)__bfloat16_as_ushort(__float2bfloat16(w1)) << 16) |
+                           (unsigned)__bfloat16_as_ushort(__float2bfloat16(w0));
+      const unsigned p23 = ((unsigned)__bfloat16_as_ushort(__float2bfloat16(w3)) << 16) |
+                           (unsigned)__bfloat16_as_ushort(__float2bfloat16(w2));
+      r.lh = __uint_as_float(p01);
+      r.lw = __uint_as_float(p23);
+      r.scale = 0.f;
+    } else {
+      r.lh = __uint_as_float((__float_as_uint(lh) & ~3u) | vh);
+      r.lw = __uint_as_float((__float_as_uint(lw) & ~3u) | vw);
+      r.scale = scale;
+    }
+    rec[(size_t)m * g.K + tap] = r;
+  }
+}
+
+int launch_plan16(const DcnGeom& g, const float* offset, const float* mask, SampleRec16* rec, int fmt,
+                  cudaStream_t stream) {
+  const int rows = (int)plan_rows(g);
+  const long long total = (long long)rows * g.K;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  dcn_plan16_kernel<<<(int)blocks, 256, 0, stream>>>(g, offset, mask, rec, rows, fmt);
+  KG_LAUNCH_CHECK("dcn_plan16_kernel");
+  return KGDET_OK;
+}
+
 int launch_plan(const DcnGeom& g, const float* offset, const float* mask, SampleRec* rec,
                 SampleAux* aux, cudaStream_t stream) {
   const int rows = (int)plan_rows(g);

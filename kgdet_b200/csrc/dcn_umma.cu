@@ -5,22 +5,26 @@
 // The reference materialises S as the `columns` tensor in HBM (deformable_im2col,
 // deform_conv_cuda_kernel.cu:189-242: C*K x N*H*W fp32, 843 MB for one 7x7 KGDet call) and
 // hands it to a cuBLAS SGEMM (deform_conv_cuda.cpp:230-233).  Here the column tile only ever
-// exists in shared memory:
+// exists in shared memory.  One CTA = 128 output positions x all Cout, 16 warps in two groups:
 //
-//   warps 0-7  producers : bilinear-gather a 128-position x 128-byte slab of S from the NHWC
-//                          input (16-byte vector loads, 8 lanes cover one pixel's slab) using
-//                          the precomputed sample plan, and store it straight into the
-//                          128B-swizzled K-major layout tcgen05.mma reads;
-//                          afterwards the same warps run the epilogue (TMEM -> NCHW output).
-//   warp 8     loader    : one thread streams the matching pre-swizzled weight slab with
-//                          cp.async.bulk (UBLKCP) -- the pack step laid it out so that a
-//                          linear copy lands in UMMA layout, no tensor map needed.
-//   warp 9     MMA       : one thread issues tcgen05.mma (UTCHMMA), accumulators live in TMEM;
-//                          tcgen05.commit releases pipeline stages / signals the epilogue.
+//   group g (8 warps) owns k-blocks g, g+2, g+4, ... and its own TMEM accumulator, so that one
+//   group's gather loads are in flight while the other group combines/stores its tile.
+//   Per k-block (64 bf16 / 32 tf32 channels of one tap):
+//     all 256 threads : decode 4 compact plan records, issue 16 predicated 16-byte gathers from
+//                       the NHWC input (8 lanes cover one pixel's 128-byte slab), prefetch the next
+//                       records, wait for the pipeline stage, bilinear-combine and store the
+//                       128-position x 128-byte A tile straight into the 128B-swizzled K-major
+//                       layout tcgen05.mma reads (fence.proxy.async + mbarrier arrive);
+//     group leader    : one thread streams the matching pre-swizzled weight slab with
+//                       cp.async.bulk (UBLKCP; a linear copy lands in UMMA layout, no tensor map),
+//                       then waits for the stage to be full and issues the tcgen05.mma's
+//                       (UTCHMMA) into the group's accumulator; tcgen05.commit frees the stage.
+//   Epilogue (all warps): out = acc[0] + acc[1] (tcgen05.ld), bias, NCHW store coalesced over
+//   positions.
 //
 // Modes: BF16   kind::f16, bf16 operands                     (1e-3 grade)
-//        TF32X3 kind::tf32, A = Ahi + Alo, B = Bhi + Blo,    (fp32 grade: the dropped term is
-//               3 MMAs per k-step: Ahi.Bhi + Alo.Bhi + Ahi.Blo   Alo.Blo ~ 2^-22)
+//        TF32X3 kind::tf32, A = Ahi + Alo, B = Bhi + Blo,    (the dropped term Alo.Blo is ~2^-22)
+//               3 MMAs per k-step: Alo.Bhi + Ahi.Blo + Ahi.Bhi
 //        TF32   kind::tf32 single pass
 // K order is (channel block, tap, channel-in-block) so that one channel block's taps hit the
 // same L1 lines back to back; umma_pack_weight uses the same order.
@@ -29,8 +33,9 @@
 namespace kgdet {
 
 static constexpr int BM = 128;                 // positions per CTA tile (UMMA M)
-static constexpr int PRODUCER_WARPS = 8;
-static constexpr int UMMA_THREADS = (PRODUCER_WARPS + 2) * 32;
+static constexpr int GROUP_WARPS = 8;           // one group covers 128 rows x 8 chunks in 4 passes
+static constexpr int NUM_GROUPS = 2;
+static constexpr int UMMA_THREADS = NUM_GROUPS * GROUP_WARPS * 32;   // 512 -> 128 registers/thread, no spills
 static constexpr int A_TILE_BYTES = BM * 128;  // 128 rows x 128 B
 
 enum { MODE_BF16 = 0, MODE_TF32X3 = 1, MODE_TF32 = 2 };
@@ -132,25 +137,17 @@ int umma_pack_weight(const DcnGeom& g, const float* weight, void* packed, int pr
 // ---- the fused kernel ----------------------------------------------------------------------
 struct UmmaParams {
   const void* in;            // NHWC, bf16 (MODE_BF16) or fp32 (TF32 modes)
-  const SampleRec* plan;     // [rows_padded][K]
+  const SampleRec16* plan;   // [rows_padded][K]
   const unsigned char* wp;   // packed weights
   const float* bias;         // [Cout] or NULL
   void* out;                 // NCHW
-  int M, C, Cout, K, HoWo;
+  int M, C, W, Cout, K, HoWo;
   int nkb;                   // (C / BK) * K
   uint32_t idesc;
   uint32_t tmem_cols;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ void fma_bf16x2(float w, uint32_t packed, float& a0, float& a1) {
-  a0 = fmaf(w, __uint_as_float(packed << 16), a0);
-  a1 = fmaf(w, __uint_as_float(packed & 0xffff0000u), a1);
-}
+
 
 template <typename T> __device__ __forceinline__ void st_out(T* p, float v);
 template <> __device__ __forceinline__ void st_out<float>(float* p, float v) { *p = v; }
@@ -158,6 +155,44 @@ template <> __device__ __forceinline__ void st_out<__nv_bfloat16>(__nv_bfloat16*
   *p = __float2bfloat16(v);
 }
 
+__device__ __forceinline__ uint32_t bf162_bcast(float w) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(r) : "f"(w));
+  return r;
+}
+__device__ __forceinline__ uint32_t bf162_mul(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t bf162_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void fma_bf16x2_f32(float w, uint32_t packed, float& a0, float& a1) {
+  a0 = fmaf(w, __uint_as_float(packed << 16), a0);
+  a1 = fmaf(w, __uint_as_float(packed & 0xffff0000u), a1);
+}
+
+// bilinear weights of the four corners from a compact plan record (see SampleRec16)
+__device__ __forceinline__ void decode_rec(const float4& r, float (&w)[4]) {
+  const uint32_t lhb = __float_as_uint(r.y), lwb = __float_as_uint(r.z);
+  const float lh = __uint_as_float(lhb & ~3u), lw = __uint_as_float(lwb & ~3u);
+  const float fh0 = (lhb & 1u) ? (1.f - lh) : 0.f, fh1 = (lhb & 2u) ? lh : 0.f;
+  const float fw0 = (lwb & 1u) ? (1.f - lw) * r.w : 0.f, fw1 = (lwb & 2u) ? lw * r.w : 0.f;
+  w[0] = fh0 * fw0; w[1] = fh0 * fw1; w[2] = fh1 * fw0; w[3] = fh1 * fw1;
+}
+
+// 16 warps in two groups of 8; group g owns k-blocks g, g+2, ... and TMEM accumulator g.  There are
+// no dedicated control warps (a 17th warp would cut the register budget from 128 to 96 per thread):
+// per k-block one warp of the group -- rotating -- additionally acts as "leader": it fetches the
+// weight slab (cp.async.bulk, one k-block ahead), waits for the stage to be full and issues the MMAs.
 template <int MODE, int NS, typename Tout>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) dcn_umma_fwd_kernel(const UmmaParams prm) {
   using MT = ModeTraits<MODE>;
@@ -175,14 +210,21 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) dcn_umma_fwd_kernel(const Umm
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM;
+  const int active_groups = prm.nkb < NUM_GROUPS ? prm.nkb : NUM_GROUPS;
+  // every thread that issued MMAs makes one final tcgen05.commit on tmem_full_bar
+  int num_issuers = 0;
+  for (int g = 0; g < NUM_GROUPS; ++g) {
+    const int n_g = (prm.nkb - g + NUM_GROUPS - 1) / NUM_GROUPS;
+    num_issuers += n_g < GROUP_WARPS ? (n_g < 0 ? 0 : n_g) : GROUP_WARPS;
+  }
 
-  if (warp == PRODUCER_WARPS + 1) {
+  if (warp == 0) {
     if (lane == 0) {
       for (int s = 0; s < NS; ++s) {
-        mbar_init(&full_bar[s], PRODUCER_WARPS + 1);
-        mbar_init(&empty_bar[s], 1);
+        mbar_init(&full_bar[s], GROUP_WARPS + 1);   // 8 producer warps + the leader's expect_tx
+        mbar_init(&empty_bar[s], 1);                // one tcgen05.commit
       }
-      mbar_init(tmem_full_bar, 1);
+      mbar_init(tmem_full_bar, num_issuers);
       fence_mbar_init();
     }
     __syncwarp();
@@ -193,170 +235,180 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) dcn_umma_fwd_kernel(const Umm
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < PRODUCER_WARPS) {
-    // ===================== producers: gather S tiles into swizzled smem =====================
-    const int chunk = tid & 7;        // 16-byte chunk of the 128-byte row
-    const int rbase = tid >> 3;       // 0..31
-    const int C = prm.C, K = prm.K;
-    for (int kb = 0; kb < prm.nkb; ++kb) {
+  {
+    const int group = warp / GROUP_WARPS;
+    const int wg = warp % GROUP_WARPS;
+    const int t = tid - group * (GROUP_WARPS * 32);
+    const int chunk = t & 7;          // 16-byte chunk of the 128-byte row
+    const int rbase = t >> 3;         // 0..31; this thread owns rows rbase + 32*ps
+    const int K = prm.K;
+    const size_t rowb = (size_t)prm.C * MT::ELEM;         // bytes per pixel
+    const size_t wrow = (size_t)prm.W * rowb;             // bytes per image row
+    const unsigned char* in_base = reinterpret_cast<const unsigned char*>(prm.in) + chunk * 16;
+    const uint4* plan_t = reinterpret_cast<const uint4*>(prm.plan) + (size_t)(m0 + rbase) * K;
+    const uint32_t acc_tmem = tmem_base + (uint32_t)(group * BN);    // this group's accumulator
+    const uint32_t b_bytes = (uint32_t)(MT::B_TILES * b_tile_bytes);
+    // the packed layout always carries hi+lo for tf32; single-pass TF32 copies only hi
+    const size_t b_src_stride = (size_t)(MODE == MODE_BF16 ? 1 : 2) * b_tile_bytes;
+    // this thread's byte offset inside an A tile (row rbase, swizzled 16-byte chunk); rows of later
+    // passes are 32 rows = 4096 bytes further and keep the same (row & 7)
+    const int a_off = rbase * 128 + ((chunk ^ (rbase & 7)) << 4);
+    bool issued_any = false;
+
+    // (tap, channel block) of k-block kb = cb * K + tap, advanced incrementally (no divisions)
+    int tap = group % K, cb = group / K;
+    uint4 rec[4];
+    if (group < prm.nkb) {
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) rec[ps] = __ldg(plan_t + (size_t)ps * 32 * K + tap);
+    }
+    for (int kb = group; kb < prm.nkb; kb += NUM_GROUPS) {
       const int s = kb % NS, it = kb / NS;
-      const int cb = kb / K, tap = kb - cb * K;
-      mbar_wait(&empty_bar[s], (it & 1) ^ 1);
+      const bool leader = ((kb / NUM_GROUPS) % GROUP_WARPS) == wg;     // warp-uniform, rotates
       unsigned char* a_tile = smem + (size_t)s * stage_bytes;
-      SampleRec rec[4];
+      const unsigned char* in_cb = in_base + (size_t)cb * 128;
+
+      // ---- issue the 16 gathers of this k-block (all four corners, unconditionally: unusable
+      //      corners carry weight 0 and a guard-band-safe address) ----
+      uint4 v[4][4];
+      uint4 cur[4];
 #pragma unroll
       for (int ps = 0; ps < 4; ++ps) {
-        const SampleRec* rp = prm.plan + (size_t)(m0 + rbase + ps * 32) * K + tap;
-        const int4 a = __ldg(reinterpret_cast<const int4*>(rp));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(rp) + 1);
-        rec[ps].pix[0] = a.x; rec[ps].pix[1] = a.y; rec[ps].pix[2] = a.z; rec[ps].pix[3] = a.w;
-        rec[ps].w[0] = b.x; rec[ps].w[1] = b.y; rec[ps].w[2] = b.z; rec[ps].w[3] = b.w;
+        cur[ps] = rec[ps];
+        const unsigned char* p0 = in_cb + (long long)(int)cur[ps].x * (long long)rowb;
+        v[ps][0] = __ldg(reinterpret_cast<const uint4*>(p0));
+        v[ps][1] = __ldg(reinterpret_cast<const uint4*>(p0 + rowb));
+        v[ps][2] = __ldg(reinterpret_cast<const uint4*>(p0 + wrow));
+        v[ps][3] = __ldg(reinterpret_cast<const uint4*>(p0 + wrow + rowb));
       }
-      if constexpr (MODE == MODE_BF16) {
-        const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(prm.in) + cb * 64 + chunk * 8;
-        uint4 v[4][4];
+      // ---- records of this group's next k-block: in flight while we combine the current one ----
+      tap += NUM_GROUPS;
+      while (tap >= K) { tap -= K; ++cb; }
+      if (kb + NUM_GROUPS < prm.nkb) {
 #pragma unroll
-        for (int ps = 0; ps < 4; ++ps)
+        for (int ps = 0; ps < 4; ++ps) rec[ps] = __ldg(plan_t + (size_t)ps * 32 * K + tap);
+      }
+      mbar_wait(&empty_bar[s], (it & 1) ^ 1);      // the gathers above are already in flight
+      if (leader && lane == 0 && (NS < 2 * NUM_GROUPS || kb < NUM_GROUPS)) {
+        // weight slab of this k-block -> smem (async).  With >= 4 stages only the group's first
+        // k-block is fetched here; later slabs are prefetched one k-block ahead (below).
+        mbar_arrive_expect_tx(&full_bar[s], b_bytes);
+        bulk_g2s(a_tile + MT::A_TILES * A_TILE_BYTES, prm.wp + (size_t)kb * b_src_stride, b_bytes,
+                 &full_bar[s]);
+      }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            v[ps][i] = make_uint4(0u, 0u, 0u, 0u);
-            if (rec[ps].w[i] != 0.f)
-              v[ps][i] = __ldg(reinterpret_cast<const uint4*>(in + (size_t)rec[ps].pix[i] * C));
-          }
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float w = rec[ps].w[i];
-            fma_bf16x2(w, v[ps][i].x, acc[0], acc[1]);
-            fma_bf16x2(w, v[ps][i].y, acc[2], acc[3]);
-            fma_bf16x2(w, v[ps][i].z, acc[4], acc[5]);
-            fma_bf16x2(w, v[ps][i].w, acc[6], acc[7]);
-          }
-          const int r = rbase + ps * 32;
+      for (int ps = 0; ps < 4; ++ps) {
+        unsigned char* dst = a_tile + a_off + ps * 4096;
+        if constexpr (MODE == MODE_BF16) {
+          // packed bf16 interpolation: the record carries bf16x2 (w0,w1) and (w2,w3)
+          const uint32_t w0 = __byte_perm(cur[ps].y, 0u, 0x1010), w1 = __byte_perm(cur[ps].y, 0u, 0x3232);
+          const uint32_t w2 = __byte_perm(cur[ps].z, 0u, 0x1010), w3 = __byte_perm(cur[ps].z, 0u, 0x3232);
           uint4 o;
-          o.x = pack_bf16x2(acc[0], acc[1]);
-          o.y = pack_bf16x2(acc[2], acc[3]);
-          o.z = pack_bf16x2(acc[4], acc[5]);
-          o.w = pack_bf16x2(acc[6], acc[7]);
-          *reinterpret_cast<uint4*>(a_tile + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
-        }
-      } else {
-        const float* in = reinterpret_cast<const float*>(prm.in) + cb * 32 + chunk * 4;
-        float4 v[4][4];
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            v[ps][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rec[ps].w[i] != 0.f)
-              v[ps][i] = __ldg(reinterpret_cast<const float4*>(in + (size_t)rec[ps].pix[i] * C));
-          }
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
+          o.x = bf162_fma(w3, v[ps][3].x, bf162_fma(w2, v[ps][2].x, bf162_fma(w1, v[ps][1].x, bf162_mul(w0, v[ps][0].x))));
+          o.y = bf162_fma(w3, v[ps][3].y, bf162_fma(w2, v[ps][2].y, bf162_fma(w1, v[ps][1].y, bf162_mul(w0, v[ps][0].y))));
+          o.z = bf162_fma(w3, v[ps][3].z, bf162_fma(w2, v[ps][2].z, bf162_fma(w1, v[ps][1].z, bf162_mul(w0, v[ps][0].z))));
+          o.w = bf162_fma(w3, v[ps][3].w, bf162_fma(w2, v[ps][2].w, bf162_fma(w1, v[ps][1].w, bf162_mul(w0, v[ps][0].w))));
+          *reinterpret_cast<uint4*>(dst) = o;
+        } else {
+          float w[4];
+          decode_rec(make_float4(0.f, __uint_as_float(cur[ps].y), __uint_as_float(cur[ps].z),
+                                 __uint_as_float(cur[ps].w)), w);
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float w = rec[ps].w[i];
-            a0 = fmaf(w, v[ps][i].x, a0);
-            a1 = fmaf(w, v[ps][i].y, a1);
-            a2 = fmaf(w, v[ps][i].z, a2);
-            a3 = fmaf(w, v[ps][i].w, a3);
+            a0 = fmaf(w[i], __uint_as_float(v[ps][i].x), a0);
+            a1 = fmaf(w[i], __uint_as_float(v[ps][i].y), a1);
+            a2 = fmaf(w[i], __uint_as_float(v[ps][i].z), a2);
+            a3 = fmaf(w[i], __uint_as_float(v[ps][i].w), a3);
           }
-          const int r = rbase + ps * 32;
-          const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
           if constexpr (MODE == MODE_TF32X3) {
             const float h0 = tf32_rna(a0), h1 = tf32_rna(a1), h2 = tf32_rna(a2), h3 = tf32_rna(a3);
-            *reinterpret_cast<float4*>(a_tile + off) = make_float4(h0, h1, h2, h3);
-            *reinterpret_cast<float4*>(a_tile + A_TILE_BYTES + off) =
-                make_float4(a0 - h0, a1 - h1, a2 - h2, a3 - h3);
+            *reinterpret_cast<float4*>(dst) = make_float4(h0, h1, h2, h3);
+            *reinterpret_cast<float4*>(dst + A_TILE_BYTES) = make_float4(a0 - h0, a1 - h1, a2 - h2, a3 - h3);
           } else {
-            *reinterpret_cast<float4*>(a_tile + off) = make_float4(a0, a1, a2, a3);
+            *reinterpret_cast<float4*>(dst) = make_float4(a0, a1, a2, a3);
           }
         }
       }
       fence_proxy_async_smem();   // my generic-proxy stores -> visible to tcgen05.mma
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
+
+      if (leader) {
+        // ---- MMA issue for this k-block (one thread), into this group's accumulator ----
+        issued_any = true;
+        if (lane == 0) {
+          mbar_wait(&full_bar[s], it & 1);         // A tile from 8 warps + weight bytes landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_tile);
+          const uint32_t b_addr = a_addr + MT::A_TILES * A_TILE_BYTES;
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = make_sw128_kmajor_desc(b_addr);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {            // 4 x 32 bytes of K per 128-byte row
+            const uint32_t acc = (kb >= NUM_GROUPS || k > 0) ? 1u : 0u;
+            if constexpr (MODE == MODE_BF16) {
+              umma_f16(acc_tmem, adesc + 2 * k, bdesc + 2 * k, prm.idesc, acc);
+            } else if constexpr (MODE == MODE_TF32) {
+              umma_tf32(acc_tmem, adesc + 2 * k, bdesc + 2 * k, prm.idesc, acc);
+            } else {
+              const uint64_t adesc_lo = make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
+              const uint64_t bdesc_lo = make_sw128_kmajor_desc(b_addr + b_tile_bytes);
+              umma_tf32(acc_tmem, adesc_lo + 2 * k, bdesc + 2 * k, prm.idesc, acc);     // Alo.Bhi
+              umma_tf32(acc_tmem, adesc + 2 * k, bdesc_lo + 2 * k, prm.idesc, 1u);      // Ahi.Blo
+              umma_tf32(acc_tmem, adesc + 2 * k, bdesc + 2 * k, prm.idesc, 1u);         // Ahi.Bhi
+            }
+          }
+          tc_commit(&empty_bar[s]);                // frees the stage when these MMAs retire
+          if (NS >= 2 * NUM_GROUPS && kb + NUM_GROUPS < prm.nkb) {
+            // prefetch the weight slab of this group's next k-block: its stage was freed by an MMA
+            // issued two of the group's k-blocks ago, so this wait does not block in steady state
+            const int kn = kb + NUM_GROUPS, sn = kn % NS, itn = kn / NS;
+            mbar_wait(&empty_bar[sn], (itn & 1) ^ 1);
+            mbar_arrive_expect_tx(&full_bar[sn], b_bytes);
+            bulk_g2s(smem + (size_t)sn * stage_bytes + MT::A_TILES * A_TILE_BYTES,
+                     prm.wp + (size_t)kn * b_src_stride, b_bytes, &full_bar[sn]);
+          }
+        }
+        __syncwarp();
+      }
     }
+    if (issued_any && lane == 0) tc_commit(tmem_full_bar);   // all MMAs I issued have retired
 
     // ===================== epilogue: TMEM -> registers -> NCHW global =====================
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;      // TMEM lane quarter this warp may touch
+    const int q = warp & 3, cgrp = warp >> 2;      // TMEM lane quarter / column group of this warp
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool row_ok = m < prm.M;
     const int n = row_ok ? m / prm.HoWo : 0;
     const int pos = row_ok ? m - n * prm.HoWo : 0;
     Tout* obase = reinterpret_cast<Tout*>(prm.out) + (size_t)n * prm.Cout * prm.HoWo + pos;
-    const int half_cols = BN >> 1;
-    for (int c0 = 0; c0 < half_cols; c0 += 32) {
-      const int col = half * half_cols + c0;
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+    const int cols_per_warp = (BN / 4 >= 32) ? BN / 4 : 32;
+    for (int c0 = 0; c0 < cols_per_warp; c0 += 32) {
+      const int col = cgrp * cols_per_warp + c0;
+      if (col >= BN) break;                        // warp-uniform
+      uint32_t acc0[32], acc1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
+      tmem_ld32(taddr, acc0);
+      if (active_groups > 1) tmem_ld32(taddr + (uint32_t)BN, acc1);
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]);
+          float x = __uint_as_float(acc0[j]);
+          if (active_groups > 1) x += __uint_as_float(acc1[j]);
           if (prm.bias) x += __ldg(prm.bias + col + j);
           st_out<Tout>(obase + (size_t)(col + j) * prm.HoWo, x);   // lanes = consecutive positions
         }
       }
     }
-  } else if (warp == PRODUCER_WARPS) {
-    // ===================== weight loader (one thread, bulk async copies) =====================
-    if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(MT::B_TILES * b_tile_bytes);
-      for (int kb = 0; kb < prm.nkb; ++kb) {
-        const int s = kb % NS, it = kb / NS;
-        mbar_wait(&empty_bar[s], (it & 1) ^ 1);
-        unsigned char* b_tile = smem + (size_t)s * stage_bytes + MT::A_TILES * A_TILE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], bytes);
-        // the packed layout always carries hi+lo for tf32; single-pass TF32 copies only hi
-        const size_t src_stride = (size_t)(MODE == MODE_BF16 ? 1 : 2) * b_tile_bytes;
-        bulk_g2s(b_tile, prm.wp + (size_t)kb * src_stride, bytes, &full_bar[s]);
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      for (int kb = 0; kb < prm.nkb; ++kb) {
-        const int s = kb % NS, it = kb / NS;
-        mbar_wait(&full_bar[s], it & 1);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + MT::A_TILES * A_TILE_BYTES;
-        const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
-        const uint64_t bdesc = make_sw128_kmajor_desc(b_addr);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {           // 4 x 32 bytes of K per 128-byte row
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-          if constexpr (MODE == MODE_BF16) {
-            umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, acc);
-          } else if constexpr (MODE == MODE_TF32) {
-            umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, acc);
-          } else {
-            const uint64_t adesc_lo = make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
-            const uint64_t bdesc_lo = make_sw128_kmajor_desc(b_addr + b_tile_bytes);
-            umma_tf32(tmem_base, adesc_lo + 2 * k, bdesc + 2 * k, prm.idesc, acc);     // Alo.Bhi
-            umma_tf32(tmem_base, adesc + 2 * k, bdesc_lo + 2 * k, prm.idesc, 1u);      // Ahi.Blo
-            umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, 1u);         // Ahi.Bhi
-          }
-        }
-        tc_commit(&empty_bar[s]);               // frees the stage when these MMAs retire
-      }
-      tc_commit(tmem_full_bar);                 // accumulator complete -> epilogue
-    }
-    __syncwarp();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == PRODUCER_WARPS + 1) tmem_dealloc(tmem_base, prm.tmem_cols);
+  if (warp == 0) tmem_dealloc(tmem_base, prm.tmem_cols);
 }
 
 static size_t umma_smem_bytes(int mode, int ns, int Cout) {
@@ -379,13 +431,12 @@ template <int MODE, typename Tout>
 static int dispatch_stages(const UmmaParams& p, int grid, int ns, cudaStream_t stream) {
   switch (ns) {
     case 2: return launch_umma<MODE, 2, Tout>(p, grid, stream);
-    case 3: return launch_umma<MODE, 3, Tout>(p, grid, stream);
     case 4: return launch_umma<MODE, 4, Tout>(p, grid, stream);
     default: set_error("dcn umma: unsupported stage count %d", ns); return KGDET_ERR_INVALID_ARG;
   }
 }
 
-int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec* plan, const void* packed_w,
+int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec16* plan, const void* packed_w,
                  const float* bias, void* out_nchw, int out_dtype, int precision, cudaStream_t stream) {
   if (!umma_supported(g, precision)) {
     set_error("dcn umma: shape/precision not supported by the tensor-core path");
@@ -395,18 +446,20 @@ int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec* plan, c
   const int bk = bk_of(precision);
   UmmaParams p;
   p.in = in_nhwc; p.plan = plan; p.wp = (const unsigned char*)packed_w; p.bias = bias; p.out = out_nchw;
-  p.M = g.M; p.C = g.C; p.Cout = g.Cout; p.K = g.K; p.HoWo = g.Ho * g.Wo;
+  p.M = g.M; p.C = g.C; p.W = g.W; p.Cout = g.Cout; p.K = g.K; p.HoWo = g.Ho * g.Wo;
   p.nkb = (g.C / bk) * g.K;
   p.idesc = make_idesc(mode == MODE_BF16 ? 1u : 2u, BM, (uint32_t)g.Cout);
-  p.tmem_cols = g.Cout <= 64 ? 64 : (g.Cout <= 128 ? 128 : 256);
+  p.tmem_cols = g.Cout <= 64 ? 128 : (g.Cout <= 128 ? 256 : 512);   // two accumulators, power of two
   const int grid = ceil_div(g.M, BM);
   // pipeline depth: as deep as 227 KB allows, capped so that some L1 is left for the gather
-  int ns = (mode == MODE_TF32X3) ? 2 : 3;
+  int ns = (mode == MODE_TF32X3) ? 2 : 4;
   if (const char* e = getenv("KGDET_UMMA_STAGES")) {
     int v = atoi(e);
-    if (v >= 2 && v <= 4) ns = v;
+    if (v == 2 || v == 4) ns = v;
   }
-  while (ns > 2 && umma_smem_bytes(mode, ns, g.Cout) > 227 * 1024) --ns;
+  // The stage count must be even: stage s then always belongs to producer group s % 2, and a warp
+  // can never run a full mbarrier-parity period ahead of the MMA that frees its stage.
+  while (ns > 2 && umma_smem_bytes(mode, ns, g.Cout) > 227 * 1024) ns -= 2;
   if (umma_smem_bytes(mode, ns, g.Cout) > 227 * 1024) {
     set_error("dcn umma: tile does not fit shared memory");
     return KGDET_ERR_UNSUPPORTED;
