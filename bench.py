@@ -118,14 +118,11 @@ def run_ours(args):
     from kgdet_b200.head import KGDetHead
     from kgdet_b200.ops import _capi
 
-    rank = int(os.environ.get('RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    local = int(os.environ.get('LOCAL_RANK', 0))
+    from kgdet_b200 import dist as kdist
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    rank, world, local = kdist.init_from_env('nccl')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
     lib = _capi.lib()
     ops.set_precision(args.precision)
 
@@ -210,10 +207,8 @@ def run_ours(args):
     h2d = x_host.numel() * x_host.element_size()
     d2h = sum(h.numel() * h.element_size() for h in out_host)
 
-    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms = kdist.max_over_ranks(dev_ms, dev)       # the slowest rank sets the step time
+    e2e_ms = kdist.max_over_ranks(e2e_ms, dev)
 
     if rank == 0:
         peaks = {}
