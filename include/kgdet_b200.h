@@ -89,6 +89,25 @@ KGDET_API int kgdet_dcn_forward(const void* input, const float* offset, const fl
                       const kgdet_dcn_shape* shape, int dtype, int precision, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* Prepared form of the forward pass (inference): the NHWC copy of an input and the sample plan of an
+ * offset tensor are built once and shared by several deformable convolutions -- the six DCNs of a
+ * KGDet Kp3RepBlock stage read 2 inputs and 3 offset tensors (KP3:145-163).  The epilogue can apply the
+ * ReLU that follows every DCN in the head (KP3:145-150) and write straight into a channel slice
+ * [out_channel_offset, out_channel_offset + Cout) of a wider NCHW tensor with out_channels_total
+ * channels, which removes the torch.cat (KP3:151-153).  `prepared_input` / `plan` are opaque buffers
+ * sized by the *_bytes queries; they depend on (shape, dtype, precision) only through N, C, H, W,
+ * the kernel size / stride / padding / dilation and the path selected by `precision`. */
+KGDET_API size_t kgdet_dcn_prepared_input_bytes(const kgdet_dcn_shape* shape, int precision);
+KGDET_API int kgdet_dcn_prepare_input(const void* input, void* prepared_input, const kgdet_dcn_shape* shape,
+                            int dtype, int precision, void* stream);
+KGDET_API size_t kgdet_dcn_plan_bytes(const kgdet_dcn_shape* shape, int precision);
+KGDET_API int kgdet_dcn_prepare_plan(const float* offset, const float* mask, void* plan,
+                           const kgdet_dcn_shape* shape, int precision, void* stream);
+KGDET_API int kgdet_dcn_forward_prepared(const void* prepared_input, const void* plan, const void* weight_packed,
+                               const float* bias, void* output, int32_t out_channel_offset,
+                               int32_t out_channels_total, int fuse_relu, const kgdet_dcn_shape* shape,
+                               int dtype, int precision, void* stream);
+
 /* replaces deform_conv_backward_input_cuda     dcn/src/deform_conv_cuda.cpp:260-371
  *          (+ the input/offset/mask part of modulated_deform_conv_cuda_backward :566-679)
  * grad_input / grad_offset / grad_mask are fully overwritten (no pre-zeroing needed;
@@ -129,11 +148,15 @@ KGDET_API int kgdet_nms(const float* dets, int32_t n, float iou_thr, int cmp_mod
  * replaces the per-class Python loop of multiclass_nms_kp
  * (mmdet/core/post_processing/bbox_nms_kp.py:38-52).  Segment s owns rows
  * [seg_offsets[s], seg_offsets[s+1]) of dets; keep_flags[row] = 1 if the row survives
- * NMS within its segment.  seg_offsets: device int32 [nseg+1]; max_seg_len >= the
- * longest segment (host-side bound, e.g. nms_pre). */
+ * NMS within its segment.  seg_offsets: device int32 [nseg+1], or NULL for `nseg` uniform
+ * segments of exactly max_seg_len rows (dense mode, total == nseg * max_seg_len);
+ * max_seg_len >= the longest segment (host-side bound, e.g. nms_pre).  Rows whose score
+ * is not > score_thr are treated as absent (flag 0) -- the `scores > score_thr` filter of
+ * bbox_nms_kp.py:39 folded into the op so that a dense, fixed-shape (CUDA-graph capturable)
+ * caller needs no compaction; pass -INFINITY to keep every row. */
 KGDET_API size_t kgdet_nms_batched_workspace_bytes(int32_t total, int32_t nseg, int32_t max_seg_len);
 KGDET_API int kgdet_nms_batched(const float* dets, const int32_t* seg_offsets, int32_t nseg, int32_t total,
-                      int32_t max_seg_len, float iou_thr, int cmp_mode, uint8_t* keep_flags,
+                      int32_t max_seg_len, float iou_thr, float score_thr, int cmp_mode, uint8_t* keep_flags,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- sigmoid focal loss -----------------------------------------------------------------

@@ -55,12 +55,20 @@ int launch_plan(const DcnGeom& g, const float* offset, const float* mask, Sample
 int launch_transpose(const void* src, void* dst, int B, int R, int Cc, int src_dtype,
                      int dst_dtype, cudaStream_t stream);
 
+// Where and how a forward kernel writes its result: channel slice [coff, coff + Cout) of an NCHW tensor
+// with `ctot` channels, optional fused ReLU.
+struct OutSpec {
+  void* out;
+  int dtype;      // KGDET_F32 / KGDET_BF16
+  int coff, ctot;
+  int relu;
+};
+
 // ---- exact fp32 SIMT path (any stride / dilation / groups / deformable_groups / mask) ----
 size_t simt_packed_weight_bytes(const DcnGeom& g);
 int simt_pack_weight(const DcnGeom& g, const float* weight, float* packed, cudaStream_t stream);
 int simt_forward(const DcnGeom& g, const float* in_nhwc, const SampleRec* plan,
-                 const float* packed_w, const float* bias, void* out_nchw, int out_dtype,
-                 cudaStream_t stream);
+                 const float* packed_w, const float* bias, const OutSpec& o, cudaStream_t stream);
 // weight_dgrad: [groups][K][Cout/g][C/g] fp32 (built by simt_pack_weight_dgrad)
 int simt_pack_weight_dgrad(const DcnGeom& g, const float* weight, float* packed,
                            cudaStream_t stream);
@@ -78,7 +86,6 @@ size_t umma_packed_weight_bytes(const DcnGeom& g, int precision);
 int umma_pack_weight(const DcnGeom& g, const float* weight, void* packed, int precision,
                      cudaStream_t stream);
 int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec16* plan, const void* packed_w,
-                 const float* bias, void* out_nchw, int out_dtype, int precision,
-                 cudaStream_t stream);
+                 const float* bias, const OutSpec& o, int precision, cudaStream_t stream);
 
 }  // namespace kgdet

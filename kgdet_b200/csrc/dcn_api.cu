@@ -25,21 +25,57 @@ bool use_umma(const DcnGeom& g, int precision) {
   return precision != KGDET_PREC_FP32 && umma_supported(g, precision);
 }
 
-// in_nhwc points past a zeroed guard band of `guard_bytes` (the fused kernel loads all four bilinear
-// corners unconditionally; see dcn.cuh); the same number of bytes follows the tensor.
-struct FwdWs { void* in_nhwc; void* plan; size_t guard_bytes, in_bytes, total; };
-FwdWs carve_fwd(const DcnGeom& g, int precision, void* ws) {
-  Carver c(ws);
-  FwdWs w;
+// Prepared input: [guard | NHWC copy in the compute type | guard].  The fused kernel loads all four
+// bilinear corners unconditionally (see dcn.cuh); the guards are zeroed.
+struct PrepIn { size_t guard_bytes, in_bytes, total; int cdtype; };
+PrepIn prep_in_layout(const DcnGeom& g, int precision) {
+  PrepIn p;
   const bool fast = use_umma(g, precision);
-  const size_t esz = (fast && precision == KGDET_PREC_BF16) ? 2 : 4;
-  w.guard_bytes = fast ? align_up((size_t)dcn_guard_pixels(g) * g.C * esz, 1024) : 0;
-  w.in_bytes = (size_t)g.N * g.H * g.W * g.C * esz;
-  char* raw = c.take<char>(w.in_bytes + 2 * w.guard_bytes);
-  w.in_nhwc = raw ? raw + w.guard_bytes : nullptr;
-  w.plan = use_umma(g, precision) ? c.take<void>(plan16_bytes(g)) : c.take<void>(plan_bytes(g));
-  w.total = c.off;
-  return w;
+  p.cdtype = (fast && precision == KGDET_PREC_BF16) ? KGDET_BF16 : KGDET_F32;
+  const size_t esz = p.cdtype == KGDET_BF16 ? 2 : 4;
+  p.guard_bytes = fast ? align_up((size_t)dcn_guard_pixels(g) * g.C * esz, 1024) : 0;
+  p.in_bytes = (size_t)g.N * g.H * g.W * g.C * esz;
+  p.total = align_up(p.in_bytes + 2 * p.guard_bytes, 1024);
+  return p;
+}
+size_t plan_layout_bytes(const DcnGeom& g, int precision) {
+  return align_up(use_umma(g, precision) ? plan16_bytes(g) : plan_bytes(g), 1024);
+}
+
+int do_prepare_input(const DcnGeom& g, const void* input, void* prepared, int dtype, int precision,
+                     cudaStream_t stream) {
+  const PrepIn p = prep_in_layout(g, precision);
+  char* base = (char*)prepared;
+  if (p.guard_bytes) {
+    KG_CUDA(cudaMemsetAsync(base, 0, p.guard_bytes, stream));
+    KG_CUDA(cudaMemsetAsync(base + p.guard_bytes + p.in_bytes, 0, p.guard_bytes, stream));
+  }
+  return launch_transpose(input, base + p.guard_bytes, g.N, g.C, g.H * g.W, dtype, p.cdtype, stream);
+}
+
+int do_prepare_plan(const DcnGeom& g, const float* offset, const float* mask, void* plan, int precision,
+                    cudaStream_t stream) {
+  if (use_umma(g, precision))
+    return launch_plan16(g, offset, mask, (SampleRec16*)plan,
+                         precision == KGDET_PREC_BF16 ? PLAN16_BF16W : PLAN16_F32, stream);
+  return launch_plan(g, offset, mask, (SampleRec*)plan, nullptr, stream);
+}
+
+int do_forward_prepared(const DcnGeom& g, const void* prepared, const void* plan, const void* weight_packed,
+                        const float* bias, const OutSpec& o, int precision, cudaStream_t stream) {
+  const PrepIn p = prep_in_layout(g, precision);
+  const char* in_nhwc = (const char*)prepared + p.guard_bytes;
+  cudaEvent_t ev0 = g_prof_start, ev1 = g_prof_stop;
+  g_prof_start = g_prof_stop = nullptr;
+  if (ev0 && ev1) KG_CUDA(cudaEventRecord(ev0, stream));
+  int rc;
+  if (use_umma(g, precision))
+    rc = umma_forward(g, in_nhwc, (const SampleRec16*)plan, weight_packed, bias, o, precision, stream);
+  else
+    rc = simt_forward(g, (const float*)in_nhwc, (const SampleRec*)plan, (const float*)weight_packed, bias, o,
+                      stream);
+  if (rc == KGDET_OK && ev0 && ev1) KG_CUDA(cudaEventRecord(ev1, stream));
+  return rc;
 }
 
 struct BwdInWs { float *in_nhwc, *go_nhwc, *gin_nhwc, *w_dgrad; SampleRec* plan; SampleAux* aux; size_t total; };
@@ -107,7 +143,7 @@ extern "C" int kgdet_dcn_pack_weight(const float* weight, void* weight_packed,
 extern "C" size_t kgdet_dcn_forward_workspace_bytes(const kgdet_dcn_shape* shape, int, int precision) {
   DcnGeom g;
   if (make_geom(shape, &g) != KGDET_OK) return 0;
-  return carve_fwd(g, precision, nullptr).total;
+  return prep_in_layout(g, precision).total + plan_layout_bytes(g, precision);
 }
 
 extern "C" int kgdet_dcn_forward(const void* input, const float* offset, const float* mask,
@@ -121,29 +157,66 @@ extern "C" int kgdet_dcn_forward(const void* input, const float* offset, const f
   KG_CHECK_ARG(valid_dtype(dtype), "kgdet_dcn_forward: bad dtype %d", dtype);
   KG_CHECK_ARG(valid_prec(precision), "kgdet_dcn_forward: bad precision %d", precision);
   KG_CHECK_ARG(input && offset && weight_packed && output, "kgdet_dcn_forward: NULL pointer");
-  FwdWs w = carve_fwd(g, precision, workspace);
-  if ((rc = check_ws("kgdet_dcn_forward", workspace, workspace_bytes, w.total)) != KGDET_OK) return rc;
-  const bool fast = use_umma(g, precision);
-  const int cdtype = (fast && precision == KGDET_PREC_BF16) ? KGDET_BF16 : KGDET_F32;
-  if (w.guard_bytes) {
-    KG_CUDA(cudaMemsetAsync((char*)w.in_nhwc - w.guard_bytes, 0, w.guard_bytes, stream));
-    KG_CUDA(cudaMemsetAsync((char*)w.in_nhwc + w.in_bytes, 0, w.guard_bytes, stream));
-  }
-  if ((rc = launch_transpose(input, w.in_nhwc, g.N, g.C, g.H * g.W, dtype, cdtype, stream)) != KGDET_OK) return rc;
-  if (fast) rc = launch_plan16(g, offset, mask, (SampleRec16*)w.plan,
-                               precision == KGDET_PREC_BF16 ? PLAN16_BF16W : PLAN16_F32, stream);
-  else rc = launch_plan(g, offset, mask, (SampleRec*)w.plan, nullptr, stream);
+  const size_t in_total = prep_in_layout(g, precision).total;
+  if ((rc = check_ws("kgdet_dcn_forward", workspace, workspace_bytes,
+                     in_total + plan_layout_bytes(g, precision))) != KGDET_OK) return rc;
+  void* prepared = workspace;
+  void* plan = (char*)workspace + in_total;
+  if ((rc = do_prepare_input(g, input, prepared, dtype, precision, stream)) != KGDET_OK) return rc;
+  if ((rc = do_prepare_plan(g, offset, mask, plan, precision, stream)) != KGDET_OK) return rc;
+  OutSpec o{output, dtype, 0, g.Cout, 0};
+  return do_forward_prepared(g, prepared, plan, weight_packed, bias, o, precision, stream);
+}
+
+extern "C" size_t kgdet_dcn_prepared_input_bytes(const kgdet_dcn_shape* shape, int precision) {
+  DcnGeom g;
+  if (make_geom(shape, &g) != KGDET_OK) return 0;
+  return prep_in_layout(g, precision).total;
+}
+
+extern "C" int kgdet_dcn_prepare_input(const void* input, void* prepared_input, const kgdet_dcn_shape* shape,
+                                       int dtype, int precision, void* stream) {
+  DcnGeom g;
+  int rc = make_geom(shape, &g);
   if (rc != KGDET_OK) return rc;
-  cudaEvent_t ev0 = g_prof_start, ev1 = g_prof_stop;
-  g_prof_start = g_prof_stop = nullptr;
-  if (ev0 && ev1) KG_CUDA(cudaEventRecord(ev0, stream));
-  if (fast)
-    rc = umma_forward(g, w.in_nhwc, (const SampleRec16*)w.plan, weight_packed, bias, output, dtype, precision, stream);
-  else
-    rc = simt_forward(g, (const float*)w.in_nhwc, (const SampleRec*)w.plan, (const float*)weight_packed, bias, output, dtype,
-                      stream);
-  if (rc == KGDET_OK && ev0 && ev1) KG_CUDA(cudaEventRecord(ev1, stream));
-  return rc;
+  KG_CHECK_ARG(valid_dtype(dtype) && valid_prec(precision), "kgdet_dcn_prepare_input: bad dtype/precision");
+  KG_CHECK_ARG(input && prepared_input, "kgdet_dcn_prepare_input: NULL pointer");
+  KG_CHECK_ARG(((uintptr_t)prepared_input & 255) == 0, "kgdet_dcn_prepare_input: buffer must be 256-byte aligned");
+  return do_prepare_input(g, input, prepared_input, dtype, precision, (cudaStream_t)stream);
+}
+
+extern "C" size_t kgdet_dcn_plan_bytes(const kgdet_dcn_shape* shape, int precision) {
+  DcnGeom g;
+  if (make_geom(shape, &g) != KGDET_OK) return 0;
+  return plan_layout_bytes(g, precision);
+}
+
+extern "C" int kgdet_dcn_prepare_plan(const float* offset, const float* mask, void* plan,
+                                      const kgdet_dcn_shape* shape, int precision, void* stream) {
+  DcnGeom g;
+  int rc = make_geom(shape, &g);
+  if (rc != KGDET_OK) return rc;
+  KG_CHECK_ARG(valid_prec(precision), "kgdet_dcn_prepare_plan: bad precision %d", precision);
+  KG_CHECK_ARG(offset && plan, "kgdet_dcn_prepare_plan: NULL pointer");
+  KG_CHECK_ARG(((uintptr_t)plan & 255) == 0, "kgdet_dcn_prepare_plan: buffer must be 256-byte aligned");
+  return do_prepare_plan(g, offset, mask, plan, precision, (cudaStream_t)stream);
+}
+
+extern "C" int kgdet_dcn_forward_prepared(const void* prepared_input, const void* plan,
+                                          const void* weight_packed, const float* bias, void* output,
+                                          int32_t out_channel_offset, int32_t out_channels_total,
+                                          int fuse_relu, const kgdet_dcn_shape* shape, int dtype,
+                                          int precision, void* stream) {
+  DcnGeom g;
+  int rc = make_geom(shape, &g);
+  if (rc != KGDET_OK) return rc;
+  KG_CHECK_ARG(valid_dtype(dtype) && valid_prec(precision), "kgdet_dcn_forward_prepared: bad dtype/precision");
+  KG_CHECK_ARG(prepared_input && plan && weight_packed && output, "kgdet_dcn_forward_prepared: NULL pointer");
+  KG_CHECK_ARG(out_channel_offset >= 0 && out_channel_offset + g.Cout <= out_channels_total,
+               "kgdet_dcn_forward_prepared: channel slice [%d, %d) does not fit %d channels",
+               out_channel_offset, out_channel_offset + g.Cout, out_channels_total);
+  OutSpec o{output, dtype, out_channel_offset, out_channels_total, fuse_relu ? 1 : 0};
+  return do_forward_prepared(g, prepared_input, plan, weight_packed, bias, o, precision, (cudaStream_t)stream);
 }
 
 extern "C" void kgdet_dcn_set_profile_events(void* start_event, void* stop_event) {

@@ -100,7 +100,8 @@ template <> __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat
 template <typename Tout>
 __global__ void __launch_bounds__(NT)
 simt_fwd_kernel(DcnGeom g, const float* __restrict__ in, const SampleRec* __restrict__ plan,
-                const float* __restrict__ wp, const float* __restrict__ bias, Tout* __restrict__ out) {
+                const float* __restrict__ wp, const float* __restrict__ bias, Tout* __restrict__ out,
+                int coff, int ctot, int relu) {
   __shared__ float As[TM][TK + 1];
   __shared__ __align__(16) float Bs[TK][TN];
   const int m0 = blockIdx.x * TM, o0 = blockIdx.y * TN, grp = blockIdx.z;
@@ -145,19 +146,21 @@ simt_fwd_kernel(DcnGeom g, const float* __restrict__ in, const SampleRec* __rest
       if (o >= Og) continue;
       const int og = grp * Og + o;
       float v = acc[i][j] + (bias ? bias[og] : 0.f);
-      store_out<Tout>(out + ((size_t)n * g.Cout + og) * HoWo + p, v);
+      if (relu) v = fmaxf(v, 0.f);
+      store_out<Tout>(out + ((size_t)n * ctot + coff + og) * HoWo + p, v);
     }
   }
 }
 
 int simt_forward(const DcnGeom& g, const float* in_nhwc, const SampleRec* plan, const float* packed_w,
-                 const float* bias, void* out_nchw, int out_dtype, cudaStream_t stream) {
+                 const float* bias, const OutSpec& o, cudaStream_t stream) {
   dim3 grid(ceil_div(g.M, TM), ceil_div(g.Cout / g.groups, TN), g.groups);
-  if (out_dtype == KGDET_F32)
-    simt_fwd_kernel<float><<<grid, NT, 0, stream>>>(g, in_nhwc, plan, packed_w, bias, (float*)out_nchw);
+  if (o.dtype == KGDET_F32)
+    simt_fwd_kernel<float><<<grid, NT, 0, stream>>>(g, in_nhwc, plan, packed_w, bias, (float*)o.out, o.coff,
+                                                    o.ctot, o.relu);
   else
     simt_fwd_kernel<__nv_bfloat16><<<grid, NT, 0, stream>>>(g, in_nhwc, plan, packed_w, bias,
-                                                            (__nv_bfloat16*)out_nchw);
+                                                            (__nv_bfloat16*)o.out, o.coff, o.ctot, o.relu);
   KG_LAUNCH_CHECK("simt_fwd_kernel");
   return KGDET_OK;
 }

@@ -142,6 +142,7 @@ struct UmmaParams {
   const float* bias;         // [Cout] or NULL
   void* out;                 // NCHW
   int M, C, W, Cout, K, HoWo;
+  int out_coff, out_ctot, relu;   // channel slice of the output tensor, fused ReLU
   int nkb;                   // (C / BK) * K
   uint32_t idesc;
   uint32_t tmem_cols;
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) dcn_umma_fwd_kernel(const Umm
     const bool row_ok = m < prm.M;
     const int n = row_ok ? m / prm.HoWo : 0;
     const int pos = row_ok ? m - n * prm.HoWo : 0;
-    Tout* obase = reinterpret_cast<Tout*>(prm.out) + (size_t)n * prm.Cout * prm.HoWo + pos;
+    Tout* obase = reinterpret_cast<Tout*>(prm.out) + ((size_t)n * prm.out_ctot + prm.out_coff) * prm.HoWo + pos;
     const int cols_per_warp = (BN / 4 >= 32) ? BN / 4 : 32;
     for (int c0 = 0; c0 < cols_per_warp; c0 += 32) {
       const int col = cgrp * cols_per_warp + c0;
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) dcn_umma_fwd_kernel(const Umm
           float x = __uint_as_float(acc0[j]);
           if (active_groups > 1) x += __uint_as_float(acc1[j]);
           if (prm.bias) x += __ldg(prm.bias + col + j);
+          if (prm.relu) x = fmaxf(x, 0.f);
           st_out<Tout>(obase + (size_t)(col + j) * prm.HoWo, x);   // lanes = consecutive positions
         }
       }
@@ -437,7 +439,7 @@ static int dispatch_stages(const UmmaParams& p, int grid, int ns, cudaStream_t s
 }
 
 int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec16* plan, const void* packed_w,
-                 const float* bias, void* out_nchw, int out_dtype, int precision, cudaStream_t stream) {
+                 const float* bias, const OutSpec& o, int precision, cudaStream_t stream) {
   if (!umma_supported(g, precision)) {
     set_error("dcn umma: shape/precision not supported by the tensor-core path");
     return KGDET_ERR_UNSUPPORTED;
@@ -445,7 +447,8 @@ int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec16* plan,
   const int mode = mode_of(precision);
   const int bk = bk_of(precision);
   UmmaParams p;
-  p.in = in_nhwc; p.plan = plan; p.wp = (const unsigned char*)packed_w; p.bias = bias; p.out = out_nchw;
+  p.in = in_nhwc; p.plan = plan; p.wp = (const unsigned char*)packed_w; p.bias = bias; p.out = o.out;
+  p.out_coff = o.coff; p.out_ctot = o.ctot; p.relu = o.relu;
   p.M = g.M; p.C = g.C; p.W = g.W; p.Cout = g.Cout; p.K = g.K; p.HoWo = g.Ho * g.Wo;
   p.nkb = (g.C / bk) * g.K;
   p.idesc = make_idesc(mode == MODE_BF16 ? 1u : 2u, BM, (uint32_t)g.Cout);
@@ -464,7 +467,7 @@ int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec16* plan,
     set_error("dcn umma: tile does not fit shared memory");
     return KGDET_ERR_UNSUPPORTED;
   }
-  const bool f32 = out_dtype == KGDET_F32;
+  const bool f32 = o.dtype == KGDET_F32;
   switch (mode) {
     case MODE_BF16:
       return f32 ? dispatch_stages<MODE_BF16, float>(p, grid, ns, stream)

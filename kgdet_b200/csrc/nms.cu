@@ -27,7 +27,11 @@ __device__ __forceinline__ float box_area(const Box& b) {
   return __fmul_rn(__fadd_rn(__fsub_rn(b.x2, b.x1), 1.f), __fadd_rn(__fsub_rn(b.y2, b.y1), 1.f));
 }
 
-// true when box b (lower score) is suppressed by box a (higher score)
+// true when box b (lower score) is suppressed by box a (higher score).
+// The decision of the reference is rn(inter / union) {>, >=} thr.  IEEE division is ~10x the cost of
+// the rest of the test, so pairs that are far from the threshold are decided by a multiplication with
+// a 1e-6 guard band (well above the ~2e-7 worst-case relative error of the three roundings involved);
+// only pairs inside the band take the exact division -- the result is bit-identical either way.
 __device__ __forceinline__ bool suppresses(const Box& a, float area_a, const Box& b, float area_b,
                                            float thr, int cmp_ge) {
   float xx1 = fmaxf(a.x1, b.x1), yy1 = fmaxf(a.y1, b.y1);
@@ -35,7 +39,13 @@ __device__ __forceinline__ bool suppresses(const Box& a, float area_a, const Box
   float w = fmaxf(__fadd_rn(__fsub_rn(xx2, xx1), 1.f), 0.f);
   float h = fmaxf(__fadd_rn(__fsub_rn(yy2, yy1), 1.f), 0.f);
   float inter = __fmul_rn(w, h);
-  float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  if (uni > 0.f && thr > 0.f) {
+    const float t = __fmul_rn(thr, uni);
+    if (inter > __fmul_rn(t, 1.000001f)) return true;
+    if (inter < __fmul_rn(t, 0.999999f)) return false;
+  }
+  float ovr = __fdiv_rn(inter, uni);
   return cmp_ge ? (ovr >= thr) : (ovr > thr);
 }
 
@@ -51,17 +61,21 @@ __device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {
 // Output: flags[orig_row] = 1/0.
 __global__ void __launch_bounds__(kSmallThreads, 1)
 nms_small_kernel(const float* __restrict__ dets, const int32_t* __restrict__ seg_offsets,
-                 int single_n, float thr, int cmp_ge, uint8_t* __restrict__ flags, int P_cap) {
+                 int single_n, float thr, int cmp_ge, float score_thr, uint8_t* __restrict__ flags,
+                 int P_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int n_valid;
   int row0, n;
   if (seg_offsets) {
     row0 = seg_offsets[blockIdx.x];
     n = seg_offsets[blockIdx.x + 1] - row0;
-  } else {
-    row0 = 0;
+  } else {                                   // uniform segments of single_n rows (dense mode)
+    row0 = blockIdx.x * single_n;
     n = single_n;
   }
   if (n <= 0) return;
+  const int n_rows = n;
+  if (threadIdx.x == 0) n_valid = 0;
   int P = 1;
   while (P < n) P <<= 1;
   // carve
@@ -75,9 +89,21 @@ nms_small_kernel(const float* __restrict__ dets, const int32_t* __restrict__ seg
 
   const int tid = threadIdx.x, nt = blockDim.x;
   const float* d = dets + (size_t)row0 * 5;
-  for (int i = tid; i < P; i += nt) {
-    if (i < n) { key[i] = d[i * 5 + 4]; idx[i] = i; }
-    else { key[i] = -INFINITY; idx[i] = 0x7fffffff; }
+  __syncthreads();
+  {
+    // rows whose score does not exceed score_thr are absent (multiclass_nms_kp's `scores > score_thr`
+    // filter, bbox_nms_kp.py:39, folded into the op so that the caller needs no compaction)
+    int cnt = 0;
+    for (int i = tid; i < P; i += nt) {
+      float sc = -INFINITY;
+      if (i < n) {
+        const float v = d[i * 5 + 4];
+        if (v > score_thr) { sc = v; ++cnt; }
+      }
+      key[i] = sc;
+      idx[i] = (i < n) ? i : 0x7fffffff;
+    }
+    if (cnt) atomicAdd(&n_valid, cnt);
   }
   __syncthreads();
   // bitonic sort, ascending in the `before` order
@@ -96,6 +122,10 @@ nms_small_kernel(const float* __restrict__ dets, const int32_t* __restrict__ seg
       __syncthreads();
     }
   }
+  // absent rows sort behind every present one (their key is -inf): only the first n_valid matter
+  for (int i = n_valid + tid; i < n_rows; i += nt) flags[row0 + idx[i]] = 0;
+  n = n_valid;
+  if (n == 0) return;
   // gather boxes in sorted order
   for (int i = tid; i < n; i += nt) {
     const float* s = d + (size_t)idx[i] * 5;
@@ -110,26 +140,38 @@ nms_small_kernel(const float* __restrict__ dets, const int32_t* __restrict__ seg
   for (int blk = 0; blk < nwords; ++blk) {
     const int base = blk * 64;
     const int cnt = min(64, n - base);
-    // 64x64 diagonal bitmask: thread (r) builds the word of row r (bits c > r)
-    if (tid < 64) {
-      unsigned long long wbits = 0ull;
-      if (tid < cnt) {
-        Box a = box[base + tid];
-        float aa = area[base + tid];
-        for (int c = tid + 1; c < cnt; ++c)
-          if (suppresses(a, aa, box[base + c], area[base + c], thr, cmp_ge)) wbits |= 1ull << c;
+    // 64x64 diagonal bitmask, all 1024 threads: thread t tests row t/16 against 4 columns and the 16
+    // partial words of a row are merged with a shared-memory atomicOr
+    if (tid < 64) diag[tid] = 0ull;
+    __syncthreads();
+    {
+      const int r = tid >> 4, c0 = (tid & 15) * 4;
+      if (r < cnt) {
+        const Box a = box[base + r];
+        const float aa = area[base + r];
+        unsigned long long bits = 0ull;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + k;
+          if (c > r && c < cnt && suppresses(a, aa, box[base + c], area[base + c], thr, cmp_ge))
+            bits |= 1ull << c;
+        }
+        if (bits) atomicOr(&diag[r], bits);
       }
-      diag[tid] = wbits;
     }
     __syncthreads();
-    if (tid == 0) {
-      unsigned long long rem = removed[blk];
-      unsigned long long kept = 0ull;
-      for (int r = 0; r < cnt; ++r) {
-        if (!((rem >> r) & 1ull)) { kept |= 1ull << r; rem |= diag[r]; }
+    // serial resolve of the block by warp 0: the 64 diagonal words live in registers (two per lane)
+    // and are broadcast by shuffles that do not depend on the running `rem`, so only a short ALU
+    // chain is serial
+    if (tid < 32) {
+      const unsigned long long d_lo = diag[tid], d_hi = diag[tid + 32];
+      unsigned long long rem = removed[blk], kept = 0ull;
+#pragma unroll
+      for (int r = 0; r < 64; ++r) {
+        const unsigned long long dr = __shfl_sync(0xffffffffu, r < 32 ? d_lo : d_hi, r & 31);
+        if (r < cnt && !((rem >> r) & 1ull)) { kept |= 1ull << r; rem |= dr; }
       }
-      removed[blk] = rem;
-      *kept_word = kept;
+      if (tid == 0) { removed[blk] = rem; *kept_word = kept; }
     }
     __syncthreads();
     const unsigned long long kept = *kept_word;
@@ -345,7 +387,7 @@ extern "C" int kgdet_nms(const float* dets, int32_t n, float iou_thr, int cmp_mo
     KG_CUDA(cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     nms_small_kernel<<<1, kSmallThreads, smem, stream>>>(dets, nullptr, n, iou_thr,
-                                                         cmp_mode == KGDET_NMS_GE, flags, P_cap);
+                                                         cmp_mode == KGDET_NMS_GE, -INFINITY, flags, P_cap);
     KG_LAUNCH_CHECK("nms_small_kernel");
     compact_flags_kernel<<<1, 1024, 0, stream>>>(flags, n, keep, num_keep);
     KG_LAUNCH_CHECK("compact_flags_kernel");
@@ -376,15 +418,17 @@ extern "C" int kgdet_nms(const float* dets, int32_t n, float iou_thr, int cmp_mo
 
 extern "C" size_t kgdet_nms_batched_workspace_bytes(int32_t, int32_t, int32_t) { return 256; }
 
-extern "C" int kgdet_nms_batched(const float* dets, const int32_t* seg_offsets, int32_t nseg,
-                                 int32_t total, int32_t max_seg_len, float iou_thr, int cmp_mode,
+extern "C" int kgdet_nms_batched(const float* dets, const int32_t* seg_offsets, int32_t nseg, int32_t total,
+                                 int32_t max_seg_len, float iou_thr, float score_thr, int cmp_mode,
                                  uint8_t* keep_flags, void*, size_t, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   KG_CHECK_ARG(nseg >= 0 && total >= 0, "kgdet_nms_batched: negative sizes");
   KG_CHECK_ARG(cmp_mode == KGDET_NMS_GT || cmp_mode == KGDET_NMS_GE,
                "kgdet_nms_batched: bad cmp_mode %d", cmp_mode);
   if (nseg == 0 || total == 0) return KGDET_OK;
-  KG_CHECK_ARG(dets && seg_offsets && keep_flags, "kgdet_nms_batched: NULL pointer");
+  KG_CHECK_ARG(dets && keep_flags, "kgdet_nms_batched: NULL pointer");
+  KG_CHECK_ARG(seg_offsets || (long long)nseg * max_seg_len == total,
+               "kgdet_nms_batched: dense mode needs total == nseg * max_seg_len");
   if (max_seg_len > kSmallMax) {
     set_error("kgdet_nms_batched: max_seg_len %d exceeds the single-CTA limit %d; call kgdet_nms "
               "per segment", max_seg_len, kSmallMax);
@@ -394,9 +438,9 @@ extern "C" int kgdet_nms_batched(const float* dets, const int32_t* seg_offsets, 
   size_t smem = small_smem_bytes(P_cap);
   KG_CUDA(cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
-  nms_small_kernel<<<nseg, kSmallThreads, smem, stream>>>(dets, seg_offsets, 0, iou_thr,
-                                                          cmp_mode == KGDET_NMS_GE, keep_flags,
-                                                          P_cap);
+  nms_small_kernel<<<nseg, kSmallThreads, smem, stream>>>(dets, seg_offsets, seg_offsets ? 0 : max_seg_len,
+                                                          iou_thr, cmp_mode == KGDET_NMS_GE, score_thr,
+                                                          keep_flags, P_cap);
   KG_LAUNCH_CHECK("nms_small_kernel(batched)");
   return KGDET_OK;
 }

@@ -27,7 +27,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import DeformConv, batched_nms_flags, points2bbox_moment
+from .ops import (DeformConv, batched_nms_flags, deform_conv_prepared, points2bbox_moment, prepare_input,
+                  prepare_plan)
 
 _POINT_SETS = (3, 5, 7)          # KP3:257: 9 + 25 + 49 points regardless of cfg.num_reppts
 
@@ -99,6 +100,28 @@ class _DeformBlock(nn.Module):
         _normal(self.keypts_out)
         _normal(self.reppts_out)
 
+    def forward_fused(self, cls_prep, pts_prep, reppts_offset):
+        """Inference path on the prepared API: the NHWC copies of the two tower outputs are shared by all
+        six DCNs (and by both stages), each offset tensor's sample plan is shared by the cls and keypoint
+        branches, and every DCN applies its ReLU and writes its 256-channel slice of the concatenated
+        tensor in its epilogue (no relu / cat kernels)."""
+        n, c, h, w = cls_prep.shape4
+        feat = self.cls_dfmconv_3.out_channels
+        cls_cat = reppts_offset.new_empty((n, 3 * feat, h, w))
+        kpt_cat = reppts_offset.new_empty((n, 3 * feat, h, w))
+        lo = 0
+        for i, k in enumerate(_POINT_SETS):
+            n2 = 2 * k * k
+            dcn_offset = reppts_offset[:, lo:lo + n2] - getattr(self, '_dcn_base_%d' % k).to(reppts_offset.dtype)
+            lo += n2
+            plan = prepare_plan(dcn_offset, (n, c, h, w), feat, k, 1, (k - 1) // 2, 1, like_dtype=cls_cat.dtype)
+            deform_conv_prepared(cls_prep, plan, getattr(self, 'cls_dfmconv_%d' % k).weight, cls_cat, i * feat, True)
+            deform_conv_prepared(pts_prep, plan, getattr(self, 'keypts_dfmconv_%d' % k).weight, kpt_cat, i * feat,
+                                 True)
+        cls_out = self.cls_out(cls_cat)
+        keypts_out = self.keypts_out(kpt_cat)
+        return cls_out, keypts_out, self.reppts_out(keypts_out)
+
     def forward(self, cls_feat, pts_feat, reppts_offset):
         cls_feats, kpt_feats = [], []
         lo = 0
@@ -125,9 +148,11 @@ class KGDetHead(nn.Module):
         # The three *_cls / *_fn arguments exist for bench.py's CPU reference arm, which injects
         # oracle-backed stand-ins; the defaults are the CUDA operators of this package.
         super().__init__()
+        self._fused_inference = deform_conv_cls is None     # prepared API only with the CUDA operators
         deform_conv_cls = deform_conv_cls or DeformConv
         self._moment_fn = moment_fn or points2bbox_moment
         self._nms_flags_fn = nms_flags_fn or batched_nms_flags
+        self._lim_cache = {}
         self.num_classes = num_classes
         self.cls_out_channels = num_classes - 1                                    # sigmoid cls, KP3:283-284
         self.num_keypts = num_keypts
@@ -161,6 +186,19 @@ class KGDetHead(nn.Module):
             pts_feat = m(pts_feat)
         cls1, kpt1, rep1 = self.kp_rep_block_1(cls_feat, pts_feat)
         bbox1 = self.points2bbox(rep1)
+        if self._fused_inference and not torch.is_grad_enabled() and cls_feat.is_cuda:
+            feat = self.kp_rep_block_2.cls_dfmconv_3.out_channels
+            cls_prep = prepare_input(cls_feat, feat)
+            pts_prep = prepare_input(pts_feat, feat)
+            cls2, kpt2, rep2 = self.kp_rep_block_2.forward_fused(cls_prep, pts_prep, rep1)
+            kpt2 = kpt2 + kpt1
+            rep2 = rep2 + rep1
+            bbox2 = self.points2bbox(rep2)
+            cls3, kpt3, rep3 = self.kp_rep_block_3.forward_fused(cls_prep, pts_prep, rep2)
+            kpt3 = kpt3 + kpt2
+            rep3 = rep3 + rep2
+            bbox3 = self.points2bbox(rep3)
+            return cls1, cls2, cls3, kpt1, kpt2, kpt3, bbox1, bbox2, bbox3
         cls2, kpt2, rep2 = self.kp_rep_block_2(cls_feat, pts_feat, rep1)
         kpt2 = kpt2 + kpt1.detach()                                                # KP3:431-432
         rep2 = rep2 + rep1.detach()
@@ -190,7 +228,11 @@ class KGDetHead(nn.Module):
         """
         B = cls_scores[0].shape[0]
         dev = cls_scores[0].device
-        lim = torch.tensor([[s[1], s[0], s[1], s[0]] for s in img_shapes], dtype=torch.float32, device=dev)
+        key = (tuple(tuple(s[:2]) for s in img_shapes), str(dev))
+        lim = self._lim_cache.get(key)
+        if lim is None:       # built once per (shapes, device): keeps H2D copies out of graph capture
+            lim = torch.tensor([[s[1], s[0], s[1], s[0]] for s in img_shapes], dtype=torch.float32, device=dev)
+            self._lim_cache[key] = lim
         boxes_l, scores_l, kpts_l = [], [], []
         for lvl, (cs, kp, bp) in enumerate(zip(cls_scores, keypts_preds, bbox_preds)):
             stride = self.point_strides[lvl]
@@ -224,21 +266,13 @@ class KGDetHead(nn.Module):
         kpts = torch.cat(kpts_l, 1)
         n, C = scores.shape[1], scores.shape[2]
 
-        # one segment per (image, class): rows ordered (b, c, i) exactly like the reference's
-        # per-class loop (bbox_nms_kp.py:38-52)
+        # one dense segment of n rows per (image, class), in the order of the reference's per-class loop
+        # (bbox_nms_kp.py:38-52); its `scores > score_thr` filter (:39) is applied inside the NMS op, so
+        # every shape is static: no nonzero(), no host sync, CUDA-graph capturable
         sc_t = scores.transpose(1, 2).contiguous()                                      # [B, C, n]
-        cand = sc_t > score_thr                                                         # bbox_nms_kp.py:39
-        counts = cand.sum(-1).reshape(-1)
-        seg_offsets = torch.zeros(B * C + 1, dtype=torch.int32, device=dev)
-        seg_offsets[1:] = counts.cumsum(0)
-        idx = cand.reshape(-1).nonzero(as_tuple=False).squeeze(1)                       # sizes on device only
-        bi = idx // (C * n)
-        ii = idx % n
-        dets = torch.cat([boxes[bi, ii], sc_t.reshape(-1)[idx, None]], 1)
-        flags = self._nms_flags_fn(dets, seg_offsets, n, iou_thr)
-        keep_dense = torch.zeros(B * C * n, dtype=torch.bool, device=dev)
-        keep_dense[idx] = flags.bool()
-        masked = torch.where(keep_dense.view(B, C * n), sc_t.reshape(B, C * n), sc_t.new_full((), -1.0))
+        dets = torch.cat([boxes[:, None].expand(B, C, n, 4), sc_t[..., None]], -1).reshape(B * C * n, 5)
+        flags = self._nms_flags_fn(dets, None, n, iou_thr, score_thr=score_thr)
+        masked = torch.where(flags.view(B, C * n).bool(), sc_t.reshape(B, C * n), sc_t.new_full((), -1.0))
         k = min(max_per_img, C * n)
         top_s, top_i = masked.topk(k, dim=1)                                            # bbox_nms_kp.py:64-70
         valid = top_s > 0
@@ -251,3 +285,45 @@ class KGDetHead(nn.Module):
         vis = torch.ones_like(out_kpts[..., :1])
         out_kpts = (torch.cat([out_kpts, vis], -1) * valid[..., None, None]).reshape(B, k, -1)
         return out_dets, out_labels, out_kpts
+
+
+class GraphedInference(object):
+    """forward_single + get_bboxes of a KGDetHead captured ONCE into a CUDA graph for a fixed input shape.
+
+    The whole step (~150 kernels: cuDNN towers, 2 layout transforms, 6 sample plans, 12 fused tcgen05
+    deformable convolutions, 3 moment transforms, decode, one batched NMS, top-k) has static shapes and
+    no host synchronisation, so a replay costs one launch on the host instead of ~4 ms of Python/launch
+    overhead.  ``__call__(x)`` copies ``x`` (device or pinned host tensor) into the static input and
+    replays; the returned (dets, labels, kpts) are the graph's static output tensors.
+    """
+
+    def __init__(self, head, example_x, img_shapes, score_thr=0.05, iou_thr=0.5, nms_pre=1000, max_per_img=100,
+                 score_override=None, warmup=3):
+        assert example_x.is_cuda, 'GraphedInference needs a CUDA example input'
+        self.head = head
+        self.args = (img_shapes, score_thr, iou_thr, nms_pre, max_per_img)
+        self.score_override = score_override
+        self.static_x = example_x.detach().clone()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():       # packs weights, picks cuDNN algorithms, warms the allocator
+            for _ in range(max(warmup, 1)):
+                self._run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = self._run()
+
+    def _run(self):
+        o = self.head.forward_single(self.static_x)
+        shapes, score_thr, iou_thr, nms_pre, max_per_img = self.args
+        return self.head.get_bboxes([o[2]], [o[5]], [o[8]], shapes, score_thr, iou_thr, nms_pre, max_per_img,
+                                    score_override=None if self.score_override is None else [self.score_override])
+
+    def __call__(self, x=None):
+        if x is not None and x.data_ptr() != self.static_x.data_ptr():
+            self.static_x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

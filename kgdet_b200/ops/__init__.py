@@ -10,7 +10,8 @@ from ._out_of_scope import (ContextBlock, DeformRoIPooling, DeformRoIPoolingPack
                             roi_align, roi_pool)
 from .dcn import (DeformConv, DeformConvFunction, DeformConvPack, ModulatedDeformConv,
                   ModulatedDeformConvFunction, ModulatedDeformConvPack, deform_conv,
-                  get_precision, modulated_deform_conv, set_precision)
+                  deform_conv_prepared, get_precision, modulated_deform_conv, prepare_input,
+                  prepare_plan, set_precision)
 from .moment import points2bbox_moment
 from .nms import batched_nms_flags, nms, soft_nms
 from .sigmoid_focal_loss import SigmoidFocalLoss, sigmoid_focal_loss, sigmoid_focal_loss_sum
@@ -25,4 +26,5 @@ __all__ = [
     # extras beyond the reference surface
     'DeformConvFunction', 'ModulatedDeformConvFunction', 'points2bbox_moment',
     'sigmoid_focal_loss_sum', 'batched_nms_flags', 'set_precision', 'get_precision',
+    'prepare_input', 'prepare_plan', 'deform_conv_prepared',
 ]

@@ -40,6 +40,12 @@ SIGNATURES = {
     'kgdet_dcn_forward_workspace_bytes': (c_sz, [_SHAPE_P, ctypes.c_int, ctypes.c_int]),
     'kgdet_dcn_forward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, _SHAPE_P,
                                          ctypes.c_int, ctypes.c_int, c_ptr, c_sz, c_ptr]),
+    'kgdet_dcn_prepared_input_bytes': (c_sz, [_SHAPE_P, ctypes.c_int]),
+    'kgdet_dcn_prepare_input': (ctypes.c_int, [c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr]),
+    'kgdet_dcn_plan_bytes': (c_sz, [_SHAPE_P, ctypes.c_int]),
+    'kgdet_dcn_prepare_plan': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
+    'kgdet_dcn_forward_prepared': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, ctypes.c_int,
+                                                  _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr]),
     'kgdet_dcn_backward_input_workspace_bytes': (c_sz, [_SHAPE_P, ctypes.c_int, ctypes.c_int]),
     'kgdet_dcn_backward_input': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                                 c_ptr, _SHAPE_P, ctypes.c_int, ctypes.c_int,
@@ -52,7 +58,7 @@ SIGNATURES = {
     'kgdet_nms': (ctypes.c_int, [c_ptr, c_i32, c_f32, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_sz,
                                  c_ptr]),
     'kgdet_nms_batched_workspace_bytes': (c_sz, [c_i32, c_i32, c_i32]),
-    'kgdet_nms_batched': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_f32, ctypes.c_int,
+    'kgdet_nms_batched': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_f32, c_f32, ctypes.c_int,
                                          c_ptr, c_ptr, c_sz, c_ptr]),
     'kgdet_sigmoid_focal_loss_forward': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_f32, c_f32,
                                                         c_ptr, ctypes.c_int, c_ptr]),

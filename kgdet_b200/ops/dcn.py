@@ -205,6 +205,95 @@ def _dcn_backward_weight(input, offset, mask, weight, grad_output, with_bias, st
     return grad_weight, grad_bias
 
 
+# ---- prepared (shared) forward: inference fast path used by kgdet_b200.head ------------------------
+class PreparedInput(object):
+    """NHWC copy (+ guard band) of an activation, shareable by every deformable convolution that reads
+    it (kgdet_dcn_prepare_input)."""
+    __slots__ = ('buf', 'shape4', 'dtype_code', 'precision', 'fast', 'torch_dtype')
+
+
+class SamplePlan(object):
+    """Per-(position, tap) sampling records of one offset tensor (kgdet_dcn_prepare_plan), shareable by
+    the convolutions that use the same offsets (the cls and keypoint branches of a Kp3RepBlock)."""
+    __slots__ = ('buf', 'geom', 'precision', 'fast')
+
+
+def _geom_shape(n, c, h, w, cout, k, stride, padding, dilation):
+    s = _capi.DcnShape()
+    s.N, s.C, s.H, s.W = n, c, h, w
+    s.Cout, s.kh, s.kw = cout, k[0], k[1]
+    s.stride_h, s.stride_w = stride
+    s.pad_h, s.pad_w = padding
+    s.dil_h, s.dil_w = dilation
+    s.groups, s.deformable_groups = 1, 1
+    return s
+
+
+def prepare_input(x, out_channels, kernel_size=3, stride=1, padding=1, dilation=1, precision=None):
+    lib = _capi.lib()
+    _capi.require_cuda(x, 'prepare_input')
+    x = x.detach().contiguous()
+    prec_name = precision or get_precision(x.dtype)
+    prec = _capi.PRECISIONS[prec_name]
+    shape = _geom_shape(*x.shape, out_channels, _pair(kernel_size), _pair(stride), _pair(padding), _pair(dilation))
+    p = PreparedInput()
+    p.shape4 = tuple(x.shape)
+    p.dtype_code = _capi.dtype_code(x)
+    p.torch_dtype = x.dtype
+    p.precision = prec
+    p.fast = bool(lib.kgdet_dcn_fast_path_supported(ctypes_ref(shape), prec))
+    p.buf = torch.empty(int(lib.kgdet_dcn_prepared_input_bytes(ctypes_ref(shape), prec)), dtype=torch.uint8,
+                        device=x.device)
+    _capi.check(lib.kgdet_dcn_prepare_input(x.data_ptr(), p.buf.data_ptr(), ctypes_ref(shape), p.dtype_code, prec,
+                                            _capi.stream_of(x)), 'kgdet_dcn_prepare_input')
+    return p
+
+
+def prepare_plan(offset, input_shape, out_channels, kernel_size, stride=1, padding=0, dilation=1, mask=None,
+                 precision=None, like_dtype=torch.float32):
+    lib = _capi.lib()
+    _capi.require_cuda(offset, 'prepare_plan')
+    prec = _capi.PRECISIONS[precision or get_precision(like_dtype)]
+    k, st, pd, dl = _pair(kernel_size), _pair(stride), _pair(padding), _pair(dilation)
+    shape = _geom_shape(*input_shape, out_channels, k, st, pd, dl)
+    off = _f32c(offset)
+    msk = None if mask is None else _f32c(mask)
+    pl = SamplePlan()
+    pl.geom = (tuple(input_shape), k, st, pd, dl)
+    pl.precision = prec
+    pl.fast = bool(lib.kgdet_dcn_fast_path_supported(ctypes_ref(shape), prec))
+    pl.buf = torch.empty(int(lib.kgdet_dcn_plan_bytes(ctypes_ref(shape), prec)), dtype=torch.uint8,
+                         device=offset.device)
+    _capi.check(lib.kgdet_dcn_prepare_plan(off.data_ptr(), _capi.ptr(msk), pl.buf.data_ptr(), ctypes_ref(shape),
+                                           prec, _capi.stream_of(off)), 'kgdet_dcn_prepare_plan')
+    return pl
+
+
+def deform_conv_prepared(pin, plan, weight, out=None, channel_offset=0, relu=False, bias=None):
+    """out[:, channel_offset:channel_offset+Cout] = (relu)(deform_conv(input, offset, weight)); no autograd."""
+    lib = _capi.lib()
+    (n, c, h, w), k, st, pd, dl = plan.geom
+    assert pin.shape4 == (n, c, h, w) and pin.precision == plan.precision
+    assert tuple(weight.shape[1:]) == (c, k[0], k[1]), 'weight does not match the prepared geometry'
+    shape = _geom_shape(n, c, h, w, weight.shape[0], k, st, pd, dl)
+    fast = bool(lib.kgdet_dcn_fast_path_supported(ctypes_ref(shape), plan.precision))
+    assert fast == pin.fast == plan.fast, 'prepared buffers were built for a different kernel path'
+    packed = _packed_weight(weight, shape, plan.precision)
+    ho = (h + 2 * pd[0] - (dl[0] * (k[0] - 1) + 1)) // st[0] + 1
+    wo = (w + 2 * pd[1] - (dl[1] * (k[1] - 1) + 1)) // st[1] + 1
+    if out is None:
+        out = torch.empty((n, weight.shape[0], ho, wo), dtype=pin.torch_dtype, device=weight.device)
+        channel_offset = 0
+    assert out.is_contiguous() and out.shape[0] == n and tuple(out.shape[2:]) == (ho, wo)
+    b = None if bias is None else _f32c(bias)
+    _capi.check(lib.kgdet_dcn_forward_prepared(pin.buf.data_ptr(), plan.buf.data_ptr(), packed.data_ptr(),
+                                               _capi.ptr(b), out.data_ptr(), int(channel_offset), out.shape[1],
+                                               int(bool(relu)), ctypes_ref(shape), _capi.dtype_code(out),
+                                               plan.precision, _capi.stream_of(out)),
+                'kgdet_dcn_forward_prepared')
+    return out
+
+
 class DeformConvFunction(Function):
     """Mirror of DC.py:12-110."""
 

@@ -60,18 +60,29 @@ def nms(dets, iou_thr, device_id=None):
     return dets[inds, :], inds
 
 
-def batched_nms_flags(dets, seg_offsets, max_seg_len, iou_thr, cmp_mode=_capi.NMS_GT):
-    """dets [total,5] fp32 CUDA, seg_offsets int32 CUDA [nseg+1] -> uint8 keep flag per row."""
+def batched_nms_flags(dets, seg_offsets, max_seg_len, iou_thr, cmp_mode=_capi.NMS_GT,
+                      score_thr=float('-inf')):
+    """One launch of greedy NMS over many independent segments (one per (image, class)).
+
+    dets [total,5] fp32 CUDA.  seg_offsets: int32 CUDA [nseg+1], or None for dense mode (total is a
+    multiple of max_seg_len and every segment has exactly max_seg_len rows).  Rows with
+    score <= score_thr are treated as absent.  Returns a uint8 keep flag per row.  No host sync.
+    """
     lib = _capi.lib()
     _capi.require_cuda(dets, 'batched_nms_flags')
     d = dets.detach().to(torch.float32).contiguous()
-    so = seg_offsets.to(device=d.device, dtype=torch.int32).contiguous()
-    total, nseg = d.shape[0], so.numel() - 1
+    total = d.shape[0]
+    if seg_offsets is None:
+        assert max_seg_len > 0 and total % max_seg_len == 0
+        so_ptr, nseg = None, total // max_seg_len
+    else:
+        so = seg_offsets.to(device=d.device, dtype=torch.int32).contiguous()
+        so_ptr, nseg = so.data_ptr(), so.numel() - 1
     flags = torch.zeros(total, dtype=torch.uint8, device=d.device)
     if total == 0 or nseg <= 0:
         return flags
-    _capi.check(lib.kgdet_nms_batched(d.data_ptr(), so.data_ptr(), nseg, total, int(max_seg_len),
-                                      float(iou_thr), cmp_mode, flags.data_ptr(), None, 0,
+    _capi.check(lib.kgdet_nms_batched(d.data_ptr(), so_ptr, nseg, total, int(max_seg_len), float(iou_thr),
+                                      float(score_thr), cmp_mode, flags.data_ptr(), None, 0,
                                       _capi.stream_of(d)), 'kgdet_nms_batched')
     return flags
 

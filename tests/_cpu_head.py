@@ -13,21 +13,30 @@ from oracle import build_ref, moment_oracle, nms_oracle
 from tests import oracle_ops
 
 
-def cpu_batched_nms_flags(dets, seg_offsets, max_seg_len, iou_thr, cmp_mode=1):
+def cpu_batched_nms_flags(dets, seg_offsets, max_seg_len, iou_thr, cmp_mode=1, score_thr=float('-inf')):
     """Per-segment greedy NMS on the host: the reference's per-class loop
-    (mmdet/core/post_processing/bbox_nms_kp.py:38-52) with nms_cpu semantics ('>=')."""
+    (mmdet/core/post_processing/bbox_nms_kp.py:38-52, incl. its score filter :39) with nms_cpu
+    semantics ('>=').  Same signature as kgdet_b200.ops.batched_nms_flags."""
     ref = build_ref.load('nms_cpu')
     flags = torch.zeros(dets.shape[0], dtype=torch.uint8)
-    so = seg_offsets.tolist()
     d = dets.detach().float().contiguous()
+    if seg_offsets is None:
+        so = list(range(0, d.shape[0] + 1, max_seg_len))
+    else:
+        so = seg_offsets.tolist()
     for s in range(len(so) - 1):
         a, b = so[s], so[s + 1]
-        if b > a:
-            if ref is not None and cmp_mode == 1:
-                keep = ref.nms(d[a:b].contiguous(), float(iou_thr))
-            else:
-                keep = torch.from_numpy(nms_oracle.nms_keep(d[a:b], iou_thr, cmp_mode))
-            flags[a + keep] = 1
+        if b <= a:
+            continue
+        rows = torch.nonzero(d[a:b, 4] > score_thr).squeeze(1)
+        if rows.numel() == 0:
+            continue
+        seg = d[a:b][rows].contiguous()
+        if ref is not None and cmp_mode == 1:
+            keep = ref.nms(seg, float(iou_thr))
+        else:
+            keep = torch.from_numpy(nms_oracle.nms_keep(seg, iou_thr, cmp_mode))
+        flags[a + rows[keep]] = 1
     return flags
 
 

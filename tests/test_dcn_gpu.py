@@ -199,3 +199,31 @@ def test_oracle_matches_reference_cuda():
     got = _ours(d, 'fp32')
     assert rel_err(got['out'], out) < 1e-5
     assert rel_err(got['grad_offset'], goff) < 1e-5
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16', 'tf32x3'])
+def test_prepared_api_matches_plain_calls(precision):
+    """Shared NHWC copy + shared plan + fused ReLU / channel-slice epilogue == relu(deform_conv) + cat,
+    bit for bit (same kernels, same arithmetic)."""
+    from kgdet_b200 import ops
+    ops.set_precision(precision)
+    try:
+        d3 = dcn_case(N=2, C=64, H=12, W=10, Cout=64, k=3, seed=1)
+        d5 = dcn_case(N=2, C=64, H=12, W=10, Cout=64, k=5, seed=2)
+        x = d3['x'].cuda()
+        pin = ops.prepare_input(x, 64)
+        out = torch.full((2, 128 + 8, 12, 10), -7.0, device='cuda')
+        ref = []
+        for i, d in enumerate((d3, d5)):
+            k = d['weight'].shape[-1]
+            off, w = d['offset'].cuda(), d['weight'].cuda()
+            plan = ops.prepare_plan(off, x.shape, 64, k, 1, k // 2, 1)
+            ops.deform_conv_prepared(pin, plan, w, out, 4 + i * 64, True)
+            ref.append(torch.relu(ops.deform_conv(x, off, w, 1, k // 2)))
+        assert torch.equal(out[:, 4:132], torch.cat(ref, 1))
+        assert (out[:, :4] == -7).all() and (out[:, 132:] == -7).all()       # neighbours untouched
+        plain = ops.deform_conv_prepared(pin, ops.prepare_plan(d3['offset'].cuda(), x.shape, 64, 3, 1, 1, 1),
+                                         d3['weight'].cuda())
+        assert torch.equal(plain, ops.deform_conv(x, d3['offset'].cuda(), d3['weight'].cuda(), 1, 1))
+    finally:
+        ops.set_precision(None)

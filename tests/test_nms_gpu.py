@@ -89,3 +89,22 @@ def test_idempotent_and_sorted():
     assert np.all(np.diff(keep) > 0)
     again = _ours_keep(dets[torch.from_numpy(keep)], 0.5, 0)
     assert np.array_equal(again, np.arange(len(keep)))
+
+
+def test_batched_dense_mode_with_score_threshold():
+    """Dense segments + in-kernel `score > thr` filter == compact-then-NMS per segment."""
+    from kgdet_b200.ops import batched_nms_flags
+    nseg, n = 7, 300
+    parts = [random_boxes(n, seed=40 + i, clustered=True) for i in range(nseg)]
+    for i, p in enumerate(parts):        # push a varying share of each segment below the threshold
+        p[:, 4] = p[:, 4] * (0.3 + 0.1 * i)
+    dets = torch.cat(parts)
+    flags = batched_nms_flags(dets.cuda(), None, n, 0.5, score_thr=0.2).cpu().numpy()
+    want = np.zeros(len(dets), dtype=np.uint8)
+    for i, p in enumerate(parts):
+        rows = np.nonzero(p[:, 4].numpy() > 0.2)[0]
+        if len(rows):
+            want[i * n + rows[nms_oracle.nms_keep(p[rows], 0.5, 0)]] = 1
+    assert np.array_equal(flags, want)
+    none = batched_nms_flags(dets.cuda(), None, n, 0.5, score_thr=2.0).cpu().numpy()
+    assert none.sum() == 0
