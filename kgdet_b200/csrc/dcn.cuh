@@ -88,4 +88,15 @@ int umma_pack_weight(const DcnGeom& g, const float* weight, void* packed, int pr
 int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec16* plan, const void* packed_w,
                  const float* bias, const OutSpec& o, int precision, cudaStream_t stream);
 
+// ---- tensor-core backward (bf16 mode; dcn_bwd_tc.cu) ----
+bool bwd_tc_supported(const DcnGeom& g, int precision);
+size_t bwd_tc_input_workspace_bytes(const DcnGeom& g);
+size_t bwd_tc_weight_workspace_bytes(const DcnGeom& g);
+int bwd_tc_input(const DcnGeom& g, const void* input, const float* offset, const float* mask,
+                 const float* weight, const void* grad_output, void* grad_input, float* grad_offset,
+                 float* grad_mask, int dtype, void* ws, cudaStream_t stream);
+int bwd_tc_weight(const DcnGeom& g, const void* input, const float* offset, const float* mask,
+                  const void* grad_output, float* grad_weight, float* grad_bias, float scale, int dtype,
+                  void* ws, cudaStream_t stream);
+
 }  // namespace kgdet

@@ -224,10 +224,10 @@ extern "C" void kgdet_dcn_set_profile_events(void* start_event, void* stop_event
   g_prof_stop = (cudaEvent_t)stop_event;
 }
 
-extern "C" size_t kgdet_dcn_backward_input_workspace_bytes(const kgdet_dcn_shape* shape, int, int) {
+extern "C" size_t kgdet_dcn_backward_input_workspace_bytes(const kgdet_dcn_shape* shape, int, int precision) {
   DcnGeom g;
   if (make_geom(shape, &g) != KGDET_OK) return 0;
-  return carve_bwd_in(g, nullptr).total;
+  return bwd_tc_supported(g, precision) ? bwd_tc_input_workspace_bytes(g) : carve_bwd_in(g, nullptr).total;
 }
 
 extern "C" int kgdet_dcn_backward_input(const void* input, const float* offset, const float* mask,
@@ -245,6 +245,12 @@ extern "C" int kgdet_dcn_backward_input(const void* input, const float* offset, 
                "kgdet_dcn_backward_input: NULL pointer");
   KG_CHECK_ARG((mask == nullptr) == (grad_mask == nullptr),
                "kgdet_dcn_backward_input: mask and grad_mask must both be given or both be NULL");
+  if (bwd_tc_supported(g, precision)) {       // bf16 mode: tensor-core GEMM + warp-reduction col2im
+    if ((rc = check_ws("kgdet_dcn_backward_input", workspace, workspace_bytes,
+                       bwd_tc_input_workspace_bytes(g))) != KGDET_OK) return rc;
+    return bwd_tc_input(g, input, offset, mask, weight, grad_output, grad_input, grad_offset, grad_mask, dtype,
+                        workspace, stream);
+  }
   BwdInWs w = carve_bwd_in(g, workspace);
   if ((rc = check_ws("kgdet_dcn_backward_input", workspace, workspace_bytes, w.total)) != KGDET_OK) return rc;
   const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
@@ -261,10 +267,10 @@ extern "C" int kgdet_dcn_backward_input(const void* input, const float* offset, 
   return launch_transpose(w.gin_nhwc, grad_input, g.N, HW, g.C, KGDET_F32, dtype, stream);
 }
 
-extern "C" size_t kgdet_dcn_backward_weight_workspace_bytes(const kgdet_dcn_shape* shape, int, int) {
+extern "C" size_t kgdet_dcn_backward_weight_workspace_bytes(const kgdet_dcn_shape* shape, int, int precision) {
   DcnGeom g;
   if (make_geom(shape, &g) != KGDET_OK) return 0;
-  return carve_bwd_w(g, nullptr).total;
+  return bwd_tc_supported(g, precision) ? bwd_tc_weight_workspace_bytes(g) : carve_bwd_w(g, nullptr).total;
 }
 
 extern "C" int kgdet_dcn_backward_weight(const void* input, const float* offset, const float* mask,
@@ -279,6 +285,12 @@ extern "C" int kgdet_dcn_backward_weight(const void* input, const float* offset,
   KG_CHECK_ARG(valid_dtype(dtype), "kgdet_dcn_backward_weight: bad dtype %d", dtype);
   KG_CHECK_ARG(valid_prec(precision), "kgdet_dcn_backward_weight: bad precision %d", precision);
   KG_CHECK_ARG(input && offset && grad_output && grad_weight, "kgdet_dcn_backward_weight: NULL pointer");
+  if (bwd_tc_supported(g, precision)) {
+    if ((rc = check_ws("kgdet_dcn_backward_weight", workspace, workspace_bytes,
+                       bwd_tc_weight_workspace_bytes(g))) != KGDET_OK) return rc;
+    return bwd_tc_weight(g, input, offset, mask, grad_output, grad_weight, grad_bias, scale, dtype, workspace,
+                         stream);
+  }
   BwdWWs w = carve_bwd_w(g, workspace);
   if ((rc = check_ws("kgdet_dcn_backward_weight", workspace, workspace_bytes, w.total)) != KGDET_OK) return rc;
   const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;

@@ -1,0 +1,341 @@
+// Deformable-convolution backward on the tensor cores (bf16 mode; groups == deformable_groups == 1).
+//
+// Input / offset / mask gradient  (reference: deform_conv_cuda.cpp:260-371, kernels
+// deform_conv_cuda_kernel.cu:278-435):
+//   cg[m, (tap, c)] = sum_o gO[m, o] * W[o, c, tap]          tcgen05 GEMM (gemm_umma.cu), bf16, written in
+//                                                            tap chunks small enough to stay in the 126 MB L2
+//   col2im          one warp per (position, tap): lanes sweep the channels (16-byte loads of cg and of
+//                   the four NHWC corner rows), grad_input by vectorised fp32 red.global.add.v4 on the
+//                   NHWC gradient buffer, grad_offset / grad_mask by warp-shuffle reduction over channels
+//                   -- one writer per element, no atomics, deterministic (the reference loops over the
+//                   C channels serially in one thread, :405-433).
+// Weight gradient  (reference: deform_conv_cuda.cpp:373-484 recomputes im2col into HBM):
+//   colT[(tap, c), m] = S(m, tap, c)                         gather kernel, transposed through smem, tap chunks
+//   gW^T[(tap, c), o] = sum_m colT * gO^T[o, m]              split-K tcgen05 GEMM with fp32 red epilogue
+#include "dcn.cuh"
+
+namespace kgdet {
+
+int umma_gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, void* C,
+              long long ldc, int M, int N, int K, int out_dtype, int splits, float alpha, cudaStream_t stream);
+
+bool bwd_tc_supported(const DcnGeom& g, int precision) {
+  return precision == KGDET_PREC_BF16 && g.groups == 1 && g.dgroups == 1 && g.C % 64 == 0 &&
+         g.Cout % 64 == 0;
+}
+
+// taps per chunk so that an [M, taps*C] bf16 buffer stays around 48 MB
+static int taps_per_chunk(const DcnGeom& g, size_t rows) {
+  const size_t per_tap = rows * g.C * 2;
+  int t = (int)((48ull << 20) / (per_tap ? per_tap : 1));
+  if (t < 1) t = 1;
+  if (t > g.K) t = g.K;
+  return t;
+}
+static size_t mpad64(const DcnGeom& g) { return (size_t)ceil_div(g.M, 64) * 64; }
+
+// ---- weight layout for the column-gradient GEMM: Wd[(tap*C + c), o] = W[o, c, tap] ----------------
+__global__ void pack_wd_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd, int Cout,
+                                    int C, int K) {
+  const long long total = (long long)K * C * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)blockDim.x * gridDim.x) {
+    const int o = (int)(i % Cout);
+    const long long r = i / Cout;
+    const int c = (int)(r % C), tap = (int)(r / C);
+    wd[i] = __float2bfloat16(w[((size_t)o * C + c) * K + tap]);
+  }
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+
+// ---- col2im + offset / mask gradient ----------------------------------------------------------------
+// cg: [M, ntaps*C] bf16 (taps tap0 .. tap0+ntaps-1).  One warp per (m, local tap).
+__global__ void __launch_bounds__(256)
+col2im_tc_kernel(DcnGeom g, const __nv_bfloat16* __restrict__ cg, const __nv_bfloat16* __restrict__ in,
+                 const SampleRec* __restrict__ plan, const SampleAux* __restrict__ aux, int tap0, int ntaps,
+                 float* __restrict__ gin, float* __restrict__ goff, float* __restrict__ gmask) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long total = (long long)g.M * ntaps;
+  const int HoWo = g.Ho * g.Wo;
+  for (long long wi = warp_global; wi < total; wi += nwarps) {
+    const int m = (int)(wi / ntaps), tl = (int)(wi - (long long)m * ntaps), tap = tap0 + tl;
+    const size_t ridx = (size_t)m * g.K + tap;
+    const int4 pa = __ldg(reinterpret_cast<const int4*>(plan + ridx));
+    const float4 pw = __ldg(reinterpret_cast<const float4*>(plan + ridx) + 1);
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(aux + ridx));
+    const int pix[4] = {pa.x, pa.y, pa.z, pa.w};
+    const float wgt[4] = {pw.x, pw.y, pw.z, pw.w};
+    const float lh = a4.x, lw = a4.y, mk = a4.z;
+    const int valid = __float_as_int(a4.w);
+    const float hh = 1.f - lh, hw = 1.f - lw;
+    float pdy = 0.f, pdx = 0.f, pms = 0.f;
+    if (valid) {                                                  // warp-uniform
+      const __nv_bfloat16* cgrow = cg + ((size_t)m * ntaps + tl) * g.C;
+      for (int c0 = lane * 8; c0 < g.C; c0 += 256) {
+        float gv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(cgrow + c0)), gv);
+        float v[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (valid & (1 << i)) {
+            unpack8(__ldg(reinterpret_cast<const uint4*>(in + (size_t)pix[i] * g.C + c0)), v[i]);
+            float* dst = gin + (size_t)pix[i] * g.C + c0;
+            const float wi_ = wgt[i];
+            atomicAdd(reinterpret_cast<float4*>(dst),
+                      make_float4(gv[0] * wi_, gv[1] * wi_, gv[2] * wi_, gv[3] * wi_));
+            atomicAdd(reinterpret_cast<float4*>(dst + 4),
+                      make_float4(gv[4] * wi_, gv[5] * wi_, gv[6] * wi_, gv[7] * wi_));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dsy = -hw * v[0][e] - lw * v[1][e] + hw * v[2][e] + lw * v[3][e];
+          const float dsx = -hh * v[0][e] + hh * v[1][e] - lh * v[2][e] + lh * v[3][e];
+          const float s = hh * hw * v[0][e] + hh * lw * v[1][e] + lh * hw * v[2][e] + lh * lw * v[3][e];
+          pdy = fmaf(gv[e], dsy, pdy);
+          pdx = fmaf(gv[e], dsx, pdx);
+          pms = fmaf(gv[e], s, pms);
+        }
+      }
+    }
+    pdy = warp_sum(pdy);
+    pdx = warp_sum(pdx);
+    pms = warp_sum(pms);
+    if (lane == 0) {
+      const int n = m / HoWo, p = m - n * HoWo;
+      goff[((size_t)n * 2 * g.K + 2 * tap) * HoWo + p] = pdy * mk;       // assigned, like :433
+      goff[((size_t)n * 2 * g.K + 2 * tap + 1) * HoWo + p] = pdx * mk;
+      if (gmask) gmask[((size_t)n * g.K + tap) * HoWo + p] = pms;
+    }
+  }
+}
+
+// ---- sampled columns, transposed: colT[(tl*C + c), m] for taps tap0 .. tap0+ntaps-1 ---------------
+// CTA = 64 positions x one tap; loops over 64-channel blocks.  Gather is row-wise coalesced (8 lanes per
+// 128-byte slab), the 64x64 tile is transposed through shared memory, rows of 64 positions (128 B) go out.
+__global__ void __launch_bounds__(256)
+gather_colT_kernel(DcnGeom g, const __nv_bfloat16* __restrict__ in, const SampleRec* __restrict__ plan,
+                   int tap0, __nv_bfloat16* __restrict__ colT, long long mpad) {
+  __shared__ __nv_bfloat16 tile[64][64 + 8];       // [channel][position]
+  const int m0 = blockIdx.x * 64, tl = blockIdx.y, tap = tap0 + tl;
+  const int t = threadIdx.x, chunk = t & 7, rbase = t >> 3;
+  SampleRec rec[2];
+#pragma unroll
+  for (int ps = 0; ps < 2; ++ps) {
+    const int m = m0 + rbase + ps * 32;
+    const SampleRec* rp = plan + (size_t)m * g.K + tap;          // plan is padded to 128 rows
+    const int4 a = __ldg(reinterpret_cast<const int4*>(rp));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(rp) + 1);
+    rec[ps].pix[0] = a.x; rec[ps].pix[1] = a.y; rec[ps].pix[2] = a.z; rec[ps].pix[3] = a.w;
+    rec[ps].w[0] = b.x; rec[ps].w[1] = b.y; rec[ps].w[2] = b.z; rec[ps].w[3] = b.w;
+  }
+  for (int cb = 0; cb < g.C / 64; ++cb) {
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (rec[ps].w[i] != 0.f) {
+          float v[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(in + (size_t)rec[ps].pix[i] * g.C + cb * 64 + chunk * 8)), v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(rec[ps].w[i], v[e], acc[e]);
+        }
+      }
+      const int pos = rbase + ps * 32;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) tile[chunk * 8 + e][pos] = __float2bfloat16(acc[e]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int idx = t + r * 256;               // 512 x 16-byte pieces: 64 channels x 8 pieces
+      const int c = idx >> 3, piece = idx & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(&tile[c][piece * 8]);
+      *reinterpret_cast<uint4*>(colT + ((size_t)tl * g.C + cb * 64 + c) * mpad + m0 + piece * 8) = v;
+    }
+    __syncthreads();
+  }
+}
+
+// gO NCHW (fp32 / bf16) -> gOT[o, m] bf16 with m = n*HoWo + p (row stride mpad)
+template <typename T>
+__global__ void go_to_goT_kernel(const T* __restrict__ go, __nv_bfloat16* __restrict__ goT, int N, int Cout,
+                                 int HoWo, long long mpad) {
+  const long long total = (long long)N * Cout * HoWo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)blockDim.x * gridDim.x) {
+    const int p = (int)(i % HoWo);
+    const long long r = i / HoWo;
+    const int o = (int)(r % Cout), n = (int)(r / Cout);
+    float v;
+    if constexpr (sizeof(T) == 4) v = go[i]; else v = __bfloat162float(go[i]);
+    goT[(size_t)o * mpad + (size_t)n * HoWo + p] = __float2bfloat16(v);
+  }
+}
+
+// grad_W[o, c, tap] = scale * gWT[(tap*C + c), o]
+__global__ void unpack_gw_kernel(const float* __restrict__ gwt, float* __restrict__ gw, int Cout, int C, int K,
+                                 float scale) {
+  const long long total = (long long)Cout * C * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)blockDim.x * gridDim.x) {
+    const int tap = (int)(i % K);
+    const long long r = i / K;
+    const int c = (int)(r % C), o = (int)(r / C);
+    gw[i] = scale * gwt[((size_t)tap * C + c) * Cout + o];
+  }
+}
+
+template <typename T>
+__global__ void bias_grad_nchw_kernel(const T* __restrict__ go, int N, int Cout, int HoWo, float* __restrict__ gb) {
+  const int o = blockIdx.x;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n)
+    for (int p = threadIdx.x; p < HoWo; p += blockDim.x) {
+      const size_t i = ((size_t)n * Cout + o) * HoWo + p;
+      if constexpr (sizeof(T) == 4) s += go[i]; else s += __bfloat162float(go[i]);
+    }
+  __shared__ float part[32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) gb[o] = v;
+  }
+}
+
+// ---- workspace layouts --------------------------------------------------------------------------------
+struct TcBwdInWs {
+  __nv_bfloat16 *in_nhwc, *go_nhwc, *wd, *cg;
+  float* gin_nhwc;
+  SampleRec* plan;
+  SampleAux* aux;
+  size_t total;
+};
+static TcBwdInWs carve_tc_in(const DcnGeom& g, void* ws) {
+  TcBwdInWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* p = ws ? (char*)ws + off : nullptr; off += align_up(bytes, 1024); return p; };
+  w.in_nhwc = (__nv_bfloat16*)take((size_t)g.N * g.H * g.W * g.C * 2);
+  w.go_nhwc = (__nv_bfloat16*)take((size_t)g.M * g.Cout * 2);
+  w.wd = (__nv_bfloat16*)take((size_t)g.K * g.C * g.Cout * 2);
+  w.cg = (__nv_bfloat16*)take((size_t)g.M * taps_per_chunk(g, g.M) * g.C * 2);
+  w.gin_nhwc = (float*)take((size_t)g.N * g.H * g.W * g.C * 4);
+  w.plan = (SampleRec*)take(plan_bytes(g));
+  w.aux = (SampleAux*)take(plan_aux_bytes(g));
+  w.total = off;
+  return w;
+}
+size_t bwd_tc_input_workspace_bytes(const DcnGeom& g) { return carve_tc_in(g, nullptr).total; }
+
+struct TcBwdWWs {
+  __nv_bfloat16 *in_nhwc, *goT, *colT;
+  float* gwt;
+  SampleRec* plan;
+  size_t total;
+};
+static TcBwdWWs carve_tc_w(const DcnGeom& g, void* ws) {
+  TcBwdWWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* p = ws ? (char*)ws + off : nullptr; off += align_up(bytes, 1024); return p; };
+  const size_t mp = mpad64(g);
+  w.in_nhwc = (__nv_bfloat16*)take((size_t)g.N * g.H * g.W * g.C * 2);
+  w.goT = (__nv_bfloat16*)take((size_t)g.Cout * mp * 2);
+  w.colT = (__nv_bfloat16*)take((size_t)taps_per_chunk(g, mp) * g.C * mp * 2);
+  w.gwt = (float*)take((size_t)g.K * g.C * g.Cout * 4);
+  w.plan = (SampleRec*)take(plan_bytes(g));
+  w.total = off;
+  return w;
+}
+size_t bwd_tc_weight_workspace_bytes(const DcnGeom& g) { return carve_tc_w(g, nullptr).total; }
+
+static int grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int bwd_tc_input(const DcnGeom& g, const void* input, const float* offset, const float* mask,
+                 const float* weight, const void* grad_output, void* grad_input, float* grad_offset,
+                 float* grad_mask, int dtype, void* ws, cudaStream_t stream) {
+  TcBwdInWs w = carve_tc_in(g, ws);
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  int rc;
+  if ((rc = launch_transpose(input, w.in_nhwc, g.N, g.C, HW, dtype, KGDET_BF16, stream)) != KGDET_OK) return rc;
+  if ((rc = launch_transpose(grad_output, w.go_nhwc, g.N, g.Cout, HoWo, dtype, KGDET_BF16, stream)) != KGDET_OK) return rc;
+  if ((rc = launch_plan(g, offset, mask, w.plan, w.aux, stream)) != KGDET_OK) return rc;
+  pack_wd_bf16_kernel<<<grid_for((long long)g.K * g.C * g.Cout, 256), 256, 0, stream>>>(weight, w.wd, g.Cout, g.C, g.K);
+  KG_LAUNCH_CHECK("pack_wd_bf16_kernel");
+  KG_CUDA(cudaMemsetAsync(w.gin_nhwc, 0, (size_t)g.N * HW * g.C * 4, stream));
+  const int tpc = taps_per_chunk(g, g.M);
+  for (int tap0 = 0; tap0 < g.K; tap0 += tpc) {
+    const int nt = (g.K - tap0) < tpc ? (g.K - tap0) : tpc;
+    // cg[m, (tl, c)] = go_nhwc[m, :] . Wd[(tap0+tl)*C + c, :]
+    if ((rc = umma_gemm(w.go_nhwc, g.Cout, w.wd + (size_t)tap0 * g.C * g.Cout, g.Cout, w.cg, (long long)nt * g.C,
+                        g.M, nt * g.C, g.Cout, KGDET_BF16, 1, 1.f, stream)) != KGDET_OK) return rc;
+    const long long warps = (long long)g.M * nt;
+    col2im_tc_kernel<<<grid_for(warps * 32, 256), 256, 0, stream>>>(g, w.cg, w.in_nhwc, w.plan, w.aux, tap0, nt,
+                                                                    w.gin_nhwc, grad_offset, grad_mask);
+    KG_LAUNCH_CHECK("col2im_tc_kernel");
+  }
+  return launch_transpose(w.gin_nhwc, grad_input, g.N, HW, g.C, KGDET_F32, dtype, stream);
+}
+
+int bwd_tc_weight(const DcnGeom& g, const void* input, const float* offset, const float* mask,
+                  const void* grad_output, float* grad_weight, float* grad_bias, float scale, int dtype,
+                  void* ws, cudaStream_t stream) {
+  TcBwdWWs w = carve_tc_w(g, ws);
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  const long long mp = (long long)mpad64(g);
+  int rc;
+  if ((rc = launch_transpose(input, w.in_nhwc, g.N, g.C, HW, dtype, KGDET_BF16, stream)) != KGDET_OK) return rc;
+  if ((rc = launch_plan(g, offset, mask, w.plan, nullptr, stream)) != KGDET_OK) return rc;
+  KG_CUDA(cudaMemsetAsync(w.goT, 0, (size_t)g.Cout * mp * 2, stream));
+  const long long gototal = (long long)g.N * g.Cout * HoWo;
+  if (dtype == KGDET_F32)
+    go_to_goT_kernel<float><<<grid_for(gototal, 256), 256, 0, stream>>>((const float*)grad_output, w.goT, g.N, g.Cout, HoWo, mp);
+  else
+    go_to_goT_kernel<__nv_bfloat16><<<grid_for(gototal, 256), 256, 0, stream>>>((const __nv_bfloat16*)grad_output, w.goT, g.N, g.Cout, HoWo, mp);
+  KG_LAUNCH_CHECK("go_to_goT_kernel");
+  KG_CUDA(cudaMemsetAsync(w.gwt, 0, (size_t)g.K * g.C * g.Cout * 4, stream));
+  const int tpc = taps_per_chunk(g, (size_t)mp);
+  for (int tap0 = 0; tap0 < g.K; tap0 += tpc) {
+    const int nt = (g.K - tap0) < tpc ? (g.K - tap0) : tpc;
+    gather_colT_kernel<<<dim3((unsigned)(mp / 64), nt), 256, 0, stream>>>(g, w.in_nhwc, w.plan, tap0, w.colT, mp);
+    KG_LAUNCH_CHECK("gather_colT_kernel");
+    // gWT[(tap0+tl)*C + c, o] += sum_m colT[(tl*C + c), m] * goT[o, m]     (split over m)
+    const int mtiles = ceil_div(nt * g.C, 128) * ceil_div(g.Cout, 256);
+    int splits = (2 * num_sms() + mtiles - 1) / mtiles;
+    const int kblocks = (int)(mp / 64);
+    if (splits > kblocks) splits = kblocks;
+    if (splits < 1) splits = 1;
+    if ((rc = umma_gemm(w.colT, mp, w.goT, mp, w.gwt + (size_t)tap0 * g.C * g.Cout, g.Cout, nt * g.C, g.Cout,
+                        (int)mp, KGDET_F32, splits < 2 ? 2 : splits, 1.f, stream)) != KGDET_OK) return rc;
+  }
+  unpack_gw_kernel<<<grid_for((long long)g.Cout * g.C * g.K, 256), 256, 0, stream>>>(w.gwt, grad_weight, g.Cout, g.C, g.K, scale);
+  KG_LAUNCH_CHECK("unpack_gw_kernel");
+  if (grad_bias) {
+    if (dtype == KGDET_F32)
+      bias_grad_nchw_kernel<float><<<g.Cout, 256, 0, stream>>>((const float*)grad_output, g.N, g.Cout, HoWo, grad_bias);
+    else
+      bias_grad_nchw_kernel<__nv_bfloat16><<<g.Cout, 256, 0, stream>>>((const __nv_bfloat16*)grad_output, g.N, g.Cout, HoWo, grad_bias);
+    KG_LAUNCH_CHECK("bias_grad_nchw_kernel");
+  }
+  return KGDET_OK;
+}
+
+}  // namespace kgdet

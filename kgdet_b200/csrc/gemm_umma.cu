@@ -1,0 +1,204 @@
+// Plain bf16 tensor-core GEMM used by the deformable-convolution backward pass:
+//
+//     C[M, N] (+)= sum_k A[m, k] * B[n, k]          A, B row-major bf16 (K contiguous), fp32 accumulate
+//
+// tcgen05.mma (UTCHMMA) with both operands K-major in 128B-swizzled shared memory, accumulator in TMEM.
+// One CTA = 128 x BN output tile; 8 producer warps copy operand tiles global -> swizzled smem with
+// 16-byte vector loads/stores (rows beyond M / N are zero-filled), 1 warp issues the MMAs, the producers
+// then drain TMEM.  grid.z splits the K range; split results are combined with fp32 atomics
+// (red.global.add) into a zero-initialised C.  K must be a multiple of 64.
+#include "dcn.cuh"
+
+namespace kgdet {
+
+static constexpr int G_BM = 128;
+static constexpr int G_PROD_WARPS = 8;
+static constexpr int G_THREADS = (G_PROD_WARPS + 1) * 32;
+static constexpr int G_NS = 4;
+
+struct GemmParams {
+  const __nv_bfloat16* A;
+  const __nv_bfloat16* B;
+  void* C;
+  long long lda, ldb, ldc;
+  int M, N;
+  int kblocks_total;     // K / 64
+  int kblocks_per_split;
+  uint32_t idesc;
+  uint32_t tmem_cols;
+  int atomic;            // 1: red.add fp32 into C (split-K), 0: plain store
+  float alpha;
+};
+
+template <typename T> __device__ __forceinline__ void st4(T* p, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void st4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 v;
+  v.x = *reinterpret_cast<uint32_t*>(&lo);
+  v.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = v;
+}
+
+template <int BN, typename Tout>
+__global__ void __launch_bounds__(G_THREADS, 1) umma_gemm_kernel(const GemmParams prm) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = G_BM * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)G_NS * STAGE);
+  uint64_t* empty_bar = full_bar + G_NS;
+  uint64_t* tmem_full_bar = empty_bar + G_NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * G_BM, n0 = blockIdx.y * BN;
+  const int kb0 = blockIdx.z * prm.kblocks_per_split;
+  int nkb = prm.kblocks_total - kb0;
+  if (nkb > prm.kblocks_per_split) nkb = prm.kblocks_per_split;
+
+  if (warp == G_PROD_WARPS) {
+    if (lane == 0) {
+      for (int s = 0; s < G_NS; ++s) {
+        mbar_init(&full_bar[s], G_PROD_WARPS);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, prm.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < G_PROD_WARPS) {
+    const int chunk = tid & 7, rbase = tid >> 3;     // 32 rows per pass
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % G_NS, it = kb / G_NS;
+      const long long kofs = (long long)(kb0 + kb) * 64 + chunk * 8;
+      uint4 va[G_BM / 32], vb[BN / 32];
+#pragma unroll
+      for (int p = 0; p < G_BM / 32; ++p) {
+        const int r = m0 + rbase + p * 32;
+        va[p] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < prm.M) va[p] = __ldg(reinterpret_cast<const uint4*>(prm.A + (long long)r * prm.lda + kofs));
+      }
+#pragma unroll
+      for (int p = 0; p < BN / 32; ++p) {
+        const int r = n0 + rbase + p * 32;
+        vb[p] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < prm.N) vb[p] = __ldg(reinterpret_cast<const uint4*>(prm.B + (long long)r * prm.ldb + kofs));
+      }
+      mbar_wait(&empty_bar[s], (it & 1) ^ 1);
+      unsigned char* a_tile = smem + (size_t)s * STAGE;
+      unsigned char* b_tile = a_tile + A_BYTES;
+      const int off = rbase * 128 + ((chunk ^ (rbase & 7)) << 4);
+#pragma unroll
+      for (int p = 0; p < G_BM / 32; ++p) *reinterpret_cast<uint4*>(a_tile + off + p * 4096) = va[p];
+#pragma unroll
+      for (int p = 0; p < BN / 32; ++p) *reinterpret_cast<uint4*>(b_tile + off + p * 4096) = vb[p];
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+    // ---- epilogue ----
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    constexpr int HALF = BN / 2;
+    for (int c0 = 0; c0 < HALF; c0 += 32) {
+      const int col = half * HALF + c0;
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
+      tmem_ld_wait();
+      if (m < prm.M && nkb > 0) {
+        const int n = n0 + col;
+        if (prm.atomic) {
+          float* crow = reinterpret_cast<float*>(prm.C) + (long long)m * prm.ldc + n;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n + j < prm.N) atomicAdd(crow + j, prm.alpha * __uint_as_float(acc[j]));
+        } else {
+          Tout* crow = reinterpret_cast<Tout*>(prm.C) + (long long)m * prm.ldc + n;
+          if (n + 32 <= prm.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              st4<Tout>(crow + j, prm.alpha * __uint_as_float(acc[j]), prm.alpha * __uint_as_float(acc[j + 1]),
+                        prm.alpha * __uint_as_float(acc[j + 2]), prm.alpha * __uint_as_float(acc[j + 3]));
+          } else {
+            for (int j = 0; j < 32 && n + j < prm.N; ++j) {
+              const float v = prm.alpha * __uint_as_float(acc[j]);
+              if constexpr (sizeof(Tout) == 4) reinterpret_cast<float*>(crow)[j] = v;
+              else reinterpret_cast<__nv_bfloat16*>(crow)[j] = __float2bfloat16(v);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % G_NS, it = kb / G_NS;
+        mbar_wait(&full_bar[s], it & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * STAGE);
+        const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+        const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == G_PROD_WARPS) tmem_dealloc(tmem_base, prm.tmem_cols);
+}
+
+template <int BN, typename Tout>
+static int launch_gemm(const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  const size_t smem = 1024 + (size_t)G_NS * (G_BM * 128 + BN * 128) + (2 * G_NS + 1) * 8 + 16;
+  KG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, Tout>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_gemm_kernel<BN, Tout><<<grid, G_THREADS, smem, stream>>>(p);
+  KG_LAUNCH_CHECK("umma_gemm_kernel");
+  return KGDET_OK;
+}
+
+// C[M,N] = alpha * A[M,K] . B[N,K]^T.  out_dtype: KGDET_F32 / KGDET_BF16.  splits > 1 requires fp32 C that
+// the caller has zeroed (results are accumulated with atomics).  K % 64 == 0, lda/ldb % 8 == 0.
+int umma_gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, void* C,
+              long long ldc, int M, int N, int K, int out_dtype, int splits, float alpha,
+              cudaStream_t stream) {
+  KG_CHECK_ARG(K % 64 == 0 && lda % 8 == 0 && ldb % 8 == 0, "umma_gemm: K %% 64 and ld %% 8 required");
+  KG_CHECK_ARG(splits >= 1 && (splits == 1 || out_dtype == KGDET_F32), "umma_gemm: split-K needs fp32 output");
+  if (M <= 0 || N <= 0 || K <= 0) return KGDET_OK;
+  GemmParams p;
+  p.A = A; p.B = B; p.C = C; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.M = M; p.N = N;
+  p.kblocks_total = K / 64;
+  p.kblocks_per_split = ceil_div(p.kblocks_total, splits);
+  splits = ceil_div(p.kblocks_total, p.kblocks_per_split);
+  p.atomic = splits > 1 ? 1 : 0;
+  p.alpha = alpha;
+  const int BN = N > 128 ? 256 : 128;
+  p.idesc = make_idesc(1u, G_BM, (uint32_t)BN);
+  p.tmem_cols = BN;
+  dim3 grid(ceil_div(M, G_BM), ceil_div(N, BN), splits);
+  KG_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "umma_gemm: grid too large");
+  if (BN == 256)
+    return out_dtype == KGDET_F32 ? launch_gemm<256, float>(p, grid, stream)
+                                  : launch_gemm<256, __nv_bfloat16>(p, grid, stream);
+  return out_dtype == KGDET_F32 ? launch_gemm<128, float>(p, grid, stream)
+                                : launch_gemm<128, __nv_bfloat16>(p, grid, stream);
+}
+
+}  // namespace kgdet

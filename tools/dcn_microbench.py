@@ -71,6 +71,13 @@ def main():
             ms_k = kernel_only(f, flush)
             row[prec] = dict(call_us=round(ms_call * 1e3, 1), kernel_us=round(ms_k * 1e3, 1),
                              kernel_tflops=round(flops / ms_k / 1e9, 1))
+        ops.set_precision('bf16')
+        xg, og, wg = x.clone().requires_grad_(), off.clone().requires_grad_(), w.clone().requires_grad_()
+
+        def fb16():
+            xg.grad = og.grad = wg.grad = None
+            ops.deform_conv(xg, og, wg, 1, k // 2).backward(go)
+        row['bf16_fwd_bwd_us'] = round(timed(fb16, flush, reps=5, warm=2) * 1e3, 1)
         if N * H * W <= 20000:
             ops.set_precision('fp32')
             f = lambda: ops.deform_conv(x, off, w, 1, k // 2)
