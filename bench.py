@@ -360,6 +360,81 @@ def run_reference(args):
     }), flush=True)
 
 
+def run_train(args):
+    """BASELINE.json configs[4]: KGDet head training step (forward + losses + backward + gradient all-reduce +
+    SGD) at batch 2 per GPU.  Targets are synthetic (the reference's PointAssigner / point_target_kp are
+    host-side PyTorch outside the hot path): ~1% positive labels for the three
+    focal losses (kgdet_b200 fused focal-sum op), Smooth-L1 on the three bbox and keypoint maps.  The DCN
+    runs forward and backward on the tensor cores (bf16 mode), the moment transform through its fused
+    fwd/bwd kernels; gradients are averaged over ranks with the overlapped bucketed all-reduce."""
+    from kgdet_b200 import dist as kdist, ops
+    from kgdet_b200.head import KGDetHead
+    rank, world, local = kdist.init_from_env('nccl')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    ops.set_precision(args.precision)
+    B = args.train_batch
+    head = make_weights(KGDetHead()).to(dev).train()
+    opt = torch.optim.SGD(head.parameters(), lr=1e-6, momentum=0.9)
+    bucketer = kdist.GradBucketer(head.parameters(), bucket_size_mb=25) if world > 1 else None
+    g = torch.Generator().manual_seed(200 + rank)
+    x = torch.randn(B, C, H, W, generator=g).to(dev)
+    labels = torch.where(torch.rand(B * H * W, generator=g) < 0.01,
+                         torch.randint(1, 14, (B * H * W,), generator=g), torch.zeros(B * H * W, dtype=torch.long)).to(dev)
+    bbox_t = (torch.randn(B, 4, H, W, generator=g) * 4).to(dev)
+    kpt_t = (torch.randn(B, 588, H, W, generator=g) * 4).to(dev)
+    pos_w = (labels > 0).float()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        o = head.forward_single(x)
+        loss = 0
+        for i, lw in zip(range(3), (0.5, 0.5, 1.0)):
+            logits = o[i].permute(0, 2, 3, 1).reshape(-1, 13)
+            loss = loss + lw * ops.sigmoid_focal_loss_sum(logits, labels, None, 2.0, 0.25) / max(float(B * 10), 1.0)
+            loss = loss + lw * torch.nn.functional.smooth_l1_loss(o[6 + i], bbox_t, beta=1.0 / 9.0)
+            loss = loss + lw * torch.nn.functional.smooth_l1_loss(o[3 + i], kpt_t, beta=1.0 / 9.0)
+        loss.backward()
+        if bucketer is not None:
+            bucketer.finish()
+        torch.nn.utils.clip_grad_norm_(head.parameters(), 35.0)       # grad_clip=dict(max_norm=35) of the configs
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        loss = step()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    ms = kdist.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), dev)
+    if rank == 0:
+        nparam = sum(p.numel() for p in head.parameters())
+        print(json.dumps({
+            'metric': 'kgdet_head_train_images_per_sec', 'value': round(B * world * args.steps / (ms * 1e-3), 2),
+            'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': round(ms / args.steps, 4), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+            'config': {'workload': 'KGDet head training step (fwd + 9 losses + bwd + grad all-reduce + SGD) @800x1333 '
+                                   '(map 25x42), batch %d per GPU, synthetic targets' % B,
+                       'batch_per_gpu': B, 'allreduce': 'overlapped 25 MB buckets, %.1f MB fp32 gradients' % (nparam * 4 / 1e6)
+                       if world > 1 else 'none (1 GPU)', 'parallelism': 'dp%d' % world, 'l2': 'flushed before every step'},
+            'final_loss': float(loss.item())}), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -371,7 +446,13 @@ def main():
     ap.add_argument('--ref-images', type=int, default=1, help='images per reference step (bounded sample)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help='infer (default, the headline metric) or train (BASELINE.json configs[4])')
+    ap.add_argument('--train-batch', type=int, default=2)
     args = ap.parse_args()
+    if args.mode == 'train' and args.impl != 'reference':
+        run_train(args)
+        return
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -287,6 +287,115 @@ class KGDetHead(nn.Module):
         return out_dets, out_labels, out_kpts
 
 
+class RepPointsKpHead(nn.Module):
+    """State-dict compatible restatement of the two RepPoints-Kp baselines of the reference
+    (`RepPointsHeadKpParallel`, reppoints_head_kp_parallel.py:17-341, 6 806 475 parameters, and
+    `RepPointsHeadKpSerial`, reppoints_head_kp_serial.py:17-341, 5 638 523 parameters): 5 FPN levels,
+    9 learned points, one shared 3x3 offset tensor per level feeding 3 (parallel) or 2 (serial)
+    deformable convolutions.  Inference runs them through the prepared API: one NHWC copy per tower
+    output, ONE sample plan per level, ReLU fused in the DCN epilogue."""
+
+    def __init__(self, variant='parallel', num_classes=14, in_channels=256, feat_channels=256,
+                 point_feat_channels=256, stacked_convs=3, num_reppts=9, num_keypts=294, gradient_mul=0.1,
+                 point_strides=(8, 16, 32, 64, 128), moment_mul=0.01, num_groups=32, deform_conv_cls=None,
+                 moment_fn=None):
+        super().__init__()
+        assert variant in ('parallel', 'serial')
+        self.variant = variant
+        self._fused_inference = deform_conv_cls is None
+        deform_conv_cls = deform_conv_cls or DeformConv
+        self._moment_fn = moment_fn or points2bbox_moment
+        self.cls_out_channels = num_classes - 1
+        self.num_keypts, self.num_reppts = num_keypts, num_reppts
+        self.gradient_mul = gradient_mul
+        self.point_strides = list(point_strides)
+        self.moment_mul = moment_mul
+        self.moment_transfer = nn.Parameter(torch.zeros(2))
+        k = int(round(num_reppts ** 0.5))
+        assert k * k == num_reppts and k % 2 == 1
+        self.dcn_kernel, self.dcn_pad = k, (k - 1) // 2
+        base = np.arange(-self.dcn_pad, self.dcn_pad + 1).astype(np.float64)
+        yx = np.stack([np.repeat(base, k), np.tile(base, k)], axis=1).reshape(-1)      # PAR:108-113
+        self.register_buffer('_dcn_base', torch.tensor(yx, dtype=torch.float32).view(1, -1, 1, 1), persistent=False)
+        self.cls_convs = nn.ModuleList()
+        self.reg_convs = nn.ModuleList()
+        for i in range(stacked_convs):
+            chn = in_channels if i == 0 else feat_channels
+            self.cls_convs.append(_ConvGNReLU(chn, feat_channels, num_groups))
+            self.reg_convs.append(_ConvGNReLU(chn, feat_channels, num_groups))
+        kd, rd, pf = 2 * num_keypts, 2 * num_reppts, point_feat_channels
+        self.cls_refine_dfmconv = deform_conv_cls(feat_channels, pf, k, 1, self.dcn_pad)
+        self.cls_refine_out = nn.Conv2d(pf, self.cls_out_channels, 1, 1, 0)
+        self.keypts_init_conv = nn.Conv2d(feat_channels, pf, 3, 1, 1)
+        self.keypts_init_out = nn.Conv2d(pf, kd, 1, 1, 0)
+        self.keypts_refine_dfmconv = deform_conv_cls(feat_channels, pf, k, 1, self.dcn_pad)
+        self.keypts_refine_out = nn.Conv2d(pf, kd, 1, 1, 0)
+        if variant == 'parallel':                                                 # PAR:147-171
+            self.reppts_init_conv = nn.Conv2d(feat_channels, pf, 3, 1, 1)
+            self.reppts_init_out = nn.Conv2d(pf, rd, 1, 1, 0)
+            self.reppts_refine_dfmconv = deform_conv_cls(feat_channels, pf, k, 1, self.dcn_pad)
+            self.reppts_refine_out = nn.Conv2d(pf, rd, 1, 1, 0)
+        else:                                                                     # SER:156-168
+            self.reppts_init_out = nn.Conv2d(kd, rd, 1, 1, 0)
+            self.reppts_refine_out = nn.Conv2d(kd, rd, 1, 1, 0)
+        bias_cls = float(-math.log((1 - 0.01) / 0.01))
+        for m in list(self.cls_convs) + list(self.reg_convs):
+            _normal(m.conv)
+        for n, m in self.named_children():
+            if n.endswith(('_conv', '_out', '_dfmconv')):
+                _normal(m, bias=bias_cls if n == 'cls_refine_out' else 0.0)
+
+    def points2bbox(self, pts, y_first=True):
+        return self._moment_fn(pts, self.moment_transfer, self.moment_mul, y_first)
+
+    def forward_single(self, x):
+        cls_feat = pts_feat = x
+        for m in self.cls_convs:
+            cls_feat = m(cls_feat)
+        for m in self.reg_convs:
+            pts_feat = m(pts_feat)
+        kpt_init = self.keypts_init_out(F.relu(self.keypts_init_conv(pts_feat)))
+        if self.variant == 'parallel':
+            rep_init = self.reppts_init_out(F.relu(self.reppts_init_conv(pts_feat)))     # PAR:314-315
+        else:
+            rep_init = self.reppts_init_out(kpt_init)                                    # SER:314
+        base = self._dcn_base.to(x.dtype)
+        if self._fused_inference and not torch.is_grad_enabled() and x.is_cuda:
+            n, c, h, w = cls_feat.shape
+            pf = self.cls_refine_dfmconv.out_channels
+            plan = prepare_plan(rep_init - base, (n, c, h, w), pf, self.dcn_kernel, 1, self.dcn_pad, 1,
+                                like_dtype=x.dtype)
+            cls_prep = prepare_input(cls_feat, pf)
+            pts_prep = prepare_input(pts_feat, pf)
+            cls_out = self.cls_refine_out(deform_conv_prepared(cls_prep, plan, self.cls_refine_dfmconv.weight,
+                                                               relu=True))
+            kpt_ref = self.keypts_refine_out(deform_conv_prepared(pts_prep, plan,
+                                                                  self.keypts_refine_dfmconv.weight, relu=True))
+            if self.variant == 'parallel':
+                rep_ref = self.reppts_refine_out(deform_conv_prepared(pts_prep, plan,
+                                                                      self.reppts_refine_dfmconv.weight, relu=True))
+            else:
+                rep_ref = self.reppts_refine_out(kpt_ref)
+            return cls_out, kpt_init, kpt_ref + kpt_init, rep_init, rep_ref + rep_init
+        pts = rep_init
+        if torch.is_grad_enabled() and pts.requires_grad:
+            pts = self.gradient_mul * pts + (1 - self.gradient_mul) * pts.detach()       # PAR:322-325
+        dcn_offset = pts - base
+        cls_out = self.cls_refine_out(F.relu(self.cls_refine_dfmconv(cls_feat, dcn_offset)))
+        kpt_ref = self.keypts_refine_out(F.relu(self.keypts_refine_dfmconv(pts_feat, dcn_offset)))
+        if self.variant == 'parallel':
+            rep_ref = self.reppts_refine_out(F.relu(self.reppts_refine_dfmconv(pts_feat, dcn_offset)))
+        else:
+            rep_ref = self.reppts_refine_out(kpt_ref)                                    # SER:330
+        kpt_ref = kpt_ref + kpt_init.detach()                                            # PAR:337-338
+        rep_ref = rep_ref + rep_init.detach()
+        return cls_out, kpt_init, kpt_ref, rep_init, rep_ref
+
+    def forward(self, feats):
+        outs = [self.forward_single(x) for x in feats]
+        return tuple(map(list, zip(*outs)))
+
+
 class GraphedInference(object):
     """forward_single + get_bboxes of a KGDetHead captured ONCE into a CUDA graph for a fixed input shape.
 

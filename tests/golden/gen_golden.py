@@ -16,6 +16,7 @@ reference CUDA kernels (GPU box).  Fixtures:
   head_p7.npz      seeded weights recipe + x[2,256,7,11] -> the 9 outputs of forward_single (KP3:412-446)
   head_p5.npz      same at [1,256,25,42]: checksums and a strided sample of each output
   get_bboxes.npz   stage-3 maps + synthetic scores -> get_bboxes (KP3:770-914, multiclass_nms_kp)
+  reppoints_{parallel,serial}.npz  the two RepPoints-Kp baseline heads on three small levels (PAR/SER:292-341)
 
 Weights are not stored: `fill_state_dict` regenerates them from a seed (same torch build on both
 machines).  Inputs are stored explicitly.
@@ -146,6 +147,23 @@ def main():
         gb['labels_%d' % i] = l.numpy()
         gb['kpts_%d' % i] = k.reshape(d.shape[0], -1).numpy()
     np.savez_compressed(os.path.join(HERE, 'get_bboxes.npz'), **gb)
+    # ---- RepPoints-Kp parallel / serial heads (BASELINE.json configs[3]) ---------------------------------
+    names5 = ['cls', 'kpt_init', 'kpt_refine', 'rep_init', 'rep_refine']
+    sizes = [(13, 21), (7, 11), (4, 6)]                 # three small "levels" (P6, P7 and a ragged one)
+    for variant in ('parallel', 'serial'):
+        h2, _ = refshim.build_head('reppoints_moment_%s_r50_fpn_1x-deepfashion2.py' % variant)
+        h2.load_state_dict(fill_state_dict(h2.state_dict(), seed=4321), strict=True)
+        h2.eval()
+        dd = {}
+        for li, (hh, ww) in enumerate(sizes):
+            xl = torch.randn(2, 256, hh, ww, generator=g)
+            dd['x%d' % li] = xl.numpy()
+            with torch.no_grad():
+                outs = h2.forward_single(xl)
+                dd['bbox_refine%d' % li] = h2.points2bbox(outs[4]).numpy()
+            for n, o in zip(names5, outs):
+                dd['%s%d' % (n, li)] = o.numpy()
+        np.savez_compressed(os.path.join(HERE, 'reppoints_%s.npz' % variant), **dd)
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print('%-18s %8.1f KB' % (f, os.path.getsize(os.path.join(HERE, f)) / 1024))

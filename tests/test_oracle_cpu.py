@@ -161,3 +161,23 @@ def test_head_mirror_get_bboxes_matches_reference_golden():
         assert np.allclose(dets[i, :nv].numpy(), rd[o], rtol=0, atol=1e-4)
         assert np.array_equal(labels[i, :nv].numpy(), rl[o])
         assert np.allclose(kpts[i, :nv].numpy(), rk[o], rtol=0, atol=1e-3)
+
+
+@pytest.mark.parametrize('variant,n_params', [('parallel', 6806475), ('serial', 5638523)])
+def test_reppoints_kp_mirror_matches_reference_head_golden(variant, n_params):
+    """BASELINE.json configs[3]: the RepPoints-Kp parallel / serial head mirrors on the CPU oracles against
+    the outputs of the reference's own heads (reppoints_head_kp_{parallel,serial}.py:292-341)."""
+    from tests._cpu_head import make_cpu_reppoints_head
+    from tests.golden.gen_golden import fill_state_dict
+    g = gold('reppoints_%s.npz' % variant)
+    head = make_cpu_reppoints_head(variant)
+    assert sum(p.numel() for p in head.parameters()) == n_params
+    head.load_state_dict(fill_state_dict(head.state_dict(), seed=4321), strict=True)
+    head.eval()
+    for li in range(3):
+        with torch.no_grad():
+            outs = head.forward_single(torch.from_numpy(g['x%d' % li]))
+            bbox = head.points2bbox(outs[4])
+        for n, o in zip(['cls', 'kpt_init', 'kpt_refine', 'rep_init', 'rep_refine'], outs):
+            assert rel_err(o, torch.from_numpy(g['%s%d' % (n, li)])) < 1e-5, (n, li)
+        assert rel_err(bbox, torch.from_numpy(g['bbox_refine%d' % li])) < 1e-5
