@@ -274,8 +274,8 @@ def run_ours(args):
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': round(e2e_ms / args.steps, 4)},
             'gpu_launches': 24 * args.steps,
-            'gpu_launches_note': 'per step: 2 NCHW->NHWC + 6 sample plans + 12 fused tcgen05 DCN (ReLU + concat in the epilogue) + 3 moment + 1 batched NMS',
-            'roofline': {'kernel': 'dcn_umma_fwd_kernel (fused gather + tcgen05 GEMM), 12 launches/step',
+            'gpu_launches_note': 'per step: 2 NCHW->channel-blocked copies + 6 sample plans + 12 fused tcgen05 DCN (ReLU + concat in the epilogue) + 3 moment + 1 batched NMS',
+            'roofline': {'kernel': 'dcn_umma_stream_kernel (fused bilinear gather + tcgen05 GEMM), 12 launches/step',
                          'bound': 'tensor', 'achieved': round(achieved, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': round(achieved / peak_tf, 4), 'traffic': None, 'peak_source': peak_src,
                          'share_of_step': round(tot_ms / dev_ms, 4), 'per_kernel_size': detail,

@@ -37,15 +37,15 @@ struct __align__(16) SampleRec16 {
 // Second flavour of the same 16 bytes, used by the bf16 mode: {base, bf16x2(w0,w1), bf16x2(w2,w3), 0}
 // with the four corner weights (validity, window test and mask folded in) pre-rounded to bf16.
 // In both flavours `base` is always a safe address: the fused kernel loads all four corners
-// unconditionally (weight 0 for unusable ones) from an NHWC buffer that carries a zeroed guard band
-// of dcn_guard_pixels() pixels on each side.
+// unconditionally (weight 0 for unusable ones) from channel-blocked planes that each carry a zeroed guard
+// band of dcn_guard_pixels() pixels on both sides.
 enum { PLAN16_F32 = 0, PLAN16_BF16W = 1 };
 size_t plan16_bytes(const DcnGeom& g);
 int launch_plan16(const DcnGeom& g, const float* offset, const float* mask, SampleRec16* rec, int fmt,
                   cudaStream_t stream);
 static inline int dcn_guard_pixels(const DcnGeom& g) { return g.W + 2; }
 
-size_t plan_rows(const DcnGeom& g);                 // M rounded up to 128
+size_t plan_rows(const DcnGeom& g);                 // M rounded up to 256
 size_t plan_bytes(const DcnGeom& g);                // SampleRec array
 size_t plan_aux_bytes(const DcnGeom& g);            // SampleAux array
 int launch_plan(const DcnGeom& g, const float* offset, const float* mask, SampleRec* rec,
@@ -54,6 +54,10 @@ int launch_plan(const DcnGeom& g, const float* offset, const float* mask, Sample
 // src [B, R, Cc] -> dst [B, Cc, R] with dtype conversion (NCHW <-> NHWC)
 int launch_transpose(const void* src, void* dst, int B, int R, int Cc, int src_dtype,
                      int dst_dtype, cudaStream_t stream);
+
+// src NCHW [N][C][S] -> dst planes [C / bk][... N*S pixels ...][bk] (plane p starts plane_bytes * p after dst)
+int launch_nchw_to_blocked(const void* src, void* dst, int N, int C, int S, int bk, size_t plane_bytes,
+                           int src_dtype, int dst_dtype, cudaStream_t stream);
 
 // Where and how a forward kernel writes its result: channel slice [coff, coff + Cout) of an NCHW tensor
 // with `ctot` channels, optional fused ReLU.
@@ -85,8 +89,9 @@ bool umma_supported(const DcnGeom& g, int precision);
 size_t umma_packed_weight_bytes(const DcnGeom& g, int precision);
 int umma_pack_weight(const DcnGeom& g, const float* weight, void* packed, int precision,
                      cudaStream_t stream);
-int umma_forward(const DcnGeom& g, const void* in_nhwc, const SampleRec16* plan, const void* packed_w,
-                 const float* bias, const OutSpec& o, int precision, cudaStream_t stream);
+// in_blocked: first pixel of plane 0 of the channel-blocked input (see dcn_api.cu), planes plane_bytes apart
+int umma_forward(const DcnGeom& g, const void* in_blocked, size_t plane_bytes, const SampleRec16* plan,
+                 const void* packed_w, const float* bias, const OutSpec& o, int precision, cudaStream_t stream);
 
 // ---- tensor-core backward (bf16 mode; dcn_bwd_tc.cu) ----
 bool bwd_tc_supported(const DcnGeom& g, int precision);

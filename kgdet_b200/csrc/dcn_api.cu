@@ -25,17 +25,33 @@ bool use_umma(const DcnGeom& g, int precision) {
   return precision != KGDET_PREC_FP32 && umma_supported(g, precision);
 }
 
-// Prepared input: [guard | NHWC copy in the compute type | guard].  The fused kernel loads all four
-// bilinear corners unconditionally (see dcn.cuh); the guards are zeroed.
-struct PrepIn { size_t guard_bytes, in_bytes, total; int cdtype; };
+// Prepared input.
+//   exact SIMT path : plain NHWC copy in fp32.
+//   tensor-core path: CHANNEL-BLOCKED planes  [C / BK][guard | N*H*W pixels | guard][BK channels]  in the
+//                     compute type (BK = 64 bf16 / 32 fp32 channels = one 128-byte slab per pixel, the unit a
+//                     k-block gathers).  The slabs one k-block touches are then contiguous 128-byte lines
+//                     (NHWC with C = 256 puts them 512 bytes apart, which the L1 serves 1.4x slower:
+//                     tools/micro/l1_gather_bench, 71 vs 99 B/clk/SM).  The fused kernel loads all four
+//                     bilinear corners unconditionally (see dcn.cuh); each plane carries a zeroed guard band
+//                     of dcn_guard_pixels() pixels on both sides for the corners that fall outside.
+struct PrepIn { size_t guard_bytes, plane_bytes, in_bytes, total; int cdtype, planes, bk; };
 PrepIn prep_in_layout(const DcnGeom& g, int precision) {
   PrepIn p;
   const bool fast = use_umma(g, precision);
   p.cdtype = (fast && precision == KGDET_PREC_BF16) ? KGDET_BF16 : KGDET_F32;
   const size_t esz = p.cdtype == KGDET_BF16 ? 2 : 4;
-  p.guard_bytes = fast ? align_up((size_t)dcn_guard_pixels(g) * g.C * esz, 1024) : 0;
-  p.in_bytes = (size_t)g.N * g.H * g.W * g.C * esz;
-  p.total = align_up(p.in_bytes + 2 * p.guard_bytes, 1024);
+  if (fast) {
+    p.bk = (int)(128 / esz);
+    p.planes = g.C / p.bk;
+    p.guard_bytes = (size_t)dcn_guard_pixels(g) * 128;
+    p.in_bytes = (size_t)g.N * g.H * g.W * 128;
+    p.plane_bytes = align_up(p.in_bytes + 2 * p.guard_bytes, 1024);
+    p.total = p.plane_bytes * p.planes;
+  } else {
+    p.bk = g.C; p.planes = 1; p.guard_bytes = 0;
+    p.in_bytes = (size_t)g.N * g.H * g.W * g.C * esz;
+    p.plane_bytes = p.total = align_up(p.in_bytes, 1024);
+  }
   return p;
 }
 size_t plan_layout_bytes(const DcnGeom& g, int precision) {
@@ -46,11 +62,13 @@ int do_prepare_input(const DcnGeom& g, const void* input, void* prepared, int dt
                      cudaStream_t stream) {
   const PrepIn p = prep_in_layout(g, precision);
   char* base = (char*)prepared;
-  if (p.guard_bytes) {
-    KG_CUDA(cudaMemsetAsync(base, 0, p.guard_bytes, stream));
-    KG_CUDA(cudaMemsetAsync(base + p.guard_bytes + p.in_bytes, 0, p.guard_bytes, stream));
-  }
-  return launch_transpose(input, base + p.guard_bytes, g.N, g.C, g.H * g.W, dtype, p.cdtype, stream);
+  if (!p.guard_bytes) return launch_transpose(input, base, g.N, g.C, g.H * g.W, dtype, p.cdtype, stream);
+  // zero the two guard bands of every plane (2-D memsets: one row per plane)
+  KG_CUDA(cudaMemset2DAsync(base, p.plane_bytes, 0, p.guard_bytes, p.planes, stream));
+  KG_CUDA(cudaMemset2DAsync(base + p.guard_bytes + p.in_bytes, p.plane_bytes, 0,
+                            p.plane_bytes - p.guard_bytes - p.in_bytes, p.planes, stream));
+  return launch_nchw_to_blocked(input, base + p.guard_bytes, g.N, g.C, g.H * g.W, p.bk, p.plane_bytes, dtype,
+                                p.cdtype, stream);
 }
 
 int do_prepare_plan(const DcnGeom& g, const float* offset, const float* mask, void* plan, int precision,
@@ -64,13 +82,14 @@ int do_prepare_plan(const DcnGeom& g, const float* offset, const float* mask, vo
 int do_forward_prepared(const DcnGeom& g, const void* prepared, const void* plan, const void* weight_packed,
                         const float* bias, const OutSpec& o, int precision, cudaStream_t stream) {
   const PrepIn p = prep_in_layout(g, precision);
-  const char* in_nhwc = (const char*)prepared + p.guard_bytes;
+  const char* in_nhwc = (const char*)prepared + p.guard_bytes;     // first pixel of plane 0
   cudaEvent_t ev0 = g_prof_start, ev1 = g_prof_stop;
   g_prof_start = g_prof_stop = nullptr;
   if (ev0 && ev1) KG_CUDA(cudaEventRecord(ev0, stream));
   int rc;
   if (use_umma(g, precision))
-    rc = umma_forward(g, in_nhwc, (const SampleRec16*)plan, weight_packed, bias, o, precision, stream);
+    rc = umma_forward(g, in_nhwc, p.plane_bytes, (const SampleRec16*)plan, weight_packed, bias, o, precision,
+                      stream);
   else
     rc = simt_forward(g, (const float*)in_nhwc, (const SampleRec*)plan, (const float*)weight_packed, bias, o,
                       stream);

@@ -3,7 +3,7 @@
 
 namespace kgdet {
 
-size_t plan_rows(const DcnGeom& g) { return (size_t)ceil_div(g.M, 128) * 128; }
+size_t plan_rows(const DcnGeom& g) { return (size_t)ceil_div(g.M, 256) * 256; }   // a CTA pair covers 256 rows
 size_t plan_bytes(const DcnGeom& g) {
   return plan_rows(g) * g.dgroups * g.K * sizeof(SampleRec);
 }
@@ -120,7 +120,7 @@ __global__ void dcn_plan16_kernel(DcnGeom g, const float* __restrict__ offset,
       r.lw = __uint_as_float((__float_as_uint(lw) & ~3u) | vw);
       r.scale = scale;
     }
-    rec[(size_t)m * g.K + tap] = r;
+    rec[idx] = r;                                    // tap-major: [K][rows_padded]
   }
 }
 
@@ -195,6 +195,53 @@ int launch_transpose(const void* src, void* dst, int B, int R, int Cc, int src_d
     return KGDET_ERR_INVALID_ARG;
   }
   KG_LAUNCH_CHECK("transpose_kernel");
+  return KGDET_OK;
+}
+
+// ---- NCHW -> channel-blocked planes (input of the tensor-core path) --------------------------------
+// dst element of (n, c, p): plane c / bk, pixel n*S + p, channel c % bk.  A 32-channel tile never straddles a
+// plane (bk is 32 or 64).
+template <typename Tin, typename Tout>
+__global__ void nchw_to_blocked_kernel(const Tin* __restrict__ src, Tout* __restrict__ dst, int C, int S, int bk,
+                                       size_t plane_elems) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const Tin* s = src + (size_t)n * C * S;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int c = c0 + ty + k, p = p0 + tx;
+    if (c < C && p < S) tile[ty + k][tx] = to_f<Tin>(s[(size_t)c * S + p]);
+  }
+  __syncthreads();
+  Tout* d = dst + (size_t)(c0 / bk) * plane_elems + (c0 % bk);
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int p = p0 + ty + k, c = c0 + tx;
+    if (c < C && p < S) d[((size_t)n * S + p) * bk + tx] = from_f<Tout>(tile[tx][ty + k]);
+  }
+}
+
+int launch_nchw_to_blocked(const void* src, void* dst, int N, int C, int S, int bk, size_t plane_bytes,
+                           int src_dtype, int dst_dtype, cudaStream_t stream) {
+  if (N <= 0 || C <= 0 || S <= 0) return KGDET_OK;
+  KG_CHECK_ARG(N <= 65535 && ceil_div(C, 32) <= 65535, "nchw_to_blocked: batch/channels too large");
+  KG_CHECK_ARG(bk % 32 == 0 && C % bk == 0, "nchw_to_blocked: bad channel block %d for %d channels", bk, C);
+  dim3 grid(ceil_div(S, 32), ceil_div(C, 32), N), block(32, 8);
+  if (src_dtype == KGDET_F32 && dst_dtype == KGDET_F32)
+    nchw_to_blocked_kernel<float, float><<<grid, block, 0, stream>>>((const float*)src, (float*)dst, C, S, bk, plane_bytes / 4);
+  else if (src_dtype == KGDET_F32 && dst_dtype == KGDET_BF16)
+    nchw_to_blocked_kernel<float, __nv_bfloat16><<<grid, block, 0, stream>>>((const float*)src, (__nv_bfloat16*)dst, C, S, bk, plane_bytes / 2);
+  else if (src_dtype == KGDET_BF16 && dst_dtype == KGDET_F32)
+    nchw_to_blocked_kernel<__nv_bfloat16, float><<<grid, block, 0, stream>>>((const __nv_bfloat16*)src, (float*)dst, C, S, bk, plane_bytes / 4);
+  else if (src_dtype == KGDET_BF16 && dst_dtype == KGDET_BF16)
+    nchw_to_blocked_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, C, S, bk, plane_bytes / 2);
+  else {
+    set_error("nchw_to_blocked: bad dtype %d -> %d", src_dtype, dst_dtype);
+    return KGDET_ERR_INVALID_ARG;
+  }
+  KG_LAUNCH_CHECK("nchw_to_blocked_kernel");
   return KGDET_OK;
 }
 

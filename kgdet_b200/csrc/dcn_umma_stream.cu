@@ -1,0 +1,428 @@
+// Fused deformable-convolution forward on the 5th-generation tensor cores (sm_100a).
+//
+//   out[m, o] = sum_{tap, c} S(m, tap, c) * W[o, c, tap]       m = (n, y, x) output position
+//
+// The reference materialises S as the `columns` tensor in HBM (deformable_im2col,
+// deform_conv_cuda_kernel.cu:189-242: C*K x N*H*W fp32, 843 MB for one 7x7 KGDet call) and hands it to a
+// cuBLAS SGEMM (deform_conv_cuda.cpp:230-233).  Here the column tile only ever exists in shared memory.
+//
+// One CTA = 128 output positions x all Cout, 17 warps, NS-stage mbarrier pipeline over k-blocks
+// (k-block = 64 bf16 / 32 tf32 channels of one tap = one 128-byte slab per sampled pixel):
+//   warps 0..15  producers.  Thread t owns 16-byte chunk (t & 7) of rows (t >> 3) and (t >> 3) + 64: 8 lanes
+//                cover one pixel slab, so every gather instruction reads four whole 128-byte lines of the
+//                channel-blocked input (dcn_api.cu).  Per k-block a thread interpolates its two row-chunks
+//                (packed HFMA2.BF16 with the plan's pre-rounded corner weights), stores them into the
+//                128B-swizzled K-major A tile and immediately re-arms the same registers with the gathers of
+//                the NEXT k-block (all four corners unconditionally; unusable corners carry weight 0 and a
+//                guard-band-safe address), then fence.proxy.async + one mbarrier arrive per warp.
+//   warp 16      control (one elected lane): streams the pre-swizzled weight slabs with cp.async.bulk
+//                (UBLKCP; a linear copy lands in UMMA layout, no tensor map) NS-1 k-blocks ahead, waits for a
+//                stage to be full, issues the tcgen05.mma's (UTCHMMA, M128 x N=Cout x K16/8) into the TMEM
+//                accumulator and commits the stage's empty barrier.
+//   Epilogue     warps 0..15: tcgen05.ld, bias, ReLU, NCHW store coalesced over positions.
+//
+// Modes: BF16   kind::f16, bf16 operands                     (1e-3 grade)
+//        TF32X3 kind::tf32, A = Ahi + Alo, B = Bhi + Blo,    (the dropped term Alo.Blo is ~2^-22)
+//               3 MMAs per k-step: Alo.Bhi + Ahi.Blo + Ahi.Bhi
+//        TF32   kind::tf32 single pass
+//
+// PAIR = true runs clusters of two CTAs with 2-SM MMAs (cta_group::2, M = 256): each CTA gathers its own
+// 128 rows but holds only half of the weight slab, halving the weight bytes an SM pulls through L2.  The
+// even CTA issues all MMAs; its full barrier collects the 16 local producer warps, the 16 remote ones
+// (mbarrier.arrive on the mapa'd address), its own weight bytes and one relay arrive from the odd CTA's
+// control warp once that CTA's half has landed; tcgen05.commit multicasts the empty / accumulator-ready
+// arrivals to both CTAs.  Parity-tested; not the default because it is not faster (see dcn_umma.cu).
+#include <cuda_bf16.h>
+
+#include "dcn_umma.cuh"
+
+namespace kgdet {
+
+static constexpr int PRODUCER_WARPS = 16;
+static constexpr int STREAM_THREADS = (PRODUCER_WARPS + 1) * 32;   // 544 -> 120 registers/thread
+
+// bounded wait without the diagnostic printf of mbar_wait (keeps the hot loop small): a protocol bug
+// still traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_spin_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+
+__device__ __forceinline__ __nv_bfloat162 as_bf162(uint32_t v) {
+  return *reinterpret_cast<__nv_bfloat162*>(&v);
+}
+__device__ __forceinline__ uint32_t as_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
+
+// one 16-byte chunk of one row: sum of the four corners times their weights
+//   bf16: the record carries bf16x2 (w0,w1) and (w2,w3); nvcc folds the broadcasts into the operand
+//         selectors of HMUL2/HFMA2.BF16_V2 (no PRMT); same rounding sequence as the two-group kernel
+template <int MODE>
+__device__ __forceinline__ void combine_store(const uint4 (&v)[4], uint32_t wy, uint32_t wz, uint32_t ww,
+                                              unsigned char* dst) {
+  if constexpr (MODE == MODE_BF16) {
+    const __nv_bfloat162 w01 = as_bf162(wy), w23 = as_bf162(wz);
+    const __nv_bfloat162 w0 = __low2bfloat162(w01), w1 = __high2bfloat162(w01);
+    const __nv_bfloat162 w2 = __low2bfloat162(w23), w3 = __high2bfloat162(w23);
+    uint4 o;
+    o.x = as_u32(__hfma2(w3, as_bf162(v[3].x), __hfma2(w2, as_bf162(v[2].x), __hfma2(w1, as_bf162(v[1].x), __hmul2(w0, as_bf162(v[0].x))))));
+    o.y = as_u32(__hfma2(w3, as_bf162(v[3].y), __hfma2(w2, as_bf162(v[2].y), __hfma2(w1, as_bf162(v[1].y), __hmul2(w0, as_bf162(v[0].y))))));
+    o.z = as_u32(__hfma2(w3, as_bf162(v[3].z), __hfma2(w2, as_bf162(v[2].z), __hfma2(w1, as_bf162(v[1].z), __hmul2(w0, as_bf162(v[0].z))))));
+    o.w = as_u32(__hfma2(w3, as_bf162(v[3].w), __hfma2(w2, as_bf162(v[2].w), __hfma2(w1, as_bf162(v[1].w), __hmul2(w0, as_bf162(v[0].w))))));
+    *reinterpret_cast<uint4*>(dst) = o;
+  } else {
+    float w[4];
+    decode_rec(make_float4(0.f, __uint_as_float(wy), __uint_as_float(wz), __uint_as_float(ww)), w);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a0 = fmaf(w[i], __uint_as_float(v[i].x), a0);
+      a1 = fmaf(w[i], __uint_as_float(v[i].y), a1);
+      a2 = fmaf(w[i], __uint_as_float(v[i].z), a2);
+      a3 = fmaf(w[i], __uint_as_float(v[i].w), a3);
+    }
+    if constexpr (MODE == MODE_TF32X3) {
+      const float h0 = tf32_rna(a0), h1 = tf32_rna(a1), h2 = tf32_rna(a2), h3 = tf32_rna(a3);
+      *reinterpret_cast<float4*>(dst) = make_float4(h0, h1, h2, h3);
+      *reinterpret_cast<float4*>(dst + A_TILE_BYTES) = make_float4(a0 - h0, a1 - h1, a2 - h2, a3 - h3);
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(a0, a1, a2, a3);
+    }
+  }
+}
+
+// Schedules that were built, measured on B200 (tools/dcn_ab.py, K = 49 call: 144 us for this kernel) and
+// dropped again:
+//   * DEPTH = 2 with 16 warps at 128 registers and the control duty rotating over the producer warps
+//     (17 warps cap a thread at 96 registers: 5 warps share one SM sub-partition's register file):
+//     171 us.  Deeper load pipelining buys nothing: the producers are bound by the THROUGHPUT of the
+//     L1/LSU wavefront pipe (512 gather + 128 record + 128 A-tile-store wavefronts per k-block at the
+//     ~1.3 cycles per wavefront tools/micro/l1_gather_bench measures), not by latency.
+//   * all gathers through ld.global.cg (L1 bypass): 166 us -- same pipe, no gain.
+// What did help: channel-blocked input planes (contiguous 128-byte slabs, 1.4x faster in the L1 than slabs
+// 512 bytes apart) and tap-major plan records.
+template <int MODE, int NS, int DEPTH, typename Tout, bool PAIR>
+__global__ void __launch_bounds__(STREAM_THREADS, 1) dcn_umma_stream_kernel(const UmmaParams prm) {
+  using MT = ModeTraits<MODE>;
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // 1024-byte alignment of every tile is what the 128B swizzle pattern is anchored to
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const int BN = prm.Cout;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;      // 0 = the CTA that issues the MMAs
+  const int b_tile_bytes = (PAIR ? BN / 2 : BN) * 128;          // weight rows held by THIS CTA
+  const int stage_bytes = MT::A_TILES * A_TILE_BYTES + MT::B_TILES * b_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)NS * stage_bytes);
+  uint64_t* empty_bar = full_bar + NS;
+  uint64_t* tmem_full_bar = empty_bar + NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM;
+  const int nkb = prm.nkb;
+  constexpr int SETUP_WARP = PRODUCER_WARPS;
+
+  if (warp == SETUP_WARP) {
+    if (lane == 0) {
+      for (int s = 0; s < NS; ++s) {
+        // 16 producer warps + the control lane's expect_tx; PAIR, even CTA: + 16 remote warps + the odd
+        // CTA's relay; PAIR, odd CTA: only its own weight half (expect_tx) completes on this barrier
+        mbar_init(&full_bar[s], PAIR ? (cta_rank == 0 ? 2 * PRODUCER_WARPS + 2 : 1) : PRODUCER_WARPS + 1);
+        mbar_init(&empty_bar[s], 1);                // one tcgen05.commit
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, prm.tmem_cols);
+    else tmem_alloc(tmem_slot, prm.tmem_cols);
+  }
+  tc_fence_before();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers must exist before any remote arrive
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t full_bar0_remote = PAIR ? mapa_u32(smem_u32(&full_bar[0]), 0u) : 0u;
+
+  // ------------------------- control duties (executed by ONE lane) -------------------------
+  const uint32_t b_bytes = (uint32_t)(MT::B_TILES * b_tile_bytes);
+  auto fetch_b = [&](int kq, int sq) {
+    const size_t b_full_tile = (size_t)BN * 128;                          // one packed tile, all Cout rows
+    // the packed layout always carries hi+lo for tf32; single-pass TF32 copies only hi
+    const size_t b_src_stride = (size_t)(MODE == MODE_BF16 ? 1 : 2) * b_full_tile;
+    const unsigned char* src = prm.wp + (size_t)cta_rank * b_tile_bytes + (size_t)kq * b_src_stride;
+    unsigned char* dstb = smem + (size_t)sq * stage_bytes + MT::A_TILES * A_TILE_BYTES;
+    mbar_arrive_expect_tx(&full_bar[sq], b_bytes);
+    if (!PAIR || MT::B_TILES == 1) {
+      bulk_g2s(dstb, src, b_bytes, &full_bar[sq]);
+    } else {                                  // hi and lo tiles are Cout rows apart in the packed layout
+      bulk_g2s(dstb, src, (uint32_t)b_tile_bytes, &full_bar[sq]);
+      bulk_g2s(dstb + b_tile_bytes, src + b_full_tile, (uint32_t)b_tile_bytes, &full_bar[sq]);
+    }
+  };
+  // k-block j: wait until its stage is full, issue its MMAs (even CTA) or relay "my weight half landed"
+  // (odd CTA of a pair), then fetch the weight slab of k-block j + NS - 1 into the stage of k-block j - 1
+  auto control_duty = [&](int j) {
+    const int s = j % NS;
+    const uint32_t ph = (uint32_t)(j / NS) & 1u;
+    if (PAIR && cta_rank != 0) {
+      mbar_spin(&full_bar[s], ph);
+      mbar_arrive_remote(full_bar0_remote + (uint32_t)s * 8u);
+    } else {
+      mbar_spin(&full_bar[s], ph);     // A tile(s) from all producer warps + weight bytes (both CTAs of a pair)
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t b_addr = a_addr + MT::A_TILES * A_TILE_BYTES;
+      const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+      const uint64_t bdesc = make_sw128_kmajor_desc(b_addr);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {            // 4 x 32 bytes of K per 128-byte row
+        const uint32_t acc = (j > 0 || k > 0) ? 1u : 0u;
+        if constexpr (MODE == MODE_BF16) {
+          if constexpr (PAIR) umma_f16_pair(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, acc);
+          else umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, acc);
+        } else if constexpr (MODE == MODE_TF32) {
+          if constexpr (PAIR) umma_tf32_pair(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, acc);
+          else umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, acc);
+        } else {
+          const uint64_t adesc_lo = make_sw128_kmajor_desc(a_addr + A_TILE_BYTES);
+          const uint64_t bdesc_lo = make_sw128_kmajor_desc(b_addr + b_tile_bytes);
+          if constexpr (PAIR) {
+            umma_tf32_pair(tmem_base, adesc_lo + 2 * k, bdesc + 2 * k, prm.idesc, acc);   // Alo.Bhi
+            umma_tf32_pair(tmem_base, adesc + 2 * k, bdesc_lo + 2 * k, prm.idesc, 1u);    // Ahi.Blo
+            umma_tf32_pair(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, 1u);       // Ahi.Bhi
+          } else {
+            umma_tf32(tmem_base, adesc_lo + 2 * k, bdesc + 2 * k, prm.idesc, acc);     // Alo.Bhi
+            umma_tf32(tmem_base, adesc + 2 * k, bdesc_lo + 2 * k, prm.idesc, 1u);      // Ahi.Blo
+            umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, 1u);         // Ahi.Bhi
+          }
+        }
+      }
+      // frees the stage (in both CTAs of a pair) when these MMAs retire
+      if constexpr (PAIR) tc_commit_pair(&empty_bar[s], (uint16_t)3);
+      else tc_commit(&empty_bar[s]);
+      if (j == nkb - 1) {                          // all MMAs have retired -> accumulator readable
+        if constexpr (PAIR) tc_commit_pair(tmem_full_bar, (uint16_t)3);
+        else tc_commit(tmem_full_bar);
+      }
+    }
+    // weight slab of k-block j + NS - 1 goes into the stage of k-block j - 1, whose MMAs were issued one duty
+    // ago: this wait ends while MMA(j) is still running, so the tensor pipe never idles
+    const int kn = j + NS - 1;
+    if (kn < nkb) {
+      if (j >= 1) mbar_spin(&empty_bar[kn % NS], (uint32_t)((j - 1) / NS) & 1u);
+      fetch_b(kn, kn % NS);
+    }
+  };
+
+  if (warp == PRODUCER_WARPS) {
+    // =========================== dedicated control warp ===========================
+    if (lane == 0) {
+      for (int j = 0; j < NS - 1 && j < nkb; ++j) fetch_b(j, j);   // all stages start empty
+      for (int kb = 0; kb < nkb; ++kb) control_duty(kb);
+    }
+    __syncwarp();
+  } else {
+    // ======================================= producers =======================================
+    const int chunk = tid & 7;        // 16-byte chunk of the 128-byte row
+    const int rbase = tid >> 3;       // 0..63; this thread owns rows rbase and rbase + 64
+    const int K = prm.K;
+    constexpr long long rowb = 128;                       // bytes per pixel slab (one plane = one channel block)
+    const long long wrow = (long long)prm.W * rowb;       // bytes per image row
+    const unsigned char* in_base = reinterpret_cast<const unsigned char*>(prm.in) + chunk * 16;
+    // plan is tap-major [K][rows_padded]: the four rows a warp touches per load are 64 contiguous bytes
+    const uint4* plan0 = reinterpret_cast<const uint4*>(prm.plan) + (m0 + rbase);
+    const uint4* plan1 = plan0 + 64;
+    const size_t tap_stride = (size_t)prm.rows_padded;
+    // this thread's byte offset inside an A tile (row rbase, swizzled 16-byte chunk); row rbase + 64 is
+    // 8192 bytes further and has the same (row & 7)
+    const int a_off = rbase * 128 + ((chunk ^ (rbase & 7)) << 4);
+
+    uint4 v[DEPTH][2][4];             // corners in flight: [k-block slot][row][corner]
+    uint32_t wy[DEPTH][2], wz[DEPTH][2], ww[DEPTH][2];
+    uint4 recn[2];                    // records of the next k-block to issue
+
+    // (tap, channel block) of the k-block whose gathers are issued next, and tap of the next record fetch
+    int tapI = 0, cbI = 0, tapR = 0;
+    const unsigned char* in_plane = in_base;              // plane of the k-block whose gathers are issued next
+    auto issue = [&](int slot, int row, const uint4& rec) {
+      const unsigned char* p0 = in_plane + (long long)(int)rec.x * rowb;
+      v[slot][row][0] = __ldg(reinterpret_cast<const uint4*>(p0));
+      v[slot][row][1] = __ldg(reinterpret_cast<const uint4*>(p0 + rowb));
+      v[slot][row][2] = __ldg(reinterpret_cast<const uint4*>(p0 + wrow));
+      v[slot][row][3] = __ldg(reinterpret_cast<const uint4*>(p0 + wrow + rowb));
+      wy[slot][row] = rec.y; wz[slot][row] = rec.z;
+      if constexpr (MODE != MODE_BF16) ww[slot][row] = rec.w;
+    };
+    auto advance =[&](int& tap, int& cb) { if (++tap == K) { tap = 0; ++cb; in_plane += prm.plane_bytes; } };
+
+    // prologue: fill the pipeline with k-blocks 0 .. DEPTH-1, fetch the records of k-block DEPTH
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) {
+      if (d < nkb) {
+        recn[0] = __ldg(plan0 + tapI * tap_stride);
+        recn[1] = __ldg(plan1 + tapI * tap_stride);
+        issue(d, 0, recn[0]);
+        issue(d, 1, recn[1]);
+        advance(tapI, cbI);
+      }
+    }
+    tapR = tapI;                      // tap of k-block DEPTH
+    if (DEPTH < nkb) {
+      recn[0] = __ldg(plan0 + tapR * tap_stride);
+      recn[1] = __ldg(plan1 + tapR * tap_stride);
+    }
+    if (++tapR == K) tapR = 0;
+
+    auto body = [&](int kb, int slot) {
+      const int s = kb % NS;
+      unsigned char* a_tile = smem + (size_t)s * stage_bytes;
+      mbar_spin(&empty_bar[s], ((uint32_t)(kb / NS) & 1u) ^ 1u);     // MMAs of k-block kb - NS have retired
+      const bool more = kb + DEPTH < nkb;
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        combine_store<MODE>(v[slot][row], wy[slot][row], wz[slot][row], MODE != MODE_BF16 ? ww[slot][row] : 0u,
+                            a_tile + a_off + row * 8192);
+        if (more) issue(slot, row, recn[row]);                       // re-arm: k-block kb + DEPTH
+      }
+      if (more) advance(tapI, cbI);
+      if (kb + DEPTH + 1 < nkb) {                                    // records for the next iteration's issue
+        recn[0] = __ldg(plan0 + tapR * tap_stride);
+        recn[1] = __ldg(plan1 + tapR * tap_stride);
+        if (++tapR == K) tapR = 0;
+      }
+      fence_proxy_async_smem();   // my generic-proxy stores -> visible to tcgen05.mma
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR && cta_rank != 0) mbar_arrive_remote(full_bar0_remote + (uint32_t)s * 8u);
+        else mbar_arrive(&full_bar[s]);
+      }
+    };
+
+    for (int kb = 0; kb < nkb; kb += DEPTH) {
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d)
+        if (kb + d < nkb) body(kb + d, d);
+    }
+
+    // ===================== epilogue: TMEM -> registers -> NCHW global =====================
+    mbar_spin(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3, cgrp = warp >> 2;      // TMEM lane quarter / column group of this warp
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < prm.M;
+    const int n = row_ok ? m / prm.HoWo : 0;
+    const int pos = row_ok ? m - n * prm.HoWo : 0;
+    Tout* obase = reinterpret_cast<Tout*>(prm.out) + ((size_t)n * prm.out_ctot + prm.out_coff) * prm.HoWo + pos;
+    // 32-column chunks of the accumulator are dealt round-robin to the four column groups (Cout % 64 == 0,
+    // so every chunk is whole; e.g. Cout = 192: groups 0,1 drain two chunks, groups 2,3 one)
+    for (int col = cgrp * 32; col < BN; col += 128) {          // warp-uniform
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(acc[j]);
+          if (prm.bias) x += __ldg(prm.bias + col + j);
+          if (prm.relu) x = fmaxf(x, 0.f);
+          st_out<Tout>(obase + (size_t)(col + j) * prm.HoWo, x);   // lanes = consecutive positions
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  if constexpr (PAIR) {
+    cluster_sync_all();          // neither CTA may free the shared allocation while the other still reads
+    if (warp == SETUP_WARP) tmem_dealloc_pair(tmem_base, prm.tmem_cols);
+  } else {
+    __syncthreads();
+    if (warp == SETUP_WARP) tmem_dealloc(tmem_base, prm.tmem_cols);
+  }
+}
+
+static size_t stream_smem_bytes(int mode, int ns, int Cout, bool pair) {
+  const int a_tiles = (mode == MODE_TF32X3) ? 2 : 1, b_tiles = a_tiles;
+  const size_t stage = (size_t)a_tiles * A_TILE_BYTES + (size_t)b_tiles * (pair ? Cout / 2 : Cout) * 128;
+  return 1024 /* alignment slack */ + ns * stage + (2 * ns + 1) * 8 + 16;   // barriers, TMEM slot, duty ticket
+}
+
+template <int MODE, int NS, int DEPTH, typename Tout, bool PAIR>
+static int launch_stream(const UmmaParams& p, int grid, cudaStream_t stream) {
+  const size_t smem = stream_smem_bytes(MODE, NS, p.Cout, PAIR);
+  auto kern = dcn_umma_stream_kernel<MODE, NS, DEPTH, Tout, PAIR>;
+  KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);         // PAIR: even, one cluster = two consecutive 128-row tiles
+  cfg.blockDim = dim3(STREAM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  KG_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  KG_LAUNCH_CHECK("dcn_umma_stream_kernel");
+  return KGDET_OK;
+}
+
+template <int MODE, typename Tout, bool PAIR>
+static int dispatch_stages(const UmmaParams& p, int grid, int ns, cudaStream_t stream) {
+  switch (ns) {
+    case 2: return launch_stream<MODE, 2, 1, Tout, PAIR>(p, grid, stream);
+    case 3: return launch_stream<MODE, 3, 1, Tout, PAIR>(p, grid, stream);
+    case 4: return launch_stream<MODE, 4, 1, Tout, PAIR>(p, grid, stream);
+    default: set_error("dcn umma stream: unsupported stage count %d", ns); return KGDET_ERR_INVALID_ARG;
+  }
+}
+
+template <int MODE, typename Tout>
+static int dispatch_pair(const UmmaParams& p, int grid, int ns, bool pair, cudaStream_t stream) {
+  return pair ? dispatch_stages<MODE, Tout, true>(p, grid, ns, stream)
+              : dispatch_stages<MODE, Tout, false>(p, grid, ns, stream);
+}
+
+int umma_stream_forward(const DcnGeom& g, const UmmaParams& p0, int mode, bool pair, int out_dtype,
+                        cudaStream_t stream) {
+  UmmaParams p = p0;
+  p.tmem_cols = g.Cout <= 64 ? 64 : (g.Cout <= 128 ? 128 : 256);   // one accumulator, power of two >= 32
+  const int grid = pair ? 2 * ceil_div(g.M, 2 * BM) : ceil_div(g.M, BM);
+  // 3 stages measured best for every mode (more L1 for the gather than 4, enough slack for the MMA)
+  int ns = (mode == MODE_TF32X3 && !pair) ? 2 : 3;
+  if (const char* e = getenv("KGDET_UMMA_STAGES")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= 4) ns = v;
+  }
+
+  while (ns > 2 && stream_smem_bytes(mode, ns, g.Cout, pair) > 227 * 1024) --ns;
+  if (stream_smem_bytes(mode, ns, g.Cout, pair) > 227 * 1024) {
+    set_error("dcn umma stream: tile does not fit shared memory");
+    return KGDET_ERR_UNSUPPORTED;
+  }
+  const bool f32 = out_dtype == KGDET_F32;
+  switch (mode) {
+    case MODE_BF16:
+      return f32 ? dispatch_pair<MODE_BF16, float>(p, grid, ns, pair, stream)
+                 : dispatch_pair<MODE_BF16, __nv_bfloat16>(p, grid, ns, pair, stream);
+    case MODE_TF32X3:
+      return f32 ? dispatch_pair<MODE_TF32X3, float>(p, grid, ns, pair, stream)
+                 : dispatch_pair<MODE_TF32X3, __nv_bfloat16>(p, grid, ns, pair, stream);
+    default:
+      return f32 ? dispatch_pair<MODE_TF32, float>(p, grid, ns, pair, stream)
+                 : dispatch_pair<MODE_TF32, __nv_bfloat16>(p, grid, ns, pair, stream);
+  }
+}
+
+}  // namespace kgdet

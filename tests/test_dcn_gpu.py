@@ -89,6 +89,8 @@ UMMA_CASES = [
     dict(N=1, C=256, H=7, W=11, Cout=256, k=5),           # P7 shape, 25 points
     dict(N=1, C=256, H=7, W=11, Cout=256, k=7),           # 49 points
     dict(N=3, C=64, H=25, W=42, Cout=128, k=3, mask=True, bias=True),   # modulated through the fused path
+    dict(N=2, C=128, H=13, W=21, Cout=192, k=3),          # Cout not a multiple of 128: uneven epilogue chunks
+    dict(N=1, C=64, H=9, W=10, Cout=64, k=1, pad=0),      # a single tap, a single k-block per channel block
 ]
 
 
@@ -260,3 +262,24 @@ def test_tensor_core_backward_full_size_vs_exact():
     # grad_offset of the tensor-core path has a single writer per element: bitwise reproducible
     again = _ours(d, 'bf16')
     assert torch.equal(fast['grad_offset'], again['grad_offset'])
+
+
+@pytest.mark.parametrize('precision,tol', [('bf16', 1e-2), ('tf32x3', 2e-4), ('tf32', 5e-3)])
+def test_cta_pair_variant_matches_default(monkeypatch, precision, tol):
+    """The 2-SM (cta_group::2) variant of the fused kernel -- opt-in via KGDET_UMMA_PAIR=1 -- against the
+    fp64 oracle and, bit for bit, against the default 1-CTA launch (same arithmetic, same order).  Odd tile
+    count (M = 2*13*21 = 546 -> 5 tiles) so the padded sixth tile of the last pair is exercised."""
+    from kgdet_b200 import ops
+    d = dcn_case(N=2, C=128, H=13, W=21, Cout=192, k=3, seed=11)
+    x, off, w = (d[q].cuda() for q in ('x', 'offset', 'weight'))
+    ops.set_precision(precision)
+    try:
+        monkeypatch.setenv('KGDET_UMMA_PAIR', '0')
+        base = ops.deform_conv(x, off, w, 1, 1)
+        monkeypatch.setenv('KGDET_UMMA_PAIR', '1')
+        pair = ops.deform_conv(x, off, w, 1, 1)
+    finally:
+        ops.set_precision(None)
+    ref = dcn_oracle.deform_conv_forward(d['x'].double(), d['offset'].double(), d['weight'].double(), 1, 1)
+    assert rel_err(pair, ref) < tol
+    assert torch.equal(pair, base)
