@@ -60,6 +60,9 @@ enum { KGDET_F32 = 0, KGDET_BF16 = 1 };
  *  TF32   : tcgen05 kind::tf32, single pass (~1e-3) */
 enum { KGDET_PREC_FP32 = 0, KGDET_PREC_TF32X3 = 1, KGDET_PREC_BF16 = 2, KGDET_PREC_TF32 = 3 };
 
+/* output layouts of kgdet_dcn_forward_prepared */
+enum { KGDET_LAYOUT_NCHW = 0, KGDET_LAYOUT_TILED = 1, KGDET_LAYOUT_TILED_SPLIT = 2 };
+
 /* NMS comparator: the reference's two back-ends disagree at IoU == thr */
 enum { KGDET_NMS_GT = 0 /* nms_kernel.cu:60 */, KGDET_NMS_GE = 1 /* nms_cpu.cpp:55 */ };
 
@@ -103,10 +106,49 @@ KGDET_API int kgdet_dcn_prepare_input(const void* input, void* prepared_input, c
 KGDET_API size_t kgdet_dcn_plan_bytes(const kgdet_dcn_shape* shape, int precision);
 KGDET_API int kgdet_dcn_prepare_plan(const float* offset, const float* mask, void* plan,
                            const kgdet_dcn_shape* shape, int precision, void* stream);
+/* Plan from a channel slice [channel_offset, channel_offset + 2K) of a point-set tensor
+ * [N, channels_total, Ho, Wo] whose values are absolute point offsets: the head's `pts - dcn_base_offset`
+ * (KP3:37-67,135-143) happens inside the plan kernel, so neither the slice nor the subtraction is a kernel.
+ * deformable_groups must be 1. */
+KGDET_API int kgdet_dcn_prepare_plan_points(const float* points, int32_t channel_offset, int32_t channels_total,
+                                  void* plan, const kgdet_dcn_shape* shape, int precision, void* stream);
+/* out_layout: KGDET_LAYOUT_NCHW, or (tensor-core path, dtype KGDET_BF16) KGDET_LAYOUT_TILED = position-major
+ * rows [N*Ho*Wo, out_channels_total] stored as the UMMA-tiled A operand of kgdet_pointwise_conv_tiled
+ * (kgdet_pointwise_tiled_bytes(M, out_channels_total, 0) bytes), or KGDET_LAYOUT_TILED_SPLIT = the same with
+ * the bf16 hi parts followed by the lo parts (x - hi) for the split-precision GEMM (..._bytes(M, K, 1)). */
 KGDET_API int kgdet_dcn_forward_prepared(const void* prepared_input, const void* plan, const void* weight_packed,
                                const float* bias, void* output, int32_t out_channel_offset,
-                               int32_t out_channels_total, int fuse_relu, const kgdet_dcn_shape* shape,
-                               int dtype, int precision, void* stream);
+                               int32_t out_channels_total, int fuse_relu, int out_layout,
+                               const kgdet_dcn_shape* shape, int dtype, int precision, void* stream);
+
+/* ---- pointwise convolutions of the Kp3RepBlock ------------------------
+ * replaces  cls_out / keypts_out / reppts_out 1x1 nn.Conv2d + the cascade's residual adds
+ *           (reppoints_head_kp3rep_cas_1_assign_once.py:79-96,152-171,431-432,440-441)
+ * out[n, coff + c - col_begin, pos] = sum_k A[n*HW + pos, k] * W[c, k] + bias[c] (+ residual[same index])
+ * A: UMMA-tiled bf16 rows [M, K] (M = N*HW) written by kgdet_dcn_forward_prepared(KGDET_LAYOUT_TILED*) or
+ * kgdet_nchw_to_tiled_bf16; W: packed by kgdet_pointwise_pack_weight from fp32 [Nout, K]; bias fp32 [Nout] or
+ * NULL.  The Nout columns are split into up to KGDET_POINTWISE_MAX_SEGMENTS consecutive ranges, each written
+ * to its own NCHW fp32 tensor (e.g. keypoints 0..587 and point set 588..753 of one GEMM).  K % 64 == 0.
+ * split = 1: split-precision operands ("bf16x3": A = hi + lo, W = hi + lo, three bf16 MMAs per k-step,
+ * fp32-grade results); A and W must have been produced with the same `split`. */
+#define KGDET_POINTWISE_MAX_SEGMENTS 4
+typedef struct kgdet_pointwise_segment {
+  float* out;              /* NCHW fp32 [N, channels_total, HW] */
+  const float* residual;   /* same layout and channel range as `out`, or NULL */
+  int32_t col_begin, col_end;
+  int32_t channels_total, channel_offset;
+} kgdet_pointwise_segment;
+KGDET_API size_t kgdet_pointwise_tiled_bytes(int32_t M, int32_t K, int split);
+KGDET_API size_t kgdet_pointwise_packed_weight_bytes(int32_t Nout, int32_t K, int split);
+KGDET_API int kgdet_pointwise_pack_weight(const float* weight, void* packed, int32_t Nout, int32_t K, int split,
+                                void* stream);
+/* NCHW fp32/bf16 [N, C, S] -> UMMA-tiled bf16 rows [N*S, C] (split = 1: [hi | lo]), optional ReLU
+ * (stage-1 activations after a cuDNN convolution).  C % 64 == 0. */
+KGDET_API int kgdet_nchw_to_tiled_bf16(const void* src, void* dst, int32_t N, int32_t C, int32_t S, int src_dtype,
+                             int fuse_relu, int split, void* stream);
+KGDET_API int kgdet_pointwise_conv_tiled(const void* a_tiled, const void* w_packed, const float* bias, int32_t M,
+                               int32_t K, int32_t Nout, int32_t HW, int split,
+                               const kgdet_pointwise_segment* segs, int32_t nseg, void* stream);
 
 /* replaces deform_conv_backward_input_cuda     dcn/src/deform_conv_cuda.cpp:260-371
  *          (+ the input/offset/mask part of modulated_deform_conv_cuda_backward :566-679)

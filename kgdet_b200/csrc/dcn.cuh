@@ -41,15 +41,17 @@ struct __align__(16) SampleRec16 {
 // band of dcn_guard_pixels() pixels on both sides.
 enum { PLAN16_F32 = 0, PLAN16_BF16W = 1 };
 size_t plan16_bytes(const DcnGeom& g);
+// batch_stride: elements between images of `offset` (0 = contiguous [N, 2K, Ho, Wo]); points = 1: `offset`
+// holds absolute point offsets and the base grid is subtracted (kgdet_dcn_prepare_plan_points)
 int launch_plan16(const DcnGeom& g, const float* offset, const float* mask, SampleRec16* rec, int fmt,
-                  cudaStream_t stream);
+                  cudaStream_t stream, long long batch_stride = 0, int points = 0);
 static inline int dcn_guard_pixels(const DcnGeom& g) { return g.W + 2; }
 
 size_t plan_rows(const DcnGeom& g);                 // M rounded up to 256
 size_t plan_bytes(const DcnGeom& g);                // SampleRec array
 size_t plan_aux_bytes(const DcnGeom& g);            // SampleAux array
 int launch_plan(const DcnGeom& g, const float* offset, const float* mask, SampleRec* rec,
-                SampleAux* aux /* may be NULL */, cudaStream_t stream);
+                SampleAux* aux /* may be NULL */, cudaStream_t stream, long long batch_stride = 0, int points = 0);
 
 // src [B, R, Cc] -> dst [B, Cc, R] with dtype conversion (NCHW <-> NHWC)
 int launch_transpose(const void* src, void* dst, int B, int R, int Cc, int src_dtype,
@@ -66,6 +68,8 @@ struct OutSpec {
   int dtype;      // KGDET_F32 / KGDET_BF16
   int coff, ctot;
   int relu;
+  int nhwc;       // KGDET_LAYOUT_*: NCHW [N, ctot, Ho, Wo], or (tensor-core path only) UMMA-tiled bf16 rows
+                  // [N*Ho*Wo, ctot] / split [hi | lo] -- see pointwise_umma.cu
 };
 
 // ---- exact fp32 SIMT path (any stride / dilation / groups / deformable_groups / mask) ----

@@ -183,7 +183,7 @@ extern "C" int kgdet_dcn_forward(const void* input, const float* offset, const f
   void* plan = (char*)workspace + in_total;
   if ((rc = do_prepare_input(g, input, prepared, dtype, precision, stream)) != KGDET_OK) return rc;
   if ((rc = do_prepare_plan(g, offset, mask, plan, precision, stream)) != KGDET_OK) return rc;
-  OutSpec o{output, dtype, 0, g.Cout, 0};
+  OutSpec o{output, dtype, 0, g.Cout, 0, 0};
   return do_forward_prepared(g, prepared, plan, weight_packed, bias, o, precision, stream);
 }
 
@@ -221,10 +221,32 @@ extern "C" int kgdet_dcn_prepare_plan(const float* offset, const float* mask, vo
   return do_prepare_plan(g, offset, mask, plan, precision, (cudaStream_t)stream);
 }
 
+extern "C" int kgdet_dcn_prepare_plan_points(const float* points, int32_t channel_offset,
+                                             int32_t channels_total, void* plan, const kgdet_dcn_shape* shape,
+                                             int precision, void* stream) {
+  DcnGeom g;
+  int rc = make_geom(shape, &g);
+  if (rc != KGDET_OK) return rc;
+  KG_CHECK_ARG(valid_prec(precision), "kgdet_dcn_prepare_plan_points: bad precision %d", precision);
+  KG_CHECK_ARG(points && plan, "kgdet_dcn_prepare_plan_points: NULL pointer");
+  KG_CHECK_ARG(g.dgroups == 1, "kgdet_dcn_prepare_plan_points: deformable_groups must be 1");
+  KG_CHECK_ARG(channel_offset >= 0 && channel_offset + 2 * g.K <= channels_total,
+               "kgdet_dcn_prepare_plan_points: channels [%d, %d) do not fit %d", channel_offset,
+               channel_offset + 2 * g.K, channels_total);
+  KG_CHECK_ARG(((uintptr_t)plan & 255) == 0, "kgdet_dcn_prepare_plan_points: buffer must be 256-byte aligned");
+  const long long HoWo = (long long)g.Ho * g.Wo;
+  const float* first = points + (long long)channel_offset * HoWo;
+  const long long bstride = (long long)channels_total * HoWo;
+  if (use_umma(g, precision))
+    return launch_plan16(g, first, nullptr, (SampleRec16*)plan,
+                         precision == KGDET_PREC_BF16 ? PLAN16_BF16W : PLAN16_F32, (cudaStream_t)stream, bstride, 1);
+  return launch_plan(g, first, nullptr, (SampleRec*)plan, nullptr, (cudaStream_t)stream, bstride, 1);
+}
+
 extern "C" int kgdet_dcn_forward_prepared(const void* prepared_input, const void* plan,
                                           const void* weight_packed, const float* bias, void* output,
                                           int32_t out_channel_offset, int32_t out_channels_total,
-                                          int fuse_relu, const kgdet_dcn_shape* shape, int dtype,
+                                          int fuse_relu, int out_layout, const kgdet_dcn_shape* shape, int dtype,
                                           int precision, void* stream) {
   DcnGeom g;
   int rc = make_geom(shape, &g);
@@ -234,7 +256,16 @@ extern "C" int kgdet_dcn_forward_prepared(const void* prepared_input, const void
   KG_CHECK_ARG(out_channel_offset >= 0 && out_channel_offset + g.Cout <= out_channels_total,
                "kgdet_dcn_forward_prepared: channel slice [%d, %d) does not fit %d channels",
                out_channel_offset, out_channel_offset + g.Cout, out_channels_total);
-  OutSpec o{output, dtype, out_channel_offset, out_channels_total, fuse_relu ? 1 : 0};
+  KG_CHECK_ARG(out_layout >= KGDET_LAYOUT_NCHW && out_layout <= KGDET_LAYOUT_TILED_SPLIT,
+               "kgdet_dcn_forward_prepared: bad output layout %d", out_layout);
+  if (out_layout != KGDET_LAYOUT_NCHW) {
+    KG_CHECK_ARG(dtype == KGDET_BF16, "kgdet_dcn_forward_prepared: the tiled layouts store bf16");
+    KG_CHECK_ARG(use_umma(g, precision), "kgdet_dcn_forward_prepared: tiled output needs the tensor-core path");
+    KG_CHECK_ARG(out_channel_offset % 32 == 0 && out_channels_total % 64 == 0,
+                 "kgdet_dcn_forward_prepared: tiled output needs channel offset %% 32 == 0 and total %% 64 == 0");
+  }
+  OutSpec o{output, dtype, out_channel_offset, out_channels_total, fuse_relu ? 1 : 0,
+            out_layout};
   return do_forward_prepared(g, prepared_input, plan, weight_packed, bias, o, precision, (cudaStream_t)stream);
 }
 

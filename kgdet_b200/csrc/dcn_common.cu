@@ -13,7 +13,28 @@ size_t plan_aux_bytes(const DcnGeom& g) {
 
 // Sampling rule of deformable_im2col_gpu_kernel (deform_conv_cuda_kernel.cu:210-236) and
 // deformable_im2col_bilinear (:83-114), evaluated once per (position, dgroup, tap).
-__global__ void dcn_plan_kernel(DcnGeom g, const float* __restrict__ offset,
+//
+// OffsetSrc: where the (dy, dx) pairs come from.  Plain case: the op's `offset` tensor [N, dg*2K, Ho, Wo].
+// Points case (kgdet_dcn_prepare_plan_points): a channel slice of a wider point-set tensor whose values are
+// absolute point offsets; the head turns them into DCN offsets with `pts - base`, base = the regular k x k
+// grid in [-(k-1)/2, (k-1)/2] (KP3:37-67,135-143) -- done here in the same fp32 operation order.
+struct OffsetSrc {
+  const float* ptr;          // first channel used
+  long long batch_stride;    // elements between images
+  int points;                // 1: subtract the base grid
+};
+__device__ __forceinline__ void load_offset(const OffsetSrc& o, const DcnGeom& g, int n, int dgi, int tap,
+                                            int i, int j, int HoWo, int p, float& off_h, float& off_w) {
+  const float* q = o.ptr + (long long)n * o.batch_stride + ((size_t)dgi * 2 * g.K + 2 * tap) * HoWo + p;
+  off_h = q[0];                                          // :221,223
+  off_w = q[HoWo];                                       // :222,224
+  if (o.points) {
+    off_h = off_h - (float)(i - (g.kh - 1) / 2);
+    off_w = off_w - (float)(j - (g.kw - 1) / 2);
+  }
+}
+
+__global__ void dcn_plan_kernel(DcnGeom g, OffsetSrc osrc,
                                 const float* __restrict__ mask, SampleRec* __restrict__ rec,
                                 SampleAux* __restrict__ aux, int rows_padded) {
   const int per_row = g.dgroups * g.K;
@@ -33,9 +54,8 @@ __global__ void dcn_plan_kernel(DcnGeom g, const float* __restrict__ offset,
       const int n = m / HoWo, p = m - n * HoWo;
       const int y = p / g.Wo, x = p - y * g.Wo;
       const int i = tap / g.kw, j = tap - i * g.kw;
-      const size_t obase = ((size_t)(n * g.dgroups + dgi) * 2 * g.K + 2 * tap) * HoWo + p;
-      const float off_h = offset[obase];                    // :221,223
-      const float off_w = offset[obase + HoWo];             // :222,224
+      float off_h, off_w;
+      load_offset(osrc, g, n, dgi, tap, i, j, HoWo, p, off_h, off_w);
       const float mval = mask ? mask[((size_t)(n * g.dgroups + dgi) * g.K + tap) * HoWo + p] : 1.f;
       const float h_im = (float)(y * g.sh - g.ph + i * g.dh) + off_h;   // :226
       const float w_im = (float)(x * g.sw - g.pw + j * g.dw) + off_w;   // :227
@@ -65,7 +85,7 @@ size_t plan16_bytes(const DcnGeom& g) { return plan_rows(g) * g.K * sizeof(Sampl
 
 // Same sampling rule as dcn_plan_kernel, compact output for the tensor-core path (dgroups == 1).
 // Threads run fastest over positions so the offset reads are coalesced (offset is [N, 2K, Ho, Wo]).
-__global__ void dcn_plan16_kernel(DcnGeom g, const float* __restrict__ offset,
+__global__ void dcn_plan16_kernel(DcnGeom g, OffsetSrc osrc,
                                   const float* __restrict__ mask, SampleRec16* __restrict__ rec,
                                   int rows_padded, int fmt) {
   const long long total = (long long)rows_padded * g.K;
@@ -81,8 +101,8 @@ __global__ void dcn_plan16_kernel(DcnGeom g, const float* __restrict__ offset,
       const int n = m / HoWo, p = m - n * HoWo;
       const int y = p / g.Wo, x = p - y * g.Wo;
       const int i = tap / g.kw, j = tap - i * g.kw;
-      const size_t obase = ((size_t)n * 2 * g.K + 2 * tap) * HoWo + p;
-      const float off_h = offset[obase], off_w = offset[obase + HoWo];
+      float off_h, off_w;
+      load_offset(osrc, g, n, 0, tap, i, j, HoWo, p, off_h, off_w);
       const float mval = mask ? mask[((size_t)n * g.K + tap) * HoWo + p] : 1.f;
       const float h_im = (float)(y * g.sh - g.ph + i * g.dh) + off_h;
       const float w_im = (float)(x * g.sw - g.pw + j * g.dw) + off_w;
@@ -124,26 +144,36 @@ __global__ void dcn_plan16_kernel(DcnGeom g, const float* __restrict__ offset,
   }
 }
 
+static OffsetSrc make_offset_src(const DcnGeom& g, const float* offset, long long batch_stride, int points) {
+  OffsetSrc o;
+  o.ptr = offset;
+  o.batch_stride = batch_stride > 0 ? batch_stride : (long long)g.dgroups * 2 * g.K * g.Ho * g.Wo;
+  o.points = points;
+  return o;
+}
+
 int launch_plan16(const DcnGeom& g, const float* offset, const float* mask, SampleRec16* rec, int fmt,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, long long batch_stride, int points) {
   const int rows = (int)plan_rows(g);
   const long long total = (long long)rows * g.K;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  dcn_plan16_kernel<<<(int)blocks, 256, 0, stream>>>(g, offset, mask, rec, rows, fmt);
+  dcn_plan16_kernel<<<(int)blocks, 256, 0, stream>>>(g, make_offset_src(g, offset, batch_stride, points), mask, rec,
+                                                     rows, fmt);
   KG_LAUNCH_CHECK("dcn_plan16_kernel");
   return KGDET_OK;
 }
 
 int launch_plan(const DcnGeom& g, const float* offset, const float* mask, SampleRec* rec,
-                SampleAux* aux, cudaStream_t stream) {
+                SampleAux* aux, cudaStream_t stream, long long batch_stride, int points) {
   const int rows = (int)plan_rows(g);
   const long long total = (long long)rows * g.dgroups * g.K;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  dcn_plan_kernel<<<(int)blocks, 256, 0, stream>>>(g, offset, mask, rec, aux, rows);
+  dcn_plan_kernel<<<(int)blocks, 256, 0, stream>>>(g, make_offset_src(g, offset, batch_stride, points), mask, rec,
+                                                   aux, rows);
   KG_LAUNCH_CHECK("dcn_plan_kernel");
   return KGDET_OK;
 }

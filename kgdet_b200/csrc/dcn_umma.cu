@@ -100,7 +100,7 @@ int umma_forward(const DcnGeom& g, const void* in_blocked, size_t plane_bytes, c
   const int bk = bk_of(precision);
   UmmaParams p;
   p.in = in_blocked; p.plane_bytes = plane_bytes; p.plan = plan; p.wp = (const unsigned char*)packed_w; p.bias = bias; p.out = o.out;
-  p.out_coff = o.coff; p.out_ctot = o.ctot; p.relu = o.relu;
+  p.out_coff = o.coff; p.out_ctot = o.ctot; p.relu = o.relu; p.out_nhwc = o.nhwc;
   p.M = g.M; p.C = g.C; p.W = g.W; p.Cout = g.Cout; p.K = g.K; p.HoWo = g.Ho * g.Wo;
   p.rows_padded = (int)plan_rows(g);
   p.nkb = (g.C / bk) * g.K;

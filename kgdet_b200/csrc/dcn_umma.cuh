@@ -31,6 +31,7 @@ struct UmmaParams {
   void* out;                 // NCHW
   int M, C, W, Cout, K, HoWo, rows_padded;
   int out_coff, out_ctot, relu;   // channel slice of the output tensor, fused ReLU
+  int out_nhwc;              // KGDET_LAYOUT_*: TILED / TILED_SPLIT = UMMA-tiled bf16 rows (pointwise_umma.cu)
   int nkb;                   // (C / BK) * K
   uint32_t idesc;
   uint32_t tmem_cols;
@@ -42,6 +43,18 @@ template <typename T> __device__ __forceinline__ void st_out(T* p, float v);
 template <> __device__ __forceinline__ void st_out<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void st_out<__nv_bfloat16>(__nv_bfloat16* p, float v) {
   *p = __float2bfloat16(v);
+}
+
+template <typename T> __device__ __forceinline__ void st_out4(T* p, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void st_out4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void st_out4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 v;
+  v.x = *reinterpret_cast<const uint32_t*>(&lo);
+  v.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = v;
 }
 
 __device__ __forceinline__ uint32_t bf162_bcast(float w) {

@@ -329,12 +329,49 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dcn_umma_stream_kernel(cons
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
       tmem_ld_wait();
       if (row_ok) {
+        if (prm.out_nhwc) {
+          // "UMMA-tiled rows" (pointwise_umma.cu): bf16, [M/128 tiles][k-blocks of 64 channels][128 rows x 128 B,
+          // 16-byte chunk c of row r at chunk c ^ (r & 7)] -- exactly the A operand slabs of the 1x1-convolution
+          // GEMM that follows, which then needs one bulk copy per k-block.  Split layout: the k-blocks of the hi
+          // parts are followed by those of the lo parts (x = hi + lo).
+          if constexpr (sizeof(Tout) == 2) {
+            const bool split = prm.out_nhwc == KGDET_LAYOUT_TILED_SPLIT;
+            const int kblocks = (split ? 2 : 1) * (prm.out_ctot >> 6);
+            unsigned char* tile = reinterpret_cast<unsigned char*>(prm.out) + (size_t)(m >> 7) * kblocks * A_TILE_BYTES +
+                                  (size_t)(m & 127) * 128;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(acc[j]);
-          if (prm.bias) x += __ldg(prm.bias + col + j);
-          if (prm.relu) x = fmaxf(x, 0.f);
-          st_out<Tout>(obase + (size_t)(col + j) * prm.HoWo, x);   // lanes = consecutive positions
+            for (int j = 0; j < 32; j += 8) {
+              float x[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                x[e] = __uint_as_float(acc[j + e]);
+                if (prm.bias) x[e] += __ldg(prm.bias + col + j + e);
+                if (prm.relu) x[e] = fmaxf(x[e], 0.f);
+              }
+              const int k = prm.out_coff + col + j;                  // logical channel of x[0]
+              const size_t off = (size_t)(k >> 6) * A_TILE_BYTES + ((((k & 63) >> 3) ^ (m & 7)) << 4);
+              uint4 hi4;
+              hi4.x = pack_bf16x2(x[0], x[1]); hi4.y = pack_bf16x2(x[2], x[3]);
+              hi4.z = pack_bf16x2(x[4], x[5]); hi4.w = pack_bf16x2(x[6], x[7]);
+              *reinterpret_cast<uint4*>(tile + off) = hi4;
+              if (split) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] -= __bfloat162float(__float2bfloat16(x[e]));
+                uint4 lo4;
+                lo4.x = pack_bf16x2(x[0], x[1]); lo4.y = pack_bf16x2(x[2], x[3]);
+                lo4.z = pack_bf16x2(x[4], x[5]); lo4.w = pack_bf16x2(x[6], x[7]);
+                *reinterpret_cast<uint4*>(tile + off + (size_t)(prm.out_ctot >> 6) * A_TILE_BYTES) = lo4;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(acc[j]);
+            if (prm.bias) x += __ldg(prm.bias + col + j);
+            if (prm.relu) x = fmaxf(x, 0.f);
+            st_out<Tout>(obase + (size_t)(col + j) * prm.HoWo, x);   // lanes = consecutive positions
+          }
         }
       }
     }

@@ -27,8 +27,10 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import (DeformConv, batched_nms_flags, deform_conv_prepared, points2bbox_moment, prepare_input,
-                  prepare_plan)
+from .ops import (DeformConv, TiledRows, batched_nms_flags, deform_conv_prepared, get_precision, nchw_to_tiled,
+                  pack_weight, points2bbox_moment, pointwise_conv, prepare_input, prepare_plan,
+                  prepare_plan_points)
+from .ops.pointwise import cached
 
 _POINT_SETS = (3, 5, 7)          # KP3:257: 9 + 25 + 49 points regardless of cfg.num_reppts
 
@@ -52,6 +54,39 @@ def _normal(m, std=0.01, bias=0.0):
         nn.init.constant_(m.bias, bias)
 
 
+def _pointwise_weights(block):
+    """Packed GEMM operands of a block's three 1x1 convolutions, cached per parameter version:
+    (W_cls, b_cls, [W_kpt ; W_rep W_kpt], [b_kpt ; W_rep b_kpt + b_rep]).  reppts_out is a linear map of
+    keypts_out (KP3:100-106,164-171), so the two are composed on the host in fp32 and keypoints and point set
+    come out of ONE GEMM over the keypoint branch's activations -- the point set never sees a rounded
+    keypoint tensor."""
+    ps = (block.cls_out.weight, block.cls_out.bias, block.keypts_out.weight, block.keypts_out.bias,
+          block.reppts_out.weight, block.reppts_out.bias)
+
+    def build():
+        with torch.no_grad():
+            wc, bc, wk, bk, wr, br = (p.detach().float() for p in ps)
+            wc, wk, wr = wc.flatten(1), wk.flatten(1), wr.flatten(1)
+            w_kr = torch.cat([wk, wr @ wk], 0)
+            b_kr = torch.cat([bk, wr @ bk + br], 0)
+            return pack_weight(wc, split=True), bc.contiguous(), pack_weight(w_kr, split=True), b_kr.contiguous()
+    return cached(ps, build)
+
+
+def _pointwise_heads(block, cls_rows, kpt_rows, n, h, w, kpt_prev=None, rep_prev=None):
+    """cls / keypoint / point-set outputs (NCHW fp32, residuals of the cascade added) from position-major bf16
+    activations: two tcgen05 GEMMs instead of three cuDNN 1x1 convolutions + two adds."""
+    wc, bc, w_kr, b_kr = _pointwise_weights(block)
+    nc, nk, nr = block.cls_out.out_channels, block.keypts_out.out_channels, block.reppts_out.out_channels
+    dev = cls_rows.buf.device
+    cls_out = torch.empty((n, nc, h, w), dtype=torch.float32, device=dev)
+    kpt = torch.empty((n, nk, h, w), dtype=torch.float32, device=dev)
+    rep = torch.empty((n, nr, h, w), dtype=torch.float32, device=dev)
+    pointwise_conv(cls_rows, wc, bc, [(cls_out, None, 0, nc)], h * w)
+    pointwise_conv(kpt_rows, w_kr, b_kr, [(kpt, kpt_prev, 0, nk), (rep, rep_prev, nk, nk + nr)], h * w)
+    return cls_out, kpt, rep
+
+
 class _PlainBlock(nn.Module):
     """Kp3RepBlock(deform_conv=False), KP3:98-106,173-177."""
 
@@ -73,6 +108,14 @@ class _PlainBlock(nn.Module):
         cls_out = self.cls_out(F.relu(self.cls_conv(cls_feat)))
         keypts_out = self.keypts_out(F.relu(self.keypts_conv(pts_feat)))
         return cls_out, keypts_out, self.reppts_out(keypts_out)
+
+    def forward_tc(self, cls_feat, pts_feat):
+        """bf16 inference: the two 3x3 convolutions stay cuDNN; ReLU + layout change is one kernel each and the
+        three 1x1 convolutions are two tensor-core GEMMs."""
+        n, _, h, w = cls_feat.shape
+        cls_rows = nchw_to_tiled(self.cls_conv(cls_feat), relu=True, split=True)
+        kpt_rows = nchw_to_tiled(self.keypts_conv(pts_feat), relu=True, split=True)
+        return _pointwise_heads(self, cls_rows, kpt_rows, n, h, w)
 
 
 class _DeformBlock(nn.Module):
@@ -122,6 +165,26 @@ class _DeformBlock(nn.Module):
         keypts_out = self.keypts_out(kpt_cat)
         return cls_out, keypts_out, self.reppts_out(keypts_out)
 
+    def forward_tc(self, cls_prep, pts_prep, rep_prev, kpt_prev):
+        """bf16 inference, fully on this package's kernels: per point set one
+        sample plan read straight from the channel slice of the previous stage's point tensor, two fused DCN
+        launches that write ReLU-ed position-major bf16 rows, then two GEMMs whose epilogue adds bias and the
+        cascade residuals (KP3:431-432,440-441) and writes NCHW fp32.  12 launches per stage."""
+        n, c, h, w = cls_prep.shape4
+        feat = self.cls_dfmconv_3.out_channels
+        dev = rep_prev.device
+        cls_rows = TiledRows(n * h * w, 3 * feat, True, dev)         # split precision: [hi | lo]
+        kpt_rows = TiledRows(n * h * w, 3 * feat, True, dev)
+        lo = 0
+        for i, k in enumerate(_POINT_SETS):
+            plan = prepare_plan_points(rep_prev, lo, (n, c, h, w), feat, k, 1, (k - 1) // 2, 1, precision='bf16')
+            lo += 2 * k * k
+            deform_conv_prepared(cls_prep, plan, getattr(self, 'cls_dfmconv_%d' % k).weight, cls_rows, i * feat,
+                                 True)
+            deform_conv_prepared(pts_prep, plan, getattr(self, 'keypts_dfmconv_%d' % k).weight, kpt_rows, i * feat,
+                                 True)
+        return _pointwise_heads(self, cls_rows, kpt_rows, n, h, w, kpt_prev, rep_prev)
+
     def forward(self, cls_feat, pts_feat, reppts_offset):
         cls_feats, kpt_feats = [], []
         lo = 0
@@ -149,6 +212,7 @@ class KGDetHead(nn.Module):
         # oracle-backed stand-ins; the defaults are the CUDA operators of this package.
         super().__init__()
         self._fused_inference = deform_conv_cls is None     # prepared API only with the CUDA operators
+        self._tensor_core_heads = True                      # bf16 mode: 1x1 convolutions as tcgen05 GEMMs
         deform_conv_cls = deform_conv_cls or DeformConv
         self._moment_fn = moment_fn or points2bbox_moment
         self._nms_flags_fn = nms_flags_fn or batched_nms_flags
@@ -184,9 +248,24 @@ class KGDetHead(nn.Module):
             cls_feat = m(cls_feat)
         for m in self.reg_convs:
             pts_feat = m(pts_feat)
+        fused = self._fused_inference and not torch.is_grad_enabled() and cls_feat.is_cuda
+        if fused and self._tensor_core_heads and get_precision(cls_feat.dtype) == 'bf16' \
+                and cls_feat.dtype == torch.float32:
+            # bf16 mode: everything after the towers except the two plain 3x3 convolutions runs on this
+            # package's kernels
+            feat = self.kp_rep_block_2.cls_dfmconv_3.out_channels
+            cls1, kpt1, rep1 = self.kp_rep_block_1.forward_tc(cls_feat, pts_feat)
+            bbox1 = self.points2bbox(rep1)
+            cls_prep = prepare_input(cls_feat, feat, precision='bf16')
+            pts_prep = prepare_input(pts_feat, feat, precision='bf16')
+            cls2, kpt2, rep2 = self.kp_rep_block_2.forward_tc(cls_prep, pts_prep, rep1, kpt1)
+            bbox2 = self.points2bbox(rep2)
+            cls3, kpt3, rep3 = self.kp_rep_block_3.forward_tc(cls_prep, pts_prep, rep2, kpt2)
+            bbox3 = self.points2bbox(rep3)
+            return cls1, cls2, cls3, kpt1, kpt2, kpt3, bbox1, bbox2, bbox3
         cls1, kpt1, rep1 = self.kp_rep_block_1(cls_feat, pts_feat)
         bbox1 = self.points2bbox(rep1)
-        if self._fused_inference and not torch.is_grad_enabled() and cls_feat.is_cuda:
+        if fused:
             feat = self.kp_rep_block_2.cls_dfmconv_3.out_channels
             cls_prep = prepare_input(cls_feat, feat)
             pts_prep = prepare_input(pts_feat, feat)

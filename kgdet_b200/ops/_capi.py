@@ -30,6 +30,15 @@ class DcnShape(ctypes.Structure):
 
 _SHAPE_P = ctypes.POINTER(DcnShape)
 
+
+class PointwiseSegment(ctypes.Structure):
+    """struct kgdet_pointwise_segment"""
+    _fields_ = [('out', ctypes.c_void_p), ('residual', ctypes.c_void_p), ('col_begin', c_i32), ('col_end', c_i32),
+                ('channels_total', c_i32), ('channel_offset', c_i32)]
+
+
+LAYOUT_NCHW, LAYOUT_TILED, LAYOUT_TILED_SPLIT = 0, 1, 2
+
 # name -> (restype, argtypes); must list every KGDET_API symbol of the header
 SIGNATURES = {
     'kgdet_last_error': (ctypes.c_char_p, []),
@@ -44,8 +53,16 @@ SIGNATURES = {
     'kgdet_dcn_prepare_input': (ctypes.c_int, [c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr]),
     'kgdet_dcn_plan_bytes': (c_sz, [_SHAPE_P, ctypes.c_int]),
     'kgdet_dcn_prepare_plan': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
+    'kgdet_dcn_prepare_plan_points': (ctypes.c_int, [c_ptr, c_i32, c_i32, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
     'kgdet_dcn_forward_prepared': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, ctypes.c_int,
-                                                  _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr]),
+                                                  ctypes.c_int, _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr]),
+    'kgdet_pointwise_tiled_bytes': (c_sz, [c_i32, c_i32, ctypes.c_int]),
+    'kgdet_pointwise_packed_weight_bytes': (c_sz, [c_i32, c_i32, ctypes.c_int]),
+    'kgdet_pointwise_pack_weight': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, ctypes.c_int, c_ptr]),
+    'kgdet_nchw_to_tiled_bf16': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, c_ptr]),
+    'kgdet_pointwise_conv_tiled': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, ctypes.c_int,
+                                                  c_ptr, c_i32, c_ptr]),
     'kgdet_dcn_backward_input_workspace_bytes': (c_sz, [_SHAPE_P, ctypes.c_int, ctypes.c_int]),
     'kgdet_dcn_backward_input': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                                 c_ptr, _SHAPE_P, ctypes.c_int, ctypes.c_int,

@@ -269,8 +269,34 @@ def prepare_plan(offset, input_shape, out_channels, kernel_size, stride=1, paddi
     return pl
 
 
+def prepare_plan_points(points, channel_offset, input_shape, out_channels, kernel_size, stride=1, padding=0,
+                        dilation=1, precision=None, like_dtype=torch.float32):
+    """Sample plan of ``points[:, channel_offset:channel_offset + 2K] - base_grid`` without materialising the
+    slice or the subtraction (KP3:131-143: the head's ``dcn_offset = pts - dcn_base_offset``)."""
+    lib = _capi.lib()
+    _capi.require_cuda(points, 'prepare_plan_points')
+    assert points.dtype == torch.float32 and points.is_contiguous() and points.dim() == 4
+    prec = _capi.PRECISIONS[precision or get_precision(like_dtype)]
+    k, st, pd, dl = _pair(kernel_size), _pair(stride), _pair(padding), _pair(dilation)
+    shape = _geom_shape(*input_shape, out_channels, k, st, pd, dl)
+    pl = SamplePlan()
+    pl.geom = (tuple(input_shape), k, st, pd, dl)
+    pl.precision = prec
+    pl.fast = bool(lib.kgdet_dcn_fast_path_supported(ctypes_ref(shape), prec))
+    pl.buf = torch.empty(int(lib.kgdet_dcn_plan_bytes(ctypes_ref(shape), prec)), dtype=torch.uint8,
+                         device=points.device)
+    _capi.check(lib.kgdet_dcn_prepare_plan_points(points.data_ptr(), int(channel_offset), points.shape[1],
+                                                  pl.buf.data_ptr(), ctypes_ref(shape), prec,
+                                                  _capi.stream_of(points)), 'kgdet_dcn_prepare_plan_points')
+    return pl
+
+
 def deform_conv_prepared(pin, plan, weight, out=None, channel_offset=0, relu=False, bias=None):
-    """out[:, channel_offset:channel_offset+Cout] = (relu)(deform_conv(input, offset, weight)); no autograd."""
+    """out[:, channel_offset:channel_offset+Cout] = (relu)(deform_conv(input, offset, weight)); no autograd.
+
+    `out` is an NCHW tensor, or a ``pointwise.TiledRows`` (tensor-core path only): the kernel then writes
+    position-major bf16 rows straight into the tiled A operand of the 1x1-convolution GEMM that follows."""
+    from .pointwise import TiledRows
     lib = _capi.lib()
     (n, c, h, w), k, st, pd, dl = plan.geom
     assert pin.shape4 == (n, c, h, w) and pin.precision == plan.precision
@@ -281,15 +307,21 @@ def deform_conv_prepared(pin, plan, weight, out=None, channel_offset=0, relu=Fal
     packed = _packed_weight(weight, shape, plan.precision)
     ho = (h + 2 * pd[0] - (dl[0] * (k[0] - 1) + 1)) // st[0] + 1
     wo = (w + 2 * pd[1] - (dl[1] * (k[1] - 1) + 1)) // st[1] + 1
-    if out is None:
-        out = torch.empty((n, weight.shape[0], ho, wo), dtype=pin.torch_dtype, device=weight.device)
-        channel_offset = 0
-    assert out.is_contiguous() and out.shape[0] == n and tuple(out.shape[2:]) == (ho, wo)
     b = None if bias is None else _f32c(bias)
+    if isinstance(out, TiledRows):
+        assert out.M == n * ho * wo
+        layout = _capi.LAYOUT_TILED_SPLIT if out.split else _capi.LAYOUT_TILED
+        ptr, ctot, dt, ref = out.buf.data_ptr(), out.K, _capi.BF16, out.buf
+    else:
+        if out is None:
+            out = torch.empty((n, weight.shape[0], ho, wo), dtype=pin.torch_dtype, device=weight.device)
+            channel_offset = 0
+        assert out.is_contiguous() and out.shape[0] == n and tuple(out.shape[2:]) == (ho, wo)
+        layout = _capi.LAYOUT_NCHW
+        ptr, ctot, dt, ref = out.data_ptr(), out.shape[1], _capi.dtype_code(out), out
     _capi.check(lib.kgdet_dcn_forward_prepared(pin.buf.data_ptr(), plan.buf.data_ptr(), packed.data_ptr(),
-                                               _capi.ptr(b), out.data_ptr(), int(channel_offset), out.shape[1],
-                                               int(bool(relu)), ctypes_ref(shape), _capi.dtype_code(out),
-                                               plan.precision, _capi.stream_of(out)),
+                                               _capi.ptr(b), ptr, int(channel_offset), ctot, int(bool(relu)), layout,
+                                               ctypes_ref(shape), dt, plan.precision, _capi.stream_of(ref)),
                 'kgdet_dcn_forward_prepared')
     return out
 

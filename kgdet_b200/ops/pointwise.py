@@ -1,0 +1,106 @@
+"""Pointwise (1x1) convolutions of the Kp3RepBlock on the tensor cores.
+
+``cls_out`` / ``keypts_out`` / ``reppts_out`` of the reference block
+(reppoints_head_kp3rep_cas_1_assign_once.py:79-96,152-171) are 1x1 ``nn.Conv2d`` on the concatenated,
+ReLU-ed deformable-convolution outputs.  Here the fused DCN kernel writes those activations as position-major
+bf16 rows in the tiled layout the tensor core reads (``TiledRows``) and ONE tcgen05 GEMM
+(kgdet_pointwise_conv_tiled) per branch produces its outputs; bias, the cascade's residual adds
+(KP3:431-432,440-441) and the NCHW fp32 layout of the results are the GEMM's epilogue.  With ``split=True``
+both operands carry a bf16 hi and a bf16 lo part and the GEMM issues three MMAs per k-step ("bf16x3"): the
+1x1 convolutions stay fp32-grade although they run on the bf16 tensor cores.
+"""
+import ctypes
+import weakref
+
+import torch
+
+from . import _capi
+
+_cache = {}
+
+
+class TiledRows(object):
+    """Position-major activations [M, K] in the UMMA-tiled bf16 layout (opaque buffer)."""
+    __slots__ = ('buf', 'M', 'K', 'split')
+
+    def __init__(self, M, K, split, device):
+        lib = _capi.lib()
+        assert K % 64 == 0, 'K must be a multiple of 64'
+        nbytes = int(lib.kgdet_pointwise_tiled_bytes(M, K, int(bool(split))))
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.M, self.K, self.split = M, K, bool(split)
+
+    def to_dense(self):
+        """fp32 [M, K] view of the stored values (hi + lo when split) -- for tests."""
+        kb = (2 if self.split else 1) * (self.K // 64)
+        t = self.buf.view(torch.bfloat16).view(-1, kb, 128, 8, 8)                   # tile, k-block, row, chunk, elem
+        r = torch.arange(128, device=t.device).view(128, 1)
+        c = torch.arange(8, device=t.device).view(1, 8)
+        src = (c ^ (r & 7)).view(1, 1, 128, 8, 1).expand(t.shape[0], kb, 128, 8, 8)  # logical chunk c lives at c^(r&7)
+        logical = torch.gather(t, 3, src).float()
+        rows = logical.permute(0, 2, 1, 3, 4).reshape(t.shape[0] * 128, kb * 64)[:self.M]
+        return rows[:, :self.K] + rows[:, self.K:] if self.split else rows
+
+
+def cached(params, build):
+    """Cache of host-prepared device buffers keyed by the identity + version of the source parameters."""
+    key = tuple(id(p) for p in params)
+    sig = tuple((p._version, p.data_ptr()) for p in params)
+    ent = _cache.get(key)
+    if ent is not None and ent[0] == sig and all(r() is p for r, p in zip(ent[1], params)):
+        return ent[2]
+    val = build()
+    if len(_cache) > 64:
+        _cache.clear()
+    _cache[key] = (sig, [weakref.ref(p) for p in params], val)
+    return val
+
+
+def pack_weight(w, split=True):
+    """fp32 [Nout, K] (or [Nout, K, 1, 1]) -> packed GEMM operand (kgdet_pointwise_pack_weight)."""
+    lib = _capi.lib()
+    w = w.detach().float().flatten(1).contiguous()
+    nout, k = w.shape
+    nbytes = int(lib.kgdet_pointwise_packed_weight_bytes(nout, k, int(bool(split))))
+    if nbytes == 0:
+        raise ValueError('pointwise weights need K % 64 == 0, got %r' % (tuple(w.shape),))
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    _capi.check(lib.kgdet_pointwise_pack_weight(w.data_ptr(), packed.data_ptr(), nout, k, int(bool(split)),
+                                                _capi.stream_of(w)), 'kgdet_pointwise_pack_weight')
+    return packed, nout, k, bool(split)
+
+
+def nchw_to_tiled(x, relu=False, split=True):
+    """[N, C, H, W] fp32/bf16 -> TiledRows [N*H*W, C] (optional ReLU)."""
+    lib = _capi.lib()
+    _capi.require_cuda(x, 'nchw_to_tiled')
+    x = x.detach().contiguous()
+    n, c, h, w = x.shape
+    rows = TiledRows(n * h * w, c, split, x.device)
+    _capi.check(lib.kgdet_nchw_to_tiled_bf16(x.data_ptr(), rows.buf.data_ptr(), n, c, h * w, _capi.dtype_code(x),
+                                             int(bool(relu)), int(bool(split)), _capi.stream_of(x)),
+                'kgdet_nchw_to_tiled_bf16')
+    return rows
+
+
+def pointwise_conv(rows, packed_weight, bias, outputs, hw):
+    """One GEMM over ``rows`` (TiledRows [M, K]) with ``packed_weight`` (from ``pack_weight``, same ``split``).
+
+    outputs: list of (out NCHW fp32 tensor, residual or None, col_begin, col_end); the column ranges must tile
+    [0, Nout) in order.  Returns the list of output tensors."""
+    lib = _capi.lib()
+    packed, nout, k, split = packed_weight
+    assert isinstance(rows, TiledRows) and rows.K == k and rows.split == split, 'operands do not match'
+    segs = (_capi.PointwiseSegment * len(outputs))()
+    for i, (out, res, c0, c1) in enumerate(outputs):
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.shape[1] == c1 - c0
+        assert res is None or (res.dtype == torch.float32 and res.is_contiguous() and res.shape == out.shape)
+        segs[i].out = out.data_ptr()
+        segs[i].residual = None if res is None else res.data_ptr()
+        segs[i].col_begin, segs[i].col_end = c0, c1
+        segs[i].channels_total, segs[i].channel_offset = out.shape[1], 0
+    b = None if bias is None else bias.detach().float().contiguous()
+    _capi.check(lib.kgdet_pointwise_conv_tiled(rows.buf.data_ptr(), packed.data_ptr(), _capi.ptr(b), rows.M, k, nout,
+                                               hw, int(split), ctypes.cast(segs, ctypes.c_void_p), len(outputs),
+                                               _capi.stream_of(rows.buf)), 'kgdet_pointwise_conv_tiled')
+    return [o[0] for o in outputs]

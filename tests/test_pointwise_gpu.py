@@ -1,0 +1,106 @@
+"""GPU tests of the Kp3RepBlock pointwise stage: plan-from-points, the fused DCN
+kernel's UMMA-tiled bf16 output, the tcgen05 pointwise GEMM with its NCHW / bias / residual epilogue."""
+import pytest
+import torch
+
+from tests._data import dcn_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_nchw_to_tiled_is_a_relu_transpose():
+    from kgdet_b200 import ops
+    x = torch.randn(3, 128, 5, 9, generator=torch.Generator().manual_seed(0)).cuda()     # M = 135: ragged tile
+    for relu in (False, True):
+        want = (x.relu() if relu else x).permute(0, 2, 3, 1).reshape(-1, 128)
+        got = ops.nchw_to_tiled(x, relu=relu, split=False)
+        assert torch.equal(got.to_dense(), want.to(torch.bfloat16).float())
+        sp = ops.nchw_to_tiled(x, relu=relu, split=True)
+        assert rel_err(sp.to_dense(), want) < 2e-5                                      # hi + lo
+
+
+@pytest.mark.parametrize('split', [False, True])
+@pytest.mark.parametrize('n_hw,K,nouts', [((2, 35), 64, (13,)), ((3, 77), 768, (588, 166)), ((1, 300), 256, (7, 130, 9)),
+                                          ((2, 128), 128, (256, 300))])
+def test_pointwise_conv_matches_torch(n_hw, K, nouts, split):
+    """Plain mode: against fp32 torch on the same bf16-rounded operands (products exact in fp32, only the
+    summation order differs).  Split mode ("bf16x3"): against fp64 on the ORIGINAL fp32 operands.  Column
+    segments, bias, residual, ragged row / column tiles."""
+    from kgdet_b200 import ops
+    n, hw = n_hw
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, K, hw, 1, generator=g).cuda()
+    w = (torch.randn(sum(nouts), K, generator=g) / K ** 0.5).cuda()
+    bias = torch.randn(sum(nouts), generator=g).cuda()
+    rows = ops.nchw_to_tiled(x, split=split)
+    xr = x.permute(0, 2, 3, 1).reshape(-1, K)
+    if split:
+        ref = (xr.double() @ w.double().t() + bias.double())
+    else:
+        ref = xr.to(torch.bfloat16).float() @ w.to(torch.bfloat16).float().t() + bias
+    outs, c0 = [], 0
+    for i, no in enumerate(nouts):
+        res = torch.randn(n, no, hw, 1, generator=g).cuda() if i % 2 == 0 else None
+        outs.append((torch.empty(n, no, hw, 1, device='cuda'), res, c0, c0 + no))
+        c0 += no
+    ops.pointwise_conv(rows, ops.pack_weight(w, split=split), bias, outs, hw)
+    for out, res, a, b in outs:
+        want = ref[:, a:b].reshape(n, hw, b - a).permute(0, 2, 1).reshape(n, b - a, hw, 1)
+        if res is not None:
+            want = want + res
+        assert rel_err(out, want) < 2e-5
+    with pytest.raises(RuntimeError):           # segments must tile [0, Nout)
+        ops.pointwise_conv(rows, ops.pack_weight(w, split=split), bias, [(outs[0][0], None, 1, 1 + nouts[0])], hw)
+
+
+def test_plain_bf16_pointwise_is_only_bf16_grade():
+    """What the split buys: the single-pass bf16 GEMM of fp32 operands is ~2e-3 off, the split one 1e-5."""
+    from kgdet_b200 import ops
+    n, hw, K, no = 2, 130, 768, 200
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, K, hw, 1, generator=g).cuda()
+    w = (torch.randn(no, K, generator=g) / K ** 0.5).cuda()
+    ref = torch.nn.functional.conv2d(x.double(), w.double().view(no, K, 1, 1))
+    errs = {}
+    for split in (False, True):
+        out = torch.empty(n, no, hw, 1, device='cuda')
+        ops.pointwise_conv(ops.nchw_to_tiled(x, split=split), ops.pack_weight(w, split=split), None,
+                           [(out, None, 0, no)], hw)
+        errs[split] = rel_err(out, ref)
+    assert errs[True] < 2e-5 and 1e-4 < errs[False] < 1e-2, errs
+
+
+@pytest.mark.parametrize('k', [3, 5])
+def test_plan_from_points_and_tiled_output(k):
+    """prepare_plan_points(points, lo) == prepare_plan(points[:, lo:lo+2K] - base) bit for bit, and the tiled
+    bf16 output equals the NCHW fp32 output rounded to bf16 (split: hi + lo reproduces it to 2^-17)."""
+    from kgdet_b200 import ops
+    d = dcn_case(N=2, C=128, H=9, W=11, Cout=128, k=k, seed=5)
+    x, w = d['x'].cuda(), d['weight'].cuda()
+    K = k * k
+    g = torch.Generator().manual_seed(2)
+    pts = (torch.randn(2, 10 + 2 * K + 6, 9, 11, generator=g) * 2).cuda()
+    lo = 10
+    base = torch.arange(-(k // 2), k // 2 + 1, dtype=torch.float32)
+    yx = torch.stack([base.repeat_interleave(k), base.repeat(k)], 1).reshape(1, -1, 1, 1).cuda()
+    ops.set_precision('bf16')
+    try:
+        pin = ops.prepare_input(x, 128, k, 1, k // 2, 1)
+        p_ref = ops.prepare_plan(pts[:, lo:lo + 2 * K] - yx, x.shape, 128, k, 1, k // 2, 1)
+        p_pts = ops.prepare_plan_points(pts, lo, x.shape, 128, k, 1, k // 2, 1)
+        assert torch.equal(p_ref.buf, p_pts.buf)
+        nchw = ops.deform_conv_prepared(pin, p_pts, w, relu=True)
+        rows = ops.TiledRows(2 * 9 * 11, 256, False, 'cuda')
+        rows.buf.zero_()
+        ops.deform_conv_prepared(pin, p_pts, w, rows, 128, True)
+        srows = ops.TiledRows(2 * 9 * 11, 256, True, 'cuda')
+        srows.buf.zero_()
+        ops.deform_conv_prepared(pin, p_pts, w, srows, 128, True)
+    finally:
+        ops.set_precision(None)
+    full = nchw.permute(0, 2, 3, 1).reshape(-1, 128)
+    dense = rows.to_dense()
+    assert torch.equal(dense[:, 128:], full.to(torch.bfloat16).float())
+    assert not dense[:, :128].any()                                   # only the requested channel slice is written
+    sdense = srows.to_dense()
+    assert rel_err(sdense[:, 128:], full) < 2e-5 and not sdense[:, :128].any()
