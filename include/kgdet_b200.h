@@ -103,6 +103,9 @@ KGDET_API int kgdet_dcn_forward(const void* input, const float* offset, const fl
 KGDET_API size_t kgdet_dcn_prepared_input_bytes(const kgdet_dcn_shape* shape, int precision);
 KGDET_API int kgdet_dcn_prepare_input(const void* input, void* prepared_input, const kgdet_dcn_shape* shape,
                             int dtype, int precision, void* stream);
+/* same from position-major fp32 rows [N*H*W, C] (a channels_last activation): no transpose */
+KGDET_API int kgdet_dcn_prepare_input_rows(const float* rows, void* prepared_input, const kgdet_dcn_shape* shape,
+                                 int precision, void* stream);
 KGDET_API size_t kgdet_dcn_plan_bytes(const kgdet_dcn_shape* shape, int precision);
 KGDET_API int kgdet_dcn_prepare_plan(const float* offset, const float* mask, void* plan,
                            const kgdet_dcn_shape* shape, int precision, void* stream);
@@ -146,9 +149,20 @@ KGDET_API int kgdet_pointwise_pack_weight(const float* weight, void* packed, int
  * (stage-1 activations after a cuDNN convolution).  C % 64 == 0. */
 KGDET_API int kgdet_nchw_to_tiled_bf16(const void* src, void* dst, int32_t N, int32_t C, int32_t S, int src_dtype,
                              int fuse_relu, int split, void* stream);
+/* position-major fp32 rows [M, C] (channels_last activation) -> the same tiled rows */
+KGDET_API int kgdet_rows_to_tiled_bf16(const float* rows, void* tiled, int64_t M, int32_t C, int fuse_relu, int split,
+                             void* stream);
 KGDET_API int kgdet_pointwise_conv_tiled(const void* a_tiled, const void* w_packed, const float* bias, int32_t M,
                                int32_t K, int32_t Nout, int32_t HW, int split,
                                const kgdet_pointwise_segment* segs, int32_t nseg, void* stream);
+
+/* ---- head towers in channels_last --------------------------------------
+ * GroupNorm (+ ReLU) of ConvModule (mmdet/models/utils/conv_module.py:156-164) on position-major fp32
+ * [N, HW, C]: torch.nn.GroupNorm semantics (biased variance, eps inside the square root).  The towers'
+ * 3x3 convolutions stay cuDNN and run in channels_last, so no NCHW<->NHWC transposes remain. */
+KGDET_API int kgdet_groupnorm_relu_nhwc(const float* x, const float* gamma, const float* beta, float eps,
+                              int32_t groups, int fuse_relu, float* y, int32_t N, int32_t HW, int32_t C,
+                              void* stream);
 
 /* replaces deform_conv_backward_input_cuda     dcn/src/deform_conv_cuda.cpp:260-371
  *          (+ the input/offset/mask part of modulated_deform_conv_cuda_backward :566-679)

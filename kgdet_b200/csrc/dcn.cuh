@@ -61,6 +61,10 @@ int launch_transpose(const void* src, void* dst, int B, int R, int Cc, int src_d
 int launch_nchw_to_blocked(const void* src, void* dst, int N, int C, int S, int bk, size_t plane_bytes,
                            int src_dtype, int dst_dtype, cudaStream_t stream);
 
+// rows [M, C] fp32 (position-major) -> the same planes (tower_nhwc.cu)
+int launch_rows_to_blocked(const float* rows, void* dst, long long M, int C, int bk, size_t plane_bytes, int dst_dtype,
+                           cudaStream_t stream);
+
 // Where and how a forward kernel writes its result: channel slice [coff, coff + Cout) of an NCHW tensor
 // with `ctot` channels, optional fused ReLU.
 struct OutSpec {

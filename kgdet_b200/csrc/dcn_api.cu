@@ -71,6 +71,21 @@ int do_prepare_input(const DcnGeom& g, const void* input, void* prepared, int dt
                                 p.cdtype, stream);
 }
 
+// same, from a position-major fp32 source (channels_last activations): no transpose, one 16-byte chunk per thread
+int do_prepare_input_rows(const DcnGeom& g, const float* rows, void* prepared, int precision, cudaStream_t stream) {
+  const PrepIn p = prep_in_layout(g, precision);
+  char* base = (char*)prepared;
+  if (!p.guard_bytes) {
+    KG_CUDA(cudaMemcpyAsync(base, rows, p.in_bytes, cudaMemcpyDeviceToDevice, stream));   // SIMT path reads NHWC fp32
+    return KGDET_OK;
+  }
+  KG_CUDA(cudaMemset2DAsync(base, p.plane_bytes, 0, p.guard_bytes, p.planes, stream));
+  KG_CUDA(cudaMemset2DAsync(base + p.guard_bytes + p.in_bytes, p.plane_bytes, 0,
+                            p.plane_bytes - p.guard_bytes - p.in_bytes, p.planes, stream));
+  return launch_rows_to_blocked(rows, base + p.guard_bytes, (long long)g.N * g.H * g.W, g.C, p.bk, p.plane_bytes,
+                                p.cdtype, stream);
+}
+
 int do_prepare_plan(const DcnGeom& g, const float* offset, const float* mask, void* plan, int precision,
                     cudaStream_t stream) {
   if (use_umma(g, precision))
@@ -202,6 +217,17 @@ extern "C" int kgdet_dcn_prepare_input(const void* input, void* prepared_input, 
   KG_CHECK_ARG(input && prepared_input, "kgdet_dcn_prepare_input: NULL pointer");
   KG_CHECK_ARG(((uintptr_t)prepared_input & 255) == 0, "kgdet_dcn_prepare_input: buffer must be 256-byte aligned");
   return do_prepare_input(g, input, prepared_input, dtype, precision, (cudaStream_t)stream);
+}
+
+extern "C" int kgdet_dcn_prepare_input_rows(const float* rows, void* prepared_input, const kgdet_dcn_shape* shape,
+                                            int precision, void* stream) {
+  DcnGeom g;
+  int rc = make_geom(shape, &g);
+  if (rc != KGDET_OK) return rc;
+  KG_CHECK_ARG(valid_prec(precision), "kgdet_dcn_prepare_input_rows: bad precision");
+  KG_CHECK_ARG(rows && prepared_input, "kgdet_dcn_prepare_input_rows: NULL pointer");
+  KG_CHECK_ARG(((uintptr_t)prepared_input & 255) == 0, "kgdet_dcn_prepare_input_rows: buffer must be 256-byte aligned");
+  return do_prepare_input_rows(g, rows, prepared_input, precision, (cudaStream_t)stream);
 }
 
 extern "C" size_t kgdet_dcn_plan_bytes(const kgdet_dcn_shape* shape, int precision) {

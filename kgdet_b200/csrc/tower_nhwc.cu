@@ -1,0 +1,180 @@
+// Position-major (NHWC) glue of the head towers: the towers' 3x3 convolutions
+// stay cuDNN but run in channels_last, where they need no layout transposes; what this file adds is
+//   * GroupNorm + ReLU fused, on NHWC fp32 (mmdet ConvModule order conv -> norm -> activation,
+//     mmdet/models/utils/conv_module.py:156-164; torch.nn.GroupNorm semantics: biased variance, eps inside the
+//     square root),
+//   * NHWC fp32 rows -> the channel-blocked bf16/fp32 planes the fused DCN kernel gathers from,
+//   * NHWC fp32 rows -> UMMA-tiled bf16 rows (optionally ReLU, optionally [hi | lo]) for the pointwise GEMM.
+#include <cuda_bf16.h>
+
+#include "dcn.cuh"
+
+namespace kgdet {
+
+// one CTA per (image, group); the group's HW x cpg values are staged in shared memory, so the input is read
+// once: mean, then sum of squared deviations (no E[x^2] - mean^2 cancellation), then normalise + ReLU
+__global__ void __launch_bounds__(256) groupnorm_relu_nhwc_kernel(const float* __restrict__ x,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float eps,
+                                                                  float* __restrict__ y, int HW, int C, int cpg,
+                                                                  int relu) {
+  extern __shared__ float sm[];                 // [HW * cpg] + 32 reduction slots
+  float* red = sm + (size_t)HW * cpg;
+  const int n = blockIdx.y, g = blockIdx.x;
+  const float* xg = x + (size_t)n * HW * C + (size_t)g * cpg;
+  float* yg = y + (size_t)n * HW * C + (size_t)g * cpg;
+  const int total = HW * cpg;
+  const int vec = cpg / 4;                      // cpg % 4 == 0: float4 per (pixel, quarter-group)
+  float s = 0.f;
+  for (int i = threadIdx.x; i < HW * vec; i += blockDim.x) {
+    const int p = i / vec, q = i - p * vec;
+    const float4 v = *reinterpret_cast<const float4*>(xg + (size_t)p * C + q * 4);
+    *reinterpret_cast<float4*>(sm + (size_t)p * cpg + q * 4) = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  auto block_sum = [&](float v) -> float {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    return t;
+  };
+  const float mean = block_sum(s) / (float)total;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const float d = sm[i] - mean;
+    ss = fmaf(d, d, ss);
+  }
+  const float var = block_sum(ss) / (float)total;
+  const float rstd = rsqrtf(var + eps);
+  for (int i = threadIdx.x; i < HW * vec; i += blockDim.x) {
+    const int p = i / vec, q = i - p * vec;
+    const float4 v = *reinterpret_cast<const float4*>(sm + (size_t)p * cpg + q * 4);
+    const int c = g * cpg + q * 4;
+    float4 o;
+    o.x = (v.x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    o.y = (v.y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+    o.z = (v.z - mean) * rstd * __ldg(gamma + c + 2) + __ldg(beta + c + 2);
+    o.w = (v.w - mean) * rstd * __ldg(gamma + c + 3) + __ldg(beta + c + 3);
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    *reinterpret_cast<float4*>(yg + (size_t)p * C + q * 4) = o;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// rows [M, C] fp32 -> channel-blocked planes [C / bk][pixels][bk] in bf16 (bk = 64) or fp32 (bk = 32):
+// one thread per 16-byte output chunk
+template <typename Tout>
+__global__ void rows_to_blocked_kernel(const float* __restrict__ rows, unsigned char* __restrict__ dst, long long M,
+                                       int C, size_t plane_bytes) {
+  constexpr int EPC = 16 / (int)sizeof(Tout);   // elements per chunk: 8 bf16 / 4 fp32
+  const int chunks_per_row = C / EPC;
+  const long long total = M * chunks_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)blockDim.x * gridDim.x) {
+    const long long m = i / chunks_per_row;
+    const int ch = (int)(i - m * chunks_per_row);
+    const float* src = rows + m * C + (size_t)ch * EPC;
+    const int plane = ch / 8, within = ch % 8;  // 8 chunks = 128 bytes per pixel slab
+    unsigned char* d = dst + (size_t)plane * plane_bytes + (size_t)m * 128 + within * 16;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    if constexpr (sizeof(Tout) == 2) {
+      const float4 b = *reinterpret_cast<const float4*>(src + 4);
+      uint4 o;
+      o.x = pack2_bf16(a.x, a.y); o.y = pack2_bf16(a.z, a.w); o.z = pack2_bf16(b.x, b.y); o.w = pack2_bf16(b.z, b.w);
+      *reinterpret_cast<uint4*>(d) = o;
+    } else {
+      *reinterpret_cast<float4*>(d) = a;
+    }
+  }
+}
+
+// rows [M, C] fp32 -> UMMA-tiled bf16 rows (pointwise_umma.cu), one thread per 8 channels
+__global__ void rows_to_tiled_kernel(const float* __restrict__ rows, unsigned char* __restrict__ dst, long long M,
+                                     int C, int relu, int split) {
+  const int chunks_per_row = C / 8;
+  const int a_kblocks = (split ? 2 : 1) * (C / 64);
+  const long long total = M * chunks_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)blockDim.x * gridDim.x) {
+    const long long m = i / chunks_per_row;
+    const int ch = (int)(i - m * chunks_per_row);
+    const float* src = rows + m * C + (size_t)ch * 8;
+    float v[8];
+    *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(src);
+    *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(src + 4);
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+    const int r = (int)(m & 127);
+    unsigned char* t = dst + (size_t)(m >> 7) * a_kblocks * (128 * 128) + (size_t)r * 128 + (((ch & 7) ^ (r & 7)) << 4);
+    uint4 hi;
+    hi.x = pack2_bf16(v[0], v[1]); hi.y = pack2_bf16(v[2], v[3]); hi.z = pack2_bf16(v[4], v[5]); hi.w = pack2_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(t + (size_t)(ch >> 3) * (128 * 128)) = hi;
+    if (split) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] -= __bfloat162float(__float2bfloat16(v[e]));
+      uint4 lo;
+      lo.x = pack2_bf16(v[0], v[1]); lo.y = pack2_bf16(v[2], v[3]); lo.z = pack2_bf16(v[4], v[5]); lo.w = pack2_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(t + (size_t)((C / 64) + (ch >> 3)) * (128 * 128)) = lo;
+    }
+  }
+}
+
+static int grid_for(long long total) {
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+}
+
+int launch_rows_to_blocked(const float* rows, void* dst, long long M, int C, int bk, size_t plane_bytes, int dst_dtype,
+                           cudaStream_t stream) {
+  KG_CHECK_ARG((dst_dtype == KGDET_BF16 && bk == 64) || (dst_dtype == KGDET_F32 && bk == 32),
+               "rows_to_blocked: channel block %d does not match dtype %d", bk, dst_dtype);
+  KG_CHECK_ARG(C % bk == 0, "rows_to_blocked: C %% %d != 0", bk);
+  if (M <= 0) return KGDET_OK;
+  if (dst_dtype == KGDET_BF16)
+    rows_to_blocked_kernel<__nv_bfloat16><<<grid_for(M * (C / 8)), 256, 0, stream>>>(rows, (unsigned char*)dst, M, C, plane_bytes);
+  else
+    rows_to_blocked_kernel<float><<<grid_for(M * (C / 4)), 256, 0, stream>>>(rows, (unsigned char*)dst, M, C, plane_bytes);
+  KG_LAUNCH_CHECK("rows_to_blocked_kernel");
+  return KGDET_OK;
+}
+
+}  // namespace kgdet
+
+using namespace kgdet;
+
+extern "C" int kgdet_groupnorm_relu_nhwc(const float* x, const float* gamma, const float* beta, float eps,
+                                         int32_t groups, int fuse_relu, float* y, int32_t N, int32_t HW, int32_t C,
+                                         void* stream) {
+  KG_CHECK_ARG(x && gamma && beta && y, "kgdet_groupnorm_relu_nhwc: NULL pointer");
+  KG_CHECK_ARG(N >= 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0,
+               "kgdet_groupnorm_relu_nhwc: need C %% groups == 0 and (C / groups) %% 4 == 0");
+  if (N == 0) return KGDET_OK;
+  const int cpg = C / groups;
+  const size_t smem = ((size_t)HW * cpg + 32) * sizeof(float);
+  KG_CHECK_ARG(smem <= 200 * 1024, "kgdet_groupnorm_relu_nhwc: group of %d x %d values does not fit shared memory", HW, cpg);
+  KG_CHECK_ARG(N <= 65535, "kgdet_groupnorm_relu_nhwc: batch too large");
+  KG_CUDA(cudaFuncSetAttribute(groupnorm_relu_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  groupnorm_relu_nhwc_kernel<<<dim3(groups, N), 256, smem, (cudaStream_t)stream>>>(x, gamma, beta, eps, y, HW, C, cpg,
+                                                                                   fuse_relu ? 1 : 0);
+  KG_LAUNCH_CHECK("groupnorm_relu_nhwc_kernel");
+  return KGDET_OK;
+}
+
+extern "C" int kgdet_rows_to_tiled_bf16(const float* rows, void* tiled, int64_t M, int32_t C, int fuse_relu, int split,
+                                        void* stream) {
+  KG_CHECK_ARG(rows && tiled, "kgdet_rows_to_tiled_bf16: NULL pointer");
+  KG_CHECK_ARG(M >= 0 && C >= 64 && C % 64 == 0, "kgdet_rows_to_tiled_bf16: C %% 64 == 0 required");
+  if (M == 0) return KGDET_OK;
+  rows_to_tiled_kernel<<<grid_for(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>(rows, (unsigned char*)tiled, M, C,
+                                                                                fuse_relu ? 1 : 0, split ? 1 : 0);
+  KG_LAUNCH_CHECK("rows_to_tiled_kernel");
+  return KGDET_OK;
+}

@@ -27,9 +27,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import (DeformConv, TiledRows, batched_nms_flags, deform_conv_prepared, get_precision, nchw_to_tiled,
-                  pack_weight, points2bbox_moment, pointwise_conv, prepare_input, prepare_plan,
-                  prepare_plan_points)
+from .ops import (DeformConv, TiledRows, batched_nms_flags, deform_conv_prepared, get_precision,
+                  groupnorm_relu_nhwc, nchw_to_tiled, pack_weight, points2bbox_moment, pointwise_conv,
+                  prepare_input, prepare_plan, prepare_plan_points)
 from .ops.pointwise import cached
 
 _POINT_SETS = (3, 5, 7)          # KP3:257: 9 + 25 + 49 points regardless of cfg.num_reppts
@@ -52,6 +52,17 @@ def _normal(m, std=0.01, bias=0.0):
     nn.init.normal_(m.weight, 0, std)
     if getattr(m, 'bias', None) is not None:
         nn.init.constant_(m.bias, bias)
+
+
+def _cl_weight(w):
+    """channels_last copy of a convolution weight (cached per parameter version): cuDNN then runs the
+    convolution on channels_last activations without inserting layout transposes."""
+    return cached((w,), lambda: w.detach().contiguous(memory_format=torch.channels_last))
+
+
+def _conv3x3_nhwc(x_cl, conv):
+    b = None if conv.bias is None else conv.bias.detach()
+    return F.conv2d(x_cl, _cl_weight(conv.weight), b, conv.stride, conv.padding)
 
 
 def _pointwise_weights(block):
@@ -113,8 +124,8 @@ class _PlainBlock(nn.Module):
         """bf16 inference: the two 3x3 convolutions stay cuDNN; ReLU + layout change is one kernel each and the
         three 1x1 convolutions are two tensor-core GEMMs."""
         n, _, h, w = cls_feat.shape
-        cls_rows = nchw_to_tiled(self.cls_conv(cls_feat), relu=True, split=True)
-        kpt_rows = nchw_to_tiled(self.keypts_conv(pts_feat), relu=True, split=True)
+        cls_rows = nchw_to_tiled(_conv3x3_nhwc(cls_feat, self.cls_conv), relu=True, split=True)
+        kpt_rows = nchw_to_tiled(_conv3x3_nhwc(pts_feat, self.keypts_conv), relu=True, split=True)
         return _pointwise_heads(self, cls_rows, kpt_rows, n, h, w)
 
 
@@ -243,16 +254,16 @@ class KGDetHead(nn.Module):
         return self._moment_fn(pts, self.moment_transfer, self.moment_mul, y_first)
 
     def forward_single(self, x):
-        cls_feat = pts_feat = x
-        for m in self.cls_convs:
-            cls_feat = m(cls_feat)
-        for m in self.reg_convs:
-            pts_feat = m(pts_feat)
-        fused = self._fused_inference and not torch.is_grad_enabled() and cls_feat.is_cuda
-        if fused and self._tensor_core_heads and get_precision(cls_feat.dtype) == 'bf16' \
-                and cls_feat.dtype == torch.float32:
-            # bf16 mode: everything after the towers except the two plain 3x3 convolutions runs on this
-            # package's kernels
+        fused = self._fused_inference and not torch.is_grad_enabled() and x.is_cuda
+        if fused and self._tensor_core_heads and get_precision(x.dtype) == 'bf16' and x.dtype == torch.float32:
+            # bf16 mode: everything except the eight plain 3x3 convolutions (cuDNN, channels_last) runs on this
+            # package's kernels.  Towers: position-major activations end to end,
+            # GroupNorm + ReLU fused -- no layout transposes, no separate ReLU kernels.
+            cls_feat = pts_feat = x.contiguous(memory_format=torch.channels_last)
+            for m in self.cls_convs:
+                cls_feat = groupnorm_relu_nhwc(_conv3x3_nhwc(cls_feat, m.conv), m.gn)
+            for m in self.reg_convs:
+                pts_feat = groupnorm_relu_nhwc(_conv3x3_nhwc(pts_feat, m.conv), m.gn)
             feat = self.kp_rep_block_2.cls_dfmconv_3.out_channels
             cls1, kpt1, rep1 = self.kp_rep_block_1.forward_tc(cls_feat, pts_feat)
             bbox1 = self.points2bbox(rep1)
@@ -263,6 +274,11 @@ class KGDetHead(nn.Module):
             cls3, kpt3, rep3 = self.kp_rep_block_3.forward_tc(cls_prep, pts_prep, rep2, kpt2)
             bbox3 = self.points2bbox(rep3)
             return cls1, cls2, cls3, kpt1, kpt2, kpt3, bbox1, bbox2, bbox3
+        cls_feat = pts_feat = x
+        for m in self.cls_convs:
+            cls_feat = m(cls_feat)
+        for m in self.reg_convs:
+            pts_feat = m(pts_feat)
         cls1, kpt1, rep1 = self.kp_rep_block_1(cls_feat, pts_feat)
         bbox1 = self.points2bbox(rep1)
         if fused:

@@ -51,6 +51,7 @@ SIGNATURES = {
                                          ctypes.c_int, ctypes.c_int, c_ptr, c_sz, c_ptr]),
     'kgdet_dcn_prepared_input_bytes': (c_sz, [_SHAPE_P, ctypes.c_int]),
     'kgdet_dcn_prepare_input': (ctypes.c_int, [c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr]),
+    'kgdet_dcn_prepare_input_rows': (ctypes.c_int, [c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
     'kgdet_dcn_plan_bytes': (c_sz, [_SHAPE_P, ctypes.c_int]),
     'kgdet_dcn_prepare_plan': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
     'kgdet_dcn_prepare_plan_points': (ctypes.c_int, [c_ptr, c_i32, c_i32, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
@@ -61,6 +62,10 @@ SIGNATURES = {
     'kgdet_pointwise_pack_weight': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, ctypes.c_int, c_ptr]),
     'kgdet_nchw_to_tiled_bf16': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_int, c_ptr]),
+    'kgdet_rows_to_tiled_bf16': (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int64, c_i32, ctypes.c_int, ctypes.c_int,
+                                                c_ptr]),
+    'kgdet_groupnorm_relu_nhwc': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_f32, c_i32, ctypes.c_int, c_ptr, c_i32,
+                                                 c_i32, c_i32, c_ptr]),
     'kgdet_pointwise_conv_tiled': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, ctypes.c_int,
                                                   c_ptr, c_i32, c_ptr]),
     'kgdet_dcn_backward_input_workspace_bytes': (c_sz, [_SHAPE_P, ctypes.c_int, ctypes.c_int]),

@@ -232,7 +232,12 @@ def _geom_shape(n, c, h, w, cout, k, stride, padding, dilation):
 def prepare_input(x, out_channels, kernel_size=3, stride=1, padding=1, dilation=1, precision=None):
     lib = _capi.lib()
     _capi.require_cuda(x, 'prepare_input')
-    x = x.detach().contiguous()
+    x = x.detach()
+    # a channels_last fp32 activation is already position-major rows: no transpose kernel
+    rows_src = (x.dim() == 4 and x.dtype == torch.float32 and not x.is_contiguous()
+                and x.is_contiguous(memory_format=torch.channels_last))
+    if not rows_src:
+        x = x.contiguous()
     prec_name = precision or get_precision(x.dtype)
     prec = _capi.PRECISIONS[prec_name]
     shape = _geom_shape(*x.shape, out_channels, _pair(kernel_size), _pair(stride), _pair(padding), _pair(dilation))
@@ -244,8 +249,12 @@ def prepare_input(x, out_channels, kernel_size=3, stride=1, padding=1, dilation=
     p.fast = bool(lib.kgdet_dcn_fast_path_supported(ctypes_ref(shape), prec))
     p.buf = torch.empty(int(lib.kgdet_dcn_prepared_input_bytes(ctypes_ref(shape), prec)), dtype=torch.uint8,
                         device=x.device)
-    _capi.check(lib.kgdet_dcn_prepare_input(x.data_ptr(), p.buf.data_ptr(), ctypes_ref(shape), p.dtype_code, prec,
-                                            _capi.stream_of(x)), 'kgdet_dcn_prepare_input')
+    if rows_src:
+        _capi.check(lib.kgdet_dcn_prepare_input_rows(x.data_ptr(), p.buf.data_ptr(), ctypes_ref(shape), prec,
+                                                     _capi.stream_of(x)), 'kgdet_dcn_prepare_input_rows')
+    else:
+        _capi.check(lib.kgdet_dcn_prepare_input(x.data_ptr(), p.buf.data_ptr(), ctypes_ref(shape), p.dtype_code, prec,
+                                                _capi.stream_of(x)), 'kgdet_dcn_prepare_input')
     return p
 
 

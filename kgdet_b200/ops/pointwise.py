@@ -74,13 +74,34 @@ def nchw_to_tiled(x, relu=False, split=True):
     """[N, C, H, W] fp32/bf16 -> TiledRows [N*H*W, C] (optional ReLU)."""
     lib = _capi.lib()
     _capi.require_cuda(x, 'nchw_to_tiled')
-    x = x.detach().contiguous()
+    x = x.detach()
     n, c, h, w = x.shape
     rows = TiledRows(n * h * w, c, split, x.device)
+    if x.dtype == torch.float32 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last):
+        # channels_last source: already position-major rows, no transpose
+        _capi.check(lib.kgdet_rows_to_tiled_bf16(x.data_ptr(), rows.buf.data_ptr(), n * h * w, c, int(bool(relu)),
+                                                 int(bool(split)), _capi.stream_of(x)), 'kgdet_rows_to_tiled_bf16')
+        return rows
+    x = x.contiguous()
     _capi.check(lib.kgdet_nchw_to_tiled_bf16(x.data_ptr(), rows.buf.data_ptr(), n, c, h * w, _capi.dtype_code(x),
                                              int(bool(relu)), int(bool(split)), _capi.stream_of(x)),
                 'kgdet_nchw_to_tiled_bf16')
     return rows
+
+
+def groupnorm_relu_nhwc(x, gn, relu=True):
+    """GroupNorm (+ ReLU) of a channels_last fp32 activation in one kernel; returns a channels_last tensor.
+    `gn` is the torch.nn.GroupNorm module (same parameters and semantics)."""
+    lib = _capi.lib()
+    _capi.require_cuda(x, 'groupnorm_relu_nhwc')
+    assert x.dim() == 4 and x.dtype == torch.float32 and x.is_contiguous(memory_format=torch.channels_last)
+    n, c, h, w = x.shape
+    y = torch.empty_like(x, memory_format=torch.channels_last)
+    _capi.check(lib.kgdet_groupnorm_relu_nhwc(x.data_ptr(), gn.weight.detach().float().contiguous().data_ptr(),
+                                              gn.bias.detach().float().contiguous().data_ptr(), float(gn.eps),
+                                              int(gn.num_groups), int(bool(relu)), y.data_ptr(), n, h * w, c,
+                                              _capi.stream_of(x)), 'kgdet_groupnorm_relu_nhwc')
+    return y
 
 
 def pointwise_conv(rows, packed_weight, bias, outputs, hw):

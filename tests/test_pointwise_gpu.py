@@ -104,3 +104,36 @@ def test_plan_from_points_and_tiled_output(k):
     assert not dense[:, :128].any()                                   # only the requested channel slice is written
     sdense = srows.to_dense()
     assert rel_err(sdense[:, 128:], full) < 2e-5 and not sdense[:, :128].any()
+
+
+def test_groupnorm_relu_nhwc_matches_torch():
+    """GroupNorm(32) + ReLU of the towers (conv_module.py:156-164) on channels_last activations, incl. a
+    single-pixel-row map and non-trivial affine parameters."""
+    from kgdet_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    gn = torch.nn.GroupNorm(32, 256).cuda()
+    with torch.no_grad():
+        gn.weight.copy_(1 + 0.3 * torch.randn(256, generator=g))
+        gn.bias.copy_(0.2 * torch.randn(256, generator=g))
+    for shape in [(2, 256, 25, 42), (3, 256, 1, 5), (1, 256, 7, 11)]:
+        x = (torch.randn(*shape, generator=g) * 3 + 1).cuda().contiguous(memory_format=torch.channels_last)
+        for relu in (True, False):
+            got = ops.groupnorm_relu_nhwc(x, gn, relu=relu)
+            want = torch.nn.functional.group_norm(x.double(), 32, gn.weight.double(), gn.bias.double(), gn.eps)
+            want = want.relu() if relu else want
+            assert got.is_contiguous(memory_format=torch.channels_last)
+            assert rel_err(got, want) < 2e-6
+
+
+def test_channels_last_sources_need_no_transpose():
+    """prepare_input / nchw_to_tiled from a channels_last activation give the same buffers as from NCHW."""
+    from kgdet_b200 import ops
+    x = torch.randn(2, 128, 9, 11, generator=torch.Generator().manual_seed(8)).cuda()
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    for prec in ('bf16', 'tf32'):
+        a = ops.prepare_input(x, 128, 3, 1, 1, 1, precision=prec)
+        b = ops.prepare_input(xcl, 128, 3, 1, 1, 1, precision=prec)
+        assert torch.equal(a.buf, b.buf)
+    for split in (False, True):
+        assert torch.equal(ops.nchw_to_tiled(x, relu=True, split=split).to_dense(),
+                           ops.nchw_to_tiled(xcl, relu=True, split=split).to_dense())
