@@ -143,6 +143,11 @@ def run_ours(args):
     from kgdet_b200 import head as head_mod
     real_prepared = head_mod.deform_conv_prepared
 
+    def set_concurrent(on):
+        for m in head.modules():
+            if hasattr(m, 'concurrent_dcn'):
+                m.concurrent_dcn = on
+
     def timed_prepared(pin, plan, weight, *a, **k):
         if recording['on']:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -200,6 +205,7 @@ def run_ours(args):
     # ---- the fused DCN kernel alone: same K steps run eagerly with the C-ABI event hook armed around every
     #      launch (a CUDA graph cannot carry timing events; the kernels and their inputs are identical) ----
     recording['on'] = True
+    set_concurrent(False)        # one DCN at a time, so that each kernel's event pair times that kernel alone
     eager_evs = []
     for _ in range(args.steps):
         flush.fill_(1)
@@ -210,6 +216,7 @@ def run_ours(args):
         eager_evs.append((a, b))
     torch.cuda.synchronize()
     recording['on'] = False
+    set_concurrent(True)
     eager_ms = sum(a.elapsed_time(b) for a, b in eager_evs)
 
     # ---- end-to-end through the public API with host buffers ("e2e") -----------------------------
@@ -239,6 +246,10 @@ def run_ours(args):
         eager_step(x_dev)
     cpu_ms = (time.perf_counter() - c0) / 5 * 1e3
     torch.cuda.synchronize()
+    from kgdet_b200.ops import _capi as _kcapi
+    l0 = _kcapi.lib().kgdet_launch_count()
+    eager_step(x_dev)
+    launches_per_step = int(_kcapi.lib().kgdet_launch_count() - l0)    # kernels of libkgdet_b200.so in one step
     log('[bench] rank %d: device %.3f ms/step, e2e %.3f ms/step (per-iter %s), host launch (eager) %.3f ms/step'
         % (rank, dev_ms / args.steps, e2e_ms / args.steps, ['%.2f' % v for v in e2e_evs[:6]], cpu_ms))
     h2d = x_host.numel() * x_host.element_size()
@@ -273,13 +284,16 @@ def run_ours(args):
             'e2e': {'value': round(args.batch * world * args.steps / (e2e_ms * 1e-3), 2), 'unit': UNIT,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': round(e2e_ms / args.steps, 4)},
-            'gpu_launches': 24 * args.steps,
-            'gpu_launches_note': 'per step: 2 NCHW->channel-blocked copies + 6 sample plans + 12 fused tcgen05 DCN (ReLU + concat in the epilogue) + 3 moment + 1 batched NMS',
+            'gpu_launches': launches_per_step * args.steps,
+            'gpu_launches_note': '%d kernels of libkgdet_b200.so per step, counted by the library (kgdet_launch_count): '
+                                 '6 GroupNorm+ReLU, 2 rows->DCN planes, 2 rows->GEMM tiles, 6 sample plans, 12 fused '
+                                 'tcgen05 DCN, 6 pointwise tcgen05 GEMMs, 3 moment, 1 batched NMS; the 8 plain 3x3 '
+                                 'convolutions are cuDNN' % launches_per_step,
             'roofline': {'kernel': 'dcn_umma_stream_kernel (fused bilinear gather + tcgen05 GEMM), 12 launches/step',
                          'bound': 'tensor', 'achieved': round(achieved, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': round(achieved / peak_tf, 4), 'traffic': None, 'peak_source': peak_src,
                          'share_of_step': round(tot_ms / dev_ms, 4), 'per_kernel_size': detail,
-                         'timed_in': 'eager pass of the same K steps with CUDA events around each launch (C-ABI hook); '
+                         'timed_in': 'eager pass of the same K steps, DCN launches serialised, with CUDA events around each launch (C-ABI hook); '
                                      'share_of_step = those kernel times / graph-replayed step time'},
             'launch_mode': 'cuda_graph' if graphed is not None else 'eager',
             'eager_ms_per_step': round(eager_ms / args.steps, 4),

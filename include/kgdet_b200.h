@@ -75,6 +75,9 @@ typedef struct kgdet_dcn_shape {
 
 KGDET_API const char* kgdet_last_error(void);
 KGDET_API int kgdet_abi_version(void);
+/* number of kernels this library has launched in this process (a launch inside a CUDA-graph capture counts
+ * once, at capture) -- bench.py reports it as gpu_launches */
+KGDET_API uint64_t kgdet_launch_count(void);
 /* 1 when the fused tcgen05 path supports (shape, precision); 0 -> the exact SIMT path runs */
 KGDET_API int kgdet_dcn_fast_path_supported(const kgdet_dcn_shape* shape, int precision);
 
@@ -123,6 +126,27 @@ KGDET_API int kgdet_dcn_forward_prepared(const void* prepared_input, const void*
                                const float* bias, void* output, int32_t out_channel_offset,
                                int32_t out_channels_total, int fuse_relu, int out_layout,
                                const kgdet_dcn_shape* shape, int dtype, int precision, void* stream);
+
+/* ---- post-head decode around the batched NMS --------------------------
+ * replaces the PyTorch glue of get_bboxes_single (KP3:843-903) and multiclass_nms_kp
+ * (core/post_processing/bbox_nms_kp.py:6-75) for ONE head level, batched over images, static shapes:
+ *   select   order[b, r] = position of the r-th largest max-over-classes score (topk(nms_pre), KP3:863-874;
+ *            ties by ascending position; identity when n == HW).  scores: [B, C, HW] logits
+ *            (apply_sigmoid = 1) or probabilities.
+ *   decode   boxes [B, n, 4] = clamp(bbox * stride + centre) (KP3:875-886) and the dense NMS input
+ *            dets [B, C, n, 5] for kgdet_nms_batched (one segment per (image, class)).  img_wh: [B, 2].
+ *   finalize for top_i [B, k] (= class * n + candidate, from a top-k over the NMS-masked scores, top_s <= 0 =
+ *            empty slot): out_dets [B, k, 5], out_labels [B, k] (-1 = empty), out_kpts [B, k, num_keypts * 3]
+ *            = (x, y, 1) decoded from keypts [B, 2 * num_keypts, HW] (y-first pairs) only for the survivors. */
+KGDET_API int kgdet_bbox_select(const float* scores, int apply_sigmoid, int32_t B, int32_t C, int32_t HW, int32_t n,
+                      int32_t* order, void* stream);
+KGDET_API int kgdet_bbox_decode(const float* scores, int apply_sigmoid, const float* bbox, const int32_t* order,
+                      const float* img_wh, float stride, int32_t map_w, int32_t B, int32_t C, int32_t HW,
+                      int32_t n, float* boxes, float* dets, void* stream);
+KGDET_API int kgdet_bbox_finalize(const float* boxes, const float* keypts, const int32_t* order, const int64_t* top_i,
+                        const float* top_s, const float* img_wh, float stride, int32_t map_w, int32_t B,
+                        int32_t HW, int32_t n, int32_t k, int32_t num_keypts, float* out_dets,
+                        int64_t* out_labels, float* out_kpts, void* stream);
 
 /* ---- pointwise convolutions of the Kp3RepBlock ------------------------
  * replaces  cls_out / keypts_out / reppts_out 1x1 nn.Conv2d + the cascade's residual adds

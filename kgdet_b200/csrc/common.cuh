@@ -12,6 +12,7 @@ namespace kgdet {
 // ---- error plumbing -------------------------------------------------------
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void note_launch();   // every kernel this library launches is counted (kgdet_launch_count)
 
 #define KG_CHECK_ARG(cond, ...)                      \
   do {                                               \
@@ -31,6 +32,7 @@ int cuda_fail(cudaError_t e, const char* what);
   do {                                                                \
     cudaError_t _e = cudaGetLastError();                              \
     if (_e != cudaSuccess) return ::kgdet::cuda_fail(_e, name);       \
+    ::kgdet::note_launch();                                           \
   } while (0)
 
 __host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -1,0 +1,162 @@
+// Post-head decode around the batched NMS: the candidate selection, box /
+// keypoint decode, clamp and result gather of get_bboxes_single + multiclass_nms_kp
+// (reppoints_head_kp3rep_cas_1_assign_once.py:843-903, core/post_processing/bbox_nms_kp.py:6-75) as three
+// kernels with static shapes and no host synchronisation.  The reference does this with ~40 PyTorch kernels
+// per image and gathers the 588-value keypoint vector of every one of the nms_pre candidates; here keypoints
+// are decoded only for the max_per_img detections that survive.
+//
+// Arithmetic mirrors the PyTorch expressions operation by operation (separate mul / add roundings, no FMA
+// contraction) so that boxes and scores are bit-identical to the reference path and NMS sees identical inputs.
+#include "common.cuh"
+
+namespace kgdet {
+
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }   // ATen sigmoid
+
+// ---- 1. candidate selection: order[b, r] = position with the r-th largest max-over-classes score -------------
+// (KP3:863-874: max_scores.topk(nms_pre); ties broken by ascending position).  Rank by counting: O(HW^2) per
+// image, fine for the <= 4096 positions of a head level; order is ascending identity when HW <= nms_pre.
+__global__ void __launch_bounds__(256) bbox_select_kernel(const float* __restrict__ scores, int apply_sigmoid, int C,
+                                                          int HW, int n, int* __restrict__ order) {
+  extern __shared__ float smax[];               // [HW]
+  const int b = blockIdx.y;
+  const float* sb = scores + (size_t)b * C * HW;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      float v = sb[(size_t)c * HW + p];
+      if (apply_sigmoid) v = sigmoid_ref(v);
+      m = fmaxf(m, v);
+    }
+    smax[p] = m;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  if (n >= HW) {                                // no top-k in the reference: original order
+    order[(size_t)b * n + p] = p;
+    return;
+  }
+  const float mine = smax[p];
+  int rank = 0;
+  for (int j = 0; j < HW; ++j) {
+    const float o = smax[j];
+    rank += (o > mine || (o == mine && j < p)) ? 1 : 0;
+  }
+  if (rank < n) order[(size_t)b * n + rank] = p;
+}
+
+// ---- 2. decode the candidates: boxes [B, n, 4] and the dense NMS input dets [B, C, n, 5] ---------------------
+__global__ void bbox_decode_kernel(const float* __restrict__ scores, int apply_sigmoid, const float* __restrict__ bbox,
+                                   const int* __restrict__ order, const float* __restrict__ lim /*[B,2]: w,h*/,
+                                   float stride, int Wmap, int C, int HW, int n, float* __restrict__ boxes,
+                                   float* __restrict__ dets) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int p = order[(size_t)b * n + r];
+  const float cx = (float)(p % Wmap) * stride, cy = (float)(p / Wmap) * stride;      // point_generator.py:14-23
+  const float w = lim[b * 2], h = lim[b * 2 + 1];
+  const float* bb = bbox + (size_t)b * 4 * HW + p;
+  float box[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float v = __fadd_rn(__fmul_rn(bb[(size_t)i * HW], stride), (i & 1) ? cy : cx);   // KP3:875-877
+    box[i] = fminf(fmaxf(v, 0.f), (i & 1) ? h : w);                                        // KP3:882-886
+  }
+  *reinterpret_cast<float4*>(boxes + ((size_t)b * n + r) * 4) = make_float4(box[0], box[1], box[2], box[3]);
+  const float* sb = scores + (size_t)b * C * HW + p;
+  for (int c = 0; c < C; ++c) {
+    float s = sb[(size_t)c * HW];
+    if (apply_sigmoid) s = sigmoid_ref(s);
+    float* d = dets + (((size_t)b * C + c) * n + r) * 5;
+    d[0] = box[0]; d[1] = box[1]; d[2] = box[2]; d[3] = box[3]; d[4] = s;
+  }
+}
+
+// ---- 3. results: for the k best surviving (class, candidate) pairs of every image ---------------------------
+// top_i[b, j] = class * n + candidate (bbox_nms_kp.py:64-70 order), top_s its score (<= 0: empty slot).
+// out_dets [B, k, 5], out_labels [B, k] (-1 = empty), out_kpts [B, k, P*3] = (x, y, 1) decoded and clamped
+// (points2kpt KP3:393-410, decode KP3:878-880,887-888, visibility KP3:856-861); one warp per detection.
+__global__ void bbox_finalize_kernel(const float* __restrict__ boxes, const float* __restrict__ kp,
+                                     const int* __restrict__ order, const long long* __restrict__ top_i,
+                                     const float* __restrict__ top_s, const float* __restrict__ lim, float stride,
+                                     int Wmap, int HW, int n, int k, int P, float* __restrict__ out_dets,
+                                     long long* __restrict__ out_labels, float* __restrict__ out_kpts) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= k) return;
+  const long long ti = top_i[(size_t)b * k + j];
+  const float s = top_s[(size_t)b * k + j];
+  const bool valid = s > 0.f;
+  const int r = (int)(ti % n), cls = (int)(ti / n);
+  float* od = out_dets + ((size_t)b * k + j) * 5;
+  float* ok = out_kpts + ((size_t)b * k + j) * P * 3;
+  if (lane < 5) {
+    // the reference path multiplies by the validity flag: an empty slot reads 0 (or -0 for the -1 filler score)
+    const float v = lane < 4 ? boxes[((size_t)b * n + r) * 4 + lane] : s;
+    od[lane] = valid ? v : __fmul_rn(v, 0.f);
+  }
+  if (lane == 0) out_labels[(size_t)b * k + j] = valid ? (long long)cls : -1ll;
+  const int p = order[(size_t)b * n + r];
+  const float cx = (float)(p % Wmap) * stride, cy = (float)(p / Wmap) * stride;
+  const float w = lim[b * 2], h = lim[b * 2 + 1];
+  const float* kb = kp + (size_t)b * 2 * P * HW + p;
+  for (int i = lane; i < P; i += 32) {
+    const float y = kb[(size_t)(2 * i) * HW], x = kb[(size_t)(2 * i + 1) * HW];         // y-first pairs
+    const float xo = fminf(fmaxf(__fadd_rn(__fmul_rn(x, stride), cx), 0.f), w);
+    const float yo = fminf(fmaxf(__fadd_rn(__fmul_rn(y, stride), cy), 0.f), h);
+    ok[i * 3 + 0] = valid ? xo : __fmul_rn(xo, 0.f);
+    ok[i * 3 + 1] = valid ? yo : __fmul_rn(yo, 0.f);
+    ok[i * 3 + 2] = valid ? 1.f : 0.f;
+  }
+}
+
+}  // namespace kgdet
+
+using namespace kgdet;
+
+extern "C" int kgdet_bbox_select(const float* scores, int apply_sigmoid, int32_t B, int32_t C, int32_t HW,
+                                 int32_t n, int32_t* order, void* stream) {
+  KG_CHECK_ARG(scores && order, "kgdet_bbox_select: NULL pointer");
+  KG_CHECK_ARG(B >= 0 && C >= 1 && HW >= 1 && n >= 1 && n <= HW, "kgdet_bbox_select: bad sizes");
+  KG_CHECK_ARG(HW <= 16384 && B <= 65535, "kgdet_bbox_select: at most 16384 positions per image and level");
+  if (B == 0) return KGDET_OK;
+  const size_t smem = (size_t)HW * sizeof(float);
+  KG_CUDA(cudaFuncSetAttribute(bbox_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bbox_select_kernel<<<dim3(ceil_div(HW, 256), B), 256, smem, (cudaStream_t)stream>>>(scores, apply_sigmoid, C, HW, n,
+                                                                                     order);
+  KG_LAUNCH_CHECK("bbox_select_kernel");
+  return KGDET_OK;
+}
+
+extern "C" int kgdet_bbox_decode(const float* scores, int apply_sigmoid, const float* bbox, const int32_t* order,
+                                 const float* img_wh, float stride, int32_t map_w, int32_t B, int32_t C, int32_t HW,
+                                 int32_t n, float* boxes, float* dets, void* stream) {
+  KG_CHECK_ARG(scores && bbox && order && img_wh && boxes && dets, "kgdet_bbox_decode: NULL pointer");
+  KG_CHECK_ARG(B >= 0 && C >= 1 && HW >= 1 && n >= 1 && n <= HW && map_w >= 1 && B <= 65535,
+               "kgdet_bbox_decode: bad sizes");
+  if (B == 0) return KGDET_OK;
+  bbox_decode_kernel<<<dim3(ceil_div(n, 128), B), 128, 0, (cudaStream_t)stream>>>(scores, apply_sigmoid, bbox, order,
+                                                                                  img_wh, stride, map_w, C, HW, n,
+                                                                                  boxes, dets);
+  KG_LAUNCH_CHECK("bbox_decode_kernel");
+  return KGDET_OK;
+}
+
+extern "C" int kgdet_bbox_finalize(const float* boxes, const float* keypts, const int32_t* order,
+                                   const int64_t* top_i, const float* top_s, const float* img_wh, float stride,
+                                   int32_t map_w, int32_t B, int32_t HW, int32_t n, int32_t k, int32_t num_keypts,
+                                   float* out_dets, int64_t* out_labels, float* out_kpts, void* stream) {
+  KG_CHECK_ARG(boxes && keypts && order && top_i && top_s && img_wh && out_dets && out_labels && out_kpts,
+               "kgdet_bbox_finalize: NULL pointer");
+  KG_CHECK_ARG(B >= 0 && HW >= 1 && n >= 1 && k >= 1 && num_keypts >= 1 && map_w >= 1 && B <= 65535,
+               "kgdet_bbox_finalize: bad sizes");
+  if (B == 0) return KGDET_OK;
+  bbox_finalize_kernel<<<dim3(ceil_div(k, 8), B), 256, 0, (cudaStream_t)stream>>>(
+      boxes, keypts, order, (const long long*)top_i, top_s, img_wh, stride, map_w, HW, n, k, num_keypts, out_dets,
+      (long long*)out_labels, out_kpts);
+  KG_LAUNCH_CHECK("bbox_finalize_kernel");
+  return KGDET_OK;
+}

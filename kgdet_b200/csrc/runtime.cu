@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace kgdet {
@@ -19,6 +21,9 @@ int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
   return KGDET_ERR_CUDA;
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int num_sms() {
   static int sms = 0;
@@ -77,3 +82,4 @@ int make_geom(const kgdet_dcn_shape* s, DcnGeom* g) {
 
 extern "C" const char* kgdet_last_error(void) { return kgdet::g_err; }
 extern "C" int kgdet_abi_version(void) { return KGDET_ABI_VERSION; }
+extern "C" uint64_t kgdet_launch_count(void) { return kgdet::g_launches.load(std::memory_order_relaxed); }

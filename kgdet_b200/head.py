@@ -30,6 +30,7 @@ import torch.nn.functional as F
 from .ops import (DeformConv, TiledRows, batched_nms_flags, deform_conv_prepared, get_precision,
                   groupnorm_relu_nhwc, nchw_to_tiled, pack_weight, points2bbox_moment, pointwise_conv,
                   prepare_input, prepare_plan, prepare_plan_points)
+from .ops.decode import bbox_decode, bbox_finalize, bbox_select
 from .ops.pointwise import cached
 
 _POINT_SETS = (3, 5, 7)          # KP3:257: 9 + 25 + 49 points regardless of cfg.num_reppts
@@ -52,6 +53,18 @@ def _normal(m, std=0.01, bias=0.0):
     nn.init.normal_(m.weight, 0, std)
     if getattr(m, 'bias', None) is not None:
         nn.init.constant_(m.bias, bias)
+
+
+_side_streams = {}
+
+
+def _streams(device, n):
+    """`n` cached side streams of `device` (created once: stream creation is not allowed during graph capture)."""
+    key = (device.type, device.index)
+    lst = _side_streams.setdefault(key, [])
+    while len(lst) < n:
+        lst.append(torch.cuda.Stream(device=device))
+    return lst[:n]
 
 
 def _cl_weight(w):
@@ -135,6 +148,7 @@ class _DeformBlock(nn.Module):
     def __init__(self, cls_out, cin, feat, keypts_dim, reppts_dim, gradient_mul, deform_conv_cls=DeformConv):
         super().__init__()
         self.gradient_mul = gradient_mul
+        self.concurrent_dcn = True          # forward_tc: the six DCNs of the stage on six streams
         for k in _POINT_SETS:
             pad = (k - 1) // 2
             setattr(self, 'cls_dfmconv_%d' % k, deform_conv_cls(cin, feat, k, 1, pad))
@@ -187,13 +201,28 @@ class _DeformBlock(nn.Module):
         cls_rows = TiledRows(n * h * w, 3 * feat, True, dev)         # split precision: [hi | lo]
         kpt_rows = TiledRows(n * h * w, 3 * feat, True, dev)
         lo = 0
+        jobs = []
         for i, k in enumerate(_POINT_SETS):
             plan = prepare_plan_points(rep_prev, lo, (n, c, h, w), feat, k, 1, (k - 1) // 2, 1, precision='bf16')
             lo += 2 * k * k
-            deform_conv_prepared(cls_prep, plan, getattr(self, 'cls_dfmconv_%d' % k).weight, cls_rows, i * feat,
-                                 True)
-            deform_conv_prepared(pts_prep, plan, getattr(self, 'keypts_dfmconv_%d' % k).weight, kpt_rows, i * feat,
-                                 True)
+            jobs.append((cls_prep, plan, getattr(self, 'cls_dfmconv_%d' % k).weight, cls_rows, i * feat))
+            jobs.append((pts_prep, plan, getattr(self, 'keypts_dfmconv_%d' % k).weight, kpt_rows, i * feat))
+        jobs.reverse()                                   # longest first (49, 49, 25, 25, 9, 9 points)
+        if self.concurrent_dcn:
+            # The six DCNs of a stage are independent and each fills only 132 of the 148 SMs (M = 16 800 ->
+            # 132 tiles, one CTA per SM): issued on six streams, the block scheduler packs the tiles of all six
+            # onto whatever SM is free (forks/joins become parallel branches of the captured CUDA graph).
+            main = torch.cuda.current_stream(dev)
+            fork = main.record_event()
+            for job, st in zip(jobs, _streams(dev, len(jobs))):
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    deform_conv_prepared(*job, True)
+                    done = st.record_event()
+                main.wait_event(done)
+        else:
+            for job in jobs:
+                deform_conv_prepared(*job, True)
         return _pointwise_heads(self, cls_rows, kpt_rows, n, h, w, kpt_prev, rep_prev)
 
     def forward(self, cls_feat, pts_feat, reppts_offset):
@@ -224,6 +253,7 @@ class KGDetHead(nn.Module):
         super().__init__()
         self._fused_inference = deform_conv_cls is None     # prepared API only with the CUDA operators
         self._tensor_core_heads = True                      # bf16 mode: 1x1 convolutions as tcgen05 GEMMs
+        self._fused_decode = True                           # get_bboxes: decode kernels instead of PyTorch glue
         deform_conv_cls = deform_conv_cls or DeformConv
         self._moment_fn = moment_fn or points2bbox_moment
         self._nms_flags_fn = nms_flags_fn or batched_nms_flags
@@ -328,6 +358,24 @@ class KGDetHead(nn.Module):
         if lim is None:       # built once per (shapes, device): keeps H2D copies out of graph capture
             lim = torch.tensor([[s[1], s[0], s[1], s[0]] for s in img_shapes], dtype=torch.float32, device=dev)
             self._lim_cache[key] = lim
+        if (self._fused_decode and len(cls_scores) == 1 and cls_scores[0].is_cuda
+                and self._nms_flags_fn is batched_nms_flags and cls_scores[0].shape[-2] * cls_scores[0].shape[-1] <= 16384):
+            # one head level on the GPU: three decode kernels + the batched NMS + one top-k (section 8(f) rank 1)
+            cs, kp, bp = cls_scores[0], keypts_preds[0], bbox_preds[0]
+            H, W = cs.shape[-2:]
+            src = (cs if score_override is None else score_override[0]).float().contiguous()
+            sig = score_override is None
+            n = min(nms_pre, H * W) if nms_pre > 0 else H * W
+            wh = lim[:, :2].contiguous() if lim.shape[1] == 4 else lim
+            stride = self.point_strides[0]
+            order = bbox_select(src, sig, n)
+            boxes, dets = bbox_decode(src, sig, bp.float().contiguous(), order, wh, stride)
+            C = dets.shape[1]
+            flags = self._nms_flags_fn(dets.view(-1, 5), None, n, iou_thr, score_thr=score_thr)
+            masked = torch.where(flags.view(B, C * n).bool(), dets[..., 4].reshape(B, C * n),
+                                 dets.new_full((), -1.0))
+            top_s, top_i = masked.topk(min(max_per_img, C * n), dim=1)                 # bbox_nms_kp.py:64-70
+            return bbox_finalize(boxes, kp.float().contiguous(), order, top_i, top_s, wh, stride, (H, W))
         boxes_l, scores_l, kpts_l = [], [], []
         for lvl, (cs, kp, bp) in enumerate(zip(cls_scores, keypts_preds, bbox_preds)):
             stride = self.point_strides[lvl]

@@ -43,6 +43,7 @@ LAYOUT_NCHW, LAYOUT_TILED, LAYOUT_TILED_SPLIT = 0, 1, 2
 SIGNATURES = {
     'kgdet_last_error': (ctypes.c_char_p, []),
     'kgdet_abi_version': (ctypes.c_int, []),
+    'kgdet_launch_count': (ctypes.c_uint64, []),
     'kgdet_dcn_fast_path_supported': (ctypes.c_int, [_SHAPE_P, ctypes.c_int]),
     'kgdet_dcn_packed_weight_bytes': (c_sz, [_SHAPE_P, ctypes.c_int]),
     'kgdet_dcn_pack_weight': (ctypes.c_int, [c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
@@ -57,6 +58,11 @@ SIGNATURES = {
     'kgdet_dcn_prepare_plan_points': (ctypes.c_int, [c_ptr, c_i32, c_i32, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
     'kgdet_dcn_forward_prepared': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, ctypes.c_int,
                                                   ctypes.c_int, _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr]),
+    'kgdet_bbox_select': (ctypes.c_int, [c_ptr, ctypes.c_int, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
+    'kgdet_bbox_decode': (ctypes.c_int, [c_ptr, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32,
+                                         c_i32, c_ptr, c_ptr, c_ptr]),
+    'kgdet_bbox_finalize': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32,
+                                           c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     'kgdet_pointwise_tiled_bytes': (c_sz, [c_i32, c_i32, ctypes.c_int]),
     'kgdet_pointwise_packed_weight_bytes': (c_sz, [c_i32, c_i32, ctypes.c_int]),
     'kgdet_pointwise_pack_weight': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, ctypes.c_int, c_ptr]),
