@@ -6,20 +6,21 @@
 // deform_conv_cuda_kernel.cu:189-242: C*K x N*H*W fp32, 843 MB for one 7x7 KGDet call) and hands it to a
 // cuBLAS SGEMM (deform_conv_cuda.cpp:230-233).  Here the column tile only ever exists in shared memory.
 //
-// One CTA = 128 output positions x all Cout, 17 warps, NS-stage mbarrier pipeline over k-blocks
+// One CTA = 128 output positions x all Cout, 9 warps, NS-stage mbarrier pipeline over k-blocks
 // (k-block = 64 bf16 / 32 tf32 channels of one tap = one 128-byte slab per sampled pixel):
-//   warps 0..15  producers.  Thread t owns 16-byte chunk (t & 7) of rows (t >> 3) and (t >> 3) + 64: 8 lanes
+//   warps 0..7   producers.  Thread t owns 16-byte chunk (t & 7) of rows (t >> 3) + 32 i, i < 4: 8 lanes
 //                cover one pixel slab, so every gather instruction reads four whole 128-byte lines of the
-//                channel-blocked input (dcn_api.cu).  Per k-block a thread interpolates its two row-chunks
+//                channel-blocked input (dcn_api.cu).  Per k-block a thread interpolates its four row-chunks
 //                (packed HFMA2.BF16 with the plan's pre-rounded corner weights), stores them into the
 //                128B-swizzled K-major A tile and immediately re-arms the same registers with the gathers of
 //                the NEXT k-block (all four corners unconditionally; unusable corners carry weight 0 and a
 //                guard-band-safe address), then fence.proxy.async + one mbarrier arrive per warp.
-//   warp 16      control (one elected lane): streams the pre-swizzled weight slabs with cp.async.bulk
+//   warp 8       control (one elected lane): streams the pre-swizzled weight slabs with cp.async.bulk
 //                (UBLKCP; a linear copy lands in UMMA layout, no tensor map) NS-1 k-blocks ahead, waits for a
 //                stage to be full, issues the tcgen05.mma's (UTCHMMA, M128 x N=Cout x K16/8) into the TMEM
 //                accumulator and commits the stage's empty barrier.
-//   Epilogue     warps 0..15: tcgen05.ld, bias, ReLU, NCHW store coalesced over positions.
+//   Epilogue     warps 0..7: tcgen05.ld, bias, ReLU, then either an NCHW store coalesced over positions or
+//                bf16 rows in the UMMA-tiled layout of the pointwise GEMM that follows (pointwise_umma.cu).
 //
 // Modes: BF16   kind::f16, bf16 operands                     (1e-3 grade)
 //        TF32X3 kind::tf32, A = Ahi + Alo, B = Bhi + Blo,    (the dropped term Alo.Blo is ~2^-22)
@@ -38,8 +39,16 @@
 
 namespace kgdet {
 
-static constexpr int PRODUCER_WARPS = 16;
-static constexpr int STREAM_THREADS = (PRODUCER_WARPS + 1) * 32;   // 544 -> 120 registers/thread
+// RPT = rows (of the 128-row tile) per producer thread: 2 -> 16 producer warps (96 registers per thread with
+// the control warp), 4 -> 8 producer warps (168 registers).  The producers are bound by instruction issue
+// (ablation on B200: with gathers, record loads, fence, A-tile stores, MMAs and weight copies ALL removed the
+// K = 49 call still takes 94 of its 144 us), so fewer, fatter threads -- half the per-thread loop / barrier /
+// address overhead per row -- win.
+template <int RPT> struct Producers {
+  static constexpr int WARPS = 32 / RPT;                   // 128 rows x 8 chunks / RPT / 32 lanes
+  static constexpr int THREADS = (WARPS + 1) * 32;         // + the control warp
+  static constexpr int ROW_STEP = 128 / RPT;               // rows of one thread are ROW_STEP apart
+};
 
 // bounded wait without the diagnostic printf of mbar_wait (keeps the hot loop small): a protocol bug
 // still traps instead of hanging the GPU
@@ -98,19 +107,24 @@ __device__ __forceinline__ void combine_store(const uint4 (&v)[4], uint32_t wy, 
   }
 }
 
-// Schedules that were built, measured on B200 (tools/dcn_ab.py, K = 49 call: 144 us for this kernel) and
-// dropped again:
-//   * DEPTH = 2 with 16 warps at 128 registers and the control duty rotating over the producer warps
-//     (17 warps cap a thread at 96 registers: 5 warps share one SM sub-partition's register file):
-//     171 us.  Deeper load pipelining buys nothing: the producers are bound by the THROUGHPUT of the
-//     L1/LSU wavefront pipe (512 gather + 128 record + 128 A-tile-store wavefronts per k-block at the
-//     ~1.3 cycles per wavefront tools/micro/l1_gather_bench measures), not by latency.
-//   * all gathers through ld.global.cg (L1 bypass): 166 us -- same pipe, no gain.
-// What did help: channel-blocked input planes (contiguous 128-byte slabs, 1.4x faster in the L1 than slabs
-// 512 bytes apart) and tap-major plan records.
-template <int MODE, int NS, int DEPTH, typename Tout, bool PAIR>
-__global__ void __launch_bounds__(STREAM_THREADS, 1) dcn_umma_stream_kernel(const UmmaParams prm) {
+// What bounds it (ablations on B200, K = 49 KGDet call, 16 warps x 2 rows, 144 us):
+//   no gathers at all 143 us | no record loads 145 | no fence.proxy.async 145 | no A-tile stores 141 |
+//   no weight copies 135 | no MMAs 119 | ALL of those removed 94 us.
+// I.e. memory is fully hidden; two thirds of the time is the instruction / barrier skeleton of the producers
+// (issue-bound: ~110 SASS instructions per thread and k-block on 4-5 warps per scheduler) and the rest is the
+// tensor core's operand reads competing with the producers for the SM's shared-memory bandwidth.  Hence:
+//   * 4 rows per thread (8 producer warps, 160 registers): half the per-thread loop overhead per row: 137 us;
+//     8 rows per thread (4 warps): 161 us -- too few warps to cover instruction latency.
+//   * built, measured and dropped: DEPTH = 2 with 16 warps at 128 registers and the control duty rotating over
+//     the producer warps (17 warps cap a thread at 96 registers) 171 us; all gathers through ld.global.cg
+//     166 us; 148 balanced 114-row tiles instead of 132 128-row tiles 150 us; CTA pairs 152 us.
+//   * what did help earlier: channel-blocked input planes (contiguous 128-byte slabs are served 1.4x faster by
+//     the L1 than slabs 512 bytes apart, tools/micro/l1_gather_bench) and tap-major plan records.
+template <int MODE, int NS, int DEPTH, typename Tout, bool PAIR, int RPT>
+__global__ void __launch_bounds__(Producers<RPT>::THREADS, 1) dcn_umma_stream_kernel(const UmmaParams prm) {
   using MT = ModeTraits<MODE>;
+  constexpr int PRODUCER_WARPS = Producers<RPT>::WARPS;
+  constexpr int ROW_STEP = Producers<RPT>::ROW_STEP;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // 1024-byte alignment of every tile is what the 128B swizzle pattern is anchored to
   unsigned char* smem = reinterpret_cast<unsigned char*>(
@@ -232,22 +246,25 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dcn_umma_stream_kernel(cons
   } else {
     // ======================================= producers =======================================
     const int chunk = tid & 7;        // 16-byte chunk of the 128-byte row
-    const int rbase = tid >> 3;       // 0..63; this thread owns rows rbase and rbase + 64
+    const int rbase = tid >> 3;       // this thread owns rows rbase + i * ROW_STEP, i < RPT
     const int K = prm.K;
     constexpr long long rowb = 128;                       // bytes per pixel slab (one plane = one channel block)
     const long long wrow = (long long)prm.W * rowb;       // bytes per image row
     const unsigned char* in_base = reinterpret_cast<const unsigned char*>(prm.in) + chunk * 16;
     // plan is tap-major [K][rows_padded]: the four rows a warp touches per load are 64 contiguous bytes
     const uint4* plan0 = reinterpret_cast<const uint4*>(prm.plan) + (m0 + rbase);
-    const uint4* plan1 = plan0 + 64;
     const size_t tap_stride = (size_t)prm.rows_padded;
-    // this thread's byte offset inside an A tile (row rbase, swizzled 16-byte chunk); row rbase + 64 is
-    // 8192 bytes further and has the same (row & 7)
+    // this thread's byte offset inside an A tile (row rbase, swizzled 16-byte chunk); its other rows are
+    // ROW_STEP * 128 bytes further each and have the same (row & 7)
     const int a_off = rbase * 128 + ((chunk ^ (rbase & 7)) << 4);
 
-    uint4 v[DEPTH][2][4];             // corners in flight: [k-block slot][row][corner]
-    uint32_t wy[DEPTH][2], wz[DEPTH][2], ww[DEPTH][2];
-    uint4 recn[2];                    // records of the next k-block to issue
+    uint4 v[DEPTH][RPT][4];           // corners in flight: [k-block slot][row][corner]
+    uint32_t wy[DEPTH][RPT], wz[DEPTH][RPT], ww[DEPTH][RPT];
+    uint4 recn[RPT];                  // records of the next k-block to issue
+    auto load_recs = [&](int tap) {
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) recn[i] = __ldg(plan0 + (size_t)i * ROW_STEP + tap * tap_stride);
+    };
 
     // (tap, channel block) of the k-block whose gathers are issued next, and tap of the next record fetch
     int tapI = 0, cbI = 0, tapR = 0;
@@ -267,18 +284,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dcn_umma_stream_kernel(cons
 #pragma unroll
     for (int d = 0; d < DEPTH; ++d) {
       if (d < nkb) {
-        recn[0] = __ldg(plan0 + tapI * tap_stride);
-        recn[1] = __ldg(plan1 + tapI * tap_stride);
-        issue(d, 0, recn[0]);
-        issue(d, 1, recn[1]);
+        load_recs(tapI);
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) issue(d, i, recn[i]);
         advance(tapI, cbI);
       }
     }
     tapR = tapI;                      // tap of k-block DEPTH
-    if (DEPTH < nkb) {
-      recn[0] = __ldg(plan0 + tapR * tap_stride);
-      recn[1] = __ldg(plan1 + tapR * tap_stride);
-    }
+    if (DEPTH < nkb) load_recs(tapR);
     if (++tapR == K) tapR = 0;
 
     auto body = [&](int kb, int slot) {
@@ -287,15 +300,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dcn_umma_stream_kernel(cons
       mbar_spin(&empty_bar[s], ((uint32_t)(kb / NS) & 1u) ^ 1u);     // MMAs of k-block kb - NS have retired
       const bool more = kb + DEPTH < nkb;
 #pragma unroll
-      for (int row = 0; row < 2; ++row) {
+      for (int row = 0; row < RPT; ++row) {
         combine_store<MODE>(v[slot][row], wy[slot][row], wz[slot][row], MODE != MODE_BF16 ? ww[slot][row] : 0u,
-                            a_tile + a_off + row * 8192);
+                            a_tile + a_off + row * (ROW_STEP * 128));
         if (more) issue(slot, row, recn[row]);                       // re-arm: k-block kb + DEPTH
       }
       if (more) advance(tapI, cbI);
       if (kb + DEPTH + 1 < nkb) {                                    // records for the next iteration's issue
-        recn[0] = __ldg(plan0 + tapR * tap_stride);
-        recn[1] = __ldg(plan1 + tapR * tap_stride);
+        load_recs(tapR);
         if (++tapR == K) tapR = 0;
       }
       fence_proxy_async_smem();   // my generic-proxy stores -> visible to tcgen05.mma
@@ -322,9 +334,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1) dcn_umma_stream_kernel(cons
     const int n = row_ok ? m / prm.HoWo : 0;
     const int pos = row_ok ? m - n * prm.HoWo : 0;
     Tout* obase = reinterpret_cast<Tout*>(prm.out) + ((size_t)n * prm.out_ctot + prm.out_coff) * prm.HoWo + pos;
-    // 32-column chunks of the accumulator are dealt round-robin to the four column groups (Cout % 64 == 0,
-    // so every chunk is whole; e.g. Cout = 192: groups 0,1 drain two chunks, groups 2,3 one)
-    for (int col = cgrp * 32; col < BN; col += 128) {          // warp-uniform
+    // 32-column chunks of the accumulator are dealt round-robin to the PRODUCER_WARPS / 4 column groups
+    // (Cout % 64 == 0, so every chunk is whole)
+    for (int col = cgrp * 32; col < BN; col += 8 * PRODUCER_WARPS) {          // warp-uniform
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
       tmem_ld_wait();
@@ -393,14 +405,14 @@ static size_t stream_smem_bytes(int mode, int ns, int Cout, bool pair) {
   return 1024 /* alignment slack */ + ns * stage + (2 * ns + 1) * 8 + 16;   // barriers, TMEM slot, duty ticket
 }
 
-template <int MODE, int NS, int DEPTH, typename Tout, bool PAIR>
+template <int MODE, int NS, int DEPTH, typename Tout, bool PAIR, int RPT>
 static int launch_stream(const UmmaParams& p, int grid, cudaStream_t stream) {
   const size_t smem = stream_smem_bytes(MODE, NS, p.Cout, PAIR);
-  auto kern = dcn_umma_stream_kernel<MODE, NS, DEPTH, Tout, PAIR>;
+  auto kern = dcn_umma_stream_kernel<MODE, NS, DEPTH, Tout, PAIR, RPT>;
   KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);         // PAIR: even, one cluster = two consecutive 128-row tiles
-  cfg.blockDim = dim3(STREAM_THREADS, 1, 1);
+  cfg.blockDim = dim3(Producers<RPT>::THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -417,12 +429,16 @@ static int launch_stream(const UmmaParams& p, int grid, cudaStream_t stream) {
 
 template <int MODE, typename Tout, bool PAIR>
 static int dispatch_stages(const UmmaParams& p, int grid, int ns, cudaStream_t stream) {
+  // rows per producer thread: 4 (8 producer warps) measured best -- K = 49 call 137 us vs 145 us with 2 rows
+  // (16 warps) and 161 us with 8 rows (4 warps)
   switch (ns) {
-    case 2: return launch_stream<MODE, 2, 1, Tout, PAIR>(p, grid, stream);
-    case 3: return launch_stream<MODE, 3, 1, Tout, PAIR>(p, grid, stream);
-    case 4: return launch_stream<MODE, 4, 1, Tout, PAIR>(p, grid, stream);
-    default: set_error("dcn umma stream: unsupported stage count %d", ns); return KGDET_ERR_INVALID_ARG;
+    case 2: return launch_stream<MODE, 2, 1, Tout, PAIR, 4>(p, grid, stream);
+    case 3: return launch_stream<MODE, 3, 1, Tout, PAIR, 4>(p, grid, stream);
+    case 4: return launch_stream<MODE, 4, 1, Tout, PAIR, 4>(p, grid, stream);
+    default: break;
   }
+  set_error("dcn umma stream: unsupported stage count %d", ns);
+  return KGDET_ERR_INVALID_ARG;
 }
 
 template <int MODE, typename Tout>
