@@ -90,6 +90,9 @@ int umma_pack_weight(const DcnGeom& g, const float* weight, void* packed, int pr
   return KGDET_OK;
 }
 
+thread_local long long* g_timeline = nullptr;
+thread_local long long g_timeline_entries = 0;
+
 int umma_forward(const DcnGeom& g, const void* in_blocked, size_t plane_bytes, const SampleRec16* plan,
                  const void* packed_w, const float* bias, const OutSpec& o, int precision, cudaStream_t stream) {
   if (!umma_supported(g, precision)) {
@@ -111,7 +114,15 @@ int umma_forward(const DcnGeom& g, const void* in_blocked, size_t plane_bytes, c
   if (const char* e = getenv("KGDET_UMMA_PAIR")) pair = atoi(e) != 0;
   p.idesc = make_idesc(mode == MODE_BF16 ? 1u : 2u, pair ? 2 * BM : BM, (uint32_t)g.Cout);
   p.tmem_cols = 0;   // set by the kernel launcher
+  p.timeline = nullptr;
+  if (g_timeline && g_timeline_entries >= (long long)ceil_div(g.M, BM) * (2 * p.nkb + 8)) p.timeline = g_timeline;
+  g_timeline = nullptr;
   return umma_stream_forward(g, p, mode, pair, o.dtype, stream);
 }
 
 }  // namespace kgdet
+
+extern "C" void kgdet_dcn_set_timeline(void* device_buffer, long long entries) {
+  kgdet::g_timeline = (long long*)device_buffer;
+  kgdet::g_timeline_entries = entries;
+}

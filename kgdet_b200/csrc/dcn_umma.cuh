@@ -35,6 +35,10 @@ struct UmmaParams {
   int nkb;                   // (C / BK) * K
   uint32_t idesc;
   uint32_t tmem_cols;
+  // development hook (kgdet_dcn_set_timeline): per CTA 2 * nkb + 8 clock64() stamps, or NULL
+  //   [0] kernel entry, [1] set-up done, [2 + j] control lane saw k-block j full, [2 + nkb] accumulator ready,
+  //   [3 + nkb] epilogue done, [4 + nkb + j] producer thread 0 finished k-block j
+  long long* timeline;
 };
 
 

@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(Producers<RPT>::THREADS, 1) dcn_umma_stream_ke
   const int m0 = blockIdx.x * BM;
   const int nkb = prm.nkb;
   constexpr int SETUP_WARP = PRODUCER_WARPS;
+  long long* const tl = prm.timeline ? prm.timeline + (size_t)blockIdx.x * (2 * nkb + 8) : nullptr;
+  if (tl && tid == 0) tl[0] = clock64();
 
   if (warp == SETUP_WARP) {
     if (lane == 0) {
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(Producers<RPT>::THREADS, 1) dcn_umma_stream_ke
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tl && tid == 0) tl[1] = clock64();
   const uint32_t full_bar0_remote = PAIR ? mapa_u32(smem_u32(&full_bar[0]), 0u) : 0u;
 
   // ------------------------- control duties (executed by ONE lane) -------------------------
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(Producers<RPT>::THREADS, 1) dcn_umma_stream_ke
       mbar_arrive_remote(full_bar0_remote + (uint32_t)s * 8u);
     } else {
       mbar_spin(&full_bar[s], ph);     // A tile(s) from all producer warps + weight bytes (both CTAs of a pair)
+      if (tl) tl[2 + j] = clock64();
       tc_fence_after();
       const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
       const uint32_t b_addr = a_addr + MT::A_TILES * A_TILE_BYTES;
@@ -316,6 +320,7 @@ __global__ void __launch_bounds__(Producers<RPT>::THREADS, 1) dcn_umma_stream_ke
         if (PAIR && cta_rank != 0) mbar_arrive_remote(full_bar0_remote + (uint32_t)s * 8u);
         else mbar_arrive(&full_bar[s]);
       }
+      if (tl && tid == 0) tl[4 + nkb + kb] = clock64();
     };
 
     for (int kb = 0; kb < nkb; kb += DEPTH) {
@@ -326,6 +331,7 @@ __global__ void __launch_bounds__(Producers<RPT>::THREADS, 1) dcn_umma_stream_ke
 
     // ===================== epilogue: TMEM -> registers -> NCHW global =====================
     mbar_spin(tmem_full_bar, 0);
+    if (tl && tid == 0) tl[2 + nkb] = clock64();
     tc_fence_after();
     const int q = warp & 3, cgrp = warp >> 2;      // TMEM lane quarter / column group of this warp
     const int row = q * 32 + lane;
@@ -389,6 +395,7 @@ __global__ void __launch_bounds__(Producers<RPT>::THREADS, 1) dcn_umma_stream_ke
     }
   }
 
+  if (tl && tid == 0) tl[3 + nkb] = clock64();
   tc_fence_before();
   if constexpr (PAIR) {
     cluster_sync_all();          // neither CTA may free the shared allocation while the other still reads

@@ -42,6 +42,67 @@ __global__ void moment_fwd_kernel(const float* __restrict__ pts, const float* __
   }
 }
 
+// Large point sets on small maps (KGDet: P = 83 on 25x42, 16 800 positions per batch of 16): one thread per
+// position leaves most of the machine idle and serialises 2P dependent loads.  Here a warp covers 32
+// consecutive positions (coalesced) and G warps of the CTA split the P points; every thread keeps its <= MAXK
+// points in registers, so the tensor is read exactly once; the partial sums meet in shared memory and are added
+// in a fixed order (deterministic).
+template <int G, int MAXK>
+__global__ void __launch_bounds__(32 * G) moment_fwd_split_kernel(const float* __restrict__ pts,
+                                                                  const float* __restrict__ mt, int N, int P, int S,
+                                                                  int y_first, float* __restrict__ bbox) {
+  __shared__ float red[2][2][G][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const bool ok = i < N * S;
+  const int n = ok ? i / S : 0, s = ok ? i - n * S : 0;
+  const int yo = y_first ? 0 : 1, xo = 1 - yo;
+  const float* base = pts + (size_t)n * 2 * P * S + s;
+  float y[MAXK], x[MAXK];
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) {
+    const int k = g + j * G;
+    const bool in = ok && k < P;
+    y[j] = in ? __ldg(base + (size_t)(2 * k + yo) * S) : 0.f;
+    x[j] = in ? __ldg(base + (size_t)(2 * k + xo) * S) : 0.f;
+  }
+  float sy = 0.f, sx = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) { sy += y[j]; sx += x[j]; }
+  red[0][0][g][lane] = sy;
+  red[0][1][g][lane] = sx;
+  __syncthreads();
+  sy = 0.f; sx = 0.f;
+#pragma unroll
+  for (int q = 0; q < G; ++q) { sy += red[0][0][q][lane]; sx += red[0][1][q][lane]; }
+  const float my = sy / (float)P, mx = sx / (float)P;          // KP3:374-375
+  float vy = 0.f, vx = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) {
+    if (g + j * G < P) {
+      const float dy = y[j] - my, dx = x[j] - mx;
+      vy += dy * dy;
+      vx += dx * dx;
+    }
+  }
+  red[1][0][g][lane] = vy;
+  red[1][1][g][lane] = vx;
+  __syncthreads();
+  if (g == 0 && ok) {
+    vy = 0.f; vx = 0.f;
+#pragma unroll
+    for (int q = 0; q < G; ++q) { vy += red[1][0][q][lane]; vx += red[1][1][q][lane]; }
+    const float ew = expf(mt[0]), eh = expf(mt[1]);
+    const float sdy = sqrtf(vy / (float)(P - 1)), sdx = sqrtf(vx / (float)(P - 1));   // unbiased, KP3:376-377
+    const float hw = sdx * ew, hh = sdy * eh;
+    float* o = bbox + (size_t)n * 4 * S + s;
+    o[0] = mx - hw;
+    o[(size_t)S] = my - hh;
+    o[(size_t)2 * S] = mx + hw;
+    o[(size_t)3 * S] = my + hh;
+  }
+}
+
 __global__ void moment_bwd_kernel(const float* __restrict__ pts, const float* __restrict__ mt,
                                   const float* __restrict__ gbox, int N, int P, int S, int y_first,
                                   float moment_mul, float* __restrict__ gpts,
@@ -122,6 +183,14 @@ extern "C" int kgdet_points2bbox_moment_forward(const float* pts, const float* m
   if (N == 0) return KGDET_OK;
   KG_CHECK_ARG(pts && moment_transfer && bbox, "kgdet_points2bbox_moment_forward: NULL pointer");
   KG_CHECK_ARG((long long)N * S < (1ll << 31), "kgdet_points2bbox_moment_forward: N*S overflow");
+  // split the points over the warps of a CTA when one thread per position cannot fill the machine
+  constexpr int G = 8, MAXK = 16;
+  if (S >= 32 && P >= 2 * G && P <= G * MAXK && (long long)N * S < 128ll * 8 * num_sms()) {
+    moment_fwd_split_kernel<G, MAXK><<<ceil_div(N * S, 32), 32 * G, 0, stream>>>(pts, moment_transfer, N, P, S,
+                                                                                y_first, bbox);
+    KG_LAUNCH_CHECK("moment_fwd_split_kernel");
+    return KGDET_OK;
+  }
   moment_fwd_kernel<<<moment_grid(N * S), 128, 0, stream>>>(pts, moment_transfer, N, P, S, y_first,
                                                             bbox);
   KG_LAUNCH_CHECK("moment_fwd_kernel");

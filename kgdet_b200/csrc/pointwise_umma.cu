@@ -11,20 +11,32 @@
 //      kgdet_nchw_to_tiled_bf16 (stage 1, after a cuDNN 3x3 convolution);
 //   W  [Nout/256 tiles][Kw/64 k-blocks][256 rows x 128 B, same swizzle] -- packed once per weight version
 //      (kgdet_pointwise_pack_weight).
-// Split precision ("bf16x3", fp32-grade): A holds [hi | lo] (Ka = 2K), W holds [W_hi | W_hi | W_lo] (Kw = 3K);
-// k-block kb of the GEMM reads A k-block kb % (Ka/64): A_hi W_hi + A_lo W_hi + A_hi W_lo.
+// Split precision ("bf16x3", fp32-grade): A holds [hi | lo] (Ka = 2K), W holds [W_hi | W_hi | W_lo] (Kw = 3K; the
+// middle copy is unused since the operands of a channel block are staged once).  A pipeline stage is one
+// 64-channel block c: {A_hi(c), A_lo(c), W_hi(c), W_lo(c)} are copied ONCE (96 KB at 256 columns) and feed the
+// twelve MMAs A_hi W_hi + A_lo W_hi + A_hi W_lo -- the GEMM is bound by L2->SM traffic (ncu: 6 TB/s aggregate at
+// 22 % tensor-pipe activity when every product re-read both operands), so bytes per MMA is what matters.
 //
-// CTA = 128 rows x 256 columns: warp 0 bulk-copy producer, warp 1 MMA issuer, warps 2..9 epilogue (TMEM ->
-// registers -> bias + residual -> NCHW fp32, coalesced over positions, 8 residual loads in flight per thread).
+// CTA = 128 rows x BN columns, BN = 256, or 64 when Nout <= 64 (cls_out has 13 columns: a 256-wide tile would
+// stream 4x the weight bytes and issue 4x the MMA columns for nothing): warp 0 bulk-copy producer, warp 1 MMA
+// issuer, warps 2..9 epilogue (TMEM -> registers -> bias + residual -> NCHW fp32, coalesced over positions,
+// 8 residual loads in flight per thread).
 #include <cuda_bf16.h>
 
 #include "dcn.cuh"
 
 namespace kgdet {
 
-static constexpr int PW_BM = 128, PW_BN = 256, PW_NS = 4;
-static constexpr int PW_A_BYTES = PW_BM * 128, PW_B_BYTES = PW_BN * 128, PW_STAGE = PW_A_BYTES + PW_B_BYTES;
+static constexpr int PW_BM = 128, PW_BN_MAX = 256;
+static constexpr int PW_A_BYTES = PW_BM * 128;
 static constexpr int PW_EPI_WARPS = 8;
+// column tile: narrow outputs get a narrow tile (the packing and the GEMM derive it from Nout the same way)
+__host__ __device__ constexpr int pw_bn(int nout) { return nout <= 64 ? 64 : PW_BN_MAX; }
+// stages: as many as fit ~200 KB (split: 2 x 96 KB at BN = 256, 4 x 48 KB at BN = 64; plain: 4 x 48 KB / 8 x 24 KB)
+static int pw_stages(int stage_bytes) {
+  int ns = (200 * 1024) / stage_bytes;
+  return ns > 6 ? 6 : (ns < 2 ? 2 : ns);
+}
 static constexpr int PW_THREADS = (2 + PW_EPI_WARPS) * 32;
 
 struct PointwiseParams {
@@ -32,16 +44,20 @@ struct PointwiseParams {
   const unsigned char* W;    // tiled, Kw/64 slabs per column tile
   const float* bias;
   int M, N, HW;
-  int a_kblocks, w_kblocks;  // Ka/64, Kw/64 (the GEMM runs w_kblocks k-blocks)
+  int a_kblocks, w_kblocks;  // Ka/64, Kw/64
+  int kgroups;               // K/64 channel blocks = pipeline stages' worth of work
+  int bn, ns, stage_bytes;   // column tile, pipeline depth, bytes of one stage
   int nseg;
   kgdet_pointwise_segment seg[KGDET_POINTWISE_MAX_SEGMENTS];
   uint32_t idesc;
 };
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const PointwiseParams prm) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const int PW_NS = prm.ns, PW_STAGE = prm.stage_bytes, PW_BN = prm.bn, PW_B_BYTES = prm.bn * 128;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)PW_NS * PW_STAGE);
   uint64_t* empty_bar = full_bar + PW_NS;
   uint64_t* tmem_full_bar = empty_bar + PW_NS;
@@ -49,7 +65,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
-  const int nkb = prm.w_kblocks;
+  const int nkb = prm.kgroups;
 
   if (warp == 1) {
     if (lane == 0) {
@@ -61,7 +77,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, PW_BN);
+    tmem_alloc(tmem_slot, (uint32_t)PW_BN);
   }
   tc_fence_before();
   __syncthreads();
@@ -77,8 +93,16 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
         mbar_wait(&empty_bar[s], ((uint32_t)(kb / PW_NS) & 1u) ^ 1u);
         unsigned char* dst = smem + (size_t)s * PW_STAGE;
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)PW_STAGE);
-        bulk_g2s(dst, a_tile + (size_t)(kb % prm.a_kblocks) * PW_A_BYTES, PW_A_BYTES, &full_bar[s]);
-        bulk_g2s(dst + PW_A_BYTES, w_tile + (size_t)kb * PW_B_BYTES, PW_B_BYTES, &full_bar[s]);
+        // stage layout: A_hi [A_lo] W_hi [W_lo]
+        bulk_g2s(dst, a_tile + (size_t)kb * PW_A_BYTES, PW_A_BYTES, &full_bar[s]);
+        if constexpr (SPLIT) {
+          bulk_g2s(dst + PW_A_BYTES, a_tile + (size_t)(nkb + kb) * PW_A_BYTES, PW_A_BYTES, &full_bar[s]);
+          bulk_g2s(dst + 2 * PW_A_BYTES, w_tile + (size_t)kb * PW_B_BYTES, PW_B_BYTES, &full_bar[s]);
+          bulk_g2s(dst + 2 * PW_A_BYTES + PW_B_BYTES, w_tile + (size_t)(2 * nkb + kb) * PW_B_BYTES, PW_B_BYTES,
+                   &full_bar[s]);
+        } else {
+          bulk_g2s(dst + PW_A_BYTES, w_tile + (size_t)kb * PW_B_BYTES, PW_B_BYTES, &full_bar[s]);
+        }
       }
     }
     __syncwarp();
@@ -90,10 +114,22 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + (size_t)s * PW_STAGE);
         const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
-        const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + PW_A_BYTES);
+        if constexpr (SPLIT) {
+          const uint64_t adesc_lo = make_sw128_kmajor_desc(a_addr + PW_A_BYTES);
+          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + 2 * PW_A_BYTES);
+          const uint64_t bdesc_lo = make_sw128_kmajor_desc(a_addr + 2 * PW_A_BYTES + PW_B_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(tmem_base, adesc_lo + 2 * k, bdesc + 2 * k, prm.idesc, (kb > 0 || k > 0) ? 1u : 0u);  // A_lo W_hi
+            umma_f16(tmem_base, adesc + 2 * k, bdesc_lo + 2 * k, prm.idesc, 1u);                          // A_hi W_lo
+            umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, 1u);                             // A_hi W_hi
+          }
+        } else {
+          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + PW_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
         tc_commit(&empty_bar[s]);
       }
       tc_commit(tmem_full_bar);
@@ -107,7 +143,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
     const int row = q * 32 + lane;
     const int m = mt * PW_BM + row;
     const int img = m < prm.M ? m / prm.HW : 0, pos = m < prm.M ? m - img * prm.HW : 0;
-    for (int c0 = 0; c0 < PW_BN / 2; c0 += 32) {
+    for (int c0 = 0; c0 < PW_BN / 2; c0 += 32) {                // PW_BN / 2 is 128 or 32: whole 32-column chunks
       const int col = half * (PW_BN / 2) + c0;
       if (nt * PW_BN + col >= prm.N) break;               // warp-uniform
       uint32_t acc[32];
@@ -146,7 +182,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, PW_BN);
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)PW_BN);
 }
 
 // byte offset of element (r, k) inside a [rows x 64] bf16 slab in the swizzled K-major layout
@@ -158,6 +194,7 @@ __device__ __forceinline__ size_t tiled_off(int r, int k) {
 __global__ void pointwise_pack_kernel(const float* __restrict__ w, unsigned char* __restrict__ p, int Nout, int K,
                                       int split) {
   const int kw = (split ? 3 : 1) * K, kblocks = kw / 64;
+  const int PW_BN = pw_bn(Nout), PW_B_BYTES = PW_BN * 128;
   const int ntiles = (Nout + PW_BN - 1) / PW_BN;
   const long long total = (long long)ntiles * PW_BN * kw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)blockDim.x * gridDim.x) {
@@ -221,7 +258,7 @@ extern "C" size_t kgdet_pointwise_tiled_bytes(int32_t M, int32_t K, int split) {
 
 extern "C" size_t kgdet_pointwise_packed_weight_bytes(int32_t Nout, int32_t K, int split) {
   if (Nout <= 0 || K <= 0 || K % 64) return 0;
-  return (size_t)ceil_div(Nout, PW_BN) * ((split ? 3 : 1) * (K / 64)) * PW_B_BYTES;
+  return (size_t)ceil_div(Nout, pw_bn(Nout)) * ((split ? 3 : 1) * (K / 64)) * pw_bn(Nout) * 128;
 }
 
 extern "C" int kgdet_pointwise_pack_weight(const float* weight, void* packed, int32_t Nout, int32_t K, int split,
@@ -229,7 +266,7 @@ extern "C" int kgdet_pointwise_pack_weight(const float* weight, void* packed, in
   KG_CHECK_ARG(weight && packed, "kgdet_pointwise_pack_weight: NULL pointer");
   KG_CHECK_ARG(Nout > 0 && K > 0 && K % 64 == 0, "kgdet_pointwise_pack_weight: Nout > 0 and K %% 64 == 0 required");
   KG_CHECK_ARG(split == 0 || split == 1, "kgdet_pointwise_pack_weight: split must be 0 or 1");
-  const long long total = (long long)ceil_div(Nout, PW_BN) * PW_BN * (split ? 3 : 1) * K;
+  const long long total = (long long)ceil_div(Nout, pw_bn(Nout)) * pw_bn(Nout) * (split ? 3 : 1) * K;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
   pointwise_pack_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(weight, (unsigned char*)packed, Nout, K, split);
@@ -282,11 +319,16 @@ extern "C" int kgdet_pointwise_conv_tiled(const void* a_tiled, const void* w_pac
   p.w_kblocks = (split ? 3 : 1) * (K / 64);
   p.nseg = nseg;
   for (int i = 0; i < KGDET_POINTWISE_MAX_SEGMENTS; ++i) p.seg[i] = segs[i < nseg ? i : nseg - 1];
-  p.idesc = make_idesc(1u, PW_BM, PW_BN);
-  const size_t smem = 1024 + (size_t)PW_NS * PW_STAGE + (2 * PW_NS + 1) * 8 + 16;
-  KG_CUDA(cudaFuncSetAttribute(pointwise_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(M, PW_BM), ceil_div(Nout, PW_BN), 1);
-  pointwise_umma_kernel<<<grid, PW_THREADS, smem, (cudaStream_t)stream>>>(p);
+  p.kgroups = K / 64;
+  p.bn = pw_bn(Nout);
+  p.stage_bytes = (split ? 2 : 1) * (PW_A_BYTES + p.bn * 128);
+  p.ns = pw_stages(p.stage_bytes);
+  p.idesc = make_idesc(1u, PW_BM, (uint32_t)p.bn);
+  const size_t smem = 1024 + (size_t)p.ns * p.stage_bytes + (2 * p.ns + 1) * 8 + 16;
+  auto kern = split ? pointwise_umma_kernel<true> : pointwise_umma_kernel<false>;
+  KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(M, PW_BM), ceil_div(Nout, p.bn), 1);
+  kern<<<grid, PW_THREADS, smem, (cudaStream_t)stream>>>(p);
   KG_LAUNCH_CHECK("pointwise_umma_kernel");
   return KGDET_OK;
 }

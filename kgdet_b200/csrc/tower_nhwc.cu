@@ -63,6 +63,77 @@ __global__ void __launch_bounds__(256) groupnorm_relu_nhwc_kernel(const float* _
   }
 }
 
+// Wide variant: one CTA per (image, 32 consecutive channels) = 8 / VEC groups, VEC = float4 chunks per group.
+// The one-group kernel above reads 4 * cpg bytes per pixel (32 B for the KGDet towers: 16 different 128-byte
+// lines per warp request); here 8 lanes cover one pixel's 128-byte line, 1024 threads keep ~8 float4 loads each in
+// flight, and the statistics of a group are reduced with xor-shuffles over the lanes that share it.
+template <int VEC>
+__global__ void __launch_bounds__(1024) groupnorm_relu_nhwc_wide_kernel(const float* __restrict__ x,
+                                                                        const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta, float eps,
+                                                                        float* __restrict__ y, int HW, int C, int relu) {
+  constexpr int GPC = 8 / VEC;                  // groups per CTA
+  extern __shared__ float sm[];                 // [HW][32] values
+  __shared__ float red[32][GPC];
+  const int n = blockIdx.y, c0 = blockIdx.x * 32;
+  const int chunk = threadIdx.x & 7, gi = chunk / VEC, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* xg = x + (size_t)n * HW * C + c0 + chunk * 4;
+  float* yg = y + (size_t)n * HW * C + c0 + chunk * 4;
+  const int prow = threadIdx.x >> 3, pstep = blockDim.x >> 3;
+  const float inv_total = 1.f / (float)(HW * VEC * 4);
+  // sum over the lanes of this warp that hold the same group (other chunks of the group, other pixels), then
+  // over the warps through shared memory; every thread ends up with its own group's total
+  auto group_sum = [&](float v) -> float {
+#pragma unroll
+    for (int o = 1; o < VEC; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    __syncthreads();                            // red[] may still be read from the previous reduction
+    if (lane < 8 && (lane % VEC) == 0) red[warp][gi] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w][gi];
+    return t;
+  };
+  float s = 0.f;
+  for (int p = prow; p < HW; p += pstep) {
+    const float4 v = *reinterpret_cast<const float4*>(xg + (size_t)p * C);
+    *reinterpret_cast<float4*>(sm + (size_t)p * 32 + chunk * 4) = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = group_sum(s) * inv_total;
+  float ss = 0.f;
+  for (int p = prow; p < HW; p += pstep) {
+    const float4 v = *reinterpret_cast<const float4*>(sm + (size_t)p * 32 + chunk * 4);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
+  }
+  const float rstd = rsqrtf(group_sum(ss) * inv_total + eps);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0 + chunk * 4));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0 + chunk * 4));
+  for (int p = prow; p < HW; p += pstep) {
+    const float4 v = *reinterpret_cast<const float4*>(sm + (size_t)p * 32 + chunk * 4);
+    float4 o;
+    o.x = (v.x - mean) * rstd * ga.x + be.x;
+    o.y = (v.y - mean) * rstd * ga.y + be.y;
+    o.z = (v.z - mean) * rstd * ga.z + be.z;
+    o.w = (v.w - mean) * rstd * ga.w + be.w;
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    *reinterpret_cast<float4*>(yg + (size_t)p * C) = o;
+  }
+}
+
+template <int VEC>
+static int launch_groupnorm_wide(const float* x, const float* gamma, const float* beta, float eps, float* y, int N,
+                                 int HW, int C, int relu, cudaStream_t stream) {
+  const size_t smem = (size_t)HW * 32 * sizeof(float);
+  KG_CUDA(cudaFuncSetAttribute(groupnorm_relu_nhwc_wide_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  groupnorm_relu_nhwc_wide_kernel<VEC><<<dim3(C / 32, N), 1024, smem, stream>>>(x, gamma, beta, eps, y, HW, C, relu);
+  KG_LAUNCH_CHECK("groupnorm_relu_nhwc_wide_kernel");
+  return KGDET_OK;
+}
+
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&v);
@@ -158,6 +229,18 @@ extern "C" int kgdet_groupnorm_relu_nhwc(const float* x, const float* gamma, con
                "kgdet_groupnorm_relu_nhwc: need C %% groups == 0 and (C / groups) %% 4 == 0");
   if (N == 0) return KGDET_OK;
   const int cpg = C / groups;
+  // wide kernel: a CTA takes 32 channels (whole groups), the map must fit shared memory next to nothing else
+  if (C % 32 == 0 && 32 % cpg == 0 && (size_t)HW * 128 <= 200 * 1024 && N <= 65535 &&
+      (((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0) {
+    const int relu = fuse_relu ? 1 : 0;
+    switch (cpg / 4) {
+      case 1: return launch_groupnorm_wide<1>(x, gamma, beta, eps, y, N, HW, C, relu, (cudaStream_t)stream);
+      case 2: return launch_groupnorm_wide<2>(x, gamma, beta, eps, y, N, HW, C, relu, (cudaStream_t)stream);
+      case 4: return launch_groupnorm_wide<4>(x, gamma, beta, eps, y, N, HW, C, relu, (cudaStream_t)stream);
+      case 8: return launch_groupnorm_wide<8>(x, gamma, beta, eps, y, N, HW, C, relu, (cudaStream_t)stream);
+      default: break;
+    }
+  }
   const size_t smem = ((size_t)HW * cpg + 32) * sizeof(float);
   KG_CHECK_ARG(smem <= 200 * 1024, "kgdet_groupnorm_relu_nhwc: group of %d x %d values does not fit shared memory", HW, cpg);
   KG_CHECK_ARG(N <= 65535, "kgdet_groupnorm_relu_nhwc: batch too large");

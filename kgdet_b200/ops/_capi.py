@@ -103,6 +103,7 @@ SIGNATURES = {
     'kgdet_points2bbox_moment_backward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32,
                                                          ctypes.c_int, c_f32, c_ptr, c_ptr, c_ptr]),
     'kgdet_dcn_set_profile_events': (None, [c_ptr, c_ptr]),
+    'kgdet_dcn_set_timeline': (None, [c_ptr, ctypes.c_longlong]),
     'kgdet_nchw_to_nhwc': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, ctypes.c_int,
                                           ctypes.c_int, c_ptr]),
 }

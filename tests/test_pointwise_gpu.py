@@ -123,6 +123,17 @@ def test_groupnorm_relu_nhwc_matches_torch():
             want = want.relu() if relu else want
             assert got.is_contiguous(memory_format=torch.channels_last)
             assert rel_err(got, want) < 2e-6
+    # other group widths (4, 16 and 32 channels per group: every lane grouping of the wide kernel) and a map too
+    # large for it (one-group-per-CTA kernel)
+    for groups, ch, hw in [(32, 128, (25, 42)), (8, 128, (13, 21)), (2, 64, (7, 11)), (32, 256, (50, 84))]:
+        gn2 = torch.nn.GroupNorm(groups, ch).cuda()
+        with torch.no_grad():
+            gn2.weight.copy_(1 + 0.3 * torch.randn(ch, generator=g))
+            gn2.bias.copy_(0.2 * torch.randn(ch, generator=g))
+        x = (torch.randn(2, ch, *hw, generator=g) * 2 - 0.5).cuda().contiguous(memory_format=torch.channels_last)
+        got = ops.groupnorm_relu_nhwc(x, gn2, relu=True)
+        want = torch.nn.functional.group_norm(x.double(), groups, gn2.weight.double(), gn2.bias.double(), gn2.eps).relu()
+        assert rel_err(got, want) < 2e-6, (groups, ch, hw)
 
 
 def test_channels_last_sources_need_no_transpose():

@@ -49,8 +49,24 @@ def kernel_only(fn, flush, reps=10, warm=3):
     return ts[len(ts) // 2]
 
 
+def quick():
+    """bf16 fused-kernel time of the three KGDet calls only (A/B runs of kernel variants via environment)."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    ops.set_precision('bf16')
+    row = {k: v for k, v in os.environ.items() if k.startswith('KGDET_')}
+    for name, k in (('k3', 3), ('k5', 5), ('k7', 7)):
+        d = dcn_case(N=16, C=256, H=25, W=42, Cout=256, k=k)
+        x, off, w = (d[q].cuda() for q in ('x', 'offset', 'weight'))
+        ms = kernel_only(lambda: ops.deform_conv(x, off, w, 1, k // 2), flush)
+        row[name + '_us'] = round(ms * 1e3, 1)
+        row[name + '_tflops'] = round(2.0 * 16 * 25 * 42 * 256 * 256 * k * k / ms / 1e9, 1)
+    print(json.dumps(row), flush=True)
+
+
 def main():
     use_ref = '--ref' in sys.argv
+    if '--quick' in sys.argv:
+        return quick()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     shapes = [('kgdet_k3', 16, 25, 42, 3), ('kgdet_k5', 16, 25, 42, 5), ('kgdet_k7', 16, 25, 42, 7),
               ('P3', 8, 100, 168, 3), ('P4', 8, 50, 84, 3), ('P5', 8, 25, 42, 3), ('P6', 8, 13, 21, 3),
