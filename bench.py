@@ -220,8 +220,9 @@ def run_ours(args):
     eager_ms = sum(a.elapsed_time(b) for a, b in eager_evs)
 
     # ---- end-to-end through the public API with host buffers ("e2e") -----------------------------
+    # (a) one batch at a time, synchronised after every step: per-batch latency through host buffers
     out_host = None
-    e2e_evs = []
+    sync_evs = []
     for it in range(args.steps + 2):
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -237,8 +238,30 @@ def run_ours(args):
         b.record()
         torch.cuda.synchronize()
         if it >= 2:
-            e2e_evs.append(a.elapsed_time(b))
-    e2e_ms = sum(e2e_evs)
+            sync_evs.append(a.elapsed_time(b))
+    e2e_sync_ms = sum(sync_evs)
+    # (b) throughput: the public serving loop (GraphedInference.serve) pipelines the pinned-host -> device copy of
+    # batch i+1 and the device -> pinned-host copy of batch i-1 under the replay of batch i.  Every step still copies
+    # its own input from host memory and its own results back, all inside the timed region, and the L2 flush now
+    # sits INSIDE the timed region too (on the compute stream before every replay).
+    if graphed is not None:
+        x_hosts = [x_host] + [x_cpu.clone().pin_memory() for _ in range(2)]
+        outs_h = [tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in graphed.static_out)
+                  for _ in range(args.steps)]
+        graphed.serve([x_hosts[i % 3] for i in range(3)], before_step=lambda i: flush.fill_(1))     # warm
+        barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graphed.serve([x_hosts[i % 3] for i in range(args.steps)], outs_h, before_step=lambda i: flush.fill_(1))
+        b.record()
+        torch.cuda.synchronize()
+        e2e_ms = a.elapsed_time(b)
+        e2e_evs = [e2e_ms / args.steps]
+        e2e_mode = 'pipelined serve(): H2D of batch i+1 and D2H of batch i-1 overlap replay i; L2 flush inside the timed region'
+    else:
+        e2e_ms, e2e_evs = e2e_sync_ms, sync_evs
+        e2e_mode = 'synchronous per step'
     # host-side launch cost of one step (no sync inside): tells whether a loop is CPU- or GPU-bound
     torch.cuda.synchronize()
     c0 = time.perf_counter()
@@ -257,6 +280,7 @@ def run_ours(args):
 
     dev_ms = kdist.max_over_ranks(dev_ms, dev)       # the slowest rank sets the step time
     e2e_ms = kdist.max_over_ranks(e2e_ms, dev)
+    e2e_sync_ms = kdist.max_over_ranks(e2e_sync_ms, dev)
 
     if rank == 0:
         peaks = {}
@@ -283,7 +307,9 @@ def run_ours(args):
             'config': workload_config(args, world),
             'e2e': {'value': round(args.batch * world * args.steps / (e2e_ms * 1e-3), 2), 'unit': UNIT,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': round(e2e_ms / args.steps, 4)},
+                    'ms_per_step': round(e2e_ms / args.steps, 4), 'mode': e2e_mode,
+                    'sync_ms_per_step': round(e2e_sync_ms / args.steps, 4),
+                    'sync_note': 'one batch at a time, host-synchronised after every step (latency, not throughput)'},
             'gpu_launches': launches_per_step * args.steps,
             'gpu_launches_note': '%d kernels of libkgdet_b200.so per step, counted by the library (kgdet_launch_count): '
                                  '6 GroupNorm+ReLU, 2 rows->DCN planes, 2 rows->GEMM tiles, 6 sample plans, 12 fused '

@@ -97,18 +97,60 @@ def _pointwise_weights(block):
     return cached(ps, build)
 
 
-def _pointwise_heads(block, cls_rows, kpt_rows, n, h, w, kpt_prev=None, rep_prev=None):
-    """cls / keypoint / point-set outputs (NCHW fp32, residuals of the cascade added) from position-major bf16
-    activations: two tcgen05 GEMMs instead of three cuDNN 1x1 convolutions + two adds."""
-    wc, bc, w_kr, b_kr = _pointwise_weights(block)
-    nc, nk, nr = block.cls_out.out_channels, block.keypts_out.out_channels, block.reppts_out.out_channels
-    dev = cls_rows.buf.device
-    cls_out = torch.empty((n, nc, h, w), dtype=torch.float32, device=dev)
+def _pointwise_cls(block, cls_rows, n, h, w):
+    """cls_out (NCHW fp32) from position-major bf16 activations: one tcgen05 GEMM (64-column tile)."""
+    wc, bc, _, _ = _pointwise_weights(block)
+    nc = block.cls_out.out_channels
+    cls_out = torch.empty((n, nc, h, w), dtype=torch.float32, device=cls_rows.buf.device)
+    pointwise_conv(cls_rows, wc, bc, [(cls_out, None, 0, nc)], h * w)
+    return cls_out
+
+
+def _pointwise_kpt(block, kpt_rows, n, h, w, kpt_prev=None, rep_prev=None):
+    """keypoint and point-set outputs (NCHW fp32, residuals of the cascade added) from ONE tcgen05 GEMM over
+    the keypoint branch's activations, instead of two cuDNN 1x1 convolutions + two adds."""
+    _, _, w_kr, b_kr = _pointwise_weights(block)
+    nk, nr = block.keypts_out.out_channels, block.reppts_out.out_channels
+    dev = kpt_rows.buf.device
     kpt = torch.empty((n, nk, h, w), dtype=torch.float32, device=dev)
     rep = torch.empty((n, nr, h, w), dtype=torch.float32, device=dev)
-    pointwise_conv(cls_rows, wc, bc, [(cls_out, None, 0, nc)], h * w)
     pointwise_conv(kpt_rows, w_kr, b_kr, [(kpt, kpt_prev, 0, nk), (rep, rep_prev, nk, nk + nr)], h * w)
+    return kpt, rep
+
+
+def _pointwise_heads(block, cls_rows, kpt_rows, n, h, w, kpt_prev=None, rep_prev=None):
+    cls_out = _pointwise_cls(block, cls_rows, n, h, w)
+    kpt, rep = _pointwise_kpt(block, kpt_rows, n, h, w, kpt_prev, rep_prev)
     return cls_out, kpt, rep
+
+
+class _SideBranch(object):
+    """Work forked from the current stream onto a cached side stream (a parallel branch of the captured CUDA
+    graph).  Tensors the branch reads must stay referenced until ``join`` (the caching allocator orders reuse
+    only against the stream a block was allocated on), so the caller hands them to ``keep``."""
+
+    def __init__(self, device, index):
+        self.main = torch.cuda.current_stream(device)
+        self.side = _streams(device, index + 1)[index]
+        self.side.wait_event(self.main.record_event())
+        self.kept = []
+        self._ctx = torch.cuda.stream(self.side)
+
+    def __enter__(self):
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self._ctx.__exit__(*exc)
+        self.done = self.side.record_event()
+        return False
+
+    def keep(self, *objs):
+        self.kept.extend(objs)
+
+    def join(self):
+        self.main.wait_event(self.done)
+        self.kept = []
 
 
 class _PlainBlock(nn.Module):
@@ -136,10 +178,18 @@ class _PlainBlock(nn.Module):
     def forward_tc(self, cls_feat, pts_feat):
         """bf16 inference: the two 3x3 convolutions stay cuDNN; ReLU + layout change is one kernel each and the
         three 1x1 convolutions are two tensor-core GEMMs."""
+        cls_out = self.forward_tc_cls(cls_feat)
+        return (cls_out,) + self.forward_tc_kpt(pts_feat)
+
+    def forward_tc_cls(self, cls_feat):
         n, _, h, w = cls_feat.shape
         cls_rows = nchw_to_tiled(_conv3x3_nhwc(cls_feat, self.cls_conv), relu=True, split=True)
+        return _pointwise_cls(self, cls_rows, n, h, w)
+
+    def forward_tc_kpt(self, pts_feat):
+        n, _, h, w = pts_feat.shape
         kpt_rows = nchw_to_tiled(_conv3x3_nhwc(pts_feat, self.keypts_conv), relu=True, split=True)
-        return _pointwise_heads(self, cls_rows, kpt_rows, n, h, w)
+        return _pointwise_kpt(self, kpt_rows, n, h, w)
 
 
 class _DeformBlock(nn.Module):
@@ -190,7 +240,7 @@ class _DeformBlock(nn.Module):
         keypts_out = self.keypts_out(kpt_cat)
         return cls_out, keypts_out, self.reppts_out(keypts_out)
 
-    def forward_tc(self, cls_prep, pts_prep, rep_prev, kpt_prev):
+    def forward_tc(self, cls_prep, pts_prep, rep_prev, kpt_prev, branches=None):
         """bf16 inference, fully on this package's kernels: per point set one
         sample plan read straight from the channel slice of the previous stage's point tensor, two fused DCN
         launches that write ReLU-ed position-major bf16 rows, then two GEMMs whose epilogue adds bias and the
@@ -223,7 +273,17 @@ class _DeformBlock(nn.Module):
         else:
             for job in jobs:
                 deform_conv_prepared(*job, True)
-        return _pointwise_heads(self, cls_rows, kpt_rows, n, h, w, kpt_prev, rep_prev)
+        if self.concurrent_dcn and branches is not None:
+            # the 13-column cls GEMM is a parallel branch: it fills the SMs the keypoint GEMM's last wave leaves idle
+            # and is only joined at the end of the head
+            with _SideBranch(dev, len(jobs)) as br:
+                cls_out = _pointwise_cls(self, cls_rows, n, h, w)
+            br.keep(cls_rows)
+            branches.append(br)
+        else:
+            cls_out = _pointwise_cls(self, cls_rows, n, h, w)
+        kpt, rep = _pointwise_kpt(self, kpt_rows, n, h, w, kpt_prev, rep_prev)
+        return cls_out, kpt, rep
 
     def forward(self, cls_feat, pts_feat, reppts_offset):
         cls_feats, kpt_feats = [], []
@@ -254,6 +314,7 @@ class KGDetHead(nn.Module):
         self._fused_inference = deform_conv_cls is None     # prepared API only with the CUDA operators
         self._tensor_core_heads = True                      # bf16 mode: 1x1 convolutions as tcgen05 GEMMs
         self._fused_decode = True                           # get_bboxes: decode kernels instead of PyTorch glue
+        self.concurrent_branches = True                     # bf16 inference: cls / point branches on two streams
         deform_conv_cls = deform_conv_cls or DeformConv
         self._moment_fn = moment_fn or points2bbox_moment
         self._nms_flags_fn = nms_flags_fn or batched_nms_flags
@@ -290,19 +351,38 @@ class KGDetHead(nn.Module):
             # package's kernels.  Towers: position-major activations end to end,
             # GroupNorm + ReLU fused -- no layout transposes, no separate ReLU kernels.
             cls_feat = pts_feat = x.contiguous(memory_format=torch.channels_last)
-            for m in self.cls_convs:
-                cls_feat = groupnorm_relu_nhwc(_conv3x3_nhwc(cls_feat, m.conv), m.gn)
-            for m in self.reg_convs:
-                pts_feat = groupnorm_relu_nhwc(_conv3x3_nhwc(pts_feat, m.conv), m.gn)
             feat = self.kp_rep_block_2.cls_dfmconv_3.out_channels
-            cls1, kpt1, rep1 = self.kp_rep_block_1.forward_tc(cls_feat, pts_feat)
-            bbox1 = self.points2bbox(rep1)
-            cls_prep = prepare_input(cls_feat, feat, precision='bf16')
-            pts_prep = prepare_input(pts_feat, feat, precision='bf16')
-            cls2, kpt2, rep2 = self.kp_rep_block_2.forward_tc(cls_prep, pts_prep, rep1, kpt1)
+
+            def cls_branch(cls_feat):
+                for m in self.cls_convs:
+                    cls_feat = groupnorm_relu_nhwc(_conv3x3_nhwc(cls_feat, m.conv), m.gn)
+                return self.kp_rep_block_1.forward_tc_cls(cls_feat), prepare_input(cls_feat, feat, precision='bf16')
+
+            def pts_branch(pts_feat):
+                for m in self.reg_convs:
+                    pts_feat = groupnorm_relu_nhwc(_conv3x3_nhwc(pts_feat, m.conv), m.gn)
+                kpt1, rep1 = self.kp_rep_block_1.forward_tc_kpt(pts_feat)
+                return kpt1, rep1, self.points2bbox(rep1), prepare_input(pts_feat, feat, precision='bf16')
+
+            branches = [] if self.concurrent_branches else None
+            if self.concurrent_branches:
+                # The classification and point branches are independent up to the first deformable stage, and a
+                # 3x3 convolution on a 25x42 map is 66 CTAs of cuDNN's 256-row tile -- under half of the SMs:
+                # the two towers run as parallel branches (two streams / two arms of the captured graph).
+                with _SideBranch(x.device, 7) as br:
+                    cls1, cls_prep = cls_branch(cls_feat)
+                br.keep(cls_feat)
+                kpt1, rep1, bbox1, pts_prep = pts_branch(pts_feat)
+                br.join()
+            else:
+                cls1, cls_prep = cls_branch(cls_feat)
+                kpt1, rep1, bbox1, pts_prep = pts_branch(pts_feat)
+            cls2, kpt2, rep2 = self.kp_rep_block_2.forward_tc(cls_prep, pts_prep, rep1, kpt1, branches)
             bbox2 = self.points2bbox(rep2)
-            cls3, kpt3, rep3 = self.kp_rep_block_3.forward_tc(cls_prep, pts_prep, rep2, kpt2)
+            cls3, kpt3, rep3 = self.kp_rep_block_3.forward_tc(cls_prep, pts_prep, rep2, kpt2, branches)
             bbox3 = self.points2bbox(rep3)
+            for br in branches or ():
+                br.join()
             return cls1, cls2, cls3, kpt1, kpt2, kpt3, bbox1, bbox2, bbox3
         cls_feat = pts_feat = x
         for m in self.cls_convs:
@@ -579,3 +659,68 @@ class GraphedInference(object):
             self.static_x.copy_(x, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+    def serve(self, host_batches, host_outputs=None, before_step=None):
+        """Throughput path for HOST inputs: a three-stage software pipeline over the batches --
+
+            copy-in stream   pinned host batch i+1 -> device staging buffer          (PCIe, host -> device)
+            compute stream   staging -> the graph's static input, graph replay i, static results -> staging
+            copy-out stream  result staging of batch i-1 -> pinned host buffers      (PCIe, device -> host)
+
+        -- with two staging buffers per direction, so both copies of neighbouring batches run under the replay of
+        the current one.  `host_batches`: iterable of pinned CPU tensors shaped like the example input.
+        `host_outputs`: optional list (one entry per batch) of pinned (dets, labels, keypoints) triples to fill;
+        allocated when omitted.  `before_step(i)`: optional callable issued on the compute stream before replay i
+        (bench.py flushes the L2 there).  Returns the list of host triples; everything has completed on return."""
+        dev = self.static_x.device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, '_pipe'):
+            cin, cout = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            xs = [torch.empty_like(self.static_x) for _ in range(2)]
+            outs = [[torch.empty_like(t) for t in self.static_out] for _ in range(2)]
+            self._pipe = (cin, cout, xs, outs)
+        cin, cout, xs, outs = self._pipe
+        start = main.record_event()
+        cin.wait_event(start)
+        cout.wait_event(start)
+        x_free = [None, None]          # compute has consumed staging input b
+        out_done = [None, None]        # copy-out has drained result staging b
+        results = []
+        batches = list(host_batches)
+
+        def copy_in(i):
+            b = i % 2
+            if x_free[b] is not None:
+                cin.wait_event(x_free[b])
+            with torch.cuda.stream(cin):
+                xs[b].copy_(batches[i], non_blocking=True)
+                return cin.record_event()
+
+        ready = copy_in(0) if batches else None
+        for i in range(len(batches)):
+            b = i % 2
+            nxt = copy_in(i + 1) if i + 1 < len(batches) else None     # overlaps replay i
+            main.wait_event(ready)
+            self.static_x.copy_(xs[b], non_blocking=True)
+            x_free[b] = main.record_event()
+            if before_step is not None:
+                before_step(i)
+            self.graph.replay()
+            if out_done[b] is not None:
+                main.wait_event(out_done[b])
+            for d, t in zip(outs[b], self.static_out):
+                d.copy_(t, non_blocking=True)
+            staged = main.record_event()
+            host = host_outputs[i] if host_outputs is not None else \
+                tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in self.static_out)
+            cout.wait_event(staged)
+            with torch.cuda.stream(cout):
+                for h, d in zip(host, outs[b]):
+                    h.copy_(d, non_blocking=True)
+                out_done[b] = cout.record_event()
+            results.append(host)
+            ready = nxt
+        main.wait_stream(cout)
+        main.wait_stream(cin)
+        main.synchronize()
+        return results
