@@ -98,6 +98,10 @@ size_t umma_packed_weight_bytes(const DcnGeom& g, int precision);
 int umma_pack_weight(const DcnGeom& g, const float* weight, void* packed, int precision,
                      cudaStream_t stream);
 // in_blocked: first pixel of plane 0 of the channel-blocked input (see dcn_api.cu), planes plane_bytes apart
+// development timeline hook (kgdet_dcn_set_timeline): consumed by the next fused DCN forward or pointwise GEMM
+extern thread_local long long* g_timeline;
+extern thread_local long long g_timeline_entries;
+
 int umma_forward(const DcnGeom& g, const void* in_blocked, size_t plane_bytes, const SampleRec16* plan,
                  const void* packed_w, const float* bias, const OutSpec& o, int precision, cudaStream_t stream);
 

@@ -47,6 +47,7 @@ struct PointwiseParams {
   int a_kblocks, w_kblocks;  // Ka/64, Kw/64
   int kgroups;               // K/64 channel blocks = pipeline stages' worth of work
   int bn, ns, stage_bytes;   // column tile, pipeline depth, bytes of one stage
+  long long* timeline;       // development hook: per CTA kgroups + 8 clock64() stamps, or NULL
   int nseg;
   kgdet_pointwise_segment seg[KGDET_POINTWISE_MAX_SEGMENTS];
   uint32_t idesc;
@@ -66,6 +67,10 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
   const int nkb = prm.kgroups;
+  // [0] entry, [1] set-up done, [2 + j] issuer saw stage j full, [2 + nkb] accumulator ready (warp 2),
+  // [3 + nkb] epilogue of warp 2 done
+  long long* const tl = prm.timeline ? prm.timeline + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (nkb + 8) : nullptr;
+  if (tl && tid == 0) tl[0] = clock64();
 
   if (warp == 1) {
     if (lane == 0) {
@@ -83,6 +88,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tl && tid == 0) tl[1] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -111,6 +117,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % PW_NS;
         mbar_wait(&full_bar[s], (uint32_t)(kb / PW_NS) & 1u);
+        if (tl) tl[2 + kb] = clock64();
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + (size_t)s * PW_STAGE);
         const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
@@ -138,6 +145,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
   } else {
     // ---- epilogue: TMEM -> bias + residual -> NCHW fp32 ----
     mbar_wait(tmem_full_bar, 0);
+    if (tl && tid == 64) tl[2 + nkb] = clock64();
     tc_fence_after();
     const int q = warp & 3, half = (warp - 2) >> 2;       // TMEM lane quarter (hardware: warp % 4), column half
     const int row = q * 32 + lane;
@@ -150,36 +158,70 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
       tmem_ld_wait();
       if (m < prm.M) {
+        const int cbase = nt * PW_BN + col;               // first output column of this chunk (warp-uniform)
+        int si0 = 0;
 #pragma unroll
-        for (int j0 = 0; j0 < 32; j0 += 8) {             // 8 residual loads in flight before the first add
-          size_t o[8];
-          float r[8];
-          float* outp[8];
+        for (int q2 = 0; q2 + 1 < KGDET_POINTWISE_MAX_SEGMENTS; ++q2)
+          si0 += (q2 + 1 < prm.nseg && cbase >= prm.seg[q2].col_end) ? 1 : 0;
+        if (cbase + 32 <= prm.N && cbase + 32 <= prm.seg[si0].col_end) {
+          // Fast path (all chunks but the ones straddling a segment boundary): one segment, so a column is a
+          // constant stride HW from the previous one.  The general path below spends ~30 dependent instructions
+          // per element on the segment search and 64-bit index arithmetic, which made the epilogue 34-46 k
+          // cycles per CTA against a 20 k-cycle main loop (tools/pointwise_timeline.py).
+          const kgdet_pointwise_segment sg = prm.seg[si0];
+          const size_t o0 = ((size_t)img * sg.channels_total + sg.channel_offset + (cbase - sg.col_begin)) * prm.HW + pos;
+          float* __restrict__ op = sg.out + o0;
+          const float* __restrict__ rp = sg.residual ? sg.residual + o0 : nullptr;
+          const float* __restrict__ bp = prm.bias ? prm.bias + cbase : nullptr;
+          const size_t hw = (size_t)prm.HW;
+          if (rp) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = nt * PW_BN + col + j0 + e;
-            int si = 0;
+            for (int j0 = 0; j0 < 32; j0 += 16) {        // 16 unconditional residual loads in flight per thread
+              float r[16];
 #pragma unroll
-            for (int q2 = 0; q2 + 1 < KGDET_POINTWISE_MAX_SEGMENTS; ++q2)
-              si += (q2 + 1 < prm.nseg && c >= prm.seg[q2].col_end) ? 1 : 0;
-            const kgdet_pointwise_segment& sg = prm.seg[si];
-            o[e] = ((size_t)img * sg.channels_total + sg.channel_offset + (c - sg.col_begin)) * prm.HW + pos;
-            outp[e] = sg.out;
-            r[e] = (c < prm.N && sg.residual) ? __ldg(sg.residual + o[e]) : 0.f;
+              for (int e = 0; e < 16; ++e) r[e] = __ldg(rp + (size_t)(j0 + e) * hw);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) acc[j0 + e] = __float_as_uint(__uint_as_float(acc[j0 + e]) + r[e]);
+            }
           }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = nt * PW_BN + col + j0 + e;
-            if (c < prm.N) {
-              float v = __uint_as_float(acc[j0 + e]) + r[e];
-              if (prm.bias) v += __ldg(prm.bias + c);
-              outp[e][o[e]] = v;                           // lanes = consecutive positions: coalesced
+          for (int j = 0; j < 32; ++j) {
+            const float b = bp ? __ldg(bp + j) : 0.f;                         // warp-uniform address
+            op[(size_t)j * hw] = __uint_as_float(acc[j]) + b;                 // lanes = consecutive positions
+          }
+        } else {
+#pragma unroll
+          for (int j0 = 0; j0 < 32; j0 += 8) {
+            size_t o[8];
+            float r[8];
+            float* outp[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = cbase + j0 + e;
+              int si = 0;
+#pragma unroll
+              for (int q2 = 0; q2 + 1 < KGDET_POINTWISE_MAX_SEGMENTS; ++q2)
+                si += (q2 + 1 < prm.nseg && c >= prm.seg[q2].col_end) ? 1 : 0;
+              const kgdet_pointwise_segment& sg = prm.seg[si];
+              o[e] = ((size_t)img * sg.channels_total + sg.channel_offset + (c - sg.col_begin)) * prm.HW + pos;
+              outp[e] = sg.out;
+              r[e] = (c < prm.N && sg.residual) ? __ldg(sg.residual + o[e]) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = cbase + j0 + e;
+              if (c < prm.N) {
+                float v = __uint_as_float(acc[j0 + e]) + r[e];
+                if (prm.bias) v += __ldg(prm.bias + c);
+                outp[e][o[e]] = v;
+              }
             }
           }
         }
       }
     }
   }
+  if (tl && tid == 64) tl[3 + nkb] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)PW_BN);
@@ -324,6 +366,10 @@ extern "C" int kgdet_pointwise_conv_tiled(const void* a_tiled, const void* w_pac
   p.stage_bytes = (split ? 2 : 1) * (PW_A_BYTES + p.bn * 128);
   p.ns = pw_stages(p.stage_bytes);
   p.idesc = make_idesc(1u, PW_BM, (uint32_t)p.bn);
+  p.timeline = nullptr;
+  if (g_timeline && g_timeline_entries >= (long long)ceil_div(M, PW_BM) * ceil_div(Nout, p.bn) * (p.kgroups + 8))
+    p.timeline = g_timeline;
+  g_timeline = nullptr;
   const size_t smem = 1024 + (size_t)p.ns * p.stage_bytes + (2 * p.ns + 1) * 8 + 16;
   auto kern = split ? pointwise_umma_kernel<true> : pointwise_umma_kernel<false>;
   KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
