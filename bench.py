@@ -288,6 +288,12 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
+        traffic = None
+        try:      # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dcn_traffic.json')))
+            traffic = int(tr['dram_bytes_read']) + int(tr['dram_bytes_write'])
+        except Exception:
+            pass
         peak_tf = peaks.get('bf16_tflops_sustained') or 1400.0
         peak_src = 'bf16_tflops_sustained of MEASURED_PEAKS.json' if peaks else 'fallback 1.4 PFLOP/s sustained'
         per_k = {}
@@ -317,7 +323,10 @@ def run_ours(args):
                                  'convolutions are cuDNN' % launches_per_step,
             'roofline': {'kernel': 'dcn_umma_stream_kernel (fused bilinear gather + tcgen05 GEMM), 12 launches/step',
                          'bound': 'tensor', 'achieved': round(achieved, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
-                         'frac': round(achieved / peak_tf, 4), 'traffic': None, 'peak_source': peak_src,
+                         'frac': round(achieved / peak_tf, 4), 'traffic': traffic,
+                         'traffic_note': 'DRAM read+write bytes of one K=49 launch (ncu --set full, profiles/r1_dcn_traffic.json); '
+                                         'algorithmic bytes of that launch 54.4 MB, inputs are L2 hits',
+                         'peak_source': peak_src,
                          'share_of_step': round(tot_ms / dev_ms, 4), 'per_kernel_size': detail,
                          'timed_in': 'eager pass of the same K steps, DCN launches serialised, with CUDA events around each launch (C-ABI hook); '
                                      'share_of_step = those kernel times / graph-replayed step time'},
@@ -442,9 +451,65 @@ def run_train(args):
         opt.step()
         return loss
 
+    def fwd_bwd():
+        o = head.forward_single(x)
+        loss = 0
+        for i, lw in zip(range(3), (0.5, 0.5, 1.0)):
+            logits = o[i].permute(0, 2, 3, 1).reshape(-1, 13)
+            loss = loss + lw * ops.sigmoid_focal_loss_sum(logits, labels, None, 2.0, 0.25) / max(float(B * 10), 1.0)
+            loss = loss + lw * torch.nn.functional.smooth_l1_loss(o[6 + i], bbox_t, beta=1.0 / 9.0)
+            loss = loss + lw * torch.nn.functional.smooth_l1_loss(o[3 + i], kpt_t, beta=1.0 / 9.0)
+        loss.backward()
+        return loss
+
+    def update():
+        torch.nn.utils.clip_grad_norm_(head.parameters(), 35.0)
+        opt.step()
+
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
+
+    # The step is launch-bound at batch 2 (about 600 kernels for ~0.3 TFLOP): capture forward + losses + backward
+    # into one CUDA graph and clip + SGD into a second one; the gradient all-reduce (world > 1) runs between the
+    # two on the static gradient tensors, coalesced into one NCCL call (reference semantics: sum, then / world).
+    mode = 'eager'
+    if not args.no_graph:
+        if bucketer is not None:                         # its hooks would launch NCCL inside the capture
+            bucketer.remove()
+            bucketer = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    opt.zero_grad(set_to_none=True)
+                    fwd_bwd()
+                    update()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            opt.zero_grad(set_to_none=True)
+            g_fb, g_up = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fb):
+                static_loss = fwd_bwd()
+            with torch.cuda.graph(g_up, pool=g_fb.pool()):
+                update()
+            params = [p for p in head.parameters() if p.grad is not None]
+
+            def step():                                   # noqa: F811
+                g_fb.replay()
+                if world > 1:
+                    kdist.allreduce_grads(params, coalesce=True)
+                g_up.replay()
+                return static_loss
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            mode = 'cuda_graph (fwd+losses+bwd | all-reduce | clip+SGD)'
+        except Exception as e:
+            log('[bench] training-step graph capture failed (%r); running eagerly' % (e,))
+            torch.cuda.synchronize()
+            bucketer = kdist.GradBucketer(head.parameters(), bucket_size_mb=25) if world > 1 else None
     if world > 1:
         torch.distributed.barrier()
     evs = []
@@ -468,8 +533,10 @@ def run_train(args):
             'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
             'config': {'workload': 'KGDet head training step (fwd + 9 losses + bwd + grad all-reduce + SGD) @800x1333 '
                                    '(map 25x42), batch %d per GPU, synthetic targets' % B,
-                       'batch_per_gpu': B, 'allreduce': 'overlapped 25 MB buckets, %.1f MB fp32 gradients' % (nparam * 4 / 1e6)
+                       'batch_per_gpu': B, 'allreduce': ('one coalesced NCCL all-reduce between the two graphs' if mode != 'eager' else
+                                                         'overlapped 25 MB buckets') + ', %.1f MB fp32 gradients' % (nparam * 4 / 1e6)
                        if world > 1 else 'none (1 GPU)', 'parallelism': 'dp%d' % world, 'l2': 'flushed before every step'},
+            'launch_mode': mode,
             'final_loss': float(loss.item())}), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
