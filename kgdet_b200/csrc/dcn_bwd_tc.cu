@@ -319,7 +319,8 @@ int bwd_tc_weight(const DcnGeom& g, const void* input, const float* offset, cons
     KG_LAUNCH_CHECK("gather_colT_kernel");
     // gWT[(tap0+tl)*C + c, o] += sum_m colT[(tl*C + c), m] * goT[o, m]     (split over m)
     const int mtiles = ceil_div(nt * g.C, 128) * ceil_div(g.Cout, 256);
-    int splits = (2 * num_sms() + mtiles - 1) / mtiles;
+    // one wave of CTAs: every extra split is another 128 x 256 fp32 reduction epilogue into L2
+    int splits = num_sms() / mtiles;
     const int kblocks = (int)(mp / 64);
     if (splits > kblocks) splits = kblocks;
     if (splits < 1) splits = 1;

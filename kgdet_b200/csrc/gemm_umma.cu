@@ -4,8 +4,8 @@
 //
 // tcgen05.mma (UTCHMMA) with both operands K-major in 128B-swizzled shared memory, accumulator in TMEM.
 // One CTA = 128 x BN output tile; 8 producer warps copy operand tiles global -> swizzled smem with
-// 16-byte vector loads/stores (rows beyond M / N are zero-filled), 1 warp issues the MMAs, the producers
-// then drain TMEM.  grid.z splits the K range; split results are combined with fp32 atomics
+// 16-byte cp.async, three k-blocks in flight (rows beyond M / N are zero-filled), 1 warp issues the MMAs, the
+// producers then drain TMEM.  grid.z splits the K range; split results are combined with fp32 atomics
 // (red.global.add) into a zero-initialised C.  K must be a multiple of 64.
 #include "dcn.cuh"
 
@@ -40,6 +40,11 @@ template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p,
   v.x = *reinterpret_cast<uint32_t*>(&lo);
   v.y = *reinterpret_cast<uint32_t*>(&hi);
   *reinterpret_cast<uint2*>(p) = v;
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
 }
 
 template <int BN, typename Tout>
@@ -77,34 +82,46 @@ __global__ void __launch_bounds__(G_THREADS, 1) umma_gemm_kernel(const GemmParam
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < G_PROD_WARPS) {
+    // Producers: 16-byte cp.async (LDGSTS) straight into the swizzled tiles, no register staging; DEPTH
+    // k-blocks of copies stay in flight per thread (one commit group per k-block).  A thread's group for
+    // k-block kb has landed after cp.async.wait_group DEPTH-1; it then makes its bytes visible to the async
+    // proxy (tcgen05.mma reads) and arrives on the stage's full barrier.  The old loop held one k-block in
+    // registers and paid a full L2 round trip per k-block (~2 000 clk against a 512-clk MMA).
     const int chunk = tid & 7, rbase = tid >> 3;     // 32 rows per pass
-    for (int kb = 0; kb < nkb; ++kb) {
+    constexpr int DEPTH = 3;                         // < G_NS: the stage of kb + DEPTH was freed by MMA(kb + DEPTH - G_NS)
+    const int off = rbase * 128 + ((chunk ^ (rbase & 7)) << 4);
+    auto issue = [&](int kb) {
       const int s = kb % G_NS, it = kb / G_NS;
+      mbar_wait(&empty_bar[s], (it & 1) ^ 1);
       const long long kofs = (long long)(kb0 + kb) * 64 + chunk * 8;
-      uint4 va[G_BM / 32], vb[BN / 32];
+      const uint32_t a_dst = smem_u32(smem + (size_t)s * STAGE + off);
+      const uint32_t b_dst = a_dst + A_BYTES;
 #pragma unroll
       for (int p = 0; p < G_BM / 32; ++p) {
         const int r = m0 + rbase + p * 32;
-        va[p] = make_uint4(0u, 0u, 0u, 0u);
-        if (r < prm.M) va[p] = __ldg(reinterpret_cast<const uint4*>(prm.A + (long long)r * prm.lda + kofs));
+        const bool ok = r < prm.M;
+        const __nv_bfloat16* src = prm.A + (long long)(ok ? r : 0) * prm.lda + kofs;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_dst + p * 4096), "l"(src), "r"(ok ? 16 : 0) : "memory");
       }
 #pragma unroll
       for (int p = 0; p < BN / 32; ++p) {
         const int r = n0 + rbase + p * 32;
-        vb[p] = make_uint4(0u, 0u, 0u, 0u);
-        if (r < prm.N) vb[p] = __ldg(reinterpret_cast<const uint4*>(prm.B + (long long)r * prm.ldb + kofs));
+        const bool ok = r < prm.N;
+        const __nv_bfloat16* src = prm.B + (long long)(ok ? r : 0) * prm.ldb + kofs;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(b_dst + p * 4096), "l"(src), "r"(ok ? 16 : 0) : "memory");
       }
-      mbar_wait(&empty_bar[s], (it & 1) ^ 1);
-      unsigned char* a_tile = smem + (size_t)s * STAGE;
-      unsigned char* b_tile = a_tile + A_BYTES;
-      const int off = rbase * 128 + ((chunk ^ (rbase & 7)) << 4);
-#pragma unroll
-      for (int p = 0; p < G_BM / 32; ++p) *reinterpret_cast<uint4*>(a_tile + off + p * 4096) = va[p];
-#pragma unroll
-      for (int p = 0; p < BN / 32; ++p) *reinterpret_cast<uint4*>(b_tile + off + p * 4096) = vb[p];
+    };
+    for (int kb = 0; kb < DEPTH - 1; ++kb) {
+      if (kb < nkb) issue(kb);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+      if (kb + DEPTH - 1 < nkb) issue(kb + DEPTH - 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");          // (possibly empty) group of k-block kb + DEPTH - 1
+      asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");   // k-block kb has landed
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
+      if (lane == 0) mbar_arrive(&full_bar[kb % G_NS]);
     }
     // ---- epilogue ----
     mbar_wait(tmem_full_bar, 0);
@@ -122,12 +139,32 @@ __global__ void __launch_bounds__(G_THREADS, 1) umma_gemm_kernel(const GemmParam
         const int n = n0 + col;
         if (prm.atomic) {
           float* crow = reinterpret_cast<float*>(prm.C) + (long long)m * prm.ldc + n;
+          if (n + 32 <= prm.N && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+            // red.global.add.v4.f32: 8 vector reductions per thread instead of 32 scalar ones (lanes are
+            // different rows, so every scalar atomic was its own L2 transaction)
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n + j < prm.N) atomicAdd(crow + j, prm.alpha * __uint_as_float(acc[j]));
+            for (int j = 0; j < 32; j += 4)
+              atomicAdd(reinterpret_cast<float4*>(crow + j),
+                        make_float4(prm.alpha * __uint_as_float(acc[j]), prm.alpha * __uint_as_float(acc[j + 1]),
+                                    prm.alpha * __uint_as_float(acc[j + 2]), prm.alpha * __uint_as_float(acc[j + 3])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < prm.N) atomicAdd(crow + j, prm.alpha * __uint_as_float(acc[j]));
+          }
         } else {
           Tout* crow = reinterpret_cast<Tout*>(prm.C) + (long long)m * prm.ldc + n;
-          if (n + 32 <= prm.N) {
+          if (n + 32 <= prm.N && sizeof(Tout) == 2 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {            // 16-byte stores: whole 32-byte sectors after two of them
+              uint4 v;
+              v.x = pack2(prm.alpha * __uint_as_float(acc[j]), prm.alpha * __uint_as_float(acc[j + 1]));
+              v.y = pack2(prm.alpha * __uint_as_float(acc[j + 2]), prm.alpha * __uint_as_float(acc[j + 3]));
+              v.z = pack2(prm.alpha * __uint_as_float(acc[j + 4]), prm.alpha * __uint_as_float(acc[j + 5]));
+              v.w = pack2(prm.alpha * __uint_as_float(acc[j + 6]), prm.alpha * __uint_as_float(acc[j + 7]));
+              *reinterpret_cast<uint4*>(crow + j) = v;
+            }
+          } else if (n + 32 <= prm.N) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               st4<Tout>(crow + j, prm.alpha * __uint_as_float(acc[j]), prm.alpha * __uint_as_float(acc[j + 1]),

@@ -60,6 +60,14 @@ def quick():
         ms = kernel_only(lambda: ops.deform_conv(x, off, w, 1, k // 2), flush)
         row[name + '_us'] = round(ms * 1e3, 1)
         row[name + '_tflops'] = round(2.0 * 16 * 25 * 42 * 256 * 256 * k * k / ms / 1e9, 1)
+        if '--bwd' in sys.argv:
+            go = d['grad_out'].cuda()
+            xg, og, wg = x.clone().requires_grad_(), off.clone().requires_grad_(), w.clone().requires_grad_()
+
+            def fb():
+                xg.grad = og.grad = wg.grad = None
+                ops.deform_conv(xg, og, wg, 1, k // 2).backward(go)
+            row[name + '_fwd_bwd_us'] = round(timed(fb, flush, reps=5, warm=2) * 1e3, 1)
     print(json.dumps(row), flush=True)
 
 
