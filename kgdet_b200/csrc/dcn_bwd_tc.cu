@@ -16,6 +16,13 @@
 
 namespace kgdet {
 
+// gather-fused weight gradient (dcn_wgrad_umma.cu)
+bool wgrad_fused_supported(const DcnGeom& g);
+size_t wgrad_fused_go_bytes(const DcnGeom& g);
+int launch_go_to_tiled(const DcnGeom& g, const void* grad_output, void* tiled, int dtype, cudaStream_t stream);
+int wgrad_fused(const DcnGeom& g, const void* in_blocked, size_t plane_bytes, const SampleRec16* plan,
+                const void* go_tiled, float* gwt, cudaStream_t stream);
+
 int umma_gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, void* C,
               long long ldc, int M, int N, int K, int out_dtype, int splits, float alpha, cudaStream_t stream);
 
@@ -296,7 +303,38 @@ static TcBwdWWs carve_tc_w(const DcnGeom& g, void* ws) {
   w.total = off;
   return w;
 }
-size_t bwd_tc_weight_workspace_bytes(const DcnGeom& g) { return carve_tc_w(g, nullptr).total; }
+// fused path: channel-blocked bf16 planes with guard bands (as the forward), compact plan, tiled gO, gW^T
+struct TcWFusedWs {
+  unsigned char* planes;
+  size_t guard_bytes, in_bytes, plane_bytes;
+  SampleRec16* plan;
+  unsigned char* go_tiled;
+  float* gwt;
+  size_t total;
+};
+static TcWFusedWs carve_tc_w_fused(const DcnGeom& g, void* ws) {
+  TcWFusedWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* p = ws ? (char*)ws + off : nullptr; off += align_up(bytes, 1024); return p; };
+  w.guard_bytes = (size_t)dcn_guard_pixels(g) * 128;
+  w.in_bytes = (size_t)g.N * g.H * g.W * 128;
+  w.plane_bytes = align_up(w.in_bytes + 2 * w.guard_bytes, 1024);
+  w.planes = (unsigned char*)take(w.plane_bytes * (g.C / 64));
+  w.plan = (SampleRec16*)take(plan16_bytes(g));
+  w.go_tiled = (unsigned char*)take(wgrad_fused_go_bytes(g));
+  w.gwt = (float*)take((size_t)g.K * g.C * g.Cout * 4);
+  w.total = off;
+  return w;
+}
+static bool use_fused_wgrad(const DcnGeom& g) {
+  if (const char* e = getenv("KGDET_WGRAD_FUSED")) return atoi(e) != 0 && wgrad_fused_supported(g);
+  return wgrad_fused_supported(g);
+}
+size_t bwd_tc_weight_workspace_bytes(const DcnGeom& g) {
+  const size_t a = carve_tc_w(g, nullptr).total;
+  const size_t b = wgrad_fused_supported(g) ? carve_tc_w_fused(g, nullptr).total : 0;
+  return a > b ? a : b;
+}
 
 static int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
@@ -333,10 +371,35 @@ int bwd_tc_input(const DcnGeom& g, const void* input, const float* offset, const
 int bwd_tc_weight(const DcnGeom& g, const void* input, const float* offset, const float* mask,
                   const void* grad_output, float* grad_weight, float* grad_bias, float scale, int dtype,
                   void* ws, cudaStream_t stream) {
-  TcBwdWWs w = carve_tc_w(g, ws);
   const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
-  const long long mp = (long long)mpad64(g);
   int rc;
+  if (use_fused_wgrad(g)) {
+    TcWFusedWs f = carve_tc_w_fused(g, ws);
+    const int planes = g.C / 64;
+    KG_CUDA(cudaMemset2DAsync(f.planes, f.plane_bytes, 0, f.guard_bytes, planes, stream));
+    KG_CUDA(cudaMemset2DAsync(f.planes + f.guard_bytes + f.in_bytes, f.plane_bytes, 0,
+                              f.plane_bytes - f.guard_bytes - f.in_bytes, planes, stream));
+    if ((rc = launch_nchw_to_blocked(input, f.planes + f.guard_bytes, g.N, g.C, HW, 64, f.plane_bytes, dtype,
+                                     KGDET_BF16, stream)) != KGDET_OK) return rc;
+    if ((rc = launch_plan16(g, offset, mask, f.plan, PLAN16_BF16W, stream)) != KGDET_OK) return rc;
+    if ((rc = launch_go_to_tiled(g, grad_output, f.go_tiled, dtype, stream)) != KGDET_OK) return rc;
+    KG_CUDA(cudaMemsetAsync(f.gwt, 0, (size_t)g.K * g.C * g.Cout * 4, stream));
+    if ((rc = wgrad_fused(g, f.planes + f.guard_bytes, f.plane_bytes, f.plan, f.go_tiled, f.gwt, stream)) != KGDET_OK)
+      return rc;
+    unpack_gw_kernel<<<grid_for((long long)g.Cout * g.C * g.K, 256), 256, 0, stream>>>(f.gwt, grad_weight, g.Cout, g.C,
+                                                                                       g.K, scale);
+    KG_LAUNCH_CHECK("unpack_gw_kernel");
+    if (grad_bias) {
+      if (dtype == KGDET_F32)
+        bias_grad_nchw_kernel<float><<<g.Cout, 256, 0, stream>>>((const float*)grad_output, g.N, g.Cout, HoWo, grad_bias);
+      else
+        bias_grad_nchw_kernel<__nv_bfloat16><<<g.Cout, 256, 0, stream>>>((const __nv_bfloat16*)grad_output, g.N, g.Cout, HoWo, grad_bias);
+      KG_LAUNCH_CHECK("bias_grad_nchw_kernel");
+    }
+    return KGDET_OK;
+  }
+  TcBwdWWs w = carve_tc_w(g, ws);
+  const long long mp = (long long)mpad64(g);
   if ((rc = launch_transpose(input, w.in_nhwc, g.N, g.C, HW, dtype, KGDET_BF16, stream)) != KGDET_OK) return rc;
   if ((rc = launch_plan(g, offset, mask, w.plan, nullptr, stream)) != KGDET_OK) return rc;
   KG_CUDA(cudaMemsetAsync(w.goT, 0, (size_t)g.Cout * mp * 2, stream));

@@ -3,6 +3,8 @@
 Tolerances (BASELINE.json north_star): rel 1e-5 for the fp32-grade modes ('fp32', 'tf32x3'),
 1e-2 for 'bf16'; 'tf32' (single pass) is checked at 5e-3.  rel = max|d| / max|ref|.
 """
+import os
+
 import pytest
 import torch
 
@@ -262,6 +264,15 @@ def test_tensor_core_backward_full_size_vs_exact():
     # grad_offset of the tensor-core path has a single writer per element: bitwise reproducible
     again = _ours(d, 'bf16')
     assert torch.equal(fast['grad_offset'], again['grad_offset'])
+    # the weight gradient above came from the gather-fused kernel (dcn_wgrad_umma.cu: C = 256); the unfused
+    # path (transposed columns + split-K GEMM) must agree with it to bf16 rounding of the sampled values
+    os.environ['KGDET_WGRAD_FUSED'] = '0'
+    try:
+        unfused = _ours(d, 'bf16')
+    finally:
+        del os.environ['KGDET_WGRAD_FUSED']
+    assert rel_err(unfused['grad_weight'], exact['grad_weight']) < TOL['bf16']
+    assert rel_err(unfused['grad_weight'], fast['grad_weight']) < 5e-3
 
 
 @pytest.mark.parametrize('precision,tol', [('bf16', 1e-2), ('tf32x3', 2e-4), ('tf32', 5e-3)])
