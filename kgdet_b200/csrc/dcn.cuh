@@ -103,7 +103,9 @@ extern thread_local long long* g_timeline;
 extern thread_local long long g_timeline_entries;
 
 int umma_forward(const DcnGeom& g, const void* in_blocked, size_t plane_bytes, const SampleRec16* plan,
-                 const void* packed_w, const float* bias, const OutSpec& o, int precision, cudaStream_t stream);
+                 const void* packed_w, const float* bias, const OutSpec& o, int precision, cudaStream_t stream, void* split_ws = nullptr);
+int umma_splits(const DcnGeom& g, int precision);
+size_t umma_split_ws_bytes(const DcnGeom& g, int precision);   // 0 when the call is not split
 
 // ---- tensor-core backward (bf16 mode; dcn_bwd_tc.cu) ----
 bool bwd_tc_supported(const DcnGeom& g, int precision);

@@ -95,7 +95,8 @@ int do_prepare_plan(const DcnGeom& g, const float* offset, const float* mask, vo
 }
 
 int do_forward_prepared(const DcnGeom& g, const void* prepared, const void* plan, const void* weight_packed,
-                        const float* bias, const OutSpec& o, int precision, cudaStream_t stream) {
+                        const float* bias, const OutSpec& o, int precision, cudaStream_t stream,
+                        void* split_ws = nullptr) {
   const PrepIn p = prep_in_layout(g, precision);
   const char* in_nhwc = (const char*)prepared + p.guard_bytes;     // first pixel of plane 0
   cudaEvent_t ev0 = g_prof_start, ev1 = g_prof_stop;
@@ -104,7 +105,7 @@ int do_forward_prepared(const DcnGeom& g, const void* prepared, const void* plan
   int rc;
   if (use_umma(g, precision))
     rc = umma_forward(g, in_nhwc, p.plane_bytes, (const SampleRec16*)plan, weight_packed, bias, o, precision,
-                      stream);
+                      stream, split_ws);
   else
     rc = simt_forward(g, (const float*)in_nhwc, (const SampleRec*)plan, (const float*)weight_packed, bias, o,
                       stream);
@@ -177,7 +178,8 @@ extern "C" int kgdet_dcn_pack_weight(const float* weight, void* weight_packed,
 extern "C" size_t kgdet_dcn_forward_workspace_bytes(const kgdet_dcn_shape* shape, int, int precision) {
   DcnGeom g;
   if (make_geom(shape, &g) != KGDET_OK) return 0;
-  return prep_in_layout(g, precision).total + plan_layout_bytes(g, precision);
+  return prep_in_layout(g, precision).total + plan_layout_bytes(g, precision) +
+         (use_umma(g, precision) ? umma_split_ws_bytes(g, precision) : 0);
 }
 
 extern "C" int kgdet_dcn_forward(const void* input, const float* offset, const float* mask,
@@ -192,14 +194,17 @@ extern "C" int kgdet_dcn_forward(const void* input, const float* offset, const f
   KG_CHECK_ARG(valid_prec(precision), "kgdet_dcn_forward: bad precision %d", precision);
   KG_CHECK_ARG(input && offset && weight_packed && output, "kgdet_dcn_forward: NULL pointer");
   const size_t in_total = prep_in_layout(g, precision).total;
-  if ((rc = check_ws("kgdet_dcn_forward", workspace, workspace_bytes,
-                     in_total + plan_layout_bytes(g, precision))) != KGDET_OK) return rc;
+  const size_t plan_total = plan_layout_bytes(g, precision);
+  const size_t split_total = use_umma(g, precision) ? umma_split_ws_bytes(g, precision) : 0;
+  if ((rc = check_ws("kgdet_dcn_forward", workspace, workspace_bytes, in_total + plan_total + split_total)) != KGDET_OK)
+    return rc;
   void* prepared = workspace;
   void* plan = (char*)workspace + in_total;
+  void* split_ws = split_total ? (char*)workspace + in_total + plan_total : nullptr;
   if ((rc = do_prepare_input(g, input, prepared, dtype, precision, stream)) != KGDET_OK) return rc;
   if ((rc = do_prepare_plan(g, offset, mask, plan, precision, stream)) != KGDET_OK) return rc;
   OutSpec o{output, dtype, 0, g.Cout, 0, 0};
-  return do_forward_prepared(g, prepared, plan, weight_packed, bias, o, precision, stream);
+  return do_forward_prepared(g, prepared, plan, weight_packed, bias, o, precision, stream, split_ws);
 }
 
 extern "C" size_t kgdet_dcn_prepared_input_bytes(const kgdet_dcn_shape* shape, int precision) {

@@ -90,11 +90,64 @@ int umma_pack_weight(const DcnGeom& g, const float* weight, void* packed, int pr
   return KGDET_OK;
 }
 
+// ---- split-K over CTAs for small maps ------------------------------------------------------------------
+// The fused kernel is one CTA per 128 positions, each a serial pipeline of nkb k-blocks at ~1 155 clk: a map of
+// M = 2 100 positions (KGDet training at batch 2, or FPN P6 / P7) keeps 17 of 148 SMs busy for the whole call.
+// When the tiles cover less than half of the SMs the k-blocks are split over gridDim.y CTAs per tile; the partial
+// accumulators go through an fp32 buffer and are combined by umma_split_reduce_kernel (deterministic order).
+int umma_splits(const DcnGeom& g, int precision) {
+  if (!umma_supported(g, precision)) return 1;
+  const int tiles = ceil_div(g.M, BM);
+  const int nkb = (g.C / bk_of(precision)) * g.K;
+  int s = num_sms() / tiles;
+  if (s > nkb / 6) s = nkb / 6;                 // at least 6 k-blocks per CTA
+  if (s > 16) s = 16;
+  if (s < 4) s = 1;                             // measured: 2 splits (FPN P5 at batch 8, 66 tiles) lose to the reduction pass
+  if (const char* e = getenv("KGDET_UMMA_SPLITS")) s = atoi(e);
+  return s < 1 ? 1 : s;
+}
+size_t umma_split_ws_bytes(const DcnGeom& g, int precision) {
+  const int s = umma_splits(g, precision);
+  return s > 1 ? (size_t)s * ceil_div(g.M, BM) * BM * g.Cout * sizeof(float) : 0;
+}
+
+// out[n, coff + o, p] = act(bias[o] + sum_s partial[s][m][o]),  m = n * HoWo + p;  32 x 32 tiles through smem
+template <typename Tout>
+__global__ void umma_split_reduce_kernel(const float* __restrict__ partial, int splits, long long split_stride,
+                                         const float* __restrict__ bias, Tout* __restrict__ out, int M, int Cout,
+                                         int HoWo, int coff, int ctot, int relu) {
+  __shared__ float tile[32][33];
+  const int m0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int m = m0 + ty + k, o = o0 + tx;
+    float v = 0.f;
+    if (m < M && o < Cout) {
+      const float* p = partial + (size_t)m * Cout + o;
+      for (int s = 0; s < splits; ++s) v += p[(size_t)s * split_stride];
+      if (bias) v += __ldg(bias + o);
+      if (relu) v = fmaxf(v, 0.f);
+    }
+    tile[ty + k][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int o = o0 + ty + k, m = m0 + tx;
+    if (m < M && o < Cout) {
+      const int n = m / HoWo, pos = m - n * HoWo;
+      st_out<Tout>(out + ((size_t)n * ctot + coff + o) * HoWo + pos, tile[tx][ty + k]);
+    }
+  }
+}
+
 thread_local long long* g_timeline = nullptr;
 thread_local long long g_timeline_entries = 0;
 
 int umma_forward(const DcnGeom& g, const void* in_blocked, size_t plane_bytes, const SampleRec16* plan,
-                 const void* packed_w, const float* bias, const OutSpec& o, int precision, cudaStream_t stream) {
+                 const void* packed_w, const float* bias, const OutSpec& o, int precision, cudaStream_t stream,
+                 void* split_ws) {
   if (!umma_supported(g, precision)) {
     set_error("dcn umma: shape/precision not supported by the tensor-core path");
     return KGDET_ERR_UNSUPPORTED;
@@ -117,7 +170,25 @@ int umma_forward(const DcnGeom& g, const void* in_blocked, size_t plane_bytes, c
   p.timeline = nullptr;
   if (g_timeline && g_timeline_entries >= (long long)ceil_div(g.M, BM) * (2 * p.nkb + 8)) p.timeline = g_timeline;
   g_timeline = nullptr;
-  return umma_stream_forward(g, p, mode, pair, o.dtype, stream);
+  p.partial = nullptr; p.kb_per_split = p.nkb; p.m_pad = ceil_div(g.M, BM) * BM;
+  const int splits = (split_ws && !pair && !o.nhwc) ? umma_splits(g, precision) : 1;
+  if (splits <= 1) return umma_stream_forward(g, p, mode, pair, o.dtype, stream);
+  p.partial = (float*)split_ws;
+  p.kb_per_split = ceil_div(p.nkb, splits);
+  const int used = ceil_div(p.nkb, p.kb_per_split);             // every split owns at least one k-block
+  int rc = umma_stream_forward(g, p, mode, false, o.dtype, stream, used);
+  if (rc != KGDET_OK) return rc;
+  const dim3 grid((unsigned)ceil_div(g.M, 32), (unsigned)ceil_div(g.Cout, 32)), block(32, 8);
+  const long long stride = (long long)p.m_pad * g.Cout;
+  if (o.dtype == KGDET_F32)
+    umma_split_reduce_kernel<float><<<grid, block, 0, stream>>>(p.partial, used, stride, bias, (float*)o.out, g.M, g.Cout,
+                                                               g.Ho * g.Wo, o.coff, o.ctot, o.relu);
+  else
+    umma_split_reduce_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(p.partial, used, stride, bias,
+                                                                       (__nv_bfloat16*)o.out, g.M, g.Cout, g.Ho * g.Wo,
+                                                                       o.coff, o.ctot, o.relu);
+  KG_LAUNCH_CHECK("umma_split_reduce_kernel");
+  return KGDET_OK;
 }
 
 }  // namespace kgdet

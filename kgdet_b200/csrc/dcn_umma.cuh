@@ -39,6 +39,11 @@ struct UmmaParams {
   //   [0] kernel entry, [1] set-up done, [2 + j] control lane saw k-block j full, [2 + nkb] accumulator ready,
   //   [3 + nkb] epilogue done, [4 + nkb + j] producer thread 0 finished k-block j
   long long* timeline;
+  // split-K over CTAs (small maps: fewer than half as many tiles as SMs): blockIdx.y owns k-blocks
+  // [y * kb_per_split, ...), and writes its raw fp32 accumulator tile to partial[y][m][Cout]; a second
+  // kernel adds the splits, bias and ReLU and writes the output layout.  NULL = no split.
+  float* partial;
+  int kb_per_split, m_pad;
 };
 
 
@@ -97,6 +102,6 @@ __device__ __forceinline__ void decode_rec(const float4& r, float (&w)[4]) {
 
 // streaming kernel (dcn_umma_stream.cu)
 int umma_stream_forward(const DcnGeom& g, const UmmaParams& p, int mode, bool pair, int out_dtype,
-                        cudaStream_t stream);
+                        cudaStream_t stream, int splits = 1);
 
 }  // namespace kgdet

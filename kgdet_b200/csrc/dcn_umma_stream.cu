@@ -140,9 +140,11 @@ __global__ void __launch_bounds__(Producers<RPT>::THREADS, 1) dcn_umma_stream_ke
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM;
-  const int nkb = prm.nkb;
+  // k-block range of this CTA: everything, or one split of it (prm.partial != NULL)
+  const int kb_lo = prm.partial ? (int)blockIdx.y * prm.kb_per_split : 0;
+  const int nkb = prm.partial ? min(prm.nkb - kb_lo, prm.kb_per_split) : prm.nkb;
   constexpr int SETUP_WARP = PRODUCER_WARPS;
-  long long* const tl = prm.timeline ? prm.timeline + (size_t)blockIdx.x * (2 * nkb + 8) : nullptr;
+  long long* const tl = (prm.timeline && !prm.partial) ? prm.timeline + (size_t)blockIdx.x * (2 * nkb + 8) : nullptr;
   if (tl && tid == 0) tl[0] = clock64();
 
   if (warp == SETUP_WARP) {
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(Producers<RPT>::THREADS, 1) dcn_umma_stream_ke
     const size_t b_full_tile = (size_t)BN * 128;                          // one packed tile, all Cout rows
     // the packed layout always carries hi+lo for tf32; single-pass TF32 copies only hi
     const size_t b_src_stride = (size_t)(MODE == MODE_BF16 ? 1 : 2) * b_full_tile;
-    const unsigned char* src = prm.wp + (size_t)cta_rank * b_tile_bytes + (size_t)kq * b_src_stride;
+    const unsigned char* src = prm.wp + (size_t)cta_rank * b_tile_bytes + (size_t)(kb_lo + kq) * b_src_stride;
     unsigned char* dstb = smem + (size_t)sq * stage_bytes + MT::A_TILES * A_TILE_BYTES;
     mbar_arrive_expect_tx(&full_bar[sq], b_bytes);
     if (!PAIR || MT::B_TILES == 1) {
@@ -271,8 +273,8 @@ __global__ void __launch_bounds__(Producers<RPT>::THREADS, 1) dcn_umma_stream_ke
     };
 
     // (tap, channel block) of the k-block whose gathers are issued next, and tap of the next record fetch
-    int tapI = 0, cbI = 0, tapR = 0;
-    const unsigned char* in_plane = in_base;              // plane of the k-block whose gathers are issued next
+    int tapI = kb_lo % K, cbI = kb_lo / K, tapR = 0;
+    const unsigned char* in_plane = in_base + (size_t)cbI * prm.plane_bytes;   // plane of the k-block whose gathers are issued next
     auto issue = [&](int slot, int row, const uint4& rec) {
       const unsigned char* p0 = in_plane + (long long)(int)rec.x * rowb;
       v[slot][row][0] = __ldg(reinterpret_cast<const uint4*>(p0));
@@ -346,7 +348,14 @@ __global__ void __launch_bounds__(Producers<RPT>::THREADS, 1) dcn_umma_stream_ke
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
       tmem_ld_wait();
-      if (row_ok) {
+      if (prm.partial) {
+        // split-K: raw accumulators, position-major (m_pad = whole tiles, so every row may be written)
+        float* prow = prm.partial + ((size_t)blockIdx.y * prm.m_pad + m0 + row) * BN + col;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(prow + j) = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
+                                                             __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+      } else if (row_ok) {
         if (prm.out_nhwc) {
           // "UMMA-tiled rows" (pointwise_umma.cu): bf16, [M/128 tiles][k-blocks of 64 channels][128 rows x 128 B,
           // 16-byte chunk c of row r at chunk c ^ (r & 7)] -- exactly the A operand slabs of the 1x1-convolution
@@ -413,12 +422,12 @@ static size_t stream_smem_bytes(int mode, int ns, int Cout, bool pair) {
 }
 
 template <int MODE, int NS, int DEPTH, typename Tout, bool PAIR, int RPT>
-static int launch_stream(const UmmaParams& p, int grid, cudaStream_t stream) {
+static int launch_stream(const UmmaParams& p, int grid, cudaStream_t stream, int splits) {
   const size_t smem = stream_smem_bytes(MODE, NS, p.Cout, PAIR);
   auto kern = dcn_umma_stream_kernel<MODE, NS, DEPTH, Tout, PAIR, RPT>;
   KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid, 1, 1);         // PAIR: even, one cluster = two consecutive 128-row tiles
+  cfg.gridDim = dim3((unsigned)grid, (unsigned)splits, 1);   // PAIR: even, one cluster = two consecutive 128-row tiles
   cfg.blockDim = dim3(Producers<RPT>::THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -435,13 +444,13 @@ static int launch_stream(const UmmaParams& p, int grid, cudaStream_t stream) {
 }
 
 template <int MODE, typename Tout, bool PAIR>
-static int dispatch_stages(const UmmaParams& p, int grid, int ns, cudaStream_t stream) {
+static int dispatch_stages(const UmmaParams& p, int grid, int ns, cudaStream_t stream, int splits) {
   // rows per producer thread: 4 (8 producer warps) measured best -- K = 49 call 137 us vs 145 us with 2 rows
   // (16 warps) and 161 us with 8 rows (4 warps)
   switch (ns) {
-    case 2: return launch_stream<MODE, 2, 1, Tout, PAIR, 4>(p, grid, stream);
-    case 3: return launch_stream<MODE, 3, 1, Tout, PAIR, 4>(p, grid, stream);
-    case 4: return launch_stream<MODE, 4, 1, Tout, PAIR, 4>(p, grid, stream);
+    case 2: return launch_stream<MODE, 2, 1, Tout, PAIR, 4>(p, grid, stream, splits);
+    case 3: return launch_stream<MODE, 3, 1, Tout, PAIR, 4>(p, grid, stream, splits);
+    case 4: return launch_stream<MODE, 4, 1, Tout, PAIR, 4>(p, grid, stream, splits);
     default: break;
   }
   set_error("dcn umma stream: unsupported stage count %d", ns);
@@ -449,13 +458,13 @@ static int dispatch_stages(const UmmaParams& p, int grid, int ns, cudaStream_t s
 }
 
 template <int MODE, typename Tout>
-static int dispatch_pair(const UmmaParams& p, int grid, int ns, bool pair, cudaStream_t stream) {
-  return pair ? dispatch_stages<MODE, Tout, true>(p, grid, ns, stream)
-              : dispatch_stages<MODE, Tout, false>(p, grid, ns, stream);
+static int dispatch_pair(const UmmaParams& p, int grid, int ns, bool pair, cudaStream_t stream, int splits) {
+  return pair ? dispatch_stages<MODE, Tout, true>(p, grid, ns, stream, splits)
+              : dispatch_stages<MODE, Tout, false>(p, grid, ns, stream, splits);
 }
 
 int umma_stream_forward(const DcnGeom& g, const UmmaParams& p0, int mode, bool pair, int out_dtype,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int splits) {
   UmmaParams p = p0;
   p.tmem_cols = g.Cout <= 64 ? 64 : (g.Cout <= 128 ? 128 : 256);   // one accumulator, power of two >= 32
   const int grid = pair ? 2 * ceil_div(g.M, 2 * BM) : ceil_div(g.M, BM);
@@ -474,14 +483,14 @@ int umma_stream_forward(const DcnGeom& g, const UmmaParams& p0, int mode, bool p
   const bool f32 = out_dtype == KGDET_F32;
   switch (mode) {
     case MODE_BF16:
-      return f32 ? dispatch_pair<MODE_BF16, float>(p, grid, ns, pair, stream)
-                 : dispatch_pair<MODE_BF16, __nv_bfloat16>(p, grid, ns, pair, stream);
+      return f32 ? dispatch_pair<MODE_BF16, float>(p, grid, ns, pair, stream, splits)
+                 : dispatch_pair<MODE_BF16, __nv_bfloat16>(p, grid, ns, pair, stream, splits);
     case MODE_TF32X3:
-      return f32 ? dispatch_pair<MODE_TF32X3, float>(p, grid, ns, pair, stream)
-                 : dispatch_pair<MODE_TF32X3, __nv_bfloat16>(p, grid, ns, pair, stream);
+      return f32 ? dispatch_pair<MODE_TF32X3, float>(p, grid, ns, pair, stream, splits)
+                 : dispatch_pair<MODE_TF32X3, __nv_bfloat16>(p, grid, ns, pair, stream, splits);
     default:
-      return f32 ? dispatch_pair<MODE_TF32, float>(p, grid, ns, pair, stream)
-                 : dispatch_pair<MODE_TF32, __nv_bfloat16>(p, grid, ns, pair, stream);
+      return f32 ? dispatch_pair<MODE_TF32, float>(p, grid, ns, pair, stream, splits)
+                 : dispatch_pair<MODE_TF32, __nv_bfloat16>(p, grid, ns, pair, stream, splits);
   }
 }
 

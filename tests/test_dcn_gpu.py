@@ -208,9 +208,12 @@ def test_oracle_matches_reference_cuda():
 @pytest.mark.parametrize('precision', ['fp32', 'bf16', 'tf32x3'])
 def test_prepared_api_matches_plain_calls(precision):
     """Shared NHWC copy + shared plan + fused ReLU / channel-slice epilogue == relu(deform_conv) + cat,
-    bit for bit (same kernels, same arithmetic)."""
+    bit for bit (same kernels, same arithmetic).  The plain call would split these tiny maps over k-blocks
+    (different fp32 summation order, test_split_k_forward_equals_unsplit); the split is switched off here so that
+    the comparison stays bitwise."""
     from kgdet_b200 import ops
     ops.set_precision(precision)
+    os.environ['KGDET_UMMA_SPLITS'] = '1'
     try:
         d3 = dcn_case(N=2, C=64, H=12, W=10, Cout=64, k=3, seed=1)
         d5 = dcn_case(N=2, C=64, H=12, W=10, Cout=64, k=5, seed=2)
@@ -230,6 +233,7 @@ def test_prepared_api_matches_plain_calls(precision):
                                          d3['weight'].cuda())
         assert torch.equal(plain, ops.deform_conv(x, d3['offset'].cuda(), d3['weight'].cuda(), 1, 1))
     finally:
+        del os.environ['KGDET_UMMA_SPLITS']
         ops.set_precision(None)
 
 
@@ -284,6 +288,7 @@ def test_cta_pair_variant_matches_default(monkeypatch, precision, tol):
     d = dcn_case(N=2, C=128, H=13, W=21, Cout=192, k=3, seed=11)
     x, off, w = (d[q].cuda() for q in ('x', 'offset', 'weight'))
     ops.set_precision(precision)
+    monkeypatch.setenv('KGDET_UMMA_SPLITS', '1')       # the pair variant never splits the k-blocks; keep both launches whole
     try:
         monkeypatch.setenv('KGDET_UMMA_PAIR', '0')
         base = ops.deform_conv(x, off, w, 1, 1)
@@ -294,3 +299,31 @@ def test_cta_pair_variant_matches_default(monkeypatch, precision, tol):
     ref = dcn_oracle.deform_conv_forward(d['x'].double(), d['offset'].double(), d['weight'].double(), 1, 1)
     assert rel_err(pair, ref) < tol
     assert torch.equal(pair, base)
+
+
+@pytest.mark.parametrize('precision,tol', [('bf16', 1e-2), ('tf32', 5e-3)])
+def test_split_k_forward_equals_unsplit(precision, tol):
+    """Small maps split the k-blocks of a tile over several CTAs (dcn_umma.cu: umma_splits) and combine the fp32
+    partial tiles in a fixed order: same result as the one-CTA-per-tile kernel up to fp32 summation order, and
+    both within the mode's tolerance of the oracle; bias, bf16 output and a ragged last tile included."""
+    from kgdet_b200 import ops
+    d = dcn_case(N=2, C=128, H=13, W=21, Cout=192, k=5, seed=5)
+    ref_out, _ = _oracle(d)
+    x, off, w = (d[q].cuda() for q in ('x', 'offset', 'weight'))
+    ops.set_precision(precision)
+    try:
+        split = ops.deform_conv(x, off, w, 1, 2)
+        os.environ['KGDET_UMMA_SPLITS'] = '1'
+        try:
+            whole = ops.deform_conv(x, off, w, 1, 2)
+        finally:
+            del os.environ['KGDET_UMMA_SPLITS']
+        os.environ['KGDET_UMMA_SPLITS'] = '7'          # uneven: 50 k-blocks in 7 splits of 8 (last one 2)
+        try:
+            uneven = ops.deform_conv(x, off, w, 1, 2)
+        finally:
+            del os.environ['KGDET_UMMA_SPLITS']
+    finally:
+        ops.set_precision(None)
+    assert rel_err(split, ref_out) < tol and rel_err(whole, ref_out) < tol
+    assert rel_err(split, whole) < 1e-5 and rel_err(uneven, whole) < 1e-5
