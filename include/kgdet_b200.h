@@ -288,7 +288,7 @@ KGDET_API int kgdet_points2bbox_moment_backward(const float* pts, const float* m
 KGDET_API void kgdet_dcn_set_profile_events(void* start_event, void* stop_event);
 
 /* Development hook: the NEXT fused tensor-core forward writes clock64() stamps of its pipeline
- * (per CTA 2 * nkb + 8 int64: entry, set-up done, per-k-block "stage full" seen by the MMA
+ * (per CTA 4 * nkb + 8 int64: entry, set-up done, per-k-block "stage full" seen by the MMA
  * issuer, accumulator ready, epilogue done, per-k-block producer progress) into `device_buffer`
  * if `entries` is large enough, then clears the hook.  tools/dcn_timeline.py reads it. */
 KGDET_API void kgdet_dcn_set_timeline(void* device_buffer, long long entries);

@@ -168,7 +168,7 @@ int umma_forward(const DcnGeom& g, const void* in_blocked, size_t plane_bytes, c
   p.idesc = make_idesc(mode == MODE_BF16 ? 1u : 2u, pair ? 2 * BM : BM, (uint32_t)g.Cout);
   p.tmem_cols = 0;   // set by the kernel launcher
   p.timeline = nullptr;
-  if (g_timeline && g_timeline_entries >= (long long)ceil_div(g.M, BM) * (2 * p.nkb + 8)) p.timeline = g_timeline;
+  if (g_timeline && g_timeline_entries >= (long long)ceil_div(g.M, BM) * (12 * p.nkb + 8)) p.timeline = g_timeline;
   g_timeline = nullptr;
   p.partial = nullptr; p.kb_per_split = p.nkb; p.m_pad = ceil_div(g.M, BM) * BM;
   const int splits = (split_ws && !pair && !o.nhwc) ? umma_splits(g, precision) : 1;

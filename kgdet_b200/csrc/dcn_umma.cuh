@@ -35,9 +35,10 @@ struct UmmaParams {
   int nkb;                   // (C / BK) * K
   uint32_t idesc;
   uint32_t tmem_cols;
-  // development hook (kgdet_dcn_set_timeline): per CTA 2 * nkb + 8 clock64() stamps, or NULL
+  // development hook (kgdet_dcn_set_timeline): per CTA 4 * nkb + 8 clock64() stamps, or NULL
   //   [0] kernel entry, [1] set-up done, [2 + j] control lane saw k-block j full, [2 + nkb] accumulator ready,
-  //   [3 + nkb] epilogue done, [4 + nkb + j] producer thread 0 finished k-block j
+  //   [3 + nkb] epilogue done, [4 + nkb + j] producer thread 0 arrived for k-block j,
+  //   [4 + 2 nkb + j] producer thread 0 acquired the stage of k-block j, [4 + 3 nkb + j] its stores are issued
   long long* timeline;
   // split-K over CTAs (small maps: fewer than half as many tiles as SMs): blockIdx.y owns k-blocks
   // [y * kb_per_split, ...), and writes its raw fp32 accumulator tile to partial[y][m][Cout]; a second

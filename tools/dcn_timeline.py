@@ -31,7 +31,7 @@ def main():
         x, off, w = (d[q].cuda() for q in ('x', 'offset', 'weight'))
         nkb = 4 * k * k
         ctas = (N * H * W + 127) // 128
-        per = 2 * nkb + 8
+        per = 12 * nkb + 8
         for _ in range(3):
             ops.deform_conv(x, off, w, 1, k // 2)
         buf = torch.zeros(ctas * per, dtype=torch.int64, device='cuda')
@@ -43,6 +43,8 @@ def main():
         t0 = t[:, 0:1]
         full = t[:, 2:2 + nkb] - t0                      # control lane saw stage j full
         prod = t[:, 4 + nkb:4 + 2 * nkb] - t0            # producer thread 0 finished k-block j
+        acq = t[:, 4 + 2 * nkb:4 + 3 * nkb] - t0         # producer thread 0 acquired the stage
+        sto = t[:, 4 + 3 * nkb:4 + 4 * nkb] - t0         # ... its combine / stores / re-arm are issued
         d_full = full[:, 1:] - full[:, :-1]
         med = lambda v: float(v.median())
         iv = d_full.median(0).values                     # per-k-block interval, median over CTAs
@@ -56,6 +58,15 @@ def main():
                    last_full_to_acc_ready=med(t[:, 2 + nkb] - t[:, 1 + nkb]),
                    epilogue=med(t[:, 3 + nkb] - t[:, 2 + nkb]),
                    total=med(t[:, 3 + nkb] - t[:, 0]),
+                   # steady state (k-blocks 8 .. nkb-4), medians over k-blocks and CTAs, in clocks
+                   prod_wait_empty=med((acq[:, 8:-4] - prod[:, 7:-5])),         # arrive(kb-1) -> stage of kb acquired
+                   prod_work=med((sto[:, 8:-4] - acq[:, 8:-4])),                # combine + stores + re-arm
+                   prod_fence_arrive=med((prod[:, 8:-4] - sto[:, 8:-4])),       # fence.proxy.async + syncwarp + arrive
+                   full_lag_after_thread0=med((full[:, 8:-4] - prod[:, 8:-4])), # slowest warp + control poll
+                   recycle=med((acq[:, 11:-1] - full[:, 8:-4])),                # full(kb) seen -> stage re-acquired for kb+3
+                   # arrival of each producer warp relative to the barrier completing (control lane's view), clocks
+                   warp_arrive_before_full=[round(med(full[:, 8:-4] - (t[:, 4 + (4 + wq) * nkb:4 + (5 + wq) * nkb] - t0)[:, 8:-4]))
+                                            for wq in range(8)],
                    intervals_first_60=[round(float(v)) for v in iv[:60]])
         print(json.dumps(row), flush=True)
 
