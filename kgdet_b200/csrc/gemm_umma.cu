@@ -130,7 +130,42 @@ __global__ void __launch_bounds__(G_THREADS, 1) umma_gemm_kernel(const GemmParam
     const int row = q * 32 + lane;
     const int m = m0 + row;
     constexpr int HALF = BN / 2;
-    for (int c0 = 0; c0 < HALF; c0 += 32) {
+    bool staged = false;
+    if constexpr (sizeof(Tout) == 2 && BN == 256) {
+      // bf16 output, full-width tile: stage the 128 x 256 tile in shared memory (the pipeline buffers are idle
+      // once the accumulator is complete) and write whole 512-byte rows, one per warp instruction.  A thread owns
+      // an accumulator ROW, so direct stores put 32 different lines (16 bytes each) into every instruction; the
+      // column-gradient GEMM of the DCN backward has only 4 k-blocks per tile and was bound by exactly that.
+      if (!prm.atomic && n0 + BN <= prm.N && nkb > 0 && (prm.ldc & 7) == 0 &&
+          (reinterpret_cast<uintptr_t>(prm.C) & 15) == 0) {
+        constexpr int PITCH = BN * 2 + 16;                  // bytes; +16 keeps the 16-byte row writes conflict-free
+        unsigned char* st = smem;
+        for (int c0 = 0; c0 < HALF; c0 += 32) {
+          const int col = half * HALF + c0;
+          uint32_t acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 v;
+            v.x = pack2(prm.alpha * __uint_as_float(acc[j]), prm.alpha * __uint_as_float(acc[j + 1]));
+            v.y = pack2(prm.alpha * __uint_as_float(acc[j + 2]), prm.alpha * __uint_as_float(acc[j + 3]));
+            v.z = pack2(prm.alpha * __uint_as_float(acc[j + 4]), prm.alpha * __uint_as_float(acc[j + 5]));
+            v.w = pack2(prm.alpha * __uint_as_float(acc[j + 6]), prm.alpha * __uint_as_float(acc[j + 7]));
+            *reinterpret_cast<uint4*>(st + (size_t)row * PITCH + (col + j) * 2) = v;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(G_PROD_WARPS * 32) : "memory");      // the eight epilogue warps only
+        __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(prm.C) + n0;
+        for (int r = warp; r < G_BM; r += G_PROD_WARPS) {
+          if (m0 + r < prm.M)
+            *reinterpret_cast<uint4*>(cbase + (long long)(m0 + r) * prm.ldc + lane * 8) =
+                *reinterpret_cast<const uint4*>(st + (size_t)r * PITCH + lane * 16);
+        }
+        staged = true;
+      }
+    }
+    for (int c0 = 0; c0 < HALF && !staged; c0 += 32) {
       const int col = half * HALF + c0;
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
