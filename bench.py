@@ -384,6 +384,8 @@ def run_reference(args):
     world = int(os.environ.get('WORLD_SIZE', 1))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is one process using all host cores
+    torch.set_num_threads(os.cpu_count() or 1)
     n = args.ref_images
     step = _cpu_step_fn(args, n)
     for _ in range(min(max(args.warmup, 1), 2)):     # CPU arm: at most two untimed warm-up steps
