@@ -318,9 +318,9 @@ def run_ours(args):
                     'sync_note': 'one batch at a time, host-synchronised after every step (latency, not throughput)'},
             'gpu_launches': launches_per_step * args.steps,
             'gpu_launches_note': '%d kernels of libkgdet_b200.so per step, counted by the library (kgdet_launch_count): '
-                                 '6 GroupNorm+ReLU, 2 rows->DCN planes, 2 rows->GEMM tiles, 6 sample plans, 12 fused '
-                                 'tcgen05 DCN, 6 pointwise tcgen05 GEMMs, 3 moment, 1 batched NMS; the 8 plain 3x3 '
-                                 'convolutions are cuDNN' % launches_per_step,
+                                 '1 NCHW->NHWC, 6 GroupNorm+ReLU, 2 rows->DCN planes, 2 rows->GEMM tiles (+bias+ReLU), 6 sample '
+                                 'plans, 12 fused tcgen05 DCN, 6 pointwise tcgen05 GEMMs, 3 moment, 3 decode (select / decode / '
+                                 'finalize), 1 batched NMS, 1 top-k; the 8 plain 3x3 convolutions are cuDNN' % launches_per_step,
             'roofline': {'kernel': 'dcn_umma_stream_kernel (fused bilinear gather + tcgen05 GEMM), 12 launches/step',
                          'bound': 'tensor', 'achieved': round(achieved, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': round(achieved / peak_tf, 4), 'traffic': traffic,

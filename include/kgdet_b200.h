@@ -127,6 +127,14 @@ KGDET_API int kgdet_dcn_forward_prepared(const void* prepared_input, const void*
                                int32_t out_channels_total, int fuse_relu, int out_layout,
                                const kgdet_dcn_shape* shape, int dtype, int precision, void* stream);
 
+/* Global top-k over the survivors of the batched NMS (mmdet/core/post_processing/bbox_nms_kp.py:64-70:
+ * sort the concatenated per-class results by score, keep max_num).  dets [B, L, 5] (score in column 4), flags
+ * [B*L] uint8 (1 = kept by kgdet_nms_batched), L = classes * candidates <= 16384.  top_s [B, k] scores in
+ * descending order (ties: lower index first; -1 for empty slots), top_i [B, k] int64 index into L (0 for empty
+ * slots).  One CTA per image, no host synchronisation. */
+KGDET_API int kgdet_topk_flagged(const float* dets, const uint8_t* flags, int32_t B, int32_t L, int32_t k,
+                       float* top_s, int64_t* top_i, void* stream);
+
 /* ---- post-head decode around the batched NMS --------------------------
  * replaces the PyTorch glue of get_bboxes_single (KP3:843-903) and multiclass_nms_kp
  * (core/post_processing/bbox_nms_kp.py:6-75) for ONE head level, batched over images, static shapes:
@@ -173,9 +181,10 @@ KGDET_API int kgdet_pointwise_pack_weight(const float* weight, void* packed, int
  * (stage-1 activations after a cuDNN convolution).  C % 64 == 0. */
 KGDET_API int kgdet_nchw_to_tiled_bf16(const void* src, void* dst, int32_t N, int32_t C, int32_t S, int src_dtype,
                              int fuse_relu, int split, void* stream);
-/* position-major fp32 rows [M, C] (channels_last activation) -> the same tiled rows */
-KGDET_API int kgdet_rows_to_tiled_bf16(const float* rows, void* tiled, int64_t M, int32_t C, int fuse_relu, int split,
-                             void* stream);
+/* position-major fp32 rows [M, C] (channels_last activation) -> the same tiled rows; `bias` (fp32 [C] or NULL) is
+ * added before the optional ReLU (the bias of the 3x3 convolution that produced the rows, conv -> +b -> ReLU) */
+KGDET_API int kgdet_rows_to_tiled_bf16(const float* rows, const float* bias, void* tiled, int64_t M, int32_t C,
+                             int fuse_relu, int split, void* stream);
 KGDET_API int kgdet_pointwise_conv_tiled(const void* a_tiled, const void* w_packed, const float* bias, int32_t M,
                                int32_t K, int32_t Nout, int32_t HW, int split,
                                const kgdet_pointwise_segment* segs, int32_t nseg, void* stream);

@@ -113,9 +113,81 @@ __global__ void bbox_finalize_kernel(const float* __restrict__ boxes, const floa
   }
 }
 
+// Global top-k over the survivors of the batched NMS (bbox_nms_kp.py:64-70: `scores.sort(descending)[:max_num]`
+// over the concatenated per-class results): one CTA per image.  The kept (class, candidate) pairs are compacted
+// into shared memory (typically a few hundred of the 13 x 1000 candidates), sorted there by (score desc,
+// index asc) with a bitonic network sized to the kept count, and the first k leave.  Replaces
+// torch.where + torch.topk (one 16-CTA radix-select launch of ~59 us on the critical path of the step).
+// top_s of an empty slot is -1 (the PyTorch path's filler), its top_i 0.
+static constexpr int kTopkCap = 16384;
+
+__device__ __forceinline__ bool topk_before(float sa, int ia, float sb, int ib) {
+  return (sa > sb) || (sa == sb && ia < ib);
+}
+
+__global__ void __launch_bounds__(1024, 1)
+topk_flagged_kernel(const float* __restrict__ dets, const uint8_t* __restrict__ flags, int L, int k,
+                    float* __restrict__ top_s, long long* __restrict__ top_i) {
+  extern __shared__ __align__(16) unsigned char topk_smem[];
+  float* key = reinterpret_cast<float*>(topk_smem);
+  int* idx = reinterpret_cast<int*>(key + kTopkCap);
+  __shared__ int cnt;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) cnt = 0;
+  __syncthreads();
+  const uint8_t* f = flags + (size_t)b * L;
+  const float* d = dets + (size_t)b * L * 5;
+  for (int i = tid; i < L; i += nt) {
+    if (f[i]) {
+      const int slot = atomicAdd(&cnt, 1);               // order is irrelevant: the sort key is (score, index)
+      key[slot] = d[(size_t)i * 5 + 4];
+      idx[slot] = i;
+    }
+  }
+  __syncthreads();
+  const int m = cnt;
+  int P = 32;
+  while (P < m) P <<= 1;
+  for (int i = m + tid; i < P; i += nt) { key[i] = -INFINITY; idx[i] = 0x7fffffff; }
+  __syncthreads();
+  for (int kk = 2; kk <= P; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += nt) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float si = key[i], sl = key[l];
+          const int ii = idx[i], il = idx[l];
+          const bool up = ((i & kk) == 0);
+          const bool swap = up ? topk_before(sl, il, si, ii) : topk_before(si, ii, sl, il);
+          if (swap) { key[i] = sl; key[l] = si; idx[i] = il; idx[l] = ii; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = tid; j < k; j += nt) {
+    const bool has = j < m;
+    top_s[(size_t)b * k + j] = has ? key[j] : -1.f;
+    top_i[(size_t)b * k + j] = has ? (long long)idx[j] : 0ll;
+  }
+}
+
 }  // namespace kgdet
 
 using namespace kgdet;
+
+extern "C" int kgdet_topk_flagged(const float* dets, const uint8_t* flags, int32_t B, int32_t L, int32_t k,
+                                  float* top_s, int64_t* top_i, void* stream) {
+  KG_CHECK_ARG(dets && flags && top_s && top_i, "kgdet_topk_flagged: NULL pointer");
+  KG_CHECK_ARG(B >= 0 && L >= 1 && k >= 1 && B <= 65535, "kgdet_topk_flagged: bad sizes");
+  KG_CHECK_ARG(L <= kTopkCap, "kgdet_topk_flagged: at most %d candidates per image", kTopkCap);
+  if (B == 0) return KGDET_OK;
+  const size_t smem = (size_t)kTopkCap * 8;
+  KG_CUDA(cudaFuncSetAttribute(topk_flagged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_flagged_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(dets, flags, L, k, top_s, (long long*)top_i);
+  KG_LAUNCH_CHECK("topk_flagged_kernel");
+  return KGDET_OK;
+}
 
 extern "C" int kgdet_bbox_select(const float* scores, int apply_sigmoid, int32_t B, int32_t C, int32_t HW,
                                  int32_t n, int32_t* order, void* stream) {

@@ -166,8 +166,8 @@ __global__ void rows_to_blocked_kernel(const float* __restrict__ rows, unsigned 
 }
 
 // rows [M, C] fp32 -> UMMA-tiled bf16 rows (pointwise_umma.cu), one thread per 8 channels
-__global__ void rows_to_tiled_kernel(const float* __restrict__ rows, unsigned char* __restrict__ dst, long long M,
-                                     int C, int relu, int split) {
+__global__ void rows_to_tiled_kernel(const float* __restrict__ rows, const float* __restrict__ bias,
+                                     unsigned char* __restrict__ dst, long long M, int C, int relu, int split) {
   const int chunks_per_row = C / 8;
   const int a_kblocks = (split ? 2 : 1) * (C / 64);
   const long long total = M * chunks_per_row;
@@ -178,6 +178,12 @@ __global__ void rows_to_tiled_kernel(const float* __restrict__ rows, unsigned ch
     float v[8];
     *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(src);
     *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(src + 4);
+    if (bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ch * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ch * 8 + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
     if (relu) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
@@ -251,12 +257,13 @@ extern "C" int kgdet_groupnorm_relu_nhwc(const float* x, const float* gamma, con
   return KGDET_OK;
 }
 
-extern "C" int kgdet_rows_to_tiled_bf16(const float* rows, void* tiled, int64_t M, int32_t C, int fuse_relu, int split,
-                                        void* stream) {
+extern "C" int kgdet_rows_to_tiled_bf16(const float* rows, const float* bias, void* tiled, int64_t M, int32_t C,
+                                        int fuse_relu, int split, void* stream) {
   KG_CHECK_ARG(rows && tiled, "kgdet_rows_to_tiled_bf16: NULL pointer");
+  KG_CHECK_ARG(!bias || ((uintptr_t)bias & 15) == 0, "kgdet_rows_to_tiled_bf16: bias must be 16-byte aligned");
   KG_CHECK_ARG(M >= 0 && C >= 64 && C % 64 == 0, "kgdet_rows_to_tiled_bf16: C %% 64 == 0 required");
   if (M == 0) return KGDET_OK;
-  rows_to_tiled_kernel<<<grid_for(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>(rows, (unsigned char*)tiled, M, C,
+  rows_to_tiled_kernel<<<grid_for(M * (C / 8)), 256, 0, (cudaStream_t)stream>>>(rows, bias, (unsigned char*)tiled, M, C,
                                                                                 fuse_relu ? 1 : 0, split ? 1 : 0);
   KG_LAUNCH_CHECK("rows_to_tiled_kernel");
   return KGDET_OK;

@@ -30,8 +30,8 @@ import torch.nn.functional as F
 from .ops import (DeformConv, TiledRows, batched_nms_flags, deform_conv_prepared, get_precision,
                   groupnorm_relu_nhwc, nchw_to_tiled, pack_weight, points2bbox_moment, pointwise_conv,
                   prepare_input, prepare_plan, prepare_plan_points)
-from .ops.decode import bbox_decode, bbox_finalize, bbox_select
-from .ops.pointwise import cached
+from .ops.decode import bbox_decode, bbox_finalize, bbox_select, topk_flagged
+from .ops.pointwise import cached, to_channels_last
 
 _POINT_SETS = (3, 5, 7)          # KP3:257: 9 + 25 + 49 points regardless of cfg.num_reppts
 
@@ -73,8 +73,8 @@ def _cl_weight(w):
     return cached((w,), lambda: w.detach().contiguous(memory_format=torch.channels_last))
 
 
-def _conv3x3_nhwc(x_cl, conv):
-    b = None if conv.bias is None else conv.bias.detach()
+def _conv3x3_nhwc(x_cl, conv, with_bias=True):
+    b = None if (conv.bias is None or not with_bias) else conv.bias.detach()
     return F.conv2d(x_cl, _cl_weight(conv.weight), b, conv.stride, conv.padding)
 
 
@@ -183,12 +183,15 @@ class _PlainBlock(nn.Module):
 
     def forward_tc_cls(self, cls_feat):
         n, _, h, w = cls_feat.shape
-        cls_rows = nchw_to_tiled(_conv3x3_nhwc(cls_feat, self.cls_conv), relu=True, split=True)
+        # the convolution's bias is added by the tiling kernel (cuDNN would launch a separate add)
+        cls_rows = nchw_to_tiled(_conv3x3_nhwc(cls_feat, self.cls_conv, False), relu=True, split=True,
+                                 bias=self.cls_conv.bias)
         return _pointwise_cls(self, cls_rows, n, h, w)
 
     def forward_tc_kpt(self, pts_feat):
         n, _, h, w = pts_feat.shape
-        kpt_rows = nchw_to_tiled(_conv3x3_nhwc(pts_feat, self.keypts_conv), relu=True, split=True)
+        kpt_rows = nchw_to_tiled(_conv3x3_nhwc(pts_feat, self.keypts_conv, False), relu=True, split=True,
+                                 bias=self.keypts_conv.bias)
         return _pointwise_kpt(self, kpt_rows, n, h, w)
 
 
@@ -350,7 +353,7 @@ class KGDetHead(nn.Module):
             # bf16 mode: everything except the eight plain 3x3 convolutions (cuDNN, channels_last) runs on this
             # package's kernels.  Towers: position-major activations end to end,
             # GroupNorm + ReLU fused -- no layout transposes, no separate ReLU kernels.
-            cls_feat = pts_feat = x.contiguous(memory_format=torch.channels_last)
+            cls_feat = pts_feat = to_channels_last(x)
             feat = self.kp_rep_block_2.cls_dfmconv_3.out_channels
 
             def cls_branch(cls_feat):
@@ -452,9 +455,13 @@ class KGDetHead(nn.Module):
             boxes, dets = bbox_decode(src, sig, bp.float().contiguous(), order, wh, stride)
             C = dets.shape[1]
             flags = self._nms_flags_fn(dets.view(-1, 5), None, n, iou_thr, score_thr=score_thr)
-            masked = torch.where(flags.view(B, C * n).bool(), dets[..., 4].reshape(B, C * n),
-                                 dets.new_full((), -1.0))
-            top_s, top_i = masked.topk(min(max_per_img, C * n), dim=1)                 # bbox_nms_kp.py:64-70
+            if C * n <= 16384:
+                # survivors compacted + sorted inside one CTA per image (bbox_nms_kp.py:64-70)
+                top_s, top_i = topk_flagged(dets.view(B, C * n, 5), flags.view(B, C * n), min(max_per_img, C * n))
+            else:
+                masked = torch.where(flags.view(B, C * n).bool(), dets[..., 4].reshape(B, C * n),
+                                     dets.new_full((), -1.0))
+                top_s, top_i = masked.topk(min(max_per_img, C * n), dim=1)
             return bbox_finalize(boxes, kp.float().contiguous(), order, top_i, top_s, wh, stride, (H, W))
         boxes_l, scores_l, kpts_l = [], [], []
         for lvl, (cs, kp, bp) in enumerate(zip(cls_scores, keypts_preds, bbox_preds)):

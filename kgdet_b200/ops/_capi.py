@@ -68,7 +68,7 @@ SIGNATURES = {
     'kgdet_pointwise_pack_weight': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, ctypes.c_int, c_ptr]),
     'kgdet_nchw_to_tiled_bf16': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_int, c_ptr]),
-    'kgdet_rows_to_tiled_bf16': (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int64, c_i32, ctypes.c_int, ctypes.c_int,
+    'kgdet_rows_to_tiled_bf16': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, ctypes.c_int64, c_i32, ctypes.c_int, ctypes.c_int,
                                                 c_ptr]),
     'kgdet_groupnorm_relu_nhwc': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_f32, c_i32, ctypes.c_int, c_ptr, c_i32,
                                                  c_i32, c_i32, c_ptr]),
@@ -102,6 +102,7 @@ SIGNATURES = {
                                                         ctypes.c_int, c_ptr, c_ptr]),
     'kgdet_points2bbox_moment_backward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32,
                                                          ctypes.c_int, c_f32, c_ptr, c_ptr, c_ptr]),
+    'kgdet_topk_flagged': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     'kgdet_dcn_set_profile_events': (None, [c_ptr, c_ptr]),
     'kgdet_dcn_set_timeline': (None, [c_ptr, ctypes.c_longlong]),
     'kgdet_nchw_to_nhwc': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, ctypes.c_int,

@@ -52,3 +52,16 @@ def bbox_finalize(boxes, keypts, order, top_i, top_s, img_wh, stride, map_hw):
                                         out_dets.data_ptr(), out_labels.data_ptr(), out_kpts.data_ptr(),
                                         _capi.stream_of(boxes)), 'kgdet_bbox_finalize')
     return out_dets, out_labels, out_kpts
+
+
+def topk_flagged(dets, flags, k):
+    """Top-k by score over the rows of `dets` [B, L, 5] whose `flags` [B, L] (uint8) are set: -> (top_s [B, k]
+    descending, -1 for empty slots; top_i [B, k] int64).  L <= 16384."""
+    lib = _capi.lib()
+    assert dets.dtype == torch.float32 and dets.is_contiguous() and flags.dtype == torch.uint8 and flags.is_contiguous()
+    B, L = dets.shape[0], dets.shape[1]
+    top_s = torch.empty((B, k), dtype=torch.float32, device=dets.device)
+    top_i = torch.empty((B, k), dtype=torch.int64, device=dets.device)
+    _capi.check(lib.kgdet_topk_flagged(dets.data_ptr(), flags.data_ptr(), B, L, k, top_s.data_ptr(), top_i.data_ptr(),
+                                       _capi.stream_of(dets)), 'kgdet_topk_flagged')
+    return top_s, top_i

@@ -108,3 +108,22 @@ def test_batched_dense_mode_with_score_threshold():
     assert np.array_equal(flags, want)
     none = batched_nms_flags(dets.cuda(), None, n, 0.5, score_thr=2.0).cpu().numpy()
     assert none.sum() == 0
+
+
+def test_topk_flagged_matches_torch_topk():
+    """Top-k over the NMS survivors (bbox_nms_kp.py:64-70) in one CTA per image == torch.where + torch.topk on
+    distinct scores: plenty of survivors, fewer than k, none at all, and a full-size 13 x 1000 candidate list."""
+    import torch
+    from kgdet_b200.ops.decode import topk_flagged
+    g = torch.Generator().manual_seed(3)
+    for B, L, k, p_keep in [(3, 500, 100, 0.5), (2, 300, 100, 0.1), (2, 64, 10, 0.0), (4, 13000, 100, 0.08),
+                            (1, 16384, 100, 1.0)]:
+        dets = torch.rand(B, L, 5, generator=g).cuda()
+        flags = (torch.rand(B, L, generator=g) < p_keep).to(torch.uint8).cuda()
+        top_s, top_i = topk_flagged(dets, flags, k)
+        masked = torch.where(flags.bool(), dets[..., 4], dets.new_full((), -1.0))
+        ws, wi = masked.topk(k, dim=1)
+        assert torch.equal(top_s, ws)
+        kept = ws > 0
+        assert torch.equal(top_i[kept], wi[kept])
+        assert (top_i[~kept] == 0).all()
