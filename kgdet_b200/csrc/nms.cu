@@ -92,19 +92,25 @@ nms_small_kernel(const float* __restrict__ dets, const int32_t* __restrict__ seg
   __syncthreads();
   {
     // rows whose score does not exceed score_thr are absent (multiclass_nms_kp's `scores > score_thr`
-    // filter, bbox_nms_kp.py:39, folded into the op so that the caller needs no compaction)
-    int cnt = 0;
-    for (int i = tid; i < P; i += nt) {
-      float sc = -INFINITY;
-      if (i < n) {
-        const float v = d[i * 5 + 4];
-        if (v > score_thr) { sc = v; ++cnt; }
+    // filter, bbox_nms_kp.py:39, folded into the op so that the caller needs no compaction).  Present rows are
+    // compacted to the front (slot order is irrelevant: the sort key (score, index) is a total order), so the
+    // sort below runs on the next power of two above the PRESENT count, not above the segment length -- with
+    // ~10 % of 1000 candidates above the threshold that is 128 elements and 28 passes instead of 1024 and 55.
+    for (int i = tid; i < n; i += nt) {
+      const float v = d[i * 5 + 4];
+      if (v > score_thr) {
+        const int slot = atomicAdd(&n_valid, 1);
+        key[slot] = v;
+        idx[slot] = i;
+      } else {
+        flags[row0 + i] = 0;
       }
-      key[i] = sc;
-      idx[i] = (i < n) ? i : 0x7fffffff;
     }
-    if (cnt) atomicAdd(&n_valid, cnt);
   }
+  __syncthreads();
+  P = 32;
+  while (P < n_valid) P <<= 1;
+  for (int i = n_valid + tid; i < P; i += nt) { key[i] = -INFINITY; idx[i] = 0x7fffffff; }
   __syncthreads();
   // bitonic sort, ascending in the `before` order
   for (int k = 2; k <= P; k <<= 1) {
@@ -122,8 +128,7 @@ nms_small_kernel(const float* __restrict__ dets, const int32_t* __restrict__ seg
       __syncthreads();
     }
   }
-  // absent rows sort behind every present one (their key is -inf): only the first n_valid matter
-  for (int i = n_valid + tid; i < n_rows; i += nt) flags[row0 + idx[i]] = 0;
+  // only the first n_valid slots hold rows (absent rows were flagged 0 above)
   n = n_valid;
   if (n == 0) return;
   // gather boxes in sorted order
