@@ -46,6 +46,7 @@ struct PointwiseParams {
   int M, N, HW;
   int a_kblocks, w_kblocks;  // Ka/64, Kw/64
   int kgroups;               // K/64 channel blocks = pipeline stages' worth of work
+  int tiles_m, tiles_n;      // output tiles (128 rows x bn columns); CTAs are persistent over them
   int bn, ns, stage_bytes;   // column tile, pipeline depth, bytes of one stage
   long long* timeline;       // development hook: per CTA kgroups + 8 clock64() stamps, or NULL
   int nseg;
@@ -61,15 +62,20 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
   const int PW_NS = prm.ns, PW_STAGE = prm.stage_bytes, PW_BN = prm.bn, PW_B_BYTES = prm.bn * 128;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)PW_NS * PW_STAGE);
   uint64_t* empty_bar = full_bar + PW_NS;
-  uint64_t* tmem_full_bar = empty_bar + PW_NS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + PW_NS;        // [2]: accumulator a is complete
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]: accumulator a has been drained by the epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int mt = blockIdx.x, nt = blockIdx.y;
   const int nkb = prm.kgroups;
-  // [0] entry, [1] set-up done, [2 + j] issuer saw stage j full, [2 + nkb] accumulator ready (warp 2),
-  // [3 + nkb] epilogue of warp 2 done
-  long long* const tl = prm.timeline ? prm.timeline + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (nkb + 8) : nullptr;
+  // Persistent CTAs: tile t = blockIdx.x + i * gridDim.x (i = 0, 1, ...), column tile fastest so that the CTAs
+  // working on one row tile at the same time share its A slabs in L2.  Two TMEM accumulators: the epilogue
+  // warps drain accumulator i & 1 while the MMA warp already fills the other one for tile i + 1 -- the epilogue
+  // (15-17 k clk with residuals) used to be serial with a 20 k-clk main loop.
+  const int ntiles = prm.tiles_m * prm.tiles_n;
+  // development stamps for the CTA's FIRST tile: [0] entry, [1] set-up done, [2 + j] issuer saw stage j full,
+  // [2 + nkb] accumulator ready (warp 2), [3 + nkb] epilogue of warp 2 done
+  long long* const tl = prm.timeline ? prm.timeline + (size_t)blockIdx.x * (nkb + 8) : nullptr;
   if (tl && tid == 0) tl[0] = clock64();
 
   if (warp == 1) {
@@ -78,11 +84,14 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
         mbar_init(&full_bar[s], 1);      // the producer's expect_tx arrive
         mbar_init(&empty_bar[s], 1);     // one tcgen05.commit
       }
-      mbar_init(tmem_full_bar, 1);
+      for (int a2 = 0; a2 < 2; ++a2) {
+        mbar_init(&tmem_full_bar[a2], 1);
+        mbar_init(&tmem_empty_bar[a2], PW_EPI_WARPS);
+      }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, (uint32_t)PW_BN);
+    tmem_alloc(tmem_slot, (uint32_t)(2 * PW_BN));
   }
   tc_fence_before();
   __syncthreads();
@@ -92,60 +101,78 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
 
   if (warp == 0) {
     if (lane == 0) {
-      const unsigned char* a_tile = prm.A + (size_t)mt * prm.a_kblocks * PW_A_BYTES;
-      const unsigned char* w_tile = prm.W + (size_t)nt * prm.w_kblocks * PW_B_BYTES;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % PW_NS;
-        mbar_wait(&empty_bar[s], ((uint32_t)(kb / PW_NS) & 1u) ^ 1u);
-        unsigned char* dst = smem + (size_t)s * PW_STAGE;
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)PW_STAGE);
-        // stage layout: A_hi [A_lo] W_hi [W_lo]
-        bulk_g2s(dst, a_tile + (size_t)kb * PW_A_BYTES, PW_A_BYTES, &full_bar[s]);
-        if constexpr (SPLIT) {
-          bulk_g2s(dst + PW_A_BYTES, a_tile + (size_t)(nkb + kb) * PW_A_BYTES, PW_A_BYTES, &full_bar[s]);
-          bulk_g2s(dst + 2 * PW_A_BYTES, w_tile + (size_t)kb * PW_B_BYTES, PW_B_BYTES, &full_bar[s]);
-          bulk_g2s(dst + 2 * PW_A_BYTES + PW_B_BYTES, w_tile + (size_t)(2 * nkb + kb) * PW_B_BYTES, PW_B_BYTES,
-                   &full_bar[s]);
-        } else {
-          bulk_g2s(dst + PW_A_BYTES, w_tile + (size_t)kb * PW_B_BYTES, PW_B_BYTES, &full_bar[s]);
+      int it = 0;                                         // running stage counter across tiles
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int mt = t / prm.tiles_n, nt = t - mt * prm.tiles_n;
+        const unsigned char* a_tile = prm.A + (size_t)mt * prm.a_kblocks * PW_A_BYTES;
+        const unsigned char* w_tile = prm.W + (size_t)nt * prm.w_kblocks * PW_B_BYTES;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % PW_NS;
+          mbar_wait(&empty_bar[s], ((uint32_t)(it / PW_NS) & 1u) ^ 1u);
+          unsigned char* dst = smem + (size_t)s * PW_STAGE;
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)PW_STAGE);
+          // stage layout: A_hi [A_lo] W_hi [W_lo]
+          bulk_g2s(dst, a_tile + (size_t)kb * PW_A_BYTES, PW_A_BYTES, &full_bar[s]);
+          if constexpr (SPLIT) {
+            bulk_g2s(dst + PW_A_BYTES, a_tile + (size_t)(nkb + kb) * PW_A_BYTES, PW_A_BYTES, &full_bar[s]);
+            bulk_g2s(dst + 2 * PW_A_BYTES, w_tile + (size_t)kb * PW_B_BYTES, PW_B_BYTES, &full_bar[s]);
+            bulk_g2s(dst + 2 * PW_A_BYTES + PW_B_BYTES, w_tile + (size_t)(2 * nkb + kb) * PW_B_BYTES, PW_B_BYTES,
+                     &full_bar[s]);
+          } else {
+            bulk_g2s(dst + PW_A_BYTES, w_tile + (size_t)kb * PW_B_BYTES, PW_B_BYTES, &full_bar[s]);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % PW_NS;
-        mbar_wait(&full_bar[s], (uint32_t)(kb / PW_NS) & 1u);
-        if (tl) tl[2 + kb] = clock64();
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * PW_STAGE);
-        const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
-        if constexpr (SPLIT) {
-          const uint64_t adesc_lo = make_sw128_kmajor_desc(a_addr + PW_A_BYTES);
-          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + 2 * PW_A_BYTES);
-          const uint64_t bdesc_lo = make_sw128_kmajor_desc(a_addr + 2 * PW_A_BYTES + PW_B_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_f16(tmem_base, adesc_lo + 2 * k, bdesc + 2 * k, prm.idesc, (kb > 0 || k > 0) ? 1u : 0u);  // A_lo W_hi
-            umma_f16(tmem_base, adesc + 2 * k, bdesc_lo + 2 * k, prm.idesc, 1u);                          // A_hi W_lo
-            umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, 1u);                             // A_hi W_hi
-          }
-        } else {
-          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + PW_A_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, prm.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      int it = 0, i = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+        const int a2 = i & 1;
+        const uint32_t acc = tmem_base + (uint32_t)(a2 * PW_BN);
+        if (i >= 2) {                                     // accumulator a2 was used by tile i - 2: wait until drained
+          mbar_wait(&tmem_empty_bar[a2], (uint32_t)((i >> 1) - 1) & 1u);
+          tc_fence_after();
         }
-        tc_commit(&empty_bar[s]);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % PW_NS;
+          mbar_wait(&full_bar[s], (uint32_t)(it / PW_NS) & 1u);
+          if (tl && i == 0) tl[2 + kb] = clock64();
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * PW_STAGE);
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+          if constexpr (SPLIT) {
+            const uint64_t adesc_lo = make_sw128_kmajor_desc(a_addr + PW_A_BYTES);
+            const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + 2 * PW_A_BYTES);
+            const uint64_t bdesc_lo = make_sw128_kmajor_desc(a_addr + 2 * PW_A_BYTES + PW_B_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(acc, adesc_lo + 2 * k, bdesc + 2 * k, prm.idesc, (kb > 0 || k > 0) ? 1u : 0u);  // A_lo W_hi
+              umma_f16(acc, adesc + 2 * k, bdesc_lo + 2 * k, prm.idesc, 1u);                          // A_hi W_lo
+              umma_f16(acc, adesc + 2 * k, bdesc + 2 * k, prm.idesc, 1u);                             // A_hi W_hi
+            }
+          } else {
+            const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + PW_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(acc, adesc + 2 * k, bdesc + 2 * k, prm.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(&tmem_full_bar[a2]);
       }
-      tc_commit(tmem_full_bar);
     }
     __syncwarp();
   } else {
+   int i = 0;
+   for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+    const int mt = t / prm.tiles_n, nt = t - mt * prm.tiles_n;
+    const int a2 = i & 1;
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(a2 * PW_BN);
     // ---- epilogue: TMEM -> bias + residual -> NCHW fp32 ----
-    mbar_wait(tmem_full_bar, 0);
-    if (tl && tid == 64) tl[2 + nkb] = clock64();
+    mbar_wait(&tmem_full_bar[a2], (uint32_t)(i >> 1) & 1u);
+    if (tl && tid == 64 && i == 0) tl[2 + nkb] = clock64();
     tc_fence_after();
     const int q = warp & 3, half = (warp - 2) >> 2;       // TMEM lane quarter (hardware: warp % 4), column half
     const int row = q * 32 + lane;
@@ -155,7 +182,7 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
       const int col = half * (PW_BN / 2) + c0;
       if (nt * PW_BN + col >= prm.N) break;               // warp-uniform
       uint32_t acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
       tmem_ld_wait();
       if (m < prm.M) {
         const int cbase = nt * PW_BN + col;               // first output column of this chunk (warp-uniform)
@@ -220,11 +247,16 @@ __global__ void __launch_bounds__(PW_THREADS, 1) pointwise_umma_kernel(const Poi
         }
       }
     }
+    // this warp's share of accumulator a2 is in registers / memory: hand the accumulator back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty_bar[a2]);
+    if (tl && tid == 64 && i == 0) tl[3 + nkb] = clock64();
+   }
   }
-  if (tl && tid == 64) tl[3 + nkb] = clock64();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)PW_BN);
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)(2 * PW_BN));
 }
 
 // byte offset of element (r, k) inside a [rows x 64] bf16 slab in the swizzled K-major layout
@@ -367,13 +399,15 @@ extern "C" int kgdet_pointwise_conv_tiled(const void* a_tiled, const void* w_pac
   p.ns = pw_stages(p.stage_bytes);
   p.idesc = make_idesc(1u, PW_BM, (uint32_t)p.bn);
   p.timeline = nullptr;
-  if (g_timeline && g_timeline_entries >= (long long)ceil_div(M, PW_BM) * ceil_div(Nout, p.bn) * (p.kgroups + 8))
-    p.timeline = g_timeline;
+  p.tiles_m = ceil_div(M, PW_BM);
+  p.tiles_n = ceil_div(Nout, p.bn);
+  if (g_timeline && g_timeline_entries >= (long long)p.tiles_m * p.tiles_n * (p.kgroups + 8)) p.timeline = g_timeline;
   g_timeline = nullptr;
-  const size_t smem = 1024 + (size_t)p.ns * p.stage_bytes + (2 * p.ns + 1) * 8 + 16;
+  const size_t smem = 1024 + (size_t)p.ns * p.stage_bytes + (2 * p.ns + 4) * 8 + 16;
   auto kern = split ? pointwise_umma_kernel<true> : pointwise_umma_kernel<false>;
   KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(M, PW_BM), ceil_div(Nout, p.bn), 1);
+  const int ntiles = p.tiles_m * p.tiles_n;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();      // one persistent CTA per SM
   kern<<<grid, PW_THREADS, smem, (cudaStream_t)stream>>>(p);
   KG_LAUNCH_CHECK("pointwise_umma_kernel");
   return KGDET_OK;

@@ -43,7 +43,8 @@ def main():
             ops.pointwise_conv(rows, pw, bias, outs, h * w)
             b.record()
             torch.cuda.synchronize()
-            t = buf.view(ctas, per).cpu().double()
+            grid = min(ctas, torch.cuda.get_device_properties(0).multi_processor_count)   # persistent CTAs: first tile of each
+            t = buf.view(ctas, per)[:grid].cpu().double()
             med = lambda v: float(v.median())
             full = t[:, 2:2 + kg]
             iv = (full[:, 1:] - full[:, :-1]).median(0).values
