@@ -146,6 +146,39 @@ def test_zero_offset_equals_plain_convolution():
         assert rel_err(_ours(d, prec, need_bw=False)['out'], ref) < TOL[prec]
 
 
+def test_full_size_p3_zero_offset_equals_conv2d_forward_and_backward():
+    """BASELINE configs[1] at its largest shape (FPN P3, batch 8: 134 400 positions -- too big for the CPU oracle)
+    through a size-independent property: with zero offsets the deformable convolution IS the plain convolution, so
+    forward, input gradient and weight gradient must match cuDNN's (fp32, TF32 off) in the bf16 mode's tolerance.
+    At this size the backward takes its one-tap-per-chunk path and the fused weight gradient splits 2 100 position
+    blocks over the SMs."""
+    from kgdet_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(8, 256, 100, 168, generator=g).cuda()
+    w = (torch.randn(256, 256, 3, 3, generator=g) * 0.02).cuda()
+    go = torch.randn(8, 256, 100, 168, generator=g).cuda()
+    off = torch.zeros(8, 18, 100, 168, device='cuda')
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+        ref = torch.nn.functional.conv2d(xr, wr, padding=1)
+        ref.backward(go)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    ops.set_precision('bf16')
+    try:
+        xo, wo, oo = x.clone().requires_grad_(), w.clone().requires_grad_(), off.clone().requires_grad_()
+        out = ops.deform_conv(xo, oo, wo, 1, 1)
+        out.backward(go)
+    finally:
+        ops.set_precision(None)
+    assert rel_err(out, ref) < TOL['bf16']
+    assert rel_err(xo.grad, xr.grad) < TOL['bf16']
+    assert rel_err(wo.grad, wr.grad) < TOL['bf16']
+    assert torch.isfinite(oo.grad).all()
+
+
 def test_bf16_tensors_end_to_end():
     d = dcn_case(N=2, C=64, H=9, W=11, Cout=64, k=3, dtype=torch.bfloat16)
     d['weight'] = d['weight'].to(torch.bfloat16).float()
