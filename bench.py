@@ -413,9 +413,9 @@ def run_reference(args):
 
 def run_train(args):
     """BASELINE.json configs[4]: KGDet head training step (forward + losses + backward + gradient all-reduce +
-    SGD) at batch 2 per GPU.  Targets are synthetic (the reference's PointAssigner / point_target_kp are
-    host-side PyTorch outside the hot path): ~1% positive labels for the three
-    focal losses (kgdet_b200 fused focal-sum op), Smooth-L1 on the three bbox and keypoint maps.  The DCN
+    SGD) at batch 2 per GPU.  Ground truth is synthetic; target assignment (PointAssigner, pos_num 25) and the
+    nine losses of the reference head run inside the step through the sync-free device mirror
+    (kgdet_b200/targets.py; focal losses through the fused focal-sum op).  The DCN
     runs forward and backward on the tensor cores (bf16 mode), the moment transform through its fused
     fwd/bwd kernels; gradients are averaged over ranks with the overlapped bucketed all-reduce."""
     from kgdet_b200 import dist as kdist, ops
@@ -430,22 +430,29 @@ def run_train(args):
     bucketer = kdist.GradBucketer(head.parameters(), bucket_size_mb=25) if world > 1 else None
     g = torch.Generator().manual_seed(200 + rank)
     x = torch.randn(B, C, H, W, generator=g).to(dev)
-    labels = torch.where(torch.rand(B * H * W, generator=g) < 0.01,
-                         torch.randint(1, 14, (B * H * W,), generator=g), torch.zeros(B * H * W, dtype=torch.long)).to(dev)
-    bbox_t = (torch.randn(B, 4, H, W, generator=g) * 4).to(dev)
-    kpt_t = (torch.randn(B, 588, H, W, generator=g) * 4).to(dev)
-    pos_w = (labels > 0).float()
+    # synthetic ground truth as SURVEY.md section 8(d) config 5: per image 1-3 boxes (w, h ~ U(100, 600) inside
+    # 800x1333), labels U{1..13}, 294 keypoints of which a 30-keypoint class range is visible; padded to 3 boxes.
+    # Targets come from the device-side PointAssigner / point_target_kp mirror (kgdet_b200/targets.py) INSIDE the step.
+    from kgdet_b200 import targets as T
+    gtb, gtl, gtk = [], [], []
+    for _ in range(B):
+        ng = int(torch.randint(1, 4, (1,), generator=g))
+        wh = torch.rand(ng, 2, generator=g) * 500 + 100
+        xy = torch.rand(ng, 2, generator=g) * (torch.tensor([1333., 800.]) - wh)
+        gtb.append(torch.cat([xy, xy + wh], 1))
+        gtl.append(torch.randint(1, 14, (ng,), generator=g))
+        k = torch.zeros(ng, 294, 3)
+        lo = int(torch.randint(0, 264, (1,), generator=g))
+        k[:, lo:lo + 30, :2] = xy[:, None] + torch.rand(ng, 30, 2, generator=g) * wh[:, None]
+        k[:, lo:lo + 30, 2] = (torch.rand(ng, 30, generator=g) > 0.3).float() * 2
+        gtk.append(k)
+    gt_boxes, gt_labels, gt_kps, gt_valid = T.pad_ground_truth(gtb, gtl, gtk, device=dev, max_gts=3)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step():
         opt.zero_grad(set_to_none=True)
         o = head.forward_single(x)
-        loss = 0
-        for i, lw in zip(range(3), (0.5, 0.5, 1.0)):
-            logits = o[i].permute(0, 2, 3, 1).reshape(-1, 13)
-            loss = loss + lw * ops.sigmoid_focal_loss_sum(logits, labels, None, 2.0, 0.25) / max(float(B * 10), 1.0)
-            loss = loss + lw * torch.nn.functional.smooth_l1_loss(o[6 + i], bbox_t, beta=1.0 / 9.0)
-            loss = loss + lw * torch.nn.functional.smooth_l1_loss(o[3 + i], kpt_t, beta=1.0 / 9.0)
+        loss = sum(head.loss(o, gt_boxes, gt_labels, gt_kps, gt_valid).values())      # assignment + nine losses
         loss.backward()
         if bucketer is not None:
             bucketer.finish()
@@ -455,12 +462,7 @@ def run_train(args):
 
     def fwd_bwd():
         o = head.forward_single(x)
-        loss = 0
-        for i, lw in zip(range(3), (0.5, 0.5, 1.0)):
-            logits = o[i].permute(0, 2, 3, 1).reshape(-1, 13)
-            loss = loss + lw * ops.sigmoid_focal_loss_sum(logits, labels, None, 2.0, 0.25) / max(float(B * 10), 1.0)
-            loss = loss + lw * torch.nn.functional.smooth_l1_loss(o[6 + i], bbox_t, beta=1.0 / 9.0)
-            loss = loss + lw * torch.nn.functional.smooth_l1_loss(o[3 + i], kpt_t, beta=1.0 / 9.0)
+        loss = sum(head.loss(o, gt_boxes, gt_labels, gt_kps, gt_valid).values())      # assignment + nine losses
         loss.backward()
         return loss
 
@@ -533,8 +535,8 @@ def run_train(args):
             'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': round(ms / args.steps, 4), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
-            'config': {'workload': 'KGDet head training step (fwd + 9 losses + bwd + grad all-reduce + SGD) @800x1333 '
-                                   '(map 25x42), batch %d per GPU, synthetic targets' % B,
+            'config': {'workload': 'KGDet head training step (fwd + target assignment + 9 losses + bwd + grad all-reduce + '
+                                   'clip + SGD) @800x1333 (map 25x42), batch %d per GPU, synthetic ground truth' % B,
                        'batch_per_gpu': B, 'allreduce': ('one coalesced NCCL all-reduce between the two graphs' if mode != 'eager' else
                                                          'overlapped 25 MB buckets') + ', %.1f MB fp32 gradients' % (nparam * 4 / 1e6)
                        if world > 1 else 'none (1 GPU)', 'parallelism': 'dp%d' % world, 'l2': 'flushed before every step'},

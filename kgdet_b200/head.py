@@ -421,6 +421,24 @@ class KGDetHead(nn.Module):
         outs = [self.forward_single(x) for x in feats]
         return tuple(map(list, zip(*outs)))                                        # multi_apply layout
 
+    def loss(self, outs, gt_bboxes, gt_labels, gt_keypoints, gt_valid, assigner_scale=4, pos_num=25,
+             point_base_scale=4):
+        """The nine training losses of the reference head (KP3:670-768) for the single KGDet level, from the
+        9-tuple of `forward_single` and PADDED ground truth (`targets.pad_ground_truth`): target assignment
+        (PointAssigner + point_target_kp, "assign once": the same targets serve all three stages) and the loss
+        reductions run batched on the device without host synchronisation (kgdet_b200/targets.py), so the whole
+        training step can be replayed as a CUDA graph.  Loss weights are the reference configs' (0.5, 0.5, 1.0)."""
+        from . import targets as T
+        h, w = outs[0].shape[-2:]
+        stride = self.point_strides[0]
+        key = (h, w, stride, outs[0].device)
+        pts = self._lim_cache.get(('points',) + key)
+        if pts is None:
+            pts = T.grid_points(h, w, stride, outs[0].device)
+            self._lim_cache[('points',) + key] = pts
+        tg = T.point_targets(pts, gt_bboxes, gt_labels, gt_keypoints, gt_valid, assigner_scale, pos_num)
+        return T.kgdet_losses(outs, pts, stride, tg, point_base_scale)
+
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def get_bboxes(self, cls_scores, keypts_preds, bbox_preds, img_shapes, score_thr=0.05, iou_thr=0.5,
