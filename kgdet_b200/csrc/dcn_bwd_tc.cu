@@ -72,7 +72,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 // writes it -- one writer per element, no atomics on grad_offset / grad_mask, deterministic.
 static constexpr int COL2IM_TB = 5;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 col2im_tc_kernel(DcnGeom g, const __nv_bfloat16* __restrict__ cg, const __nv_bfloat16* __restrict__ in,
                  const SampleRec* __restrict__ plan, const SampleAux* __restrict__ aux, int tap0, int ntaps,
                  float* __restrict__ gin, float* __restrict__ goff, float* __restrict__ gmask) {
