@@ -84,6 +84,13 @@ __device__ __forceinline__ void mbar_spin_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// shared -> global bulk store (async proxy); the caller commits the group and waits for the reads
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+
 __device__ __forceinline__ __nv_bfloat162 as_bf162(uint32_t v) {
   return *reinterpret_cast<__nv_bfloat162*>(&v);
 }
@@ -375,13 +382,47 @@ __global__ void __launch_bounds__(Layout<RPT, SPREAD>::THREADS, 1) dcn_umma_stre
     const int n = row_ok ? m / prm.HoWo : 0;
     const int pos = row_ok ? m - n * prm.HoWo : 0;
     Tout* obase = reinterpret_cast<Tout*>(prm.out) + ((size_t)n * prm.out_ctot + prm.out_coff) * prm.HoWo + pos;
+    // Tiled bf16 output whose channel slice starts on a 64-channel slab: the tile's slabs are staged in shared
+    // memory (the pipeline stages are idle once the accumulator is complete) in exactly the global slab layout and
+    // leave as 16 KB cp.async.bulk stores -- a thread owns an accumulator ROW, so direct stores put 32 different
+    // lines (16 bytes each) into every store instruction.
+    const bool staged = sizeof(Tout) == 2 && prm.out_nhwc && !prm.partial && (prm.out_coff & 63) == 0 && !PAIR;
+    const int nslab = BN >> 6;
     // 32-column chunks of the accumulator are dealt round-robin to the PRODUCER_WARPS / 4 column groups
     // (Cout % 64 == 0, so every chunk is whole)
     for (int col = cgrp * 32; col < BN; col += 32 * LY::EPI_GROUPS) {         // warp-uniform
       uint32_t acc[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
       tmem_ld_wait();
-      if (prm.partial) {
+      if (staged) {
+        if constexpr (sizeof(Tout) == 2) {
+          const bool split = prm.out_nhwc == KGDET_LAYOUT_TILED_SPLIT;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              x[e] = __uint_as_float(acc[j + e]);
+              if (prm.bias) x[e] += __ldg(prm.bias + col + j + e);
+              if (prm.relu) x[e] = fmaxf(x[e], 0.f);
+            }
+            const int c = col + j;                                   // channel within this call's Cout
+            unsigned char* dst = smem + (size_t)(c >> 6) * A_TILE_BYTES + row * 128 + ((((c & 63) >> 3) ^ (row & 7)) << 4);
+            uint4 hi4;
+            hi4.x = pack_bf16x2(x[0], x[1]); hi4.y = pack_bf16x2(x[2], x[3]);
+            hi4.z = pack_bf16x2(x[4], x[5]); hi4.w = pack_bf16x2(x[6], x[7]);
+            *reinterpret_cast<uint4*>(dst) = hi4;
+            if (split) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] -= __bfloat162float(__float2bfloat16(x[e]));
+              uint4 lo4;
+              lo4.x = pack_bf16x2(x[0], x[1]); lo4.y = pack_bf16x2(x[2], x[3]);
+              lo4.z = pack_bf16x2(x[4], x[5]); lo4.w = pack_bf16x2(x[6], x[7]);
+              *reinterpret_cast<uint4*>(dst + (size_t)nslab * A_TILE_BYTES) = lo4;
+            }
+          }
+        }
+      } else if (prm.partial) {
         // split-K: raw accumulators, position-major (m_pad = whole tiles, so every row may be written)
         float* prow = prm.partial + ((size_t)blockIdx.y * prm.m_pad + m0 + row) * BN + col;
 #pragma unroll
@@ -433,6 +474,26 @@ __global__ void __launch_bounds__(Layout<RPT, SPREAD>::THREADS, 1) dcn_umma_stre
             st_out<Tout>(obase + (size_t)(col + j) * prm.HoWo, x);   // lanes = consecutive positions
           }
         }
+      }
+    }
+    if (staged) {
+      // every epilogue thread has written its share of the slabs; one thread ships them
+      fence_proxy_async_smem();
+      constexpr int EPI_THREADS = SPREAD ? LY::THREADS : PRODUCER_WARPS * 32;
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      if (warp == (SPREAD ? 0 : 0) && lane == 0) {
+        const bool split = prm.out_nhwc == KGDET_LAYOUT_TILED_SPLIT;
+        const int kblocks = (split ? 2 : 1) * (prm.out_ctot >> 6);
+        unsigned char* tile = reinterpret_cast<unsigned char*>(prm.out) + (size_t)(m0 >> 7) * kblocks * A_TILE_BYTES +
+                              (size_t)(prm.out_coff >> 6) * A_TILE_BYTES;
+        for (int sl = 0; sl < nslab; ++sl) {
+          bulk_s2g(tile + (size_t)sl * A_TILE_BYTES, smem + (size_t)sl * A_TILE_BYTES, A_TILE_BYTES);
+          if (split)
+            bulk_s2g(tile + (size_t)((prm.out_ctot >> 6) + sl) * A_TILE_BYTES,
+                     smem + (size_t)(nslab + sl) * A_TILE_BYTES, A_TILE_BYTES);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads
       }
     }
   }
