@@ -547,6 +547,9 @@ def run_train(args):
 
 
 def main():
+    # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, in front of the one JSON line rank 0 owes the driver
+    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
