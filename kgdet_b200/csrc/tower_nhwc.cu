@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(256) groupnorm_relu_nhwc_kernel(const float* _
 }
 
 // Wide variant: one CTA per (image, 32 consecutive channels) = 8 / VEC groups, VEC = float4 chunks per group.
+// (Measured and dropped: splitting the unit over a cluster of two CTAs with a DSMEM exchange of the partial sums --
+// 67 KB instead of 134 KB of shared memory, two CTAs per SM -- is slower, 13.1 vs 11.4 us per [16,256,25,42] call.)
 // The one-group kernel above reads 4 * cpg bytes per pixel (32 B for the KGDet towers: 16 different 128-byte
 // lines per warp request); here 8 lanes cover one pixel's 128-byte line, 1024 threads keep ~8 float4 loads each in
 // flight, and the statistics of a group are reduced with xor-shuffles over the lanes that share it.
