@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(Layout<RPT, SPREAD>::THREADS, 1) dcn_umma_stre
       fence_proxy_async_smem();
       constexpr int EPI_THREADS = SPREAD ? LY::THREADS : PRODUCER_WARPS * 32;
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-      if (warp == (SPREAD ? 0 : 0) && lane == 0) {
+      if (warp == 0 && lane == 0) {                 // warp 0 takes part in the epilogue in both layouts
         const bool split = prm.out_nhwc == KGDET_LAYOUT_TILED_SPLIT;
         const int kblocks = (split ? 2 : 1) * (prm.out_ctot >> 6);
         unsigned char* tile = reinterpret_cast<unsigned char*>(prm.out) + (size_t)(m0 >> 7) * kblocks * A_TILE_BYTES +

@@ -74,7 +74,6 @@ nms_small_kernel(const float* __restrict__ dets, const int32_t* __restrict__ seg
     n = single_n;
   }
   if (n <= 0) return;
-  const int n_rows = n;
   if (threadIdx.x == 0) n_valid = 0;
   int P = 1;
   while (P < n) P <<= 1;
