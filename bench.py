@@ -336,7 +336,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             result['cpu_baseline'] = cpu_baseline(args, budget_s=20.0)
-        print(json.dumps(result), flush=True)
+        emit(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
 
@@ -401,14 +401,14 @@ def run_reference(args):
                  if build_ref.load('nms_cpu') is not None else 'oracle/nms_oracle.c'))
     a2 = argparse.Namespace(**vars(args))
     cfg = workload_config(a2, world)
-    print(json.dumps({
+    emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': round(dt / args.steps * 1e3, 3), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }), flush=True)
+    }))
 
 
 def run_train(args):
@@ -530,7 +530,7 @@ def run_train(args):
     ms = kdist.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), dev)
     if rank == 0:
         nparam = sum(p.numel() for p in head.parameters())
-        print(json.dumps({
+        emit(json.dumps({
             'metric': 'kgdet_head_train_images_per_sec', 'value': round(B * world * args.steps / (ms * 1e-3), 2),
             'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': round(ms / args.steps, 4), 'higher_is_better': True, 'scaling': 'weak',
@@ -541,15 +541,26 @@ def run_train(args):
                                                          'overlapped 25 MB buckets') + ', %.1f MB fp32 gradients' % (nparam * 4 / 1e6)
                        if world > 1 else 'none (1 GPU)', 'parallelism': 'dp%d' % world, 'l2': 'flushed before every step'},
             'launch_mode': mode,
-            'final_loss': float(loss.item())}), flush=True)
+            'final_loss': float(loss.item())}))
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE line rank 0 owes the driver, written to the process's original stdout."""
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (line + '\n').encode())
+
+
 def main():
-    # NCCL_DEBUG=VERSION makes NCCL print its banner on stdout, in front of the one JSON line rank 0 owes the driver
-    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-        os.environ['NCCL_DEBUG'] = 'WARN'
+    # Libraries chat on file descriptor 1 (NCCL prints its version banner there when a communicator is created);
+    # everything except the result line is re-routed to stderr at the descriptor level.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
