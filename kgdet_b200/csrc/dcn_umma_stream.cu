@@ -144,6 +144,11 @@ __device__ __forceinline__ void combine_store(const uint4 (&v)[4], uint32_t wy, 
 //   * built, measured and dropped: DEPTH = 2 with 16 warps at 128 registers and the control duty rotating over
 //     the producer warps (17 warps cap a thread at 96 registers) 171 us; all gathers through ld.global.cg
 //     166 us; 148 balanced 114-row tiles instead of 132 128-row tiles 150 us; CTA pairs 152 us.
+//   * built, measured and dropped (round 1, last day): a "dual" launch that runs the 3x3 and the 5x5 point set of a
+//     branch through one pipeline into two TMEM accumulators (combined plan + interleaved packed weights, the
+//     producers untouched).  Bit-identical to two launches, but 119.4 us against 38.0 + 79.3 us for the pair, and
+//     the extra control-lane / epilogue code made the UNCHANGED single-convolution path 7 % slower (K = 49:
+//     141 -> 151 us): this hot loop is sensitive to code layout, not only to instruction count.
 //   * what did help earlier: channel-blocked input planes (contiguous 128-byte slabs are served 1.4x faster by
 //     the L1 than slabs 512 bytes apart, tools/micro/l1_gather_bench) and tap-major plan records.
 template <int MODE, int NS, int DEPTH, typename Tout, bool PAIR, int RPT, bool SPREAD, bool TL>
