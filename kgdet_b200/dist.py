@@ -92,6 +92,34 @@ def allreduce_grads(params, coalesce=True, bucket_size_mb=-1):
             off += g.numel()
 
 
+class FlatGrads(object):
+    """All gradients as views of ONE flat fp32 buffer: the all-reduce of the reference
+    (mmdet/core/utils/dist_utils.py:14-25 flattens, all-reduces, divides and copies back every step) becomes a single
+    collective on memory the gradients already live in -- no flatten / unflatten copies -- and the buffer is a fixed
+    address, so a CUDA-graph-captured backward accumulates straight into it.  `zero()` once per step (inside the
+    captured region), `allreduce()` after backward; same result as `allreduce_grads` (sum, then / world size)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params, 'no trainable parameters'
+        p0 = self.params[0]
+        assert all(p.dtype == p0.dtype and p.device == p0.device for p in self.params), 'one dtype / device'
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=p0.dtype, device=p0.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce(self):
+        ws = world_size()
+        if ws > 1:
+            dist.all_reduce(self.flat)
+            self.flat.div_(ws)
+
+
 class GradBucketer(object):
     """Overlap the gradient all-reduce with backward.
 

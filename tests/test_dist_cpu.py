@@ -55,6 +55,18 @@ def _worker(rank, world, port, q):
     gb.finish()
     out['avg3_ok'] = all(torch.isfinite(p.grad).all().item() for p in net2.parameters())
     gb.remove()
+    # flat gradient buffer: backward accumulates into views of one tensor, one collective, no copies
+    net3 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    net3.load_state_dict(net.state_dict())
+    fg = kd.FlatGrads(net3.parameters())
+    for scale in (3.0, 1.0):                          # second pass: zero() really clears the first one
+        fg.zero()
+        net3(x * scale).square().sum().backward()
+    ptrs = [p.grad.data_ptr() for p in net3.parameters()]
+    fg.allreduce()
+    out['flat_views_kept'] = ptrs == [p.grad.data_ptr() for p in net3.parameters()] and \
+        ptrs[0] == fg.flat.data_ptr()
+    out['avg_flat'] = [p.grad.clone().tolist() for p in net3.parameters()]
     # non-coalesced path
     for p, l in zip(net.parameters(), local):
         p.grad.copy_(l)
@@ -83,10 +95,11 @@ def test_two_rank_gloo_host_logic():
     assert res[0]['max'] == res[1]['max'] == 2.5
     for i in range(len(res[0]['avg'])):
         want = (torch.tensor(res[0]['local'][i]) + torch.tensor(res[1]['local'][i])) / 2
-        for key in ('avg', 'avg2', 'avg_nc'):
+        for key in ('avg', 'avg2', 'avg_nc', 'avg_flat'):
             assert torch.allclose(torch.tensor(res[0][key][i]), want, atol=1e-6), key
             assert torch.allclose(torch.tensor(res[1][key][i]), want, atol=1e-6), key
     assert res[0]['avg3_ok'] and res[1]['avg3_ok']
+    assert res[0]['flat_views_kept'] and res[1]['flat_views_kept']
 
 
 def test_single_process_is_a_no_op():
