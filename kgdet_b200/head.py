@@ -367,6 +367,10 @@ class KGDetHead(nn.Module):
                 kpt1, rep1 = self.kp_rep_block_1.forward_tc_kpt(pts_feat)
                 return kpt1, rep1, self.points2bbox(rep1), prepare_input(pts_feat, feat, precision='bf16')
 
+            # packed 1x1 weights are cached per block and shared by its cls and keypoint GEMMs, which run on different
+            # streams below: build (or refresh) them here, on the stream everything forks from
+            for blk in (self.kp_rep_block_1, self.kp_rep_block_2, self.kp_rep_block_3):
+                _pointwise_weights(blk)
             branches = [] if self.concurrent_branches else None
             if self.concurrent_branches:
                 # The classification and point branches are independent up to the first deformable stage, and a
