@@ -41,18 +41,7 @@ static int taps_per_chunk(const DcnGeom& g, size_t rows) {
 }
 static size_t mpad64(const DcnGeom& g) { return (size_t)ceil_div(g.M, 64) * 64; }
 
-// ---- weight layout for the column-gradient GEMM: Wd[(tap*C + c), o] = W[o, c, tap] ----------------
-__global__ void pack_wd_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd, int Cout,
-                                    int C, int K) {
-  const long long total = (long long)K * C * Cout;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)blockDim.x * gridDim.x) {
-    const int o = (int)(i % Cout);
-    const long long r = i / Cout;
-    const int c = (int)(r % C), tap = (int)(r / C);
-    wd[i] = __float2bfloat16(w[((size_t)o * C + c) * K + tap]);
-  }
-}
+// (weight layout for the column-gradient GEMM, Wd[(tap*C + c), o] = W[o, c, tap]: pack_wd_tiled_kernel below)
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
@@ -227,17 +216,57 @@ __global__ void go_to_goT_kernel(const T* __restrict__ go, __nv_bfloat16* __rest
   }
 }
 
-// grad_W[o, c, tap] = scale * gWT[(tap*C + c), o]
-__global__ void unpack_gw_kernel(const float* __restrict__ gwt, float* __restrict__ gw, int Cout, int C, int K,
-                                 float scale) {
-  const long long total = (long long)Cout * C * K;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)blockDim.x * gridDim.x) {
-    const int tap = (int)(i % K);
-    const long long r = i / K;
-    const int c = (int)(r % C), o = (int)(r / C);
-    gw[i] = scale * gwt[((size_t)tap * C + c) * Cout + o];
+// The two weight-layout changes of the backward as 32 x 32 shared-memory transposes (one channel c per CTA row):
+// element-per-thread versions read or wrote with a stride of C * Cout floats (one 4-byte access per 128-byte line)
+// and together cost ~25 us per K = 49 call, every training step (weights change).
+//   Wd[(tap*C + c), o] = W[o, c, tap]  (bf16, operand of the column-gradient GEMM)
+//   grad_W[o, c, tap] = scale * gWT[(tap*C + c), o]
+__global__ void __launch_bounds__(256) pack_wd_tiled_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd,
+                                                            int Cout, int C, int K) {
+  __shared__ float tile[32][33];                       // [o][tap]
+  const int c = blockIdx.y, o0 = blockIdx.x * 32, tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int t0 = 0; t0 < K; t0 += 32) {
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      const int o = o0 + ty + k, t = t0 + tx;
+      tile[ty + k][tx] = (o < Cout && t < K) ? w[((size_t)o * C + c) * K + t] : 0.f;      // contiguous over taps
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      const int t = t0 + ty + k, o = o0 + tx;
+      if (t < K && o < Cout) wd[((size_t)t * C + c) * Cout + o] = __float2bfloat16(tile[tx][ty + k]);   // contiguous over o
+    }
+    __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(256) unpack_gw_tiled_kernel(const float* __restrict__ gwt, float* __restrict__ gw,
+                                                              int Cout, int C, int K, float scale) {
+  __shared__ float tile[32][33];                       // [tap][o]
+  const int c = blockIdx.y, o0 = blockIdx.x * 32, tx = threadIdx.x, ty = threadIdx.y;
+  for (int t0 = 0; t0 < K; t0 += 32) {
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      const int t = t0 + ty + k, o = o0 + tx;
+      tile[ty + k][tx] = (t < K && o < Cout) ? gwt[((size_t)t * C + c) * Cout + o] : 0.f;   // contiguous over o
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      const int o = o0 + ty + k, t = t0 + tx;
+      if (o < Cout && t < K) gw[((size_t)o * C + c) * K + t] = scale * tile[tx][ty + k];    // contiguous over taps
+    }
+    __syncthreads();
+  }
+}
+
+static void launch_pack_wd(const float* w, __nv_bfloat16* wd, int Cout, int C, int K, cudaStream_t stream) {
+  pack_wd_tiled_kernel<<<dim3((unsigned)ceil_div(Cout, 32), (unsigned)C), dim3(32, 8), 0, stream>>>(w, wd, Cout, C, K);
+}
+static void launch_unpack_gw(const float* gwt, float* gw, int Cout, int C, int K, float scale, cudaStream_t stream) {
+  unpack_gw_tiled_kernel<<<dim3((unsigned)ceil_div(Cout, 32), (unsigned)C), dim3(32, 8), 0, stream>>>(gwt, gw, Cout, C, K,
+                                                                                                   scale);
 }
 
 template <typename T>
@@ -351,8 +380,8 @@ int bwd_tc_input(const DcnGeom& g, const void* input, const float* offset, const
   if ((rc = launch_transpose(input, w.in_nhwc, g.N, g.C, HW, dtype, KGDET_BF16, stream)) != KGDET_OK) return rc;
   if ((rc = launch_transpose(grad_output, w.go_nhwc, g.N, g.Cout, HoWo, dtype, KGDET_BF16, stream)) != KGDET_OK) return rc;
   if ((rc = launch_plan(g, offset, mask, w.plan, w.aux, stream)) != KGDET_OK) return rc;
-  pack_wd_bf16_kernel<<<grid_for((long long)g.K * g.C * g.Cout, 256), 256, 0, stream>>>(weight, w.wd, g.Cout, g.C, g.K);
-  KG_LAUNCH_CHECK("pack_wd_bf16_kernel");
+  launch_pack_wd(weight, w.wd, g.Cout, g.C, g.K, stream);
+  KG_LAUNCH_CHECK("pack_wd_tiled_kernel");
   KG_CUDA(cudaMemsetAsync(w.gin_nhwc, 0, (size_t)g.N * HW * g.C * 4, stream));
   const int tpc = taps_per_chunk(g, g.M);
   for (int tap0 = 0; tap0 < g.K; tap0 += tpc) {
@@ -386,9 +415,8 @@ int bwd_tc_weight(const DcnGeom& g, const void* input, const float* offset, cons
     KG_CUDA(cudaMemsetAsync(f.gwt, 0, (size_t)g.K * g.C * g.Cout * 4, stream));
     if ((rc = wgrad_fused(g, f.planes + f.guard_bytes, f.plane_bytes, f.plan, f.go_tiled, f.gwt, stream)) != KGDET_OK)
       return rc;
-    unpack_gw_kernel<<<grid_for((long long)g.Cout * g.C * g.K, 256), 256, 0, stream>>>(f.gwt, grad_weight, g.Cout, g.C,
-                                                                                       g.K, scale);
-    KG_LAUNCH_CHECK("unpack_gw_kernel");
+    launch_unpack_gw(f.gwt, grad_weight, g.Cout, g.C, g.K, scale, stream);
+    KG_LAUNCH_CHECK("unpack_gw_tiled_kernel");
     if (grad_bias) {
       if (dtype == KGDET_F32)
         bias_grad_nchw_kernel<float><<<g.Cout, 256, 0, stream>>>((const float*)grad_output, g.N, g.Cout, HoWo, grad_bias);
@@ -425,8 +453,8 @@ int bwd_tc_weight(const DcnGeom& g, const void* input, const float* offset, cons
     if ((rc = umma_gemm(w.colT, mp, w.goT, mp, w.gwt + (size_t)tap0 * g.C * g.Cout, g.Cout, nt * g.C, g.Cout,
                         (int)mp, KGDET_F32, splits < 2 ? 2 : splits, 1.f, stream)) != KGDET_OK) return rc;
   }
-  unpack_gw_kernel<<<grid_for((long long)g.Cout * g.C * g.K, 256), 256, 0, stream>>>(w.gwt, grad_weight, g.Cout, g.C, g.K, scale);
-  KG_LAUNCH_CHECK("unpack_gw_kernel");
+  launch_unpack_gw(w.gwt, grad_weight, g.Cout, g.C, g.K, scale, stream);
+  KG_LAUNCH_CHECK("unpack_gw_tiled_kernel");
   if (grad_bias) {
     if (dtype == KGDET_F32)
       bias_grad_nchw_kernel<float><<<g.Cout, 256, 0, stream>>>((const float*)grad_output, g.N, g.Cout, HoWo, grad_bias);

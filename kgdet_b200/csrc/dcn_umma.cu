@@ -52,6 +52,33 @@ __global__ void umma_pack_bf16_kernel(const float* __restrict__ w, unsigned char
   }
 }
 
+// Same packing through shared memory: one CTA takes 2 output channels x one 64-channel block, reads their
+// 64 * K weights each as ONE contiguous run (the layout is [Cout][C][K]) and writes, per tap, the two 128-byte rows.
+// The element-per-thread kernel above reads with a stride of K floats; training repacks every step.
+__global__ void __launch_bounds__(256) umma_pack_bf16_tiled_kernel(const float* __restrict__ w, unsigned char* __restrict__ p,
+                                                                   int C, int Cout, int K) {
+  extern __shared__ float wsm[];                       // [2][64 * K]
+  const int o0 = blockIdx.x * 2, cb = blockIdx.y;
+  const int run = 64 * K;
+  for (int i = threadIdx.x; i < 2 * run; i += blockDim.x) {
+    const int oo = i / run, j = i - oo * run;
+    wsm[i] = (o0 + oo < Cout) ? w[((size_t)(o0 + oo) * C + cb * 64) * K + j] : 0.f;
+  }
+  __syncthreads();
+  // one thread per 16-byte chunk: (tap, oo, chunk)
+  for (int i = threadIdx.x; i < K * 16; i += blockDim.x) {
+    const int tap = i >> 4, oo = (i >> 3) & 1, chunk = i & 7;
+    const int o = o0 + oo;
+    if (o >= Cout) continue;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16(wsm[oo * run + (chunk * 8 + e) * K + tap]);
+    const size_t dst = (size_t)(cb * K + tap) * Cout * 128 + (size_t)(o >> 3) * 1024 + (o & 7) * 128 +
+                       ((chunk ^ (o & 7)) << 4);
+    *reinterpret_cast<uint4*>(p + dst) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
 __global__ void umma_pack_tf32_kernel(const float* __restrict__ w, unsigned char* __restrict__ p, int C,
                                       int Cout, int K) {
   // one thread per 16-byte chunk (4 channels); writes the hi and the lo tile
@@ -82,7 +109,11 @@ int umma_pack_weight(const DcnGeom& g, const float* weight, void* packed, int pr
   const int bk = bk_of(precision);
   const int total = (g.C / bk) * g.K * g.Cout * 8;
   const int blocks = ceil_div(total, 256);
-  if (precision == KGDET_PREC_BF16)
+  if (precision == KGDET_PREC_BF16 && (size_t)2 * 64 * g.K * sizeof(float) <= 48 * 1024)
+    umma_pack_bf16_tiled_kernel<<<dim3((unsigned)ceil_div(g.Cout, 2), (unsigned)(g.C / 64)), 256,
+                                  (size_t)2 * 64 * g.K * sizeof(float), stream>>>(weight, (unsigned char*)packed, g.C,
+                                                                                 g.Cout, g.K);
+  else if (precision == KGDET_PREC_BF16)
     umma_pack_bf16_kernel<<<blocks, 256, 0, stream>>>(weight, (unsigned char*)packed, g.C, g.Cout, g.K);
   else
     umma_pack_tf32_kernel<<<blocks, 256, 0, stream>>>(weight, (unsigned char*)packed, g.C, g.Cout, g.K);
