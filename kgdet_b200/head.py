@@ -689,40 +689,53 @@ class GraphedInference(object):
         self.graph.replay()
         return self.static_out
 
+    def _second_instance(self):
+        """A second capture of the same step with its own static input / outputs (lazy: only `serve` needs it)."""
+        if getattr(self, '_twin', None) is None:
+            twin = object.__new__(GraphedInference)
+            twin.head, twin.args, twin.score_override = self.head, self.args, self.score_override
+            twin.static_x = self.static_x.clone()
+            torch.cuda.synchronize()
+            twin.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(twin.graph), torch.no_grad():
+                twin.static_out = twin._run()
+            twin._twin = None
+            self._twin = twin
+        return self._twin
+
     def serve(self, host_batches, host_outputs=None, before_step=None):
         """Throughput path for HOST inputs: a three-stage software pipeline over the batches --
 
-            copy-in stream   pinned host batch i+1 -> device staging buffer          (PCIe, host -> device)
-            compute stream   staging -> the graph's static input, graph replay i, static results -> staging
-            copy-out stream  result staging of batch i-1 -> pinned host buffers      (PCIe, device -> host)
+            copy-in stream   pinned host batch i+1 -> static input of graph instance (i+1) % 2   (PCIe, host -> device)
+            compute stream   replay of instance i % 2
+            copy-out stream  static results of instance (i-1) % 2 -> pinned host buffers         (PCIe, device -> host)
 
-        -- with two staging buffers per direction, so both copies of neighbouring batches run under the replay of
-        the current one.  `host_batches`: iterable of pinned CPU tensors shaped like the example input.
-        `host_outputs`: optional list (one entry per batch) of pinned (dets, labels, keypoints) triples to fill;
-        allocated when omitted.  `before_step(i)`: optional callable issued on the compute stream before replay i
-        (bench.py flushes the L2 there).  Returns the list of host triples; everything has completed on return."""
+        -- the step is captured twice (two instances with their own static input and outputs), so both copies of
+        neighbouring batches run under the replay of the current one and no device-side staging copy is needed.
+        `host_batches`: iterable of pinned CPU tensors shaped like the example input.  `host_outputs`: optional list
+        (one entry per batch) of pinned (dets, labels, keypoints) triples to fill; allocated when omitted.
+        `before_step(i)`: optional callable issued on the compute stream before replay i (bench.py flushes the L2
+        there).  Returns the list of host triples; everything has completed on return."""
         dev = self.static_x.device
         main = torch.cuda.current_stream(dev)
+        inst = (self, self._second_instance())
         if not hasattr(self, '_pipe'):
-            cin, cout = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-            xs = [torch.empty_like(self.static_x) for _ in range(2)]
-            outs = [[torch.empty_like(t) for t in self.static_out] for _ in range(2)]
-            self._pipe = (cin, cout, xs, outs)
-        cin, cout, xs, outs = self._pipe
+            self._pipe = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        cin, cout = self._pipe
         start = main.record_event()
         cin.wait_event(start)
         cout.wait_event(start)
-        x_free = [None, None]          # compute has consumed staging input b
-        out_done = [None, None]        # copy-out has drained result staging b
+        replayed = [None, None]        # instance b has consumed its static input (and rewritten its outputs)
+        drained = [None, None]         # copy-out has read instance b's static outputs
         results = []
         batches = list(host_batches)
 
         def copy_in(i):
             b = i % 2
-            if x_free[b] is not None:
-                cin.wait_event(x_free[b])
+            if replayed[b] is not None:
+                cin.wait_event(replayed[b])
             with torch.cuda.stream(cin):
-                xs[b].copy_(batches[i], non_blocking=True)
+                inst[b].static_x.copy_(batches[i], non_blocking=True)
                 return cin.record_event()
 
         ready = copy_in(0) if batches else None
@@ -730,23 +743,19 @@ class GraphedInference(object):
             b = i % 2
             nxt = copy_in(i + 1) if i + 1 < len(batches) else None     # overlaps replay i
             main.wait_event(ready)
-            self.static_x.copy_(xs[b], non_blocking=True)
-            x_free[b] = main.record_event()
+            if drained[b] is not None:
+                main.wait_event(drained[b])                            # results of batch i - 2 have left the device
             if before_step is not None:
                 before_step(i)
-            self.graph.replay()
-            if out_done[b] is not None:
-                main.wait_event(out_done[b])
-            for d, t in zip(outs[b], self.static_out):
-                d.copy_(t, non_blocking=True)
-            staged = main.record_event()
+            inst[b].graph.replay()
+            replayed[b] = main.record_event()
             host = host_outputs[i] if host_outputs is not None else \
                 tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in self.static_out)
-            cout.wait_event(staged)
+            cout.wait_event(replayed[b])
             with torch.cuda.stream(cout):
-                for h, d in zip(host, outs[b]):
+                for h, d in zip(host, inst[b].static_out):
                     h.copy_(d, non_blocking=True)
-                out_done[b] = cout.record_event()
+                drained[b] = cout.record_event()
             results.append(host)
             ready = nxt
         main.wait_stream(cout)
