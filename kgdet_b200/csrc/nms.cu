@@ -175,6 +175,7 @@ nms_small_kernel(const float* __restrict__ dets, const int32_t* __restrict__ seg
         const unsigned long long dr = __shfl_sync(0xffffffffu, r < 32 ? d_lo : d_hi, r & 31);
         if (r < cnt && !((rem >> r) & 1ull)) { kept |= 1ull << r; rem |= dr; }
       }
+      __syncwarp();                              // every lane has read removed[blk] before lane 0 rewrites it
       if (tid == 0) { removed[blk] = rem; *kept_word = kept; }
     }
     __syncthreads();
