@@ -111,6 +111,120 @@ def dcn_flops(batch, k):
     return 2.0 * batch * H * W * C * C * k * k
 
 
+
+# --------------------------------------------------------------------------------------------
+# Sub-records of the default run (world == 1): the same step with fp32 cuDNN towers, the fp32-grade mode of the
+# deformable convolution, and the reference's own CUDA op rebuilt for sm_100a (the GPU incumbent).
+def _time_graph_steps(graphed, x_dev, flush, steps):
+    for _ in range(3):
+        flush.fill_(1)
+        graphed(x_dev)
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graphed(x_dev)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / steps
+
+
+def fp32_towers_record(args, head, head_mod, x_dev, sc_dev, shapes, flush):
+    """The benched step again with cuDNN TF32 switched OFF for the eight plain 3x3 convolutions (the setting the
+    golden parity tests of tests/test_head_gpu.py run under): same kernels of this library, fp32 towers."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = head_mod.GraphedInference(head, x_dev, shapes, 0.05, 0.5, 1000, 100, score_override=sc_dev)
+        ms = _time_graph_steps(g, x_dev, flush, args.steps)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    return {'value': round(args.batch / (ms * 1e-3), 2), 'unit': UNIT, 'ms_per_step': round(ms, 4),
+            'note': 'same step, torch.backends.cudnn.allow_tf32 = False for the eight cuDNN 3x3 convolutions '
+                    '(fp32 towers, the configuration of the golden parity tests); device-resident, graph replay'}
+
+
+def fp32_mode_record(args, head, head_mod, ops, lib, x_dev, sc_dev, shapes, flush, prof, recording, peak_tf):
+    """The reference's own precision end to end: DCN in the fp32-grade tensor-core mode (tf32x3 with accumulator
+    promotion, rel 1e-5), towers / 1x1 convolutions cuDNN fp32 (TF32 off)."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    ops.set_precision('tf32x3')
+    try:
+        g = head_mod.GraphedInference(head, x_dev, shapes, 0.05, 0.5, 1000, 100, score_override=sc_dev)
+        ms = _time_graph_steps(g, x_dev, flush, max(args.steps // 2, 5))
+        del prof[:]
+        recording['on'] = True
+        for _ in range(3):
+            flush.fill_(1)
+            with torch.no_grad():
+                o = head.forward_single(x_dev)
+        torch.cuda.synchronize()
+        recording['on'] = False
+        per_k = {}
+        for k, e0, e1 in prof:
+            per_k.setdefault(k, []).append(e0.elapsed_time(e1))
+        del prof[:]
+    finally:
+        ops.set_precision(args.precision)
+        torch.backends.cudnn.allow_tf32 = old
+    tot_flop = sum(dcn_flops(args.batch, k) * len(v) for k, v in per_k.items())
+    tot_ms = sum(sum(v) for v in per_k.values())
+    tf = tot_flop / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+    dcn_ms_per_step = tot_ms / 3.0
+    return {'value': round(args.batch / (ms * 1e-3), 2), 'unit': UNIT, 'ms_per_step': round(ms, 4),
+            'dcn_precision': 'tf32x3 (tcgen05 kind::tf32, hi/lo split operands, 3 MMAs per k-step, accumulator '
+                             'promotion every 16 k-blocks; rel 1e-5 vs the fp64 reference)',
+            'dcn_ms_per_step': round(dcn_ms_per_step, 4), 'dcn_tflops': round(tf, 1),
+            'dcn_frac_of_half_bf16_peak': round(tf / (0.5 * peak_tf), 4),
+            'peak_note': 'TF32 peak is not in MEASURED_PEAKS.json: 1/2 of the measured sustained bf16 peak is used '
+                         '(nominal 1.1 vs 2.25 PFLOP/s dense); the 3 MMAs per k-step are NOT counted as useful flops',
+            'per_kernel_size': {('k%d' % k): {'launches': len(v), 'avg_us': round(1e3 * sum(v) / len(v), 2)}
+                                for k, v in sorted(per_k.items())},
+            'note': 'forward_single + get_bboxes, batch %d, CUDA-graph replay, device-resident; towers and 1x1 '
+                    'convolutions cuDNN fp32 (TF32 off)' % args.batch}
+
+
+def gpu_incumbent_record(args, dev):
+    """The reference's own deform_conv_forward_cuda (mmdet/ops/dcn/src/deform_conv_cuda.cpp:151-258: im2col kernel +
+    cuBLAS SGEMM per im2col_step chunk), compiled UNMODIFIED for sm_100a into oracle/_ref, timed on the 12 calls of
+    one step (2 stages x 2 branches x {9, 25, 49} points at batch 16).  Checker/incumbent only: never on the
+    product path."""
+    from oracle import build_ref
+    ref = build_ref.load('deform_conv_cuda')
+    if ref is None:
+        return {'unavailable': 'oracle/_ref/deform_conv_cuda.so not built'}
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(args.batch, C, H, W, generator=g).to(dev)
+    per_k = {}
+    for k in (3, 5, 7):
+        w = (torch.randn(C, C, k, k, generator=g) * 0.02).to(dev)
+        off = (torch.randn(args.batch, 2 * k * k, H, W, generator=g) * 2).to(dev)
+        out = x.new_empty(args.batch, C, H, W)
+        bufs = [x.new_empty(0), x.new_empty(0)]
+        step = min(64, args.batch)
+        times = []
+        for it in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ref.deform_conv_forward_cuda(x, w, off, out, bufs[0], bufs[1], k, k, 1, 1, k // 2, k // 2, 1, 1, 1, 1, step)
+            b.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                times.append(a.elapsed_time(b))
+        ms = sum(times) / len(times)
+        per_k['k%d' % k] = {'avg_us': round(ms * 1e3, 1), 'tflops': round(dcn_flops(args.batch, k) / (ms * 1e-3) / 1e12, 1)}
+    tot_ms = 4 * sum(v['avg_us'] for v in per_k.values()) * 1e-3
+    tot_flop = 4 * sum(dcn_flops(args.batch, k) for k in (3, 5, 7))
+    return {'kind': 'reference CUDA op (deform_conv_forward_cuda, oracle/_ref), fp32: deformable_im2col + cuBLAS SGEMM',
+            'dcn_ms_per_step': round(tot_ms, 4), 'dcn_tflops': round(tot_flop / (tot_ms * 1e-3) / 1e12, 1),
+            'per_kernel_size': per_k, 'allow_tf32_matmul': bool(torch.backends.cuda.matmul.allow_tf32),
+            'note': '12 forward calls of one step at batch %d; CUDA events around each call (3 timed of 5)' % args.batch}
+
+
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
@@ -283,6 +397,36 @@ def run_ours(args):
     e2e_ms = kdist.max_over_ranks(e2e_ms, dev)
     e2e_sync_ms = kdist.max_over_ranks(e2e_sync_ms, dev)
 
+    # ---- sub-records --------------------------------------------------------------------------------
+    launch_mode = 'cuda_graph' if graphed is not None else 'eager'
+    main_prof = list(prof)
+    sub = {}
+    if world == 1 and not args.no_sub_records and graphed is not None:
+        peaks0 = {}
+        try:
+            peaks0 = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        for name, fn in (('fp32_towers', lambda: fp32_towers_record(args, head, head_mod, x_dev, sc_dev, shapes, flush)),
+                         ('fp32_mode', lambda: fp32_mode_record(args, head, head_mod, ops, lib, x_dev, sc_dev, shapes, flush,
+                                                                prof, recording, peaks0.get('bf16_tflops_sustained') or 1400.0)),
+                         ('gpu_incumbent', lambda: gpu_incumbent_record(args, dev))):
+            try:
+                sub[name] = fn()
+            except Exception as e:
+                sub[name] = {'error': repr(e)}
+                torch.cuda.synchronize()
+    prof = main_prof
+    head_mod.deform_conv_prepared = real_prepared
+    train = None
+    if not args.no_train_record:
+        del graphed
+        torch.cuda.empty_cache()
+        try:
+            train = train_record(args, rank, world, local)          # collective: every rank takes part
+        except Exception as e:
+            train = {'error': repr(e)}
+
     if rank == 0:
         peaks = {}
         try:
@@ -331,10 +475,15 @@ def run_ours(args):
                          'share_of_step': round(tot_ms / dev_ms, 4), 'per_kernel_size': detail,
                          'timed_in': 'eager pass of the same K steps, DCN launches serialised, with CUDA events around each launch (C-ABI hook); '
                                      'share_of_step = those kernel times / graph-replayed step time'},
-            'launch_mode': 'cuda_graph' if graphed is not None else 'eager',
+            'launch_mode': launch_mode,
             'eager_ms_per_step': round(eager_ms / args.steps, 4),
             'clocks': clocks, 'wall_s_timed_region': round(wall, 3),
         }
+        result['config']['towers'] = ('eight plain 3x3 convolutions: cuDNN, TF32 allowed (PyTorch default, what the '
+                                      'reference runs on this GPU); fp32_towers = the same step with TF32 off')
+        result.update(sub)
+        if train is not None:
+            result['train'] = train
         if world == 1 and not args.no_cpu_baseline:
             result['cpu_baseline'] = cpu_baseline(args, budget_s=20.0)
         emit(json.dumps(result))
@@ -412,23 +561,26 @@ def run_reference(args):
     }))
 
 
-def run_train(args):
+def train_record(args, rank=None, world=None, local=None):
     """BASELINE.json configs[4]: KGDet head training step (forward + losses + backward + gradient all-reduce +
     SGD) at batch 2 per GPU.  Ground truth is synthetic; target assignment (PointAssigner, pos_num 25) and the
     nine losses of the reference head run inside the step through the sync-free device mirror
     (kgdet_b200/targets.py; focal losses through the fused focal-sum op).  The DCN
     runs forward and backward on the tensor cores (bf16 mode), the moment transform through its fused
-    fwd/bwd kernels; gradients are averaged over ranks with the overlapped bucketed all-reduce."""
+    fwd/bwd kernels.  With more than one rank the gradients live in one flat buffer and are all-reduced in
+    ~25 MB buckets on a side stream AS THE CAPTURED BACKWARD PRODUCES THEM (NCCL captured into the same CUDA
+    graph as a parallel branch); the exposed all-reduce time is measured as (step) - (step without all-reduce).
+    Returns the record on rank 0 (None elsewhere); collective -- every rank must call it."""
     from kgdet_b200 import dist as kdist, ops
     from kgdet_b200.head import KGDetHead
-    rank, world, local = kdist.init_from_env('nccl')
+    if rank is None:
+        rank, world, local = kdist.init_from_env('nccl')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     ops.set_precision(args.precision)
     B = args.train_batch
     head = make_weights(KGDetHead()).to(dev).train()
     opt = torch.optim.SGD(head.parameters(), lr=1e-6, momentum=0.9)
-    bucketer = kdist.GradBucketer(head.parameters(), bucket_size_mb=25) if world > 1 else None
     g = torch.Generator().manual_seed(200 + rank)
     x = torch.randn(B, C, H, W, generator=g).to(dev)
     # synthetic ground truth as SURVEY.md section 8(d) config 5: per image 1-3 boxes (w, h ~ U(100, 600) inside
@@ -450,17 +602,6 @@ def run_train(args):
     gt_boxes, gt_labels, gt_kps, gt_valid = T.pad_ground_truth(gtb, gtl, gtk, device=dev, max_gts=3)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        o = head.forward_single(x)
-        loss = sum(head.loss(o, gt_boxes, gt_labels, gt_kps, gt_valid).values())      # assignment + nine losses
-        loss.backward()
-        if bucketer is not None:
-            bucketer.finish()
-        torch.nn.utils.clip_grad_norm_(head.parameters(), 35.0)       # grad_clip=dict(max_norm=35) of the configs
-        opt.step()
-        return loss
-
     def fwd_bwd():
         o = head.forward_single(x)
         loss = sum(head.loss(o, gt_boxes, gt_labels, gt_kps, gt_valid).values())      # assignment + nine losses
@@ -468,89 +609,165 @@ def run_train(args):
         return loss
 
     def update():
-        torch.nn.utils.clip_grad_norm_(head.parameters(), 35.0)
+        torch.nn.utils.clip_grad_norm_(head.parameters(), 35.0)       # grad_clip=dict(max_norm=35) of the configs
         opt.step()
 
+    def eager_step(bucketer):
+        opt.zero_grad(set_to_none=True)
+        loss = fwd_bwd()
+        if bucketer is not None:
+            bucketer.finish()
+        update()
+        return loss
+
+    bucketer = kdist.GradBucketer(head.parameters(), bucket_size_mb=25) if world > 1 else None
     for _ in range(max(args.warmup, 3)):
-        step()
+        eager_step(bucketer)
     torch.cuda.synchronize()
+    if bucketer is not None:
+        bucketer.remove()
 
-    # The step is launch-bound at batch 2 (about 600 kernels for ~0.3 TFLOP): capture forward + losses + backward
-    # into one CUDA graph and clip + SGD into a second one; the gradient all-reduce (world > 1) runs between the
-    # two on the static gradient tensors, coalesced into one NCCL call (reference semantics: sum, then / world).
-    mode = 'eager'
+    # The step is launch-bound at batch 2 (about 600 kernels for ~0.3 TFLOP): forward + losses + backward (+ the
+    # bucketed all-reduce as a parallel branch) are captured into one CUDA graph and clip + SGD into a second one.
+    mode, allreduce_kind, step, step_noar = 'eager', 'none (1 GPU)', None, None
     if not args.no_graph:
-        if bucketer is not None:                         # its hooks would launch NCCL inside the capture
-            bucketer.remove()
-            bucketer = None
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):
+        for in_graph in ((True, False) if world > 1 else (False,)):
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        opt.zero_grad(set_to_none=True)
+                        fwd_bwd()
+                        update()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                # gradients live in ONE flat buffer (fixed address): the captured backward accumulates into it and
+                # the all-reduce runs on slices of that buffer, without flatten / unflatten copies
+                # (one rank: plain per-parameter gradients -- the flat buffer costs a 111 MB clear and
+                # read-modify-write accumulation, 0.16 ms, and only pays for itself when there is an all-reduce)
+                flat = kdist.FlatGrads(head.parameters()) if world > 1 else None
+                if flat is None:
                     opt.zero_grad(set_to_none=True)
-                    fwd_bwd()
+                g_fb, g_up = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                overlap = None
+                if flat is not None and in_graph:
+                    overlap = kdist.FlatBucketAllReduce(flat, bucket_size_mb=25)
+                with torch.cuda.graph(g_fb):
+                    if flat is not None:
+                        flat.zero()
+                    if overlap is not None:
+                        overlap.start()
+                    static_loss = fwd_bwd()
+                    if overlap is not None:
+                        overlap.finish()
+                if overlap is not None:
+                    overlap.remove()
+                with torch.cuda.graph(g_up, pool=g_fb.pool()):
                     update()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            # gradients live in ONE flat buffer (fixed address): the captured backward accumulates into it and the
-            # all-reduce is a single collective on that buffer, without flatten / unflatten copies
-            # (one rank: plain per-parameter gradients -- the flat buffer costs a 111 MB clear and read-modify-write
-            # accumulation, 0.16 ms, and only pays for itself when there is an all-reduce to feed)
-            flat = kdist.FlatGrads(head.parameters()) if world > 1 else None
-            if flat is None:
-                opt.zero_grad(set_to_none=True)
-            g_fb, g_up = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_fb):
-                if flat is not None:
-                    flat.zero()
-                static_loss = fwd_bwd()
-            with torch.cuda.graph(g_up, pool=g_fb.pool()):
-                update()
 
-            def step():                                   # noqa: F811
-                g_fb.replay()
-                if flat is not None:
-                    flat.allreduce()
-                g_up.replay()
-                return static_loss
+                def step(flat=flat, in_graph=in_graph, g_fb=g_fb, g_up=g_up, static_loss=static_loss):
+                    g_fb.replay()
+                    if flat is not None and not in_graph:
+                        flat.allreduce()
+                    g_up.replay()
+                    return static_loss
+                for _ in range(2):
+                    step()
+                torch.cuda.synchronize()
+                mode = 'cuda_graph (fwd+losses+bwd%s | %sclip+SGD)' % (
+                    ' + bucketed NCCL all-reduce as a parallel branch' if (world > 1 and in_graph) else '',
+                    'all-reduce | ' if (world > 1 and not in_graph) else '')
+                if world > 1:
+                    allreduce_kind = ('25 MB buckets of the flat gradient buffer, NCCL captured in the backward graph on a '
+                                      'side stream (overlapped)') if in_graph else \
+                        'one NCCL all-reduce on the flat gradient buffer between the two graphs (not overlapped)'
+                    if not in_graph:
+                        def step_noar(g_fb=g_fb, g_up=g_up):
+                            g_fb.replay()
+                            g_up.replay()
+                break
+            except Exception as e:
+                log('[bench] training-step graph capture (%s) failed (%r)' % ('NCCL in graph' if in_graph else 'plain', e))
+                torch.cuda.synchronize()
+                step = None
+                for p_ in head.parameters():
+                    p_.grad = None
+    if step is None:
+        bucketer = kdist.GradBucketer(head.parameters(), bucket_size_mb=25) if world > 1 else None
+        step = lambda: eager_step(bucketer)            # noqa: E731
+        if world > 1:
+            allreduce_kind = 'overlapped 25 MB buckets (eager hooks)'
+
+    def timed(fn):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        out = None
+        for _ in range(args.steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        return kdist.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), dev), out
+
+    ms, loss = timed(step)
+    exposed_us = None
+    if world > 1:
+        # the same step WITHOUT the all-reduce (gradients stay local): the difference is what the collective
+        # leaves exposed.  Built from the un-overlapped capture so that nothing else changes.
+        try:
+            if step_noar is None:
+                flat2 = None
+                for p_ in head.parameters():
+                    p_.grad = None
+                opt.zero_grad(set_to_none=True)
+                torch.cuda.synchronize()
+                g_fb2, g_up2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                flat2 = kdist.FlatGrads(head.parameters())
+                with torch.cuda.graph(g_fb2):
+                    flat2.zero()
+                    fwd_bwd()
+                with torch.cuda.graph(g_up2, pool=g_fb2.pool()):
+                    update()
+
+                def step_noar():
+                    g_fb2.replay()
+                    g_up2.replay()
             for _ in range(2):
-                step()
-            torch.cuda.synchronize()
-            mode = 'cuda_graph (fwd+losses+bwd | all-reduce | clip+SGD)'
+                step_noar()
+            ms0, _ = timed(step_noar)
+            exposed_us = round((ms - ms0) / args.steps * 1e3, 1)
         except Exception as e:
-            log('[bench] training-step graph capture failed (%r); running eagerly' % (e,))
-            torch.cuda.synchronize()
-            bucketer = kdist.GradBucketer(head.parameters(), bucket_size_mb=25) if world > 1 else None
-    if world > 1:
-        torch.distributed.barrier()
-    evs = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        loss = step()
-        b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
-    ms = kdist.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), dev)
-    if rank == 0:
-        nparam = sum(p.numel() for p in head.parameters())
-        emit(json.dumps({
-            'metric': 'kgdet_head_train_images_per_sec', 'value': round(B * world * args.steps / (ms * 1e-3), 2),
+            log('[bench] no-all-reduce variant failed (%r)' % (e,))
+    final_loss = float(loss.item())
+    ops.set_precision(args.precision)
+    if rank != 0:
+        return None
+    nparam = sum(p.numel() for p in head.parameters())
+    return {'metric': 'kgdet_head_train_images_per_sec', 'value': round(B * world * args.steps / (ms * 1e-3), 2),
             'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': round(ms / args.steps, 4), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
             'config': {'workload': 'KGDet head training step (fwd + target assignment + 9 losses + bwd + grad all-reduce + '
                                    'clip + SGD) @800x1333 (map 25x42), batch %d per GPU, synthetic ground truth' % B,
-                       'batch_per_gpu': B, 'allreduce': ('one NCCL all-reduce on the flat gradient buffer between the two graphs' if mode != 'eager' else
-                                                         'overlapped 25 MB buckets') + ', %.1f MB fp32 gradients' % (nparam * 4 / 1e6)
-                       if world > 1 else 'none (1 GPU)', 'parallelism': 'dp%d' % world, 'l2': 'flushed before every step'},
-            'launch_mode': mode,
-            'final_loss': float(loss.item())}))
-    if world > 1:
+                       'batch_per_gpu': B, 'allreduce': allreduce_kind + (', %.1f MB fp32 gradients' % (nparam * 4 / 1e6)
+                                                                           if world > 1 else ''),
+                       'parallelism': 'dp%d' % world, 'l2': 'flushed before every step'},
+            'exposed_allreduce_us': exposed_us, 'launch_mode': mode, 'final_loss': final_loss}
+
+
+def run_train(args):
+    rec = train_record(args)
+    if rec is not None:
+        emit(json.dumps(rec))
+    if torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
 
 
@@ -582,6 +799,9 @@ def main():
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
                     help='infer (default, the headline metric) or train (BASELINE.json configs[4])')
     ap.add_argument('--train-batch', type=int, default=2)
+    ap.add_argument('--no-train-record', action='store_true', help='skip the training-step sub-record')
+    ap.add_argument('--no-sub-records', action='store_true',
+                    help='skip the fp32_towers / fp32_mode / gpu_incumbent sub-records (N = 1 only)')
     args = ap.parse_args()
     if args.mode == 'train' and args.impl != 'reference':
         run_train(args)

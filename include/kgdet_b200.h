@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define KGDET_ABI_VERSION 1
+#define KGDET_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define KGDET_API __attribute__((visibility("default")))
@@ -55,7 +55,10 @@ enum { KGDET_F32 = 0, KGDET_BF16 = 1 };
 
 /* arithmetic of the dense contraction
  *  FP32   : fp32 FFMA on the SIMT pipe (bit pattern of the sum order aside, the reference's SGEMM)
- *  TF32X3 : tcgen05 kind::tf32 with hi/lo split operands, 3 MMAs per k-step (fp32-grade, ~1e-6)
+ *  TF32X3 : tcgen05 kind::tf32 with hi/lo split operands, 3 MMAs per k-step, and accumulator promotion (no TMEM
+ *           accumulator absorbs more than 16 k-blocks; chunk results are summed in fp32 round-to-nearest):
+ *           fp32-grade, measured < 1e-5 of the tensor maximum against the fp64 reference at C = 256, K = 49.
+ *           Default for fp32 tensors on shapes the tensor-core path supports.
  *  BF16   : tcgen05 kind::f16 with bf16 operands, fp32 accumulation in TMEM (~1e-3)
  *  TF32   : tcgen05 kind::tf32, single pass (~1e-3) */
 enum { KGDET_PREC_FP32 = 0, KGDET_PREC_TF32X3 = 1, KGDET_PREC_BF16 = 2, KGDET_PREC_TF32 = 3 };
@@ -125,7 +128,11 @@ KGDET_API int kgdet_dcn_prepare_plan_points(const float* points, int32_t channel
 KGDET_API int kgdet_dcn_forward_prepared(const void* prepared_input, const void* plan, const void* weight_packed,
                                const float* bias, void* output, int32_t out_channel_offset,
                                int32_t out_channels_total, int fuse_relu, int out_layout,
-                               const kgdet_dcn_shape* shape, int dtype, int precision, void* stream);
+                               const kgdet_dcn_shape* shape, int dtype, int precision, void* workspace,
+                               size_t workspace_bytes, void* stream);
+/* scratch of the prepared call (k-block split of small maps, TF32X3 accumulator promotion); 0 = none needed.
+ * `workspace` may be NULL: the call then runs unsplit (TF32X3 without promotion: ~1e-4 instead of 1e-5). */
+KGDET_API size_t kgdet_dcn_forward_prepared_workspace_bytes(const kgdet_dcn_shape* shape, int precision);
 
 /* Global top-k over the survivors of the batched NMS (mmdet/core/post_processing/bbox_nms_kp.py:64-70:
  * sort the concatenated per-class results by score, keep max_num).  dets [B, L, 5] (score in column 4), flags

@@ -278,7 +278,7 @@ extern "C" int kgdet_dcn_forward_prepared(const void* prepared_input, const void
                                           const void* weight_packed, const float* bias, void* output,
                                           int32_t out_channel_offset, int32_t out_channels_total,
                                           int fuse_relu, int out_layout, const kgdet_dcn_shape* shape, int dtype,
-                                          int precision, void* stream) {
+                                          int precision, void* workspace, size_t workspace_bytes, void* stream) {
   DcnGeom g;
   int rc = make_geom(shape, &g);
   if (rc != KGDET_OK) return rc;
@@ -297,7 +297,20 @@ extern "C" int kgdet_dcn_forward_prepared(const void* prepared_input, const void
   }
   OutSpec o{output, dtype, out_channel_offset, out_channels_total, fuse_relu ? 1 : 0,
             out_layout};
-  return do_forward_prepared(g, prepared_input, plan, weight_packed, bias, o, precision, (cudaStream_t)stream);
+  // optional scratch for the k-block split (small maps; TF32X3 accumulator promotion): used when it is big enough
+  const size_t split_total = (use_umma(g, precision) && out_layout == KGDET_LAYOUT_NCHW) ? umma_split_ws_bytes(g, precision) : 0;
+  void* split_ws = nullptr;
+  if (split_total && workspace) {
+    if ((rc = check_ws("kgdet_dcn_forward_prepared", workspace, workspace_bytes, split_total)) != KGDET_OK) return rc;
+    split_ws = workspace;
+  }
+  return do_forward_prepared(g, prepared_input, plan, weight_packed, bias, o, precision, (cudaStream_t)stream, split_ws);
+}
+
+extern "C" size_t kgdet_dcn_forward_prepared_workspace_bytes(const kgdet_dcn_shape* shape, int precision) {
+  DcnGeom g;
+  if (make_geom(shape, &g) != KGDET_OK) return 0;
+  return use_umma(g, precision) ? umma_split_ws_bytes(g, precision) : 0;
 }
 
 extern "C" void kgdet_dcn_set_profile_events(void* start_event, void* stop_event) {

@@ -126,6 +126,14 @@ int umma_pack_weight(const DcnGeom& g, const float* weight, void* packed, int pr
 // M = 2 100 positions (KGDet training at batch 2, or FPN P6 / P7) keeps 17 of 148 SMs busy for the whole call.
 // When the tiles cover less than half of the SMs the k-blocks are split over gridDim.y CTAs per tile; the partial
 // accumulators go through an fp32 buffer and are combined by umma_split_reduce_kernel (deterministic order).
+// TF32X3 -- accumulator promotion.  The tensor core adds every MMA into the fp32 TMEM accumulator with
+// truncation, so the error of one accumulator grows linearly with the number of MMAs it absorbs (measured at
+// C = 256: 4.4e-5 after 200 k-blocks, 8.2e-5 after 392, i.e. ~2e-7 per 32-channel k-block).  The fp32-grade mode
+// therefore never lets one accumulator absorb more than kPromoteChunk k-blocks: the k-blocks are split into chunks
+// (gridDim.y), every chunk accumulates in its own TMEM tile from zero, and the chunk results are promoted to fp32
+// partial tiles that umma_split_reduce_kernel sums with round-to-nearest adds in a fixed order -- the same
+// machinery that splits small maps over the SMs.  16 k-blocks per chunk keep the truncation share below 4e-6.
+static constexpr int kPromoteChunk = 16;
 int umma_splits(const DcnGeom& g, int precision) {
   if (!umma_supported(g, precision)) return 1;
   const int tiles = ceil_div(g.M, BM);
@@ -135,6 +143,12 @@ int umma_splits(const DcnGeom& g, int precision) {
   if (s > 16) s = 16;
   if (s < 4) s = 1;                             // measured: 2 splits (FPN P5 at batch 8, 66 tiles) lose to the reduction pass
   if (const char* e = getenv("KGDET_UMMA_SPLITS")) s = atoi(e);
+  if (precision == KGDET_PREC_TF32X3) {
+    int chunk = kPromoteChunk;
+    if (const char* e = getenv("KGDET_TF32X3_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : nkb;
+    const int need = ceil_div(nkb, chunk);
+    if (s < need) s = need;
+  }
   return s < 1 ? 1 : s;
 }
 size_t umma_split_ws_bytes(const DcnGeom& g, int precision) {

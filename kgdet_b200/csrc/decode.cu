@@ -19,19 +19,30 @@ __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf
 // Every CTA recomputes the per-position maxima of its image (ceil(HW / 256) CTAs per image): one 1024-thread CTA
 // per image that computes them once was measured slower (50 vs 28 us for 16 x 1050 positions: 16 CTAs cannot
 // hide the latency of the strided score reads).
+// Ranking key: a TOTAL order on floats as unsigned integers (monotone bit pattern; -0 == +0; NaN above +inf,
+// which is where torch.topk / torch.max put it -- KP3:866-868).  With plain `>` / `==` comparisons every
+// all-NaN position (a diverged feature map) would get rank 0, ranks would collide and slots of `order` would
+// stay unwritten.
+__device__ __forceinline__ unsigned int rank_key(float v) {
+  unsigned int b = __float_as_uint(v);
+  if (v != v) return 0xFFFFFFFFu;
+  if (b == 0x80000000u) b = 0u;
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
 __global__ void __launch_bounds__(256) bbox_select_kernel(const float* __restrict__ scores, int apply_sigmoid, int C,
                                                           int HW, int n, int* __restrict__ order) {
-  extern __shared__ float smax[];               // [HW]
+  extern __shared__ unsigned int skey[];        // [HW] rank keys of the per-position maxima
   const int b = blockIdx.y;
   const float* sb = scores + (size_t)b * C * HW;
   for (int p = threadIdx.x; p < HW; p += blockDim.x) {
-    float m = -INFINITY;
+    unsigned int m = 0u;                        // below rank_key(-inf)
     for (int c = 0; c < C; ++c) {
       float v = sb[(size_t)c * HW + p];
       if (apply_sigmoid) v = sigmoid_ref(v);
-      m = fmaxf(m, v);
+      m = max(m, rank_key(v));                  // NaN propagates, like torch.max
     }
-    smax[p] = m;
+    skey[p] = m;
   }
   __syncthreads();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -40,10 +51,10 @@ __global__ void __launch_bounds__(256) bbox_select_kernel(const float* __restric
     order[(size_t)b * n + p] = p;
     return;
   }
-  const float mine = smax[p];
+  const unsigned int mine = skey[p];
   int rank = 0;
   for (int j = 0; j < HW; ++j) {
-    const float o = smax[j];
+    const unsigned int o = skey[j];
     rank += (o > mine || (o == mine && j < p)) ? 1 : 0;
   }
   if (rank < n) order[(size_t)b * n + rank] = p;
@@ -57,7 +68,7 @@ __global__ void bbox_decode_kernel(const float* __restrict__ scores, int apply_s
   const int b = blockIdx.y;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  const int p = order[(size_t)b * n + r];
+  const int p = min(max(order[(size_t)b * n + r], 0), HW - 1);     // defensive: never index outside the map
   const float cx = (float)(p % Wmap) * stride, cy = (float)(p / Wmap) * stride;      // point_generator.py:14-23
   const float w = lim[b * 2], h = lim[b * 2 + 1];
   const float* bb = bbox + (size_t)b * 4 * HW + p;
@@ -102,7 +113,7 @@ __global__ void bbox_finalize_kernel(const float* __restrict__ boxes, const floa
     od[lane] = valid ? v : __fmul_rn(v, 0.f);
   }
   if (lane == 0) out_labels[(size_t)b * k + j] = valid ? (long long)cls : -1ll;
-  const int p = order[(size_t)b * n + r];
+  const int p = min(max(order[(size_t)b * n + r], 0), HW - 1);
   const float cx = (float)(p % Wmap) * stride, cy = (float)(p / Wmap) * stride;
   const float w = lim[b * 2], h = lim[b * 2 + 1];
   const float* kb = kp + (size_t)b * 2 * P * HW + p;

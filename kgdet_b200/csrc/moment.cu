@@ -135,8 +135,11 @@ __global__ void moment_bwd_kernel(const float* __restrict__ pts, const float* __
     acc_w += g_hw * sdx * ew;                            // d/dt_w of sdx * exp(t_w)
     acc_h += g_hh * sdy * eh;
     const float g_sdx = g_hw * ew, g_sdy = g_hh * eh;
-    // d std / d x_i = (x_i - mean) / ((P-1) * std)   (0/0 -> NaN at std == 0, as PyTorch)
-    const float cx = g_sdx / ((float)(P - 1) * sdx), cy = g_sdy / ((float)(P - 1) * sdy);
+    // d std / d x_i = (x_i - mean) / ((P-1) * std); a collapsed point set (std == 0) gets a ZERO gradient, as
+    // current PyTorch's std_backward does (masked_fill(result == 0, 0)); the torch 1.x the reference targeted
+    // produced 0/0 = NaN there
+    const float cx = sdx == 0.f ? 0.f : g_sdx / ((float)(P - 1) * sdx);
+    const float cy = sdy == 0.f ? 0.f : g_sdy / ((float)(P - 1) * sdy);
     const float mxP = g_mx / (float)P, myP = g_my / (float)P;
     float* go = gpts + (size_t)n * 2 * P * S + s;
     for (int k = 0; k < P; ++k) {

@@ -113,11 +113,113 @@ class FlatGrads(object):
     def zero(self):
         self.flat.zero_()
 
-    def allreduce(self):
+    def attached(self):
+        """True while every parameter's .grad still aliases its slice of the flat buffer.  The default
+        `optimizer.zero_grad()` / `module.zero_grad()` (set_to_none=True) drops the views: use
+        `zero_grad(set_to_none=False)` or `FlatGrads.zero()` with this class."""
+        off = 0
+        base, esz = self.flat.data_ptr(), self.flat.element_size()
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != base + off * esz:
+                return False
+            off += p.numel()
+        return True
+
+    def reattach(self):
+        """Point every .grad back at its slice (copying a detached gradient's values in first)."""
+        off = 0
+        for p in self.params:
+            view = self.flat[off:off + p.numel()].view_as(p)
+            if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+            p.grad = view
+            off += p.numel()
+
+    def allreduce(self, check=True):
+        if check and not self.attached():
+            raise RuntimeError('FlatGrads: a parameter gradient no longer aliases the flat buffer (zero_grad('
+                               'set_to_none=True)?): the all-reduce would average stale data. Use FlatGrads.zero() '
+                               'or zero_grad(set_to_none=False), or call reattach().')
         ws = world_size()
         if ws > 1:
             dist.all_reduce(self.flat)
             self.flat.div_(ws)
+
+
+class FlatBucketAllReduce(object):
+    """Overlapped all-reduce on a `FlatGrads` buffer: the flat buffer is cut into contiguous buckets of whole
+    parameters (~`bucket_size_mb` each); a post-accumulate-grad hook counts the gradients of a bucket as autograd
+    finishes them and, when the last one arrives, all-reduces that SLICE of the flat buffer in place on a side
+    stream (no flatten / unflatten copies).  `finish()` joins the side stream and divides by the world size: the
+    same result as the reference's one flat all-reduce after backward (mmdet/core/utils/dist_utils.py:14-25), just
+    earlier in time.  Every call is capture-safe (stream waits + NCCL only), so when `start() ... backward ...
+    finish()` runs under `torch.cuda.graph` the collectives become a parallel branch of the captured backward."""
+
+    def __init__(self, flat, bucket_size_mb=25):
+        self.fg = flat
+        self.ws = world_size()
+        limit = int(bucket_size_mb * 1024 * 1024)
+        self.buckets = []                # (lo, hi) element ranges of the flat buffer
+        self.where = {}
+        lo = off = 0
+        esz = flat.flat.element_size()
+        for p in flat.params:
+            if off > lo and (off + p.numel() - lo) * esz > limit:
+                self.buckets.append((lo, off))
+                lo = off
+            self.where[id(p)] = len(self.buckets)
+            off += p.numel()
+        self.buckets.append((lo, off))
+        self.count = [0] * len(self.buckets)
+        for p in flat.params:
+            self.count[self.where[id(p)]] += 1
+        self.pending = None
+        self.stream = None
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in flat.params] if self.ws > 1 else []
+
+    def start(self):
+        self.pending = list(self.count)
+        self.launched = [False] * len(self.buckets)
+
+    def _hook(self, p):
+        if self.pending is None:
+            return
+        bi = self.where[id(p)]
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        if self.launched[bi]:
+            return
+        self.launched[bi] = True
+        lo, hi = self.buckets[bi]
+        flat = self.fg.flat
+        if flat.is_cuda:
+            if self.stream is None:
+                self.stream = torch.cuda.Stream(device=flat.device)
+            main = torch.cuda.current_stream(flat.device)
+            self.stream.wait_event(main.record_event())
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(flat[lo:hi])
+        else:
+            dist.all_reduce(flat[lo:hi])
+
+    def finish(self):
+        if self.ws == 1 or self.pending is None:
+            return
+        for bi in range(len(self.buckets)):          # parameters that received no gradient this step
+            self._launch(bi)
+        flat = self.fg.flat
+        if flat.is_cuda and self.stream is not None:
+            torch.cuda.current_stream(flat.device).wait_event(self.stream.record_event())
+        flat.div_(self.ws)
+        self.pending = None
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+        self.handles = []
 
 
 class GradBucketer(object):

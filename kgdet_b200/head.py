@@ -673,9 +673,29 @@ class GraphedInference(object):
                 self._run()
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        self._capture()
+
+    def _capture(self):
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.static_out = self._run()
+        # the captured kernels hold raw pointers into the derived-weight caches (packed DCN / 1x1 weights,
+        # channels_last copies): this object keeps those buffers alive whatever happens to the caches
+        from .ops.pointwise import cache_values
+        self._pinned_buffers = cache_values()
+        self._twin = None
+
+    def refresh_weights(self):
+        """Re-derive every packed weight from the head's CURRENT parameters and capture the step again.  A
+        GraphedInference is a snapshot of the weights at capture time; call this after the parameters changed
+        (optimizer steps, `load_state_dict`, in-place `.data` writes, replays of a captured training graph)."""
+        from .ops import invalidate_weight_caches
+        torch.cuda.synchronize()
+        invalidate_weight_caches()
+        with torch.no_grad():
+            self._run()
+        torch.cuda.synchronize()
+        self._capture()
 
     def _run(self):
         o = self.head.forward_single(self.static_x)
@@ -699,6 +719,8 @@ class GraphedInference(object):
             twin.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(twin.graph), torch.no_grad():
                 twin.static_out = twin._run()
+            from .ops.pointwise import cache_values
+            twin._pinned_buffers = cache_values()
             twin._twin = None
             self._twin = twin
         return self._twin

@@ -12,7 +12,8 @@ from .dcn import (DeformConv, DeformConvFunction, DeformConvPack, ModulatedDefor
                   ModulatedDeformConvFunction, ModulatedDeformConvPack, deform_conv,
                   deform_conv_prepared, get_precision, modulated_deform_conv, prepare_input,
                   prepare_plan, prepare_plan_points, set_precision)
-from .pointwise import TiledRows, groupnorm_relu_nhwc, nchw_to_tiled, pack_weight, pointwise_conv
+from .pointwise import (TiledRows, groupnorm_relu_nhwc, invalidate_weight_caches, nchw_to_tiled, pack_weight,
+                        pointwise_conv)
 from .decode import bbox_decode, bbox_finalize, bbox_select
 from .moment import points2bbox_moment
 from .nms import batched_nms_flags, nms, soft_nms
@@ -30,5 +31,5 @@ __all__ = [
     'sigmoid_focal_loss_sum', 'batched_nms_flags', 'set_precision', 'get_precision',
     'prepare_input', 'prepare_plan', 'prepare_plan_points', 'deform_conv_prepared', 'pointwise_conv',
     'nchw_to_tiled', 'pack_weight', 'TiledRows', 'groupnorm_relu_nhwc', 'bbox_select', 'bbox_decode',
-    'bbox_finalize',
+    'bbox_finalize', 'invalidate_weight_caches',
 ]

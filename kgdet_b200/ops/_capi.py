@@ -13,6 +13,7 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG, '_lib', 'libkgdet_b200.so')
 
 # enums of include/kgdet_b200.h
+ABI_VERSION = 2
 F32, BF16 = 0, 1
 PREC_FP32, PREC_TF32X3, PREC_BF16, PREC_TF32 = 0, 1, 2, 3
 NMS_GT, NMS_GE = 0, 1
@@ -57,7 +58,9 @@ SIGNATURES = {
     'kgdet_dcn_prepare_plan': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
     'kgdet_dcn_prepare_plan_points': (ctypes.c_int, [c_ptr, c_i32, c_i32, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
     'kgdet_dcn_forward_prepared': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, ctypes.c_int,
-                                                  ctypes.c_int, _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr]),
+                                                  ctypes.c_int, _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr, c_sz,
+                                                  c_ptr]),
+    'kgdet_dcn_forward_prepared_workspace_bytes': (c_sz, [_SHAPE_P, ctypes.c_int]),
     'kgdet_bbox_select': (ctypes.c_int, [c_ptr, ctypes.c_int, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
     'kgdet_bbox_decode': (ctypes.c_int, [c_ptr, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32,
                                          c_i32, c_ptr, c_ptr, c_ptr]),
@@ -125,7 +128,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.kgdet_abi_version() != 1:
+        if handle.kgdet_abi_version() != ABI_VERSION:
             raise RuntimeError('kgdet_b200: ABI version mismatch')
         _lib = handle
     return _lib
@@ -150,6 +153,14 @@ def ptr(t):
 
 
 def stream_of(t):
+    """Current stream of the tensor's device.  The library launches on the process's CURRENT device (as the
+    reference extension does: no device guard in deform_conv_cuda.cpp), so a tensor on another device is a loud
+    error here instead of a launch with a foreign stream."""
+    idx = t.device.index
+    if idx is not None and idx != torch.cuda.current_device():
+        raise RuntimeError('kgdet_b200: tensor lives on cuda:%d but the current device is cuda:%d; call '
+                           'torch.cuda.set_device(%d) (or use `with torch.cuda.device(...)`) first'
+                           % (idx, torch.cuda.current_device(), idx))
     return torch.cuda.current_stream(t.device).cuda_stream
 
 

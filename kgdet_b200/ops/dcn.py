@@ -11,9 +11,11 @@ module.  Differences, all documented in DESIGN.md:
   returns 8 for 9 inputs, which modern autograd rejects when ``im2col_step`` is passed.
 * ``im2col_step`` is validated like the reference (DC.py:47-49) but not used: the fused
   kernels never materialise the column buffer it chunks.
-* the arithmetic of the contraction is selectable (``set_precision``): ``'fp32'`` (default
-  for fp32 tensors: exact FFMA, rel 1e-5 parity), ``'bf16'`` (default for bf16 tensors; fused
-  tcgen05 kernel, rel 1e-2), ``'tf32x3'`` (tcgen05, split operands, ~1e-4) or ``'tf32'``.
+* the arithmetic of the contraction is selectable (``set_precision``): ``'tf32x3'`` (default for
+  fp32 tensors: fused tcgen05 kernel, hi/lo split operands + accumulator promotion, rel 1e-5 parity
+  with the reference's fp32 SGEMM; shapes the tensor-core path does not cover and the whole backward
+  run the exact FFMA kernels), ``'fp32'`` (exact FFMA everywhere), ``'bf16'`` (default for bf16
+  tensors; fused tcgen05 kernel forward and backward, rel 1e-2) or ``'tf32'`` (single pass, 5e-3).
 """
 import math
 import os
@@ -41,7 +43,7 @@ def set_precision(name):
 def get_precision(dtype=torch.float32):
     if _precision_override is not None:
         return _precision_override
-    return 'bf16' if dtype == torch.bfloat16 else 'fp32'
+    return 'bf16' if dtype == torch.bfloat16 else 'tf32x3'
 
 
 def _shape(input, weight, stride, padding, dilation, groups, deformable_groups):
@@ -78,12 +80,19 @@ _pack_cache = {}
 
 
 def _packed_weight(weight, shape, precision):
+    from .pointwise import _generation, cache_allowed
     lib = _capi.lib()
     key = (id(weight), precision, weight.device.index)
-    ent = _pack_cache.get(key)
-    sig = (weight._version, weight.data_ptr(), tuple(weight.shape))
-    if ent is not None and ent[0]() is weight and ent[1] == sig:
-        return ent[2]
+    use_cache = cache_allowed((weight,))
+    sig = (_generation[0], weight._version, weight.data_ptr(), tuple(weight.shape))
+    if use_cache:
+        ent = _pack_cache.get(key)
+        if ent is not None and ent[0]() is weight and ent[1] == sig:
+            return ent[2]
+    else:
+        # training call: the pack is rebuilt every time (microseconds) and any cached copy is dropped -- the
+        # weights are about to change, possibly by a replayed CUDA graph that never bumps `_version`
+        _pack_cache.pop(key, None)
     w32 = weight.detach()
     if w32.dtype != torch.float32:
         w32 = w32.float()
@@ -93,6 +102,8 @@ def _packed_weight(weight, shape, precision):
     _capi.check(lib.kgdet_dcn_pack_weight(w32.data_ptr(), packed.data_ptr(), ctypes_ref(shape),
                                           precision, _capi.stream_of(weight)),
                 'kgdet_dcn_pack_weight')
+    if not use_cache:
+        return packed
     if len(_pack_cache) > 256:
         for k in [k for k, v in _pack_cache.items() if v[0]() is None]:
             del _pack_cache[k]
@@ -328,9 +339,15 @@ def deform_conv_prepared(pin, plan, weight, out=None, channel_offset=0, relu=Fal
         assert out.is_contiguous() and out.shape[0] == n and tuple(out.shape[2:]) == (ho, wo)
         layout = _capi.LAYOUT_NCHW
         ptr, ctot, dt, ref = out.data_ptr(), out.shape[1], _capi.dtype_code(out), out
+    ws, nws = None, 0
+    if layout == _capi.LAYOUT_NCHW:
+        nws = int(lib.kgdet_dcn_forward_prepared_workspace_bytes(ctypes_ref(shape), plan.precision))
+        if nws:
+            ws = _capi.workspace(nws, ref)
     _capi.check(lib.kgdet_dcn_forward_prepared(pin.buf.data_ptr(), plan.buf.data_ptr(), packed.data_ptr(),
                                                _capi.ptr(b), ptr, int(channel_offset), ctot, int(bool(relu)), layout,
-                                               ctypes_ref(shape), dt, plan.precision, _capi.stream_of(ref)),
+                                               ctypes_ref(shape), dt, plan.precision, _capi.ptr(ws), nws,
+                                               _capi.stream_of(ref)),
                 'kgdet_dcn_forward_prepared')
     return out
 

@@ -42,18 +42,54 @@ class TiledRows(object):
         return rows[:, :self.K] + rows[:, self.K:] if self.split else rows
 
 
+_generation = [0]
+
+
+def invalidate_weight_caches():
+    """Drop every derived-weight buffer (packed DCN / 1x1 weights, channels_last copies).
+
+    The caches are keyed on (parameter identity, ``_version``, ``data_ptr``).  Two update paths change a
+    parameter WITHOUT bumping ``_version``: in-place writes through ``.data`` (``p.data.copy_``, legacy
+    optimisers, mmcv's Fp16OptimizerHook / EMAHook) and replays of a CUDA graph that contains the optimiser
+    step.  Call this after such an update and before the next inference call.  Training-mode calls (grad enabled
+    on a parameter that requires grad) never use the caches, and a ``GraphedInference`` is a snapshot of the
+    weights at capture time by contract (``GraphedInference.refresh_weights()`` re-captures)."""
+    _generation[0] += 1
+    _cache.clear()
+    from . import dcn
+    dcn._pack_cache.clear()
+
+
+def cache_allowed(params):
+    """Derived-weight caches serve inference only: while autograd is recording for a parameter the weights are
+    about to change (optimizer step, possibly inside a replayed CUDA graph that Python never sees)."""
+    return not (torch.is_grad_enabled() and any(p.requires_grad for p in params))
+
+
 def cached(params, build):
     """Cache of host-prepared device buffers keyed by the identity + version of the source parameters."""
     key = tuple(id(p) for p in params)
-    sig = tuple((p._version, p.data_ptr()) for p in params)
+    if not cache_allowed(params):
+        _cache.pop(key, None)               # a training call: whatever was derived from these weights is stale soon
+        return build()
+    sig = (_generation[0],) + tuple((p._version, p.data_ptr()) for p in params)
     ent = _cache.get(key)
     if ent is not None and ent[0] == sig and all(r() is p for r, p in zip(ent[1], params)):
         return ent[2]
     val = build()
-    if len(_cache) > 64:
-        _cache.clear()
+    if len(_cache) > 256:
+        # prune entries whose parameters are gone; live entries are never dropped (a captured CUDA graph may
+        # hold raw pointers into them -- GraphedInference additionally keeps its own references)
+        for k in [k for k, v in _cache.items() if any(r() is None for r in v[1])]:
+            del _cache[k]
     _cache[key] = (sig, [weakref.ref(p) for p in params], val)
     return val
+
+
+def cache_values():
+    """Every buffer currently held by the derived-weight caches (GraphedInference pins them)."""
+    from . import dcn
+    return [v[2] for v in _cache.values()] + [v[2] for v in dcn._pack_cache.values()]
 
 
 def pack_weight(w, split=True):

@@ -22,10 +22,18 @@ import torch.nn as nn
 
 REF_ROOT = os.environ.get('KGDET_REFERENCE_ROOT', '/root/reference')
 MMDET_PARENT = os.path.join(REF_ROOT, 'mmdetection')
+_ZIP = None
+if not os.path.isdir(os.path.join(MMDET_PARENT, 'mmdet')):
+    # GPU box: the reference tree is absent; oracle/build_ref.py archived its Python package + configs, untouched,
+    # into the git-ignored oracle/_ref/pytree.zip (it travels with the gpurun snapshot); imported by zipimport
+    _z = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref', 'pytree.zip')
+    if os.path.isfile(_z):
+        _ZIP = _z
+        MMDET_PARENT = os.path.join(_z, 'mmdetection')
 
 
 def available():
-    return os.path.isdir(os.path.join(MMDET_PARENT, 'mmdet'))
+    return _ZIP is not None or os.path.isdir(os.path.join(MMDET_PARENT, 'mmdet'))
 
 
 def _mod(name, **attrs):
@@ -104,8 +112,14 @@ def load_config(name):
     """exec a reference config file (they are plain Python) -> dict of its globals."""
     path = os.path.join(REF_ROOT, 'configs', name)
     ns = {}
-    with open(path) as f:
-        exec(compile(f.read(), path, 'exec'), ns)
+    if _ZIP is not None:
+        import zipfile
+        with zipfile.ZipFile(_ZIP) as z:
+            src = z.read('configs/' + name).decode()
+    else:
+        with open(path) as f:
+            src = f.read()
+    exec(compile(src, path, 'exec'), ns)
     return {k: v for k, v in ns.items() if not k.startswith('__')}
 
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, s), 'missing export %s' % s
     assert sorted(_capi.SIGNATURES) == syms, 'ctypes binding and header disagree'
     lib = _capi.lib()
-    assert lib.kgdet_abi_version() == 1
+    assert lib.kgdet_abi_version() == 2
     # argument validation works without a GPU (no kernel is launched on these paths)
     s = _capi.DcnShape(N=1, C=8, H=5, W=5, Cout=8, kh=0, kw=3, stride_h=1, stride_w=1, pad_h=1, pad_w=1,
                        dil_h=1, dil_w=1, groups=1, deformable_groups=1)

@@ -67,6 +67,31 @@ def _worker(rank, world, port, q):
     out['flat_views_kept'] = ptrs == [p.grad.data_ptr() for p in net3.parameters()] and \
         ptrs[0] == fg.flat.data_ptr()
     out['avg_flat'] = [p.grad.clone().tolist() for p in net3.parameters()]
+    # bucketed all-reduce on slices of the flat buffer, launched from autograd hooks (the form bench.py captures
+    # into the training graph); two steps through the same object
+    net4 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    net4.load_state_dict(net.state_dict())
+    fg4 = kd.FlatGrads(net4.parameters())
+    ov = kd.FlatBucketAllReduce(fg4, bucket_size_mb=0.0002)
+    out['n_buckets'] = len(ov.buckets)
+    for scale in (3.0, 1.0):
+        fg4.zero()
+        ov.start()
+        net4(x * scale).square().sum().backward()
+        ov.finish()
+    out['avg_flat_buckets'] = [p.grad.clone().tolist() for p in net4.parameters()]
+    ov.remove()
+    # a detached gradient view is detected (zero_grad(set_to_none=True) drops the aliases)
+    net4.zero_grad(set_to_none=True)
+    net4(x).square().sum().backward()
+    out['detached_detected'] = not fg4.attached()
+    try:
+        fg4.allreduce()
+        out['detached_raises'] = False
+    except RuntimeError:
+        out['detached_raises'] = True
+    fg4.reattach()
+    out['reattached'] = fg4.attached()
     # non-coalesced path
     for p, l in zip(net.parameters(), local):
         p.grad.copy_(l)
@@ -95,11 +120,14 @@ def test_two_rank_gloo_host_logic():
     assert res[0]['max'] == res[1]['max'] == 2.5
     for i in range(len(res[0]['avg'])):
         want = (torch.tensor(res[0]['local'][i]) + torch.tensor(res[1]['local'][i])) / 2
-        for key in ('avg', 'avg2', 'avg_nc', 'avg_flat'):
+        for key in ('avg', 'avg2', 'avg_nc', 'avg_flat', 'avg_flat_buckets'):
             assert torch.allclose(torch.tensor(res[0][key][i]), want, atol=1e-6), key
             assert torch.allclose(torch.tensor(res[1][key][i]), want, atol=1e-6), key
     assert res[0]['avg3_ok'] and res[1]['avg3_ok']
     assert res[0]['flat_views_kept'] and res[1]['flat_views_kept']
+    assert res[0]['n_buckets'] > 1
+    for r in (0, 1):
+        assert res[r]['detached_detected'] and res[r]['detached_raises'] and res[r]['reattached']
 
 
 def test_single_process_is_a_no_op():
