@@ -118,9 +118,13 @@ KGDET_API int kgdet_dcn_prepare_plan(const float* offset, const float* mask, voi
 /* Plan from a channel slice [channel_offset, channel_offset + 2K) of a point-set tensor
  * [N, channels_total, Ho, Wo] whose values are absolute point offsets: the head's `pts - dcn_base_offset`
  * (KP3:37-67,135-143) happens inside the plan kernel, so neither the slice nor the subtraction is a kernel.
+ * gradient_mul != 0: the head's `gradient_mul * pts + (1 - gradient_mul) * pts.detach()` (KP3:135-143, the identity
+ * up to fp32 rounding; the reference evaluates it in inference too) is applied first, in that operation order, with
+ * the two fp32 factors given, so that the sampled locations are bit-identical to the reference's.
  * deformable_groups must be 1. */
 KGDET_API int kgdet_dcn_prepare_plan_points(const float* points, int32_t channel_offset, int32_t channels_total,
-                                  void* plan, const kgdet_dcn_shape* shape, int precision, void* stream);
+                                  float gradient_mul, float one_minus_gradient_mul, void* plan,
+                                  const kgdet_dcn_shape* shape, int precision, void* stream);
 /* out_layout: KGDET_LAYOUT_NCHW, or (tensor-core path, dtype KGDET_BF16) KGDET_LAYOUT_TILED = position-major
  * rows [N*Ho*Wo, out_channels_total] stored as the UMMA-tiled A operand of kgdet_pointwise_conv_tiled
  * (kgdet_pointwise_tiled_bytes(M, out_channels_total, 0) bytes), or KGDET_LAYOUT_TILED_SPLIT = the same with
@@ -162,6 +166,35 @@ KGDET_API int kgdet_bbox_finalize(const float* boxes, const float* keypts, const
                         const float* top_s, const float* img_wh, float stride, int32_t map_w, int32_t B,
                         int32_t HW, int32_t n, int32_t k, int32_t num_keypts, float* out_dets,
                         int64_t* out_labels, float* out_kpts, void* stream);
+
+/* ---- plain k x k convolutions of the head towers on the tensor cores -------
+ * replaces  the cuDNN calls behind ConvModule's nn.Conv2d (mmdet/models/utils/conv_module.py:96-110,156-164;
+ *           KP3:292-313 towers, KP3:98-106 stage-1 3x3 convolutions): stride 1, padding (k-1)/2, no groups.
+ * fp32-grade arithmetic ("bf16x3": operands split into bf16 hi + lo, three tcgen05 MMAs per k-step, fp32
+ * accumulation): ~1e-5 of the tensor maximum against an fp64 convolution -- cuDNN's TF32 path is 8e-4, which the
+ * deformable stages of the head amplify to 1e-1.
+ * The activation is read as SPLIT PLANES: channel-blocked bf16 planes [C/64][guard | N*H*W pixels | guard][64] of
+ * the hi parts -- bit-identical to kgdet_dcn_prepare_input(..., KGDET_PREC_BF16), so the hi half can be handed to
+ * kgdet_dcn_forward_prepared as its prepared input -- followed by the same planes of the lo parts (x - hi).
+ * Output: NHWC fp32 [N, H, W, Cout] (a channels_last tensor), optional bias and ReLU.
+ * Requires C % 64 == 0, Cout in {64, 128, 192, 256}, odd k <= 7 (kgdet_conv_supported). */
+KGDET_API int kgdet_conv_supported(int32_t C, int32_t Cout, int32_t ksize);
+KGDET_API size_t kgdet_conv_split_planes_bytes(int32_t N, int32_t C, int32_t H, int32_t W);
+KGDET_API int kgdet_conv_split_planes_from_nchw(const float* x, void* planes, int32_t N, int32_t C, int32_t H, int32_t W,
+                                      void* stream);
+KGDET_API int kgdet_conv_split_planes_from_rows(const float* rows_nhwc, void* planes, int32_t N, int32_t C, int32_t H,
+                                      int32_t W, void* stream);
+KGDET_API size_t kgdet_conv_packed_weight_bytes(int32_t Cout, int32_t Cin, int32_t ksize);
+KGDET_API int kgdet_conv_pack_weight(const float* weight, void* weight_packed, int32_t Cout, int32_t Cin, int32_t ksize,
+                           void* stream);
+KGDET_API int kgdet_conv_forward(const void* planes, const void* weight_packed, const float* bias, float* out_nhwc,
+                       int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t ksize, int fuse_relu,
+                       void* stream);
+/* GroupNorm (+ ReLU) of an NHWC fp32 activation (torch.nn.GroupNorm semantics) written as split planes for the next
+ * convolution / the deformable stage, and optionally (y != NULL) also as NHWC fp32. */
+KGDET_API int kgdet_groupnorm_relu_nhwc_planes(const float* x, const float* gamma, const float* beta, float eps,
+                                     int32_t groups, int fuse_relu, float* y, void* planes, int32_t N, int32_t H,
+                                     int32_t W, int32_t C, void* stream);
 
 /* ---- pointwise convolutions of the Kp3RepBlock ------------------------
  * replaces  cls_out / keypts_out / reppts_out 1x1 nn.Conv2d + the cascade's residual adds

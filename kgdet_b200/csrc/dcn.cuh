@@ -44,14 +44,15 @@ size_t plan16_bytes(const DcnGeom& g);
 // batch_stride: elements between images of `offset` (0 = contiguous [N, 2K, Ho, Wo]); points = 1: `offset`
 // holds absolute point offsets and the base grid is subtracted (kgdet_dcn_prepare_plan_points)
 int launch_plan16(const DcnGeom& g, const float* offset, const float* mask, SampleRec16* rec, int fmt,
-                  cudaStream_t stream, long long batch_stride = 0, int points = 0);
+                  cudaStream_t stream, long long batch_stride = 0, int points = 0, float gm = 0.f, float gm1 = 0.f);
 static inline int dcn_guard_pixels(const DcnGeom& g) { return g.W + 2; }
 
 size_t plan_rows(const DcnGeom& g);                 // M rounded up to 256
 size_t plan_bytes(const DcnGeom& g);                // SampleRec array
 size_t plan_aux_bytes(const DcnGeom& g);            // SampleAux array
 int launch_plan(const DcnGeom& g, const float* offset, const float* mask, SampleRec* rec,
-                SampleAux* aux /* may be NULL */, cudaStream_t stream, long long batch_stride = 0, int points = 0);
+                SampleAux* aux /* may be NULL */, cudaStream_t stream, long long batch_stride = 0, int points = 0,
+                float gm = 0.f, float gm1 = 0.f);
 
 // src [B, R, Cc] -> dst [B, Cc, R] with dtype conversion (NCHW <-> NHWC)
 int launch_transpose(const void* src, void* dst, int B, int R, int Cc, int src_dtype,

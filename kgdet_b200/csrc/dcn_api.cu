@@ -253,8 +253,8 @@ extern "C" int kgdet_dcn_prepare_plan(const float* offset, const float* mask, vo
 }
 
 extern "C" int kgdet_dcn_prepare_plan_points(const float* points, int32_t channel_offset,
-                                             int32_t channels_total, void* plan, const kgdet_dcn_shape* shape,
-                                             int precision, void* stream) {
+                                             int32_t channels_total, float gradient_mul, float one_minus_gradient_mul,
+                                             void* plan, const kgdet_dcn_shape* shape, int precision, void* stream) {
   DcnGeom g;
   int rc = make_geom(shape, &g);
   if (rc != KGDET_OK) return rc;
@@ -270,8 +270,10 @@ extern "C" int kgdet_dcn_prepare_plan_points(const float* points, int32_t channe
   const long long bstride = (long long)channels_total * HoWo;
   if (use_umma(g, precision))
     return launch_plan16(g, first, nullptr, (SampleRec16*)plan,
-                         precision == KGDET_PREC_BF16 ? PLAN16_BF16W : PLAN16_F32, (cudaStream_t)stream, bstride, 1);
-  return launch_plan(g, first, nullptr, (SampleRec*)plan, nullptr, (cudaStream_t)stream, bstride, 1);
+                         precision == KGDET_PREC_BF16 ? PLAN16_BF16W : PLAN16_F32, (cudaStream_t)stream, bstride, 1,
+                         gradient_mul, one_minus_gradient_mul);
+  return launch_plan(g, first, nullptr, (SampleRec*)plan, nullptr, (cudaStream_t)stream, bstride, 1, gradient_mul,
+                     one_minus_gradient_mul);
 }
 
 extern "C" int kgdet_dcn_forward_prepared(const void* prepared_input, const void* plan,

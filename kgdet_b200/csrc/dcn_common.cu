@@ -22,6 +22,9 @@ struct OffsetSrc {
   const float* ptr;          // first channel used
   long long batch_stride;    // elements between images
   int points;                // 1: subtract the base grid
+  float gm, gm1;             // points case, gm != 0: the head's gradient-mul expression first (KP3:135-143):
+                             // p' = gm * p + (1 - gm) * p.detach() -- the identity up to fp32 rounding, evaluated
+                             // here in the reference's operation order so that the sampled locations are bit-identical
 };
 __device__ __forceinline__ void load_offset(const OffsetSrc& o, const DcnGeom& g, int n, int dgi, int tap,
                                             int i, int j, int HoWo, int p, float& off_h, float& off_w) {
@@ -29,6 +32,10 @@ __device__ __forceinline__ void load_offset(const OffsetSrc& o, const DcnGeom& g
   off_h = q[0];                                          // :221,223
   off_w = q[HoWo];                                       // :222,224
   if (o.points) {
+    if (o.gm != 0.f) {
+      off_h = __fadd_rn(__fmul_rn(o.gm, off_h), __fmul_rn(o.gm1, off_h));
+      off_w = __fadd_rn(__fmul_rn(o.gm, off_w), __fmul_rn(o.gm1, off_w));
+    }
     off_h = off_h - (float)(i - (g.kh - 1) / 2);
     off_w = off_w - (float)(j - (g.kw - 1) / 2);
   }
@@ -144,8 +151,10 @@ __global__ void dcn_plan16_kernel(DcnGeom g, OffsetSrc osrc,
   }
 }
 
-static OffsetSrc make_offset_src(const DcnGeom& g, const float* offset, long long batch_stride, int points) {
+static OffsetSrc make_offset_src(const DcnGeom& g, const float* offset, long long batch_stride, int points,
+                                 float gm = 0.f, float gm1 = 0.f) {
   OffsetSrc o;
+  o.gm = gm; o.gm1 = gm1;
   o.ptr = offset;
   o.batch_stride = batch_stride > 0 ? batch_stride : (long long)g.dgroups * 2 * g.K * g.Ho * g.Wo;
   o.points = points;
@@ -153,27 +162,27 @@ static OffsetSrc make_offset_src(const DcnGeom& g, const float* offset, long lon
 }
 
 int launch_plan16(const DcnGeom& g, const float* offset, const float* mask, SampleRec16* rec, int fmt,
-                  cudaStream_t stream, long long batch_stride, int points) {
+                  cudaStream_t stream, long long batch_stride, int points, float gm, float gm1) {
   const int rows = (int)plan_rows(g);
   const long long total = (long long)rows * g.K;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  dcn_plan16_kernel<<<(int)blocks, 256, 0, stream>>>(g, make_offset_src(g, offset, batch_stride, points), mask, rec,
-                                                     rows, fmt);
+  dcn_plan16_kernel<<<(int)blocks, 256, 0, stream>>>(g, make_offset_src(g, offset, batch_stride, points, gm, gm1), mask,
+                                                     rec, rows, fmt);
   KG_LAUNCH_CHECK("dcn_plan16_kernel");
   return KGDET_OK;
 }
 
 int launch_plan(const DcnGeom& g, const float* offset, const float* mask, SampleRec* rec,
-                SampleAux* aux, cudaStream_t stream, long long batch_stride, int points) {
+                SampleAux* aux, cudaStream_t stream, long long batch_stride, int points, float gm, float gm1) {
   const int rows = (int)plan_rows(g);
   const long long total = (long long)rows * g.dgroups * g.K;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  dcn_plan_kernel<<<(int)blocks, 256, 0, stream>>>(g, make_offset_src(g, offset, batch_stride, points), mask, rec,
-                                                   aux, rows);
+  dcn_plan_kernel<<<(int)blocks, 256, 0, stream>>>(g, make_offset_src(g, offset, batch_stride, points, gm, gm1), mask,
+                                                   rec, aux, rows);
   KG_LAUNCH_CHECK("dcn_plan_kernel");
   return KGDET_OK;
 }

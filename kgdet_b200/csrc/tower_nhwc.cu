@@ -73,14 +73,20 @@ template <int VEC>
 __global__ void __launch_bounds__(1024) groupnorm_relu_nhwc_wide_kernel(const float* __restrict__ x,
                                                                         const float* __restrict__ gamma,
                                                                         const float* __restrict__ beta, float eps,
-                                                                        float* __restrict__ y, int HW, int C, int relu) {
+                                                                        float* __restrict__ y, int HW, int C, int relu,
+                                                                        unsigned char* __restrict__ hi,
+                                                                        unsigned char* __restrict__ lo,
+                                                                        size_t plane_bytes) {
+  // y (NHWC fp32) and / or hi + lo ("split planes" of conv_umma.cu: channel-blocked bf16 planes of the values'
+  // bf16 hi parts -- the fused DCN kernel's prepared-input layout -- and of the lo parts x - hi) may be NULL
   constexpr int GPC = 8 / VEC;                  // groups per CTA
   extern __shared__ float sm[];                 // [HW][32] values
   __shared__ float red[32][GPC];
   const int n = blockIdx.y, c0 = blockIdx.x * 32;
   const int chunk = threadIdx.x & 7, gi = chunk / VEC, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* xg = x + (size_t)n * HW * C + c0 + chunk * 4;
-  float* yg = y + (size_t)n * HW * C + c0 + chunk * 4;
+  float* yg = y ? y + (size_t)n * HW * C + c0 + chunk * 4 : nullptr;
+  const size_t poff = (size_t)((c0 + chunk * 4) >> 6) * plane_bytes + (size_t)n * HW * 128 + (size_t)((c0 + chunk * 4) & 63) * 2;
   const int prow = threadIdx.x >> 3, pstep = blockDim.x >> 3;
   const float inv_total = 1.f / (float)(HW * VEC * 4);
   // sum over the lanes of this warp that hold the same group (other chunks of the group, other pixels), then
@@ -121,17 +127,29 @@ __global__ void __launch_bounds__(1024) groupnorm_relu_nhwc_wide_kernel(const fl
     o.z = (v.z - mean) * rstd * ga.z + be.z;
     o.w = (v.w - mean) * rstd * ga.w + be.w;
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    *reinterpret_cast<float4*>(yg + (size_t)p * C) = o;
+    if (yg) *reinterpret_cast<float4*>(yg + (size_t)p * C) = o;
+    if (hi) {
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - __low2float(h0), o.y - __high2float(h0));
+      const __nv_bfloat162 l1 = __floats2bfloat162_rn(o.z - __low2float(h1), o.w - __high2float(h1));
+      uint2 hv, lv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+      lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(hi + poff + (size_t)p * 128) = hv;
+      *reinterpret_cast<uint2*>(lo + poff + (size_t)p * 128) = lv;
+    }
   }
 }
 
 template <int VEC>
 static int launch_groupnorm_wide(const float* x, const float* gamma, const float* beta, float eps, float* y, int N,
-                                 int HW, int C, int relu, cudaStream_t stream) {
+                                 int HW, int C, int relu, cudaStream_t stream, unsigned char* hi = nullptr,
+                                 unsigned char* lo = nullptr, size_t plane_bytes = 0) {
   const size_t smem = (size_t)HW * 32 * sizeof(float);
   KG_CUDA(cudaFuncSetAttribute(groupnorm_relu_nhwc_wide_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
-  groupnorm_relu_nhwc_wide_kernel<VEC><<<dim3(C / 32, N), 1024, smem, stream>>>(x, gamma, beta, eps, y, HW, C, relu);
+  groupnorm_relu_nhwc_wide_kernel<VEC><<<dim3(C / 32, N), 1024, smem, stream>>>(x, gamma, beta, eps, y, HW, C, relu, hi, lo,
+                                                                                plane_bytes);
   KG_LAUNCH_CHECK("groupnorm_relu_nhwc_wide_kernel");
   return KGDET_OK;
 }
@@ -269,4 +287,40 @@ extern "C" int kgdet_rows_to_tiled_bf16(const float* rows, const float* bias, vo
                                                                                 fuse_relu ? 1 : 0, split ? 1 : 0);
   KG_LAUNCH_CHECK("rows_to_tiled_kernel");
   return KGDET_OK;
+}
+
+// GroupNorm (+ ReLU) of an NHWC fp32 activation written as the SPLIT PLANES the tensor-core convolution reads
+// (conv_umma.cu; the hi half doubles as the fused DCN kernel's prepared input), optionally also as NHWC fp32.
+// `planes` must be kgdet_conv_split_planes_bytes(N, C, H, W) bytes, 256-byte aligned; guard bands are zeroed here.
+extern "C" int kgdet_groupnorm_relu_nhwc_planes(const float* x, const float* gamma, const float* beta, float eps,
+                                                int32_t groups, int fuse_relu, float* y, void* planes, int32_t N, int32_t H,
+                                                int32_t W, int32_t C, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KG_CHECK_ARG(x && gamma && beta && planes, "kgdet_groupnorm_relu_nhwc_planes: NULL pointer");
+  const int HW = H * W;
+  KG_CHECK_ARG(N > 0 && HW > 0 && C > 0 && C % 64 == 0 && groups > 0 && C % groups == 0 && 32 % (C / groups) == 0 &&
+                   (C / groups) % 4 == 0 && (size_t)HW * 128 <= 200 * 1024 && N <= 65535,
+               "kgdet_groupnorm_relu_nhwc_planes: need C %% 64 == 0, 4 | C / groups | 32 and a map of at most 1600 positions");
+  KG_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0 && ((uintptr_t)planes & 255) == 0,
+               "kgdet_groupnorm_relu_nhwc_planes: misaligned pointer");
+  // split-plane layout of conv_umma.cu (hi planes in the DCN prepared-input layout, then the lo planes)
+  const size_t guard = (size_t)(W + 2) * 128, in_bytes = (size_t)N * HW * 128;
+  const size_t plane_bytes = align_up(in_bytes + 2 * guard, 1024), half = plane_bytes * (C / 64);
+  for (int h = 0; h < 2; ++h) {
+    unsigned char* b = (unsigned char*)planes + (size_t)h * half;
+    KG_CUDA(cudaMemset2DAsync(b, plane_bytes, 0, guard, C / 64, stream));
+    KG_CUDA(cudaMemset2DAsync(b + guard + in_bytes, plane_bytes, 0, plane_bytes - guard - in_bytes, C / 64, stream));
+  }
+  unsigned char* hi = (unsigned char*)planes + guard;
+  unsigned char* lo = hi + half;
+  const int relu = fuse_relu ? 1 : 0;
+  switch ((C / groups) / 4) {
+    case 1: return launch_groupnorm_wide<1>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes);
+    case 2: return launch_groupnorm_wide<2>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes);
+    case 4: return launch_groupnorm_wide<4>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes);
+    case 8: return launch_groupnorm_wide<8>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes);
+    default: break;
+  }
+  set_error("kgdet_groupnorm_relu_nhwc_planes: unsupported channels per group %d", C / groups);
+  return KGDET_ERR_UNSUPPORTED;
 }

@@ -30,6 +30,7 @@ import torch.nn.functional as F
 from .ops import (DeformConv, TiledRows, batched_nms_flags, deform_conv_prepared, get_precision,
                   groupnorm_relu_nhwc, nchw_to_tiled, pack_weight, points2bbox_moment, pointwise_conv,
                   prepare_input, prepare_plan, prepare_plan_points)
+from .ops.conv import conv_planes, conv_supported, groupnorm_relu_planes, split_planes
 from .ops.decode import bbox_decode, bbox_finalize, bbox_select, topk_flagged
 from .ops.pointwise import cached, to_channels_last
 
@@ -70,7 +71,7 @@ def _streams(device, n):
 def _cl_weight(w):
     """channels_last copy of a convolution weight (cached per parameter version): cuDNN then runs the
     convolution on channels_last activations without inserting layout transposes."""
-    return cached((w,), lambda: w.detach().contiguous(memory_format=torch.channels_last))
+    return cached((w,), lambda: w.detach().contiguous(memory_format=torch.channels_last), tag='channels_last')
 
 
 def _conv3x3_nhwc(x_cl, conv, with_bias=True):
@@ -94,7 +95,7 @@ def _pointwise_weights(block):
             w_kr = torch.cat([wk, wr @ wk], 0)
             b_kr = torch.cat([bk, wr @ bk + br], 0)
             return pack_weight(wc, split=True), bc.contiguous(), pack_weight(w_kr, split=True), b_kr.contiguous()
-    return cached(ps, build)
+    return cached(ps, build, tag='pointwise')
 
 
 def _pointwise_cls(block, cls_rows, n, h, w):
@@ -194,6 +195,19 @@ class _PlainBlock(nn.Module):
                                  bias=self.keypts_conv.bias)
         return _pointwise_kpt(self, kpt_rows, n, h, w)
 
+    # the same two branches with the 3x3 convolutions on this library's tensor-core kernel (split planes in)
+    def forward_planes_cls(self, planes):
+        n, _, h, w = planes.shape4
+        cls_rows = nchw_to_tiled(conv_planes(planes, self.cls_conv.weight), relu=True, split=True,
+                                 bias=self.cls_conv.bias)
+        return _pointwise_cls(self, cls_rows, n, h, w)
+
+    def forward_planes_kpt(self, planes):
+        n, _, h, w = planes.shape4
+        kpt_rows = nchw_to_tiled(conv_planes(planes, self.keypts_conv.weight), relu=True, split=True,
+                                 bias=self.keypts_conv.bias)
+        return _pointwise_kpt(self, kpt_rows, n, h, w)
+
 
 class _DeformBlock(nn.Module):
     """Kp3RepBlock(deform_conv=True), KP3:35-96,126-171: six DeformConv on three point sets."""
@@ -233,7 +247,9 @@ class _DeformBlock(nn.Module):
         lo = 0
         for i, k in enumerate(_POINT_SETS):
             n2 = 2 * k * k
-            dcn_offset = reppts_offset[:, lo:lo + n2] - getattr(self, '_dcn_base_%d' % k).to(reppts_offset.dtype)
+            pts = reppts_offset[:, lo:lo + n2]
+            pts = self.gradient_mul * pts + (1 - self.gradient_mul) * pts       # KP3:135-143, value-wise (no autograd here)
+            dcn_offset = pts - getattr(self, '_dcn_base_%d' % k).to(reppts_offset.dtype)
             lo += n2
             plan = prepare_plan(dcn_offset, (n, c, h, w), feat, k, 1, (k - 1) // 2, 1, like_dtype=cls_cat.dtype)
             deform_conv_prepared(cls_prep, plan, getattr(self, 'cls_dfmconv_%d' % k).weight, cls_cat, i * feat, True)
@@ -256,7 +272,8 @@ class _DeformBlock(nn.Module):
         lo = 0
         jobs = []
         for i, k in enumerate(_POINT_SETS):
-            plan = prepare_plan_points(rep_prev, lo, (n, c, h, w), feat, k, 1, (k - 1) // 2, 1, precision='bf16')
+            plan = prepare_plan_points(rep_prev, lo, (n, c, h, w), feat, k, 1, (k - 1) // 2, 1, precision='bf16',
+                                       gradient_mul=self.gradient_mul)
             lo += 2 * k * k
             jobs.append((cls_prep, plan, getattr(self, 'cls_dfmconv_%d' % k).weight, cls_rows, i * feat))
             jobs.append((pts_prep, plan, getattr(self, 'keypts_dfmconv_%d' % k).weight, kpt_rows, i * feat))
@@ -295,8 +312,8 @@ class _DeformBlock(nn.Module):
             n2 = 2 * k * k
             pts = reppts_offset[:, lo:lo + n2]                                     # KP3:131-133
             lo += n2
-            if torch.is_grad_enabled() and pts.requires_grad:
-                pts = self.gradient_mul * pts + (1 - self.gradient_mul) * pts.detach()   # KP3:135-143
+            # KP3:135-143 -- evaluated in inference too (the identity up to fp32 rounding), exactly as the reference
+            pts = self.gradient_mul * pts + (1 - self.gradient_mul) * pts.detach()
             dcn_offset = pts - getattr(self, '_dcn_base_%d' % k).to(pts.dtype)
             cls_feats.append(F.relu(getattr(self, 'cls_dfmconv_%d' % k)(cls_feat, dcn_offset)))
             kpt_feats.append(F.relu(getattr(self, 'keypts_dfmconv_%d' % k)(pts_feat, dcn_offset)))
@@ -317,6 +334,7 @@ class KGDetHead(nn.Module):
         self._fused_inference = deform_conv_cls is None     # prepared API only with the CUDA operators
         self._tensor_core_heads = True                      # bf16 mode: 1x1 convolutions as tcgen05 GEMMs
         self._fused_decode = True                           # get_bboxes: decode kernels instead of PyTorch glue
+        self._own_convs = True                              # bf16 inference: 3x3 convolutions on conv_umma.cu, not cuDNN
         self.concurrent_branches = True                     # bf16 inference: cls / point branches on two streams
         deform_conv_cls = deform_conv_cls or DeformConv
         self._moment_fn = moment_fn or points2bbox_moment
@@ -353,8 +371,25 @@ class KGDetHead(nn.Module):
             # bf16 mode: everything except the eight plain 3x3 convolutions (cuDNN, channels_last) runs on this
             # package's kernels.  Towers: position-major activations end to end,
             # GroupNorm + ReLU fused -- no layout transposes, no separate ReLU kernels.
-            cls_feat = pts_feat = to_channels_last(x)
             feat = self.kp_rep_block_2.cls_dfmconv_3.out_channels
+            own = self._own_convs and all(conv_supported(m.conv.in_channels, m.conv.out_channels, 3)
+                                          for m in list(self.cls_convs) + list(self.reg_convs)) and \
+                x.shape[2] * x.shape[3] <= 1600
+            # own: every 3x3 convolution on this library's fp32-grade tensor-core kernel (conv_umma.cu), activations
+            # travel as split planes (the last tower layer's hi planes ARE the deformable stage's prepared input);
+            # otherwise cuDNN in channels_last (TF32 unless the caller switched it off)
+            cls_feat = pts_feat = split_planes(x) if own else to_channels_last(x)
+
+            def cls_branch_own(p):
+                for m in self.cls_convs:
+                    p = groupnorm_relu_planes(conv_planes(p, m.conv.weight), m.gn)
+                return self.kp_rep_block_1.forward_planes_cls(p), p.as_prepared_input(feat)
+
+            def pts_branch_own(p):
+                for m in self.reg_convs:
+                    p = groupnorm_relu_planes(conv_planes(p, m.conv.weight), m.gn)
+                kpt1, rep1 = self.kp_rep_block_1.forward_planes_kpt(p)
+                return kpt1, rep1, self.points2bbox(rep1), p.as_prepared_input(feat)
 
             def cls_branch(cls_feat):
                 for m in self.cls_convs:
@@ -377,13 +412,13 @@ class KGDetHead(nn.Module):
                 # 3x3 convolution on a 25x42 map is 66 CTAs of cuDNN's 256-row tile -- under half of the SMs:
                 # the two towers run as parallel branches (two streams / two arms of the captured graph).
                 with _SideBranch(x.device, 7) as br:
-                    cls1, cls_prep = cls_branch(cls_feat)
+                    cls1, cls_prep = (cls_branch_own if own else cls_branch)(cls_feat)
                 br.keep(cls_feat)
-                kpt1, rep1, bbox1, pts_prep = pts_branch(pts_feat)
+                kpt1, rep1, bbox1, pts_prep = (pts_branch_own if own else pts_branch)(pts_feat)
                 br.join()
             else:
-                cls1, cls_prep = cls_branch(cls_feat)
-                kpt1, rep1, bbox1, pts_prep = pts_branch(pts_feat)
+                cls1, cls_prep = (cls_branch_own if own else cls_branch)(cls_feat)
+                kpt1, rep1, bbox1, pts_prep = (pts_branch_own if own else pts_branch)(pts_feat)
             cls2, kpt2, rep2 = self.kp_rep_block_2.forward_tc(cls_prep, pts_prep, rep1, kpt1, branches)
             bbox2 = self.points2bbox(rep2)
             cls3, kpt3, rep3 = self.kp_rep_block_3.forward_tc(cls_prep, pts_prep, rep2, kpt2, branches)
@@ -615,7 +650,8 @@ class RepPointsKpHead(nn.Module):
         if self._fused_inference and not torch.is_grad_enabled() and x.is_cuda:
             n, c, h, w = cls_feat.shape
             pf = self.cls_refine_dfmconv.out_channels
-            plan = prepare_plan(rep_init - base, (n, c, h, w), pf, self.dcn_kernel, 1, self.dcn_pad, 1,
+            pts = self.gradient_mul * rep_init + (1 - self.gradient_mul) * rep_init       # PAR:322-325, value-wise
+            plan = prepare_plan(pts - base, (n, c, h, w), pf, self.dcn_kernel, 1, self.dcn_pad, 1,
                                 like_dtype=x.dtype)
             cls_prep = prepare_input(cls_feat, pf)
             pts_prep = prepare_input(pts_feat, pf)
@@ -629,9 +665,8 @@ class RepPointsKpHead(nn.Module):
             else:
                 rep_ref = self.reppts_refine_out(kpt_ref)
             return cls_out, kpt_init, kpt_ref + kpt_init, rep_init, rep_ref + rep_init
-        pts = rep_init
-        if torch.is_grad_enabled() and pts.requires_grad:
-            pts = self.gradient_mul * pts + (1 - self.gradient_mul) * pts.detach()       # PAR:322-325
+        # PAR:322-325 -- evaluated in inference too (the identity up to fp32 rounding), exactly as the reference
+        pts = self.gradient_mul * rep_init + (1 - self.gradient_mul) * rep_init.detach()
         dcn_offset = pts - base
         cls_out = self.cls_refine_out(F.relu(self.cls_refine_dfmconv(cls_feat, dcn_offset)))
         kpt_ref = self.keypts_refine_out(F.relu(self.keypts_refine_dfmconv(pts_feat, dcn_offset)))

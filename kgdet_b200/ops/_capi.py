@@ -56,7 +56,8 @@ SIGNATURES = {
     'kgdet_dcn_prepare_input_rows': (ctypes.c_int, [c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
     'kgdet_dcn_plan_bytes': (c_sz, [_SHAPE_P, ctypes.c_int]),
     'kgdet_dcn_prepare_plan': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
-    'kgdet_dcn_prepare_plan_points': (ctypes.c_int, [c_ptr, c_i32, c_i32, c_ptr, _SHAPE_P, ctypes.c_int, c_ptr]),
+    'kgdet_dcn_prepare_plan_points': (ctypes.c_int, [c_ptr, c_i32, c_i32, c_f32, c_f32, c_ptr, _SHAPE_P, ctypes.c_int,
+                                                     c_ptr]),
     'kgdet_dcn_forward_prepared': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, ctypes.c_int,
                                                   ctypes.c_int, _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr, c_sz,
                                                   c_ptr]),
@@ -85,6 +86,16 @@ SIGNATURES = {
     'kgdet_dcn_backward_weight': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_f32,
                                                  _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr, c_sz,
                                                  c_ptr]),
+    'kgdet_conv_supported': (ctypes.c_int, [c_i32, c_i32, c_i32]),
+    'kgdet_conv_split_planes_bytes': (c_sz, [c_i32, c_i32, c_i32, c_i32]),
+    'kgdet_conv_split_planes_from_nchw': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_ptr]),
+    'kgdet_conv_split_planes_from_rows': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_ptr]),
+    'kgdet_conv_packed_weight_bytes': (c_sz, [c_i32, c_i32, c_i32]),
+    'kgdet_conv_pack_weight': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr]),
+    'kgdet_conv_forward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+                                          ctypes.c_int, c_ptr]),
+    'kgdet_groupnorm_relu_nhwc_planes': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_f32, c_i32, ctypes.c_int, c_ptr, c_ptr,
+                                                        c_i32, c_i32, c_i32, c_i32, c_ptr]),
     'kgdet_nms_workspace_bytes': (c_sz, [c_i32]),
     'kgdet_nms': (ctypes.c_int, [c_ptr, c_i32, c_f32, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_sz,
                                  c_ptr]),

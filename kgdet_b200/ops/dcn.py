@@ -31,6 +31,17 @@ from . import _capi
 
 _precision_override = os.environ.get('KGDET_DCN_PRECISION') or None
 
+# Grad mode of the CALLER of deform_conv / modulated_deform_conv: inside autograd.Function.forward grad mode is
+# always off and ctx.needs_input_grad ignores torch.no_grad(), so the wrappers below record it for the
+# derived-weight cache ("is autograd recording this call?").
+import threading
+_caller = threading.local()
+
+
+def _recording(ctx):
+    outer = getattr(_caller, 'grad_enabled', None)
+    return any(ctx.needs_input_grad) and (outer is None or outer)
+
 
 def set_precision(name):
     """'fp32' | 'tf32x3' | 'bf16' | 'tf32' | None (None = pick by tensor dtype)."""
@@ -79,11 +90,13 @@ def _output_size(input, weight, padding, dilation, stride):
 _pack_cache = {}
 
 
-def _packed_weight(weight, shape, precision):
+def _packed_weight(weight, shape, precision, training=False):
+    """`training`: the call is recorded by autograd (inside an autograd.Function.forward grad mode is off, so the
+    Function passes `any(ctx.needs_input_grad)` down)."""
     from .pointwise import _generation, cache_allowed
     lib = _capi.lib()
     key = (id(weight), precision, weight.device.index)
-    use_cache = cache_allowed((weight,))
+    use_cache = cache_allowed((weight,)) and not training
     sig = (_generation[0], weight._version, weight.data_ptr(), tuple(weight.shape))
     if use_cache:
         ent = _pack_cache.get(key)
@@ -137,7 +150,7 @@ def _check_offset(input, offset, weight, shape_out, deformable_groups, what='off
 
 
 def _dcn_forward(input, offset, mask, weight, bias, stride, padding, dilation, groups,
-                 deformable_groups):
+                 deformable_groups, training=False):
     lib = _capi.lib()
     _capi.require_cuda(input, 'deform_conv')
     if weight.dim() != 4:
@@ -154,7 +167,7 @@ def _dcn_forward(input, offset, mask, weight, bias, stride, padding, dilation, g
     dt = _capi.dtype_code(x)
     prec = _capi.PRECISIONS[get_precision(x.dtype)]
     shape = _shape(x, weight, stride, padding, dilation, groups, deformable_groups)
-    packed = _packed_weight(weight, shape, prec)
+    packed = _packed_weight(weight, shape, prec, training)
     off = _f32c(offset)
     msk = None if mask is None else _f32c(mask)
     b = None if bias is None else _f32c(bias)
@@ -290,9 +303,11 @@ def prepare_plan(offset, input_shape, out_channels, kernel_size, stride=1, paddi
 
 
 def prepare_plan_points(points, channel_offset, input_shape, out_channels, kernel_size, stride=1, padding=0,
-                        dilation=1, precision=None, like_dtype=torch.float32):
+                        dilation=1, precision=None, like_dtype=torch.float32, gradient_mul=0.0):
     """Sample plan of ``points[:, channel_offset:channel_offset + 2K] - base_grid`` without materialising the
-    slice or the subtraction (KP3:131-143: the head's ``dcn_offset = pts - dcn_base_offset``)."""
+    slice or the subtraction (KP3:131-143: the head's ``dcn_offset = pts - dcn_base_offset``).  With
+    ``gradient_mul`` the head's ``gradient_mul * pts + (1 - gradient_mul) * pts.detach()`` (KP3:135-143) is
+    evaluated first in fp32, as the reference does even in inference (bit-identical sample locations)."""
     lib = _capi.lib()
     _capi.require_cuda(points, 'prepare_plan_points')
     assert points.dtype == torch.float32 and points.is_contiguous() and points.dim() == 4
@@ -306,6 +321,7 @@ def prepare_plan_points(points, channel_offset, input_shape, out_channels, kerne
     pl.buf = torch.empty(int(lib.kgdet_dcn_plan_bytes(ctypes_ref(shape), prec)), dtype=torch.uint8,
                          device=points.device)
     _capi.check(lib.kgdet_dcn_prepare_plan_points(points.data_ptr(), int(channel_offset), points.shape[1],
+                                                  float(gradient_mul), float(1 - gradient_mul) if gradient_mul else 0.0,
                                                   pl.buf.data_ptr(), ctypes_ref(shape), prec,
                                                   _capi.stream_of(points)), 'kgdet_dcn_prepare_plan_points')
     return pl
@@ -372,7 +388,7 @@ class DeformConvFunction(Function):
         cur_im2col_step = min(ctx.im2col_step, input.shape[0])
         assert (input.shape[0] % cur_im2col_step) == 0, 'im2col step must divide batchsize'
         return _dcn_forward(input, offset, None, weight, None, ctx.stride, ctx.padding, ctx.dilation,
-                            ctx.groups, ctx.deformable_groups)
+                            ctx.groups, ctx.deformable_groups, training=_recording(ctx))
 
     @staticmethod
     @once_differentiable
@@ -410,7 +426,7 @@ class ModulatedDeformConvFunction(Function):
             raise NotImplementedError
         ctx.save_for_backward(input, offset, mask, weight)
         return _dcn_forward(input, offset, mask, weight, bias, _pair(stride), _pair(padding),
-                            _pair(dilation), groups, deformable_groups)
+                            _pair(dilation), groups, deformable_groups, training=_recording(ctx))
 
     @staticmethod
     @once_differentiable
@@ -437,8 +453,22 @@ class ModulatedDeformConvFunction(Function):
         return n, channels_out, height_out, width_out
 
 
-deform_conv = DeformConvFunction.apply
-modulated_deform_conv = ModulatedDeformConvFunction.apply
+def deform_conv(*args):
+    """DeformConvFunction.apply (DC.py:186) -- records the caller's grad mode for the weight cache."""
+    _caller.grad_enabled = torch.is_grad_enabled()
+    try:
+        return DeformConvFunction.apply(*args)
+    finally:
+        _caller.grad_enabled = None
+
+
+def modulated_deform_conv(*args):
+    """ModulatedDeformConvFunction.apply (DC.py:187)."""
+    _caller.grad_enabled = torch.is_grad_enabled()
+    try:
+        return ModulatedDeformConvFunction.apply(*args)
+    finally:
+        _caller.grad_enabled = None
 
 
 class DeformConv(nn.Module):

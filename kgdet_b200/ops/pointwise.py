@@ -66,9 +66,10 @@ def cache_allowed(params):
     return not (torch.is_grad_enabled() and any(p.requires_grad for p in params))
 
 
-def cached(params, build):
-    """Cache of host-prepared device buffers keyed by the identity + version of the source parameters."""
-    key = tuple(id(p) for p in params)
+def cached(params, build, tag=None):
+    """Cache of host-prepared device buffers keyed by `tag` (what is derived) + the identity + version of the
+    source parameters."""
+    key = (tag,) + tuple(id(p) for p in params)
     if not cache_allowed(params):
         _cache.pop(key, None)               # a training call: whatever was derived from these weights is stale soon
         return build()

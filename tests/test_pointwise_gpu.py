@@ -84,11 +84,19 @@ def test_plan_from_points_and_tiled_output(k):
     base = torch.arange(-(k // 2), k // 2 + 1, dtype=torch.float32)
     yx = torch.stack([base.repeat_interleave(k), base.repeat(k)], 1).reshape(1, -1, 1, 1).cuda()
     ops.set_precision('bf16')
+    import os
+    os.environ['KGDET_UMMA_SPLITS'] = '1'     # the NCHW call would split this tiny map over k-blocks (other fp32 sum order)
     try:
         pin = ops.prepare_input(x, 128, k, 1, k // 2, 1)
         p_ref = ops.prepare_plan(pts[:, lo:lo + 2 * K] - yx, x.shape, 128, k, 1, k // 2, 1)
         p_pts = ops.prepare_plan_points(pts, lo, x.shape, 128, k, 1, k // 2, 1)
         assert torch.equal(p_ref.buf, p_pts.buf)
+        # with the head's gradient-mul expression (KP3:135-143) evaluated first, in the reference's operation order
+        gm = 0.1
+        p_ref_gm = ops.prepare_plan((gm * pts[:, lo:lo + 2 * K] + (1 - gm) * pts[:, lo:lo + 2 * K]) - yx, x.shape, 128, k,
+                                    1, k // 2, 1)
+        p_pts_gm = ops.prepare_plan_points(pts, lo, x.shape, 128, k, 1, k // 2, 1, gradient_mul=gm)
+        assert torch.equal(p_ref_gm.buf, p_pts_gm.buf)
         nchw = ops.deform_conv_prepared(pin, p_pts, w, relu=True)
         rows = ops.TiledRows(2 * 9 * 11, 256, False, 'cuda')
         rows.buf.zero_()
@@ -98,6 +106,7 @@ def test_plan_from_points_and_tiled_output(k):
         ops.deform_conv_prepared(pin, p_pts, w, srows, 128, True)
     finally:
         ops.set_precision(None)
+        del os.environ['KGDET_UMMA_SPLITS']
     full = nchw.permute(0, 2, 3, 1).reshape(-1, 128)
     dense = rows.to_dense()
     assert torch.equal(dense[:, 128:], full.to(torch.bfloat16).float())
