@@ -271,6 +271,16 @@ def run_ours(args):
             prof.append((weight.shape[2], e0, e1))
         return real_prepared(pin, plan, weight, *a, **k)
     head_mod.deform_conv_prepared = timed_prepared
+    real_group = head_mod.deform_conv_prepared_group
+
+    def timed_group(jobs):
+        if recording['on']:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); e1.record()
+            lib.kgdet_dcn_group_set_profile_events(e0.cuda_event, e1.cuda_event)
+            prof.append((tuple(sorted(j[2].shape[2] for j in jobs)), e0, e1))
+        return real_group(jobs)
+    head_mod.deform_conv_prepared_group = timed_group
 
     def eager_step(x):
         with torch.no_grad():
@@ -418,6 +428,7 @@ def run_ours(args):
                 torch.cuda.synchronize()
     prof = main_prof
     head_mod.deform_conv_prepared = real_prepared
+    head_mod.deform_conv_prepared_group = real_group
     train = None
     if not args.no_train_record:
         del graphed
@@ -444,12 +455,15 @@ def run_ours(args):
         per_k = {}
         for k, e0, e1 in prof:
             per_k.setdefault(k, []).append(e0.elapsed_time(e1))
-        tot_flop = sum(dcn_flops(args.batch, k) * len(v) for k, v in per_k.items())
+        kflops = lambda k: sum(dcn_flops(args.batch, kk) for kk in k) if isinstance(k, tuple) else dcn_flops(args.batch, k)
+        kname = lambda k: ('group_' + 'x'.join('k%d' % kk for kk in k)) if isinstance(k, tuple) else 'k%d' % k
+        tot_flop = sum(kflops(k) * len(v) for k, v in per_k.items())
         tot_ms = sum(sum(v) for v in per_k.values())
         achieved = tot_flop / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
-        detail = {('k%d' % k): {'launches': len(v), 'avg_us': round(1e3 * sum(v) / len(v), 2),
-                               'tflops': round(dcn_flops(args.batch, k) / (sum(v) / len(v) * 1e-3) / 1e12, 1)}
-                  for k, v in sorted(per_k.items())}
+        detail = {kname(k): {'launches': len(v), 'avg_us': round(1e3 * sum(v) / len(v), 2),
+                             'tflops': round(kflops(k) / (sum(v) / len(v) * 1e-3) / 1e12, 1)}
+                  for k, v in sorted(per_k.items(), key=lambda kv: str(kv[0]))}
+        grouped = any(isinstance(k, tuple) for k in per_k)
         result = {
             'metric': METRIC, 'value': round(args.batch * world * args.steps / (dev_ms * 1e-3), 2), 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -464,17 +478,19 @@ def run_ours(args):
             'gpu_launches': launches_per_step * args.steps,
             'gpu_launches_note': '%d kernels of libkgdet_b200.so per step, counted by the library (kgdet_launch_count): '
                                  '1 NCHW->split planes, 8 tcgen05 3x3 convolutions, 6 GroupNorm+ReLU (-> split planes), 2 rows->GEMM '
-                                 'tiles (+bias+ReLU), 6 sample plans, 12 fused tcgen05 DCN, 6 pointwise tcgen05 GEMMs, 3 moment, 3 '
+                                 'tiles (+bias+ReLU), 6 sample plans, 2 grouped persistent tcgen05 DCN launches (6 deformable convolutions each), 6 pointwise tcgen05 GEMMs, 3 moment, 3 '
                                  'decode (select / decode / finalize), 1 batched NMS, 1 top-k; no library (cuDNN / cuBLAS) kernel'
                                  % launches_per_step,
-            'roofline': {'kernel': 'dcn_umma_stream_kernel (fused bilinear gather + tcgen05 GEMM), 12 launches/step',
+            'roofline': {'kernel': ('dcn_umma_group_kernel (fused bilinear gather + tcgen05 GEMM, persistent: the six deformable '
+                                    'convolutions of a stage per launch), 2 launches/step') if grouped else
+                                   'dcn_umma_stream_kernel (fused bilinear gather + tcgen05 GEMM), 12 launches/step',
                          'bound': 'tensor', 'achieved': round(achieved, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': round(achieved / peak_tf, 4), 'traffic': traffic,
                          'traffic_note': 'DRAM read+write bytes of one K=49 launch (ncu --set full, profiles/r1_dcn_traffic.json); '
                                          'algorithmic bytes of that launch 54.4 MB, inputs are L2 hits',
                          'peak_source': peak_src,
                          'share_of_step': round(tot_ms / dev_ms, 4), 'per_kernel_size': detail,
-                         'timed_in': 'eager pass of the same K steps, DCN launches serialised, with CUDA events around each launch (C-ABI hook); '
+                         'timed_in': 'eager pass of the same K steps with CUDA events immediately around each DCN launch on its stream (C-ABI hook); '
                                      'share_of_step = those kernel times / graph-replayed step time'},
             'launch_mode': launch_mode,
             'eager_ms_per_step': round(eager_ms / args.steps, 4),

@@ -138,6 +138,27 @@ KGDET_API int kgdet_dcn_forward_prepared(const void* prepared_input, const void*
  * `workspace` may be NULL: the call then runs unsplit (TF32X3 without promotion: ~1e-4 instead of 1e-5). */
 KGDET_API size_t kgdet_dcn_forward_prepared_workspace_bytes(const kgdet_dcn_shape* shape, int precision);
 
+/* Grouped form of kgdet_dcn_forward_prepared (bf16 mode): up to KGDET_DCN_GROUP_MAX deformable convolutions with the
+ * same Cout in ONE persistent launch -- the six DCNs of a Kp3RepBlock stage (KP3:145-163).  The tiles of all items
+ * are handed out longest first from an atomic counter to one CTA per SM: no SM idles while another item still has
+ * tiles, and launch / TMEM allocation / barrier set-up are paid once.  Results are bit-identical to the single calls.
+ * `workspace`: >= 16 bytes, 16-byte aligned (the tile counter; zeroed by the call). */
+#define KGDET_DCN_GROUP_MAX 6
+typedef struct kgdet_dcn_group_item {
+  const void* prepared_input;   /* kgdet_dcn_prepare_input(_rows) / the hi half of split planes */
+  const void* plan;             /* kgdet_dcn_prepare_plan(_points) */
+  const void* weight_packed;    /* kgdet_dcn_pack_weight */
+  const float* bias;            /* [Cout] or NULL */
+  void* output;
+  int32_t out_channel_offset, out_channels_total, fuse_relu, out_layout, dtype;
+  kgdet_dcn_shape shape;
+} kgdet_dcn_group_item;
+KGDET_API int kgdet_dcn_group_supported(const kgdet_dcn_shape* shape, int precision);
+KGDET_API int kgdet_dcn_forward_prepared_group(const kgdet_dcn_group_item* items, int32_t count, int precision,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+/* measurement hook: the next grouped call records these two CUDA events immediately around its kernel */
+KGDET_API void kgdet_dcn_group_set_profile_events(void* start_event, void* stop_event);
+
 /* Global top-k over the survivors of the batched NMS (mmdet/core/post_processing/bbox_nms_kp.py:64-70:
  * sort the concatenated per-class results by score, keep max_num).  dets [B, L, 5] (score in column 4), flags
  * [B*L] uint8 (1 = kept by kgdet_nms_batched), L = classes * candidates <= 16384.  top_s [B, k] scores in

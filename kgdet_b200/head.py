@@ -27,7 +27,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import (DeformConv, TiledRows, batched_nms_flags, deform_conv_prepared, get_precision,
+from .ops import (DeformConv, TiledRows, batched_nms_flags, deform_conv_prepared, deform_conv_prepared_group, get_precision,
                   groupnorm_relu_nhwc, nchw_to_tiled, pack_weight, points2bbox_moment, pointwise_conv,
                   prepare_input, prepare_plan, prepare_plan_points)
 from .ops.conv import conv_planes, conv_supported, groupnorm_relu_planes, split_planes
@@ -216,6 +216,7 @@ class _DeformBlock(nn.Module):
         super().__init__()
         self.gradient_mul = gradient_mul
         self.concurrent_dcn = True          # forward_tc: the six DCNs of the stage on six streams
+        self.grouped_dcn = True             # forward_tc: ... or, better, in one persistent grouped launch
         for k in _POINT_SETS:
             pad = (k - 1) // 2
             setattr(self, 'cls_dfmconv_%d' % k, deform_conv_cls(cin, feat, k, 1, pad))
@@ -278,7 +279,12 @@ class _DeformBlock(nn.Module):
             jobs.append((cls_prep, plan, getattr(self, 'cls_dfmconv_%d' % k).weight, cls_rows, i * feat))
             jobs.append((pts_prep, plan, getattr(self, 'keypts_dfmconv_%d' % k).weight, kpt_rows, i * feat))
         jobs.reverse()                                   # longest first (49, 49, 25, 25, 9, 9 points)
-        if self.concurrent_dcn:
+        if self.grouped_dcn:
+            # ONE persistent launch for the six DCNs of the stage: 792 tiles handed out longest first to one CTA per
+            # SM (kgdet_dcn_forward_prepared_group) -- no idle SMs (a single call has 132 tiles for 148 SMs), one
+            # launch / TMEM allocation / barrier set-up instead of six
+            deform_conv_prepared_group([job + (True,) for job in jobs])
+        elif self.concurrent_dcn:
             # The six DCNs of a stage are independent and each fills only 132 of the 148 SMs (M = 16 800 ->
             # 132 tiles, one CTA per SM): issued on six streams, the block scheduler packs the tiles of all six
             # onto whatever SM is free (forks/joins become parallel branches of the captured CUDA graph).
@@ -293,7 +299,7 @@ class _DeformBlock(nn.Module):
         else:
             for job in jobs:
                 deform_conv_prepared(*job, True)
-        if self.concurrent_dcn and branches is not None:
+        if (self.concurrent_dcn or self.grouped_dcn) and branches is not None:
             # the 13-column cls GEMM is a parallel branch: it fills the SMs the keypoint GEMM's last wave leaves idle
             # and is only joined at the end of the head
             with _SideBranch(dev, len(jobs)) as br:

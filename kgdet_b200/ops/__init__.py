@@ -10,7 +10,7 @@ from ._out_of_scope import (ContextBlock, DeformRoIPooling, DeformRoIPoolingPack
                             roi_align, roi_pool)
 from .dcn import (DeformConv, DeformConvFunction, DeformConvPack, ModulatedDeformConv,
                   ModulatedDeformConvFunction, ModulatedDeformConvPack, deform_conv,
-                  deform_conv_prepared, get_precision, modulated_deform_conv, prepare_input,
+                  deform_conv_prepared, deform_conv_prepared_group, get_precision, modulated_deform_conv, prepare_input,
                   prepare_plan, prepare_plan_points, set_precision)
 from .pointwise import (TiledRows, groupnorm_relu_nhwc, invalidate_weight_caches, nchw_to_tiled, pack_weight,
                         pointwise_conv)
@@ -29,7 +29,8 @@ __all__ = [
     # extras beyond the reference surface
     'DeformConvFunction', 'ModulatedDeformConvFunction', 'points2bbox_moment',
     'sigmoid_focal_loss_sum', 'batched_nms_flags', 'set_precision', 'get_precision',
-    'prepare_input', 'prepare_plan', 'prepare_plan_points', 'deform_conv_prepared', 'pointwise_conv',
+    'prepare_input', 'prepare_plan', 'prepare_plan_points', 'deform_conv_prepared', 'deform_conv_prepared_group',
+    'pointwise_conv',
     'nchw_to_tiled', 'pack_weight', 'TiledRows', 'groupnorm_relu_nhwc', 'bbox_select', 'bbox_decode',
     'bbox_finalize', 'invalidate_weight_caches',
 ]

@@ -39,6 +39,16 @@ class PointwiseSegment(ctypes.Structure):
 
 
 LAYOUT_NCHW, LAYOUT_TILED, LAYOUT_TILED_SPLIT = 0, 1, 2
+DCN_GROUP_MAX = 6
+
+
+class DcnGroupItem(ctypes.Structure):
+    """struct kgdet_dcn_group_item"""
+    _fields_ = [('prepared_input', ctypes.c_void_p), ('plan', ctypes.c_void_p), ('weight_packed', ctypes.c_void_p),
+                ('bias', ctypes.c_void_p), ('output', ctypes.c_void_p), ('out_channel_offset', c_i32),
+                ('out_channels_total', c_i32), ('fuse_relu', c_i32), ('out_layout', c_i32), ('dtype', c_i32),
+                ('shape', DcnShape)]
+
 
 # name -> (restype, argtypes); must list every KGDET_API symbol of the header
 SIGNATURES = {
@@ -62,6 +72,9 @@ SIGNATURES = {
                                                   ctypes.c_int, _SHAPE_P, ctypes.c_int, ctypes.c_int, c_ptr, c_sz,
                                                   c_ptr]),
     'kgdet_dcn_forward_prepared_workspace_bytes': (c_sz, [_SHAPE_P, ctypes.c_int]),
+    'kgdet_dcn_group_supported': (ctypes.c_int, [_SHAPE_P, ctypes.c_int]),
+    'kgdet_dcn_forward_prepared_group': (ctypes.c_int, [c_ptr, c_i32, ctypes.c_int, c_ptr, c_sz, c_ptr]),
+    'kgdet_dcn_group_set_profile_events': (None, [c_ptr, c_ptr]),
     'kgdet_bbox_select': (ctypes.c_int, [c_ptr, ctypes.c_int, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
     'kgdet_bbox_decode': (ctypes.c_int, [c_ptr, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32,
                                          c_i32, c_ptr, c_ptr, c_ptr]),

@@ -368,6 +368,59 @@ def deform_conv_prepared(pin, plan, weight, out=None, channel_offset=0, relu=Fal
     return out
 
 
+_group_counters = {}
+
+
+def deform_conv_prepared_group(jobs):
+    """ONE persistent launch for several prepared deformable convolutions (kgdet_dcn_forward_prepared_group): the
+    six DCNs of a Kp3RepBlock stage.  jobs: list of (pin, plan, weight, out, channel_offset, relu) as for
+    `deform_conv_prepared`; bf16 mode, equal Cout.  Falls back to single launches when the grouped kernel does not
+    cover a job.  Results are bit-identical either way."""
+    import ctypes
+    from .pointwise import TiledRows
+    lib = _capi.lib()
+    items = (_capi.DcnGroupItem * len(jobs))()
+    keep = []
+    ok = 1 <= len(jobs) <= _capi.DCN_GROUP_MAX
+    ref = None
+    for i, (pin, plan, weight, out, channel_offset, relu) in enumerate(jobs):
+        (n, c, h, w), k, st, pd, dl = plan.geom
+        assert pin.shape4 == (n, c, h, w) and pin.precision == plan.precision
+        shape = _geom_shape(n, c, h, w, weight.shape[0], k, st, pd, dl)
+        ok = ok and plan.precision == _capi.PREC_BF16 and bool(lib.kgdet_dcn_group_supported(ctypes_ref(shape), plan.precision))
+        ok = ok and pin.fast and plan.fast and weight.shape[0] == jobs[0][2].shape[0]
+        if not ok:
+            break
+        packed = _packed_weight(weight, shape, plan.precision)
+        keep.append(packed)
+        it = items[i]
+        it.prepared_input, it.plan, it.weight_packed, it.bias = pin.buf.data_ptr(), plan.buf.data_ptr(), packed.data_ptr(), None
+        if isinstance(out, TiledRows):
+            it.out_layout = _capi.LAYOUT_TILED_SPLIT if out.split else _capi.LAYOUT_TILED
+            it.output, it.out_channels_total, it.dtype = out.buf.data_ptr(), out.K, _capi.BF16
+            ok = ok and channel_offset % 64 == 0
+            ref = out.buf
+        else:
+            assert out.is_contiguous() and out.shape[0] == n
+            it.out_layout = _capi.LAYOUT_NCHW
+            it.output, it.out_channels_total, it.dtype = out.data_ptr(), out.shape[1], _capi.dtype_code(out)
+            ref = out
+        it.out_channel_offset, it.fuse_relu = int(channel_offset), int(bool(relu))
+        it.shape = shape
+    if not ok:
+        for job in jobs:
+            deform_conv_prepared(*job)
+        return
+    dev = ref.device
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ctr = _group_counters.get(key)
+    if ctr is None:
+        ctr = _group_counters[key] = torch.zeros(4, dtype=torch.int32, device=dev)
+    _capi.check(lib.kgdet_dcn_forward_prepared_group(ctypes.cast(items, ctypes.c_void_p), len(jobs), _capi.PREC_BF16,
+                                                     ctr.data_ptr(), 16, _capi.stream_of(ref)),
+                'kgdet_dcn_forward_prepared_group')
+
+
 class DeformConvFunction(Function):
     """Mirror of DC.py:12-110."""
 

@@ -1,5 +1,7 @@
 """GPU tests of the Kp3RepBlock pointwise stage: plan-from-points, the fused DCN
 kernel's UMMA-tiled bf16 output, the tcgen05 pointwise GEMM with its NCHW / bias / residual epilogue."""
+import os
+
 import pytest
 import torch
 
@@ -157,3 +159,65 @@ def test_channels_last_sources_need_no_transpose():
     for split in (False, True):
         assert torch.equal(ops.nchw_to_tiled(x, relu=True, split=split).to_dense(),
                            ops.nchw_to_tiled(xcl, relu=True, split=split).to_dense())
+
+
+def test_grouped_dcn_launch_equals_single_launches():
+    """kgdet_dcn_forward_prepared_group (one persistent launch, dynamic tile scheduler) == the same deformable
+    convolutions launched one by one, bit for bit: six jobs of a Kp3RepBlock stage shape (two inputs, three point
+    sets, tiled split outputs into channel slices) and a mixed NCHW / tiled group with a ragged last tile."""
+    from kgdet_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    N, C, H, W, F = 3, 256, 13, 21, 256
+    xa = torch.randn(N, C, H, W, generator=g).cuda()
+    xb = torch.randn(N, C, H, W, generator=g).cuda()
+    pts = (torch.randn(N, 166, H, W, generator=g) * 2).cuda()
+    ws = {(br, k): (torch.randn(F, C, k, k, generator=g) * (1.0 / (C * k * k) ** 0.5)).cuda()
+          for br in 'ab' for k in (3, 5, 7)}
+    ops.set_precision('bf16')
+    try:
+        pa, pb = ops.prepare_input(xa, F), ops.prepare_input(xb, F)
+        plans, lo = {}, 0
+        for k in (3, 5, 7):
+            plans[k] = ops.prepare_plan_points(pts, lo, (N, C, H, W), F, k, 1, k // 2, 1, gradient_mul=0.1)
+            lo += 2 * k * k
+
+        def run(grouped):
+            rows = {br: ops.TiledRows(N * H * W, 3 * F, True, 'cuda') for br in 'ab'}
+            for r in rows.values():
+                r.buf.zero_()
+            jobs = []
+            for i, k in enumerate((3, 5, 7)):
+                jobs.append((pa, plans[k], ws[('a', k)], rows['a'], i * F, True))
+                jobs.append((pb, plans[k], ws[('b', k)], rows['b'], i * F, True))
+            jobs.reverse()
+            if grouped:
+                ops.deform_conv_prepared_group(jobs)
+            else:
+                for j in jobs:
+                    ops.deform_conv_prepared(*j)
+            return rows
+        single, grouped = run(False), run(True)
+        for br in 'ab':
+            assert torch.equal(single[br].buf, grouped[br].buf)
+        assert float(grouped['a'].to_dense().abs().sum()) > 0
+        # NCHW fp32 outputs in the same group as a tiled one (M = 3 * 13 * 21 = 819: ragged last tile)
+        out_s = torch.full((N, 2 * F, H, W), -3.0, device='cuda')
+        out_g = out_s.clone()
+        rs, rg = ops.TiledRows(N * H * W, F, False, 'cuda'), ops.TiledRows(N * H * W, F, False, 'cuda')
+        rs.buf.zero_(); rg.buf.zero_()
+        os.environ['KGDET_UMMA_SPLITS'] = '1'      # single NCHW launches would split this small map over k-blocks
+        try:
+            for out, rows, fn in ((out_s, rs, None), (out_g, rg, ops.deform_conv_prepared_group)):
+                jobs = [(pa, plans[5], ws[('a', 5)], out, 0, False), (pb, plans[3], ws[('b', 3)], out, F, True),
+                        (pb, plans[7], ws[('b', 7)], rows, 0, True)]
+                if fn is None:
+                    for j in jobs:
+                        ops.deform_conv_prepared(*j)
+                else:
+                    fn(jobs)
+        finally:
+            del os.environ['KGDET_UMMA_SPLITS']
+        assert torch.equal(out_s, out_g) and torch.equal(rs.buf, rg.buf)
+        assert (out_g != -3.0).all()
+    finally:
+        ops.set_precision(None)
