@@ -217,6 +217,35 @@ KGDET_API int kgdet_groupnorm_relu_nhwc_planes(const float* x, const float* gamm
                                      int32_t groups, int fuse_relu, float* y, void* planes, int32_t N, int32_t H,
                                      int32_t W, int32_t C, void* stream);
 
+/* ---- target assignment + the nine training losses of the KGDet head ----------
+ * replaces  PointAssigner.assign    mmdet/core/bbox/assigners/point_assigner.py:23-116
+ *           point_target_kp         mmdet/core/anchor/point_target_kp.py:7-169  (sampling=False, every point valid)
+ *           KP3.loss / loss_single  reppoints_head_kp3rep_cas_1_assign_once.py:581-768
+ * for ONE point level (point_strides=[32] of the KGDet configs) of map_h x map_w points (<= 4096), batched over
+ * images, without host synchronisation.  Ground truth is padded to G boxes per image: gt_boxes [B, G, 4] fp32,
+ * gt_valid [B, G] uint8, gt_labels [B, G] int64 (1-based classes), gt_keypoints [B, G, K, 3] (x, y, visibility).
+ *   assign    assigned [B, P] int32 = 0 (background) or g + 1; avg_factor (device float) = sum over images of
+ *             max(#positives, 1); num_visible [B, G] = visible keypoints per box.
+ *   forward   losses[9] = loss_cls_1..3, loss_bbox_1..3, loss_kpt_1..3 (loss weight and 1 / avg_factor applied)
+ *             from the nine head outputs outs[9] = cls_1..3 [B, NC, H, W], kpt_1..3 [B, 2K, H, W] (y-first pairs),
+ *             bbox_1..3 [B, 4, H, W], all NCHW fp32, read in place.  loss_weights[9] in the same order as losses.
+ *   backward  grad_outs[i] (same shapes as outs[i]; NULL = skip) = d(sum_k grad_losses[k] * losses[k]) / d outs[i]. */
+KGDET_API int kgdet_point_assign(const float* gt_boxes, const uint8_t* gt_valid, const float* gt_keypoints, int32_t B,
+                       int32_t G, int32_t num_keypoints, int32_t map_h, int32_t map_w, float stride, int32_t pos_num,
+                       int32_t* assigned, float* avg_factor, float* num_visible, void* stream);
+KGDET_API int kgdet_point_losses_forward(const float* const* outs, const int32_t* assigned, const float* gt_boxes,
+                               const int64_t* gt_labels, const float* gt_keypoints, const float* avg_factor,
+                               const float* num_visible, int32_t B, int32_t G, int32_t map_h, int32_t map_w,
+                               int32_t num_classes, int32_t num_keypoints, float stride, float point_base_scale,
+                               const float* loss_weights, float gamma, float alpha, float beta, float* losses,
+                               void* stream);
+KGDET_API int kgdet_point_losses_backward(const float* const* outs, const int32_t* assigned, const float* gt_boxes,
+                                const int64_t* gt_labels, const float* gt_keypoints, const float* avg_factor,
+                                const float* num_visible, const float* grad_losses, int32_t B, int32_t G, int32_t map_h,
+                                int32_t map_w, int32_t num_classes, int32_t num_keypoints, float stride,
+                                float point_base_scale, const float* loss_weights, float gamma, float alpha, float beta,
+                                float* const* grad_outs, void* stream);
+
 /* ---- pointwise convolutions of the Kp3RepBlock ------------------------
  * replaces  cls_out / keypts_out / reppts_out 1x1 nn.Conv2d + the cascade's residual adds
  *           (reppoints_head_kp3rep_cas_1_assign_once.py:79-96,152-171,431-432,440-441)

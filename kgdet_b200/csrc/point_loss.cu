@@ -1,0 +1,318 @@
+// Target assignment and the nine training losses of the KGDet head as three kernels.
+//
+// The reference does this on the host side of PyTorch, per image and per ground-truth box:
+//   PointAssigner.assign            mmdet/core/bbox/assigners/point_assigner.py:23-116  (Python loop over the boxes,
+//                                   a topk each, boolean-mask updates)
+//   point_target_kp / _single       mmdet/core/anchor/point_target_kp.py:7-169          (mask indexing, nonzero())
+//   KP3.loss / loss_single          reppoints_head_kp3rep_cas_1_assign_once.py:581-768  (3 focal + 6 smooth-L1 losses,
+//                                   dozens of elementwise / reduction kernels, avg_factor on the host)
+// ~120 PyTorch kernels forward + as many backward, each mask index a device -> host round trip.  Here:
+//   point_assign_kernel    one CTA per image: for every ground-truth box in order, the normalised centre distances
+//                          of all points, the pos_num nearest by rank counting (ties: lower index), and the
+//                          reference's update rule "a later box takes a point only if strictly closer" (:98-99);
+//                          avg_factor = sum over images of max(#positives, 1) (point_target_kp.py:64) on the device.
+//   point_losses_fwd_kernel  the nine sums in one pass over the nine head outputs (NCHW, read in place: no
+//                          permute / reshape copies): focal terms with the reference CUDA kernel's arithmetic
+//                          (focal.cuh), smooth-L1 of decoded boxes / keypoints against targets looked up through
+//                          the assignment (the dense target tensors of point_target_kp are never built).
+//   point_losses_bwd_kernel  the nine gradients in one pass, scaled by the upstream gradients of the nine losses.
+// Single point level (the KGDet configs: point_strides=[32]); every point is valid (the map covers the padded
+// image) and sampling=False (PseudoSamplerKp), as in the reference configs.
+#include "focal.cuh"
+
+namespace kgdet {
+
+static constexpr int PA_THREADS = 1024;
+
+// assigned[b, p] = 0 (background) or g + 1; avg += max(#positives of image b, 1)
+__global__ void __launch_bounds__(PA_THREADS) point_assign_kernel(const float* __restrict__ gt_boxes /*[B,G,4]*/,
+                                                                  const unsigned char* __restrict__ gt_valid /*[B,G]*/,
+                                                                  const float* __restrict__ gt_kps /*[B,G,K,3]*/,
+                                                                  int G, int K, int P, int Wmap, float stride, int pos_num,
+                                                                  int* __restrict__ assigned, float* __restrict__ avg,
+                                                                  float* __restrict__ nvis /*[B,G]*/) {
+  extern __shared__ float dist[];                 // [P]
+  __shared__ int npos_sh;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) npos_sh = 0;
+  // visible keypoints per box (the keypoint-loss weights of a positive row are 4 / (2 * nvis), KP3:639-644)
+  for (int g = threadIdx.x >> 5; g < G; g += blockDim.x >> 5) {
+    const float* gk = gt_kps + ((size_t)b * G + g) * K * 3;
+    float c = 0.f;
+    for (int j = threadIdx.x & 31; j < K; j += 32) c += gk[(size_t)j * 3 + 2] != 0.f ? 1.f : 0.f;
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) nvis[(size_t)b * G + g] = c;
+  }
+  const int k = pos_num < P ? pos_num : P;
+  // every thread owns the points p = tid, tid + blockDim, ... (P <= 4 * blockDim)
+  float best[4];
+  int who[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { best[i] = INFINITY; who[i] = 0; }
+  for (int g = 0; g < G; ++g) {
+    const bool valid = gt_valid[(size_t)b * G + g] != 0;
+    const float* bx = gt_boxes + ((size_t)b * G + g) * 4;
+    const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
+    const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f), cy = __fmul_rn(__fadd_rn(y1, y2), 0.5f);   // :59 (x / 2)
+    const float w = fmaxf(__fsub_rn(x2, x1), 1e-6f), h = fmaxf(__fsub_rn(y2, y1), 1e-6f);           // :60
+    __syncthreads();                              // the previous box's ranks have been read
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      const float px = (float)(p % Wmap) * stride, py = (float)(p / Wmap) * stride;                 // point_generator.py:14-23
+      const float dx = __fdiv_rn(__fsub_rn(px, cx), w), dy = __fdiv_rn(__fsub_rn(py, cy), h);       // :84
+      dist[p] = valid ? sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) : INFINITY;
+    }
+    __syncthreads();
+    if (!valid) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = threadIdx.x + i * blockDim.x;
+      if (p >= P) continue;
+      const float mine = dist[p];
+      int rank = 0;
+      for (int j = 0; j < P; ++j) {
+        const float o = dist[j];
+        rank += (o < mine || (o == mine && j < p)) ? 1 : 0;
+      }
+      // among the k nearest of this box (:90-91) and strictly closer than what an earlier box offered (:98-99)
+      if (rank < k && mine < best[i]) { best[i] = mine; who[i] = g + 1; }
+    }
+  }
+  int mypos = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = threadIdx.x + i * blockDim.x;
+    if (p < P) {
+      assigned[(size_t)b * P + p] = who[i];
+      mypos += who[i] > 0 ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  mypos = (int)warp_sum((float)mypos);
+  if ((threadIdx.x & 31) == 0 && mypos) atomicAdd(&npos_sh, mypos);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(avg, (float)(npos_sh > 1 ? npos_sh : 1));      // small integers: exact in any order
+}
+
+struct PointLossParams {
+  const float* out[9];       // cls_1..3 [B,NC,H,W], kpt_1..3 [B,2K,H,W], bbox_1..3 [B,4,H,W]
+  float* grad[9];            // same shapes (backward), any of them may be NULL
+  const int* assigned;       // [B, P]
+  const float* gt_boxes;     // [B, G, 4]
+  const long long* gt_labels;   // [B, G]
+  const float* gt_kps;       // [B, G, K, 3]
+  const float* avg;          // device scalar
+  const float* nvis;         // [B, G] visible keypoints per box (point_assign_kernel)
+  const float* grad_losses;  // [9] upstream gradients (backward)
+  float* losses;             // [9] (forward): cls_1..3, bbox_1..3, kpt_1..3
+  int B, G, P, Wmap, NC, K;
+  float stride, nt;          // nt = point_base_scale * stride
+  float w_cls[3], w_bbox[3], w_kpt[3];
+  float gamma, alpha, beta;
+};
+
+__device__ __forceinline__ float smooth_l1(float diff, float beta) {        // losses/smooth_l1_loss.py:9-15
+  return diff < beta ? 0.5f * diff * diff / beta : diff - 0.5f * beta;
+}
+__device__ __forceinline__ float smooth_l1_grad(float d, float beta) {      // d = pred - target (signed)
+  const float a = fabsf(d);
+  return a < beta ? d / beta : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+}
+
+// acc[k] += v with the accumulators staying in registers (a dynamically indexed array would live in local memory)
+__device__ __forceinline__ void acc_add(float (&acc)[9], int k, float v) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] += (i == k) ? v : 0.f;
+}
+
+// Unified index space: [0, nA) focal elements (stage, b, c, p), [nA, nA + nB) box rows (stage, b, p),
+// [nA + nB, nA + nB + nC) keypoint elements (stage, b, ch, p); p fastest everywhere (NCHW: coalesced).
+template <bool BWD>
+__global__ void __launch_bounds__(256) point_losses_kernel(const PointLossParams q) {
+  const long long nA = 3ll * q.B * q.NC * q.P, nB = 3ll * q.B * q.P, nC = 3ll * q.B * (2 * q.K) * q.P;
+  const long long total = nA + nB + nC;
+  const float inv_avg = 1.f / *q.avg;
+  float acc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)blockDim.x * gridDim.x) {
+    if (idx < nA) {
+      // ---- sigmoid focal loss, label weight 1 (point_target_kp.py:144-149 with pos_weight <= 0) ----
+      const int p = (int)(idx % q.P);
+      long long r = idx / q.P;
+      const int c = (int)(r % q.NC); r /= q.NC;
+      const int b = (int)(r % q.B), st = (int)(r / q.B);
+      const int a = q.assigned[(size_t)b * q.P + p];
+      const int t = a > 0 ? (int)q.gt_labels[(size_t)b * q.G + a - 1] : 0;                       // :143
+      const size_t off = ((size_t)b * q.NC + c) * q.P + p;
+      const float x = q.out[st][off];
+      if (!BWD) {
+        const float v = focal_fwd_value(x, t, c, q.gamma, q.alpha);
+        acc_add(acc, st, v);
+      } else if (q.grad[st]) {
+        q.grad[st][off] = focal_bwd_value(x, t, c, q.gamma, q.alpha) * (q.w_cls[st] * inv_avg * q.grad_losses[st]);
+      }
+    } else if (idx < nA + nB) {
+      // ---- box loss: smooth-L1 of the decoded box / nt against the assigned ground-truth box / nt (KP3:614-636) ----
+      const long long i2 = idx - nA;
+      const int p = (int)(i2 % q.P);
+      const long long r = i2 / q.P;
+      const int b = (int)(r % q.B), st = (int)(r / q.B);
+      const int a = q.assigned[(size_t)b * q.P + p];
+      const float px = (float)(p % q.Wmap) * q.stride, py = (float)(p / q.Wmap) * q.stride;
+      const float* o = q.out[6 + st] + (size_t)b * 4 * q.P + p;
+      float* go = (BWD && q.grad[6 + st]) ? q.grad[6 + st] + (size_t)b * 4 * q.P + p : nullptr;
+      if (a == 0) {
+        if (go) { go[0] = 0.f; go[(size_t)q.P] = 0.f; go[(size_t)2 * q.P] = 0.f; go[(size_t)3 * q.P] = 0.f; }
+        continue;
+      }
+      const float* gb = q.gt_boxes + ((size_t)b * q.G + a - 1) * 4;
+      const float gscale = BWD ? q.w_bbox[st] * inv_avg * q.grad_losses[3 + st] * (q.stride / q.nt) : 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pred = o[(size_t)e * q.P] * q.stride + ((e & 1) ? py : px);                 // offset_to_pts, y_first=False
+        const float d = pred / q.nt - gb[e] / q.nt;
+        if (!BWD) acc_add(acc, 3 + st, smooth_l1(fabsf(d), q.beta));
+        else if (go) go[(size_t)e * q.P] = smooth_l1_grad(d, q.beta) * gscale;
+      }
+    } else {
+      // ---- keypoint loss (KP3:638-665): weights = visible keypoints of the assigned box, each positive row sums to 4 ----
+      const long long i3 = idx - nA - nB;
+      const int p = (int)(i3 % q.P);
+      long long r = i3 / q.P;
+      const int ch = (int)(r % (2 * q.K)); r /= (2 * q.K);
+      const int b = (int)(r % q.B), st = (int)(r / q.B);
+      const int a = q.assigned[(size_t)b * q.P + p];
+      const size_t off = ((size_t)b * 2 * q.K + ch) * q.P + p;
+      float* go = (BWD && q.grad[3 + st]) ? q.grad[3 + st] + off : nullptr;
+      if (a == 0) {
+        if (go) *go = 0.f;
+        continue;
+      }
+      const int kp = ch >> 1, is_x = ch & 1;                      // channel 2i = y_i, 2i + 1 = x_i (y-first pairs)
+      const float* gk = q.gt_kps + (((size_t)b * q.G + a - 1) * q.K) * 3;
+      const float vis = gk[(size_t)kp * 3 + 2];
+      if (vis == 0.f) {
+        if (go) *go = 0.f;
+        continue;
+      }
+      const float wgt = 1.f / (2.f * q.nvis[(size_t)b * q.G + a - 1]) * 4.f;    // kw / kw.sum(1) * 4, kw.sum(1) = 2 * nvis
+      const float px = (float)(p % q.Wmap) * q.stride, py = (float)(p / q.Wmap) * q.stride;
+      const float pred = q.out[3 + st][off] * q.stride + (is_x ? px : py);
+      const float tgt = gk[(size_t)kp * 3 + (is_x ? 0 : 1)];
+      const float d = pred / q.nt - tgt / q.nt;
+      if (!BWD) acc_add(acc, 6 + st, wgt * smooth_l1(fabsf(d), q.beta));
+      else if (go) *go = smooth_l1_grad(d, q.beta) * wgt * (q.w_kpt[st] * inv_avg * q.grad_losses[6 + st] * (q.stride / q.nt));
+    }
+  }
+  if (!BWD) {
+    __shared__ float part[9][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float v = warp_sum(acc[i]);
+      if (lane == 0) part[i][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+      float v = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += part[threadIdx.x][w];
+      const int i = threadIdx.x;
+      const float lw = i < 3 ? q.w_cls[i] : (i < 6 ? q.w_bbox[i - 3] : q.w_kpt[i - 6]);
+      if (v != 0.f) atomicAdd(q.losses + i, v * lw * inv_avg);
+    }
+  }
+}
+
+}  // namespace kgdet
+
+using namespace kgdet;
+
+extern "C" int kgdet_point_assign(const float* gt_boxes, const uint8_t* gt_valid, const float* gt_keypoints, int32_t B,
+                                  int32_t G, int32_t num_keypoints, int32_t map_h, int32_t map_w, float stride,
+                                  int32_t pos_num, int32_t* assigned, float* avg_factor, float* num_visible,
+                                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KG_CHECK_ARG(B >= 0 && G >= 0 && map_h > 0 && map_w > 0 && pos_num > 0, "kgdet_point_assign: bad sizes");
+  const int P = map_h * map_w;
+  KG_CHECK_ARG(P <= 4 * PA_THREADS, "kgdet_point_assign: at most %d points per level (got %d)", 4 * PA_THREADS, P);
+  KG_CHECK_ARG(assigned && avg_factor && (G == 0 || (gt_boxes && gt_valid && gt_keypoints && num_visible)),
+               "kgdet_point_assign: NULL pointer");
+  KG_CHECK_ARG(num_keypoints >= 0, "kgdet_point_assign: bad keypoint count");
+  KG_CUDA(cudaMemsetAsync(avg_factor, 0, sizeof(float), stream));
+  if (B == 0) return KGDET_OK;
+  point_assign_kernel<<<B, PA_THREADS, (size_t)P * sizeof(float), stream>>>(gt_boxes, gt_valid, gt_keypoints, G, num_keypoints,
+                                                                          P, map_w, stride, pos_num, assigned, avg_factor,
+                                                                          num_visible);
+  KG_LAUNCH_CHECK("point_assign_kernel");
+  return KGDET_OK;
+}
+
+static int fill_params(PointLossParams& q, const float* const* outs, const int32_t* assigned, const float* gt_boxes,
+                       const int64_t* gt_labels, const float* gt_keypoints, const float* avg_factor,
+                       const float* num_visible, int32_t B, int32_t G,
+                       int32_t map_h, int32_t map_w, int32_t num_classes, int32_t num_keypoints, float stride,
+                       float point_base_scale, const float* loss_weights, float gamma, float alpha, float beta) {
+  KG_CHECK_ARG(outs && assigned && gt_boxes && gt_labels && gt_keypoints && avg_factor && num_visible && loss_weights,
+               "kgdet_point_losses: NULL pointer");
+  q.nvis = num_visible;
+  KG_CHECK_ARG(B > 0 && G > 0 && map_h > 0 && map_w > 0 && num_classes > 0 && num_keypoints > 0,
+               "kgdet_point_losses: bad sizes");
+  for (int i = 0; i < 9; ++i) {
+    KG_CHECK_ARG(outs[i], "kgdet_point_losses: head output %d is NULL", i);
+    q.out[i] = outs[i];
+    q.grad[i] = nullptr;
+  }
+  q.assigned = assigned; q.gt_boxes = gt_boxes; q.gt_labels = (const long long*)gt_labels; q.gt_kps = gt_keypoints;
+  q.avg = avg_factor; q.grad_losses = nullptr; q.losses = nullptr;
+  q.B = B; q.G = G; q.P = map_h * map_w; q.Wmap = map_w; q.NC = num_classes; q.K = num_keypoints;
+  q.stride = stride; q.nt = point_base_scale * stride;
+  for (int i = 0; i < 3; ++i) { q.w_cls[i] = loss_weights[i]; q.w_bbox[i] = loss_weights[3 + i]; q.w_kpt[i] = loss_weights[6 + i]; }
+  q.gamma = gamma; q.alpha = alpha; q.beta = beta;
+  return KGDET_OK;
+}
+
+static int loss_grid(const PointLossParams& q) {
+  const long long total = 3ll * q.B * q.P * (q.NC + 1 + 2 * q.K);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+}
+
+extern "C" int kgdet_point_losses_forward(const float* const* outs, const int32_t* assigned, const float* gt_boxes,
+                                          const int64_t* gt_labels, const float* gt_keypoints, const float* avg_factor,
+                                          const float* num_visible, int32_t B, int32_t G, int32_t map_h, int32_t map_w,
+                                          int32_t num_classes,
+                                          int32_t num_keypoints, float stride, float point_base_scale,
+                                          const float* loss_weights, float gamma, float alpha, float beta, float* losses,
+                                          void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PointLossParams q;
+  int rc = fill_params(q, outs, assigned, gt_boxes, gt_labels, gt_keypoints, avg_factor, num_visible, B, G, map_h, map_w,
+                       num_classes, num_keypoints, stride, point_base_scale, loss_weights, gamma, alpha, beta);
+  if (rc != KGDET_OK) return rc;
+  KG_CHECK_ARG(losses, "kgdet_point_losses_forward: NULL pointer");
+  q.losses = losses;
+  KG_CUDA(cudaMemsetAsync(losses, 0, 9 * sizeof(float), stream));
+  point_losses_kernel<false><<<loss_grid(q), 256, 0, stream>>>(q);
+  KG_LAUNCH_CHECK("point_losses_fwd_kernel");
+  return KGDET_OK;
+}
+
+extern "C" int kgdet_point_losses_backward(const float* const* outs, const int32_t* assigned, const float* gt_boxes,
+                                           const int64_t* gt_labels, const float* gt_keypoints, const float* avg_factor,
+                                           const float* num_visible, const float* grad_losses, int32_t B, int32_t G, int32_t map_h, int32_t map_w,
+                                           int32_t num_classes, int32_t num_keypoints, float stride,
+                                           float point_base_scale, const float* loss_weights, float gamma, float alpha,
+                                           float beta, float* const* grad_outs, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PointLossParams q;
+  int rc = fill_params(q, outs, assigned, gt_boxes, gt_labels, gt_keypoints, avg_factor, num_visible, B, G, map_h, map_w,
+                       num_classes, num_keypoints, stride, point_base_scale, loss_weights, gamma, alpha, beta);
+  if (rc != KGDET_OK) return rc;
+  KG_CHECK_ARG(grad_losses && grad_outs, "kgdet_point_losses_backward: NULL pointer");
+  q.grad_losses = grad_losses;
+  for (int i = 0; i < 9; ++i) q.grad[i] = grad_outs[i];
+  point_losses_kernel<true><<<loss_grid(q), 256, 0, stream>>>(q);
+  KG_LAUNCH_CHECK("point_losses_bwd_kernel");
+  return KGDET_OK;
+}

@@ -341,6 +341,7 @@ class KGDetHead(nn.Module):
         self._tensor_core_heads = True                      # bf16 mode: 1x1 convolutions as tcgen05 GEMMs
         self._fused_decode = True                           # get_bboxes: decode kernels instead of PyTorch glue
         self._own_convs = True                              # bf16 inference: 3x3 convolutions on conv_umma.cu, not cuDNN
+        self._fused_loss = True                             # loss(): assignment + losses as CUDA kernels (point_loss.cu)
         self.concurrent_branches = True                     # bf16 inference: cls / point branches on two streams
         deform_conv_cls = deform_conv_cls or DeformConv
         self._moment_fn = moment_fn or points2bbox_moment
@@ -476,6 +477,11 @@ class KGDetHead(nn.Module):
         from . import targets as T
         h, w = outs[0].shape[-2:]
         stride = self.point_strides[0]
+        if self._fused_loss and outs[0].is_cuda and h * w <= 4096 and len(self.point_strides) == 1:
+            # assignment + the nine losses as three kernels of the library (csrc/point_loss.cu)
+            from .ops.point_loss import kgdet_point_losses
+            return kgdet_point_losses(outs, gt_bboxes, gt_labels, gt_keypoints, gt_valid, stride, assigner_scale, pos_num,
+                                      point_base_scale)
         key = (h, w, stride, outs[0].device)
         pts = self._lim_cache.get(('points',) + key)
         if pts is None:

@@ -109,6 +109,14 @@ SIGNATURES = {
                                           ctypes.c_int, c_ptr]),
     'kgdet_groupnorm_relu_nhwc_planes': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_f32, c_i32, ctypes.c_int, c_ptr, c_ptr,
                                                         c_i32, c_i32, c_i32, c_i32, c_ptr]),
+    'kgdet_point_assign': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_ptr,
+                                          c_ptr, c_ptr, c_ptr]),
+    'kgdet_point_losses_forward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32,
+                                                  c_i32, c_i32, c_i32, c_f32, c_f32, c_ptr, c_f32, c_f32, c_f32, c_ptr,
+                                                  c_ptr]),
+    'kgdet_point_losses_backward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32,
+                                                   c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_ptr, c_f32, c_f32, c_f32,
+                                                   c_ptr, c_ptr]),
     'kgdet_nms_workspace_bytes': (c_sz, [c_i32]),
     'kgdet_nms': (ctypes.c_int, [c_ptr, c_i32, c_f32, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_sz,
                                  c_ptr]),
