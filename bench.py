@@ -592,6 +592,10 @@ def train_record(args, rank=None, world=None, local=None):
     Returns the record on rank 0 (None elsewhere); collective -- every rank must call it."""
     from kgdet_b200 import dist as kdist, ops
     from kgdet_b200.head import KGDetHead
+    try:        # warm-up runs on a side stream before capture: the AccumulateGrad stream note is expected
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+    except Exception:
+        pass
     if rank is None:
         rank, world, local = kdist.init_from_env('nccl')
     torch.cuda.set_device(local)
@@ -646,68 +650,68 @@ def train_record(args, rank=None, world=None, local=None):
     if bucketer is not None:
         bucketer.remove()
 
-    # The step is launch-bound at batch 2 (about 600 kernels for ~0.3 TFLOP): forward + losses + backward (+ the
+    # The step is launch-bound at batch 2 (hundreds of kernels for ~0.3 TFLOP): forward + losses + backward (+ the
     # bucketed all-reduce as a parallel branch) are captured into one CUDA graph and clip + SGD into a second one.
-    mode, allreduce_kind, step, step_noar = 'eager', 'none (1 GPU)', None, None
-    if not args.no_graph:
-        for in_graph in ((True, False) if world > 1 else (False,)):
-            try:
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    for _ in range(2):
-                        opt.zero_grad(set_to_none=True)
-                        fwd_bwd()
-                        update()
-                torch.cuda.current_stream().wait_stream(side)
-                torch.cuda.synchronize()
-                # gradients live in ONE flat buffer (fixed address): the captured backward accumulates into it and
-                # the all-reduce runs on slices of that buffer, without flatten / unflatten copies
-                # (one rank: plain per-parameter gradients -- the flat buffer costs a 111 MB clear and
-                # read-modify-write accumulation, 0.16 ms, and only pays for itself when there is an all-reduce)
-                flat = kdist.FlatGrads(head.parameters()) if world > 1 else None
-                if flat is None:
-                    opt.zero_grad(set_to_none=True)
-                g_fb, g_up = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                overlap = None
-                if flat is not None and in_graph:
-                    overlap = kdist.FlatBucketAllReduce(flat, bucket_size_mb=25)
-                with torch.cuda.graph(g_fb):
-                    if flat is not None:
-                        flat.zero()
-                    if overlap is not None:
-                        overlap.start()
-                    static_loss = fwd_bwd()
-                    if overlap is not None:
-                        overlap.finish()
-                if overlap is not None:
-                    overlap.remove()
-                with torch.cuda.graph(g_up, pool=g_fb.pool()):
-                    update()
+    def capture(kind):
+        """kind: 'local' (no collective), 'overlap' (bucketed NCCL captured inside the backward graph) or 'serial'
+        (one all-reduce of the flat buffer between the two graphs).  Returns the step callable."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                opt.zero_grad(set_to_none=True)
+                fwd_bwd()
+                update()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        opt.zero_grad(set_to_none=True)
+        g_fb, g_up = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        flat = overlap = None
+        if kind != 'local':
+            # the averaged gradients live in ONE flat buffer (fixed address)
+            flat = kdist.FlatGrads(head.parameters())
+        if kind == 'overlap':
+            overlap = kdist.FlatBucketAllReduce(flat, bucket_size_mb=10)
+        with torch.cuda.graph(g_fb):
+            if kind == 'serial':
+                flat.zero()
+            if overlap is not None:
+                overlap.start()
+            static_loss = fwd_bwd()
+            if overlap is not None:
+                overlap.finish()
+        if overlap is not None:
+            overlap.remove()
+        with torch.cuda.graph(g_up, pool=g_fb.pool()):
+            update()
 
-                def step(flat=flat, in_graph=in_graph, g_fb=g_fb, g_up=g_up, static_loss=static_loss):
-                    g_fb.replay()
-                    if flat is not None and not in_graph:
-                        flat.allreduce()
-                    g_up.replay()
-                    return static_loss
-                for _ in range(2):
-                    step()
-                torch.cuda.synchronize()
+        def run():
+            g_fb.replay()
+            if kind == 'serial':
+                flat.allreduce()
+            g_up.replay()
+            return static_loss
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        return run
+
+    mode, allreduce_kind, step, step_local = 'eager', 'none (1 GPU)', None, None
+    if not args.no_graph:
+        for kind in ((('overlap', 'serial') if world > 1 else ('local',))):
+            try:
+                step = capture(kind)
                 mode = 'cuda_graph (fwd+losses+bwd%s | %sclip+SGD)' % (
-                    ' + bucketed NCCL all-reduce as a parallel branch' if (world > 1 and in_graph) else '',
-                    'all-reduce | ' if (world > 1 and not in_graph) else '')
-                if world > 1:
-                    allreduce_kind = ('25 MB buckets of the flat gradient buffer, NCCL captured in the backward graph on a '
-                                      'side stream (overlapped)') if in_graph else \
-                        'one NCCL all-reduce on the flat gradient buffer between the two graphs (not overlapped)'
-                    if not in_graph:
-                        def step_noar(g_fb=g_fb, g_up=g_up):
-                            g_fb.replay()
-                            g_up.replay()
+                    ' + bucketed NCCL all-reduce as a parallel branch' if kind == 'overlap' else '',
+                    'all-reduce | ' if kind == 'serial' else '')
+                if kind == 'overlap':
+                    allreduce_kind = ('10 MB buckets packed into the flat gradient buffer and averaged (ReduceOp.AVG) on a side '
+                                      'stream, NCCL captured in the backward graph (overlapped)')
+                elif kind == 'serial':
+                    allreduce_kind = 'one NCCL all-reduce on the flat gradient buffer between the two graphs (not overlapped)'
                 break
             except Exception as e:
-                log('[bench] training-step graph capture (%s) failed (%r)' % ('NCCL in graph' if in_graph else 'plain', e))
+                log('[bench] training-step graph capture (%s) failed (%r)' % (kind, e))
                 torch.cuda.synchronize()
                 step = None
                 for p_ in head.parameters():
@@ -738,33 +742,17 @@ def train_record(args, rank=None, world=None, local=None):
 
     ms, loss = timed(step)
     exposed_us = None
-    if world > 1:
-        # the same step WITHOUT the all-reduce (gradients stay local): the difference is what the collective
-        # leaves exposed.  Built from the un-overlapped capture so that nothing else changes.
+    if world > 1 and not args.no_graph:
+        # the same step WITHOUT any collective (every rank keeps its local gradients, as at N = 1): the difference
+        # is what data parallelism leaves exposed (all-reduce tail + packing the flat buffer)
         try:
-            if step_noar is None:
-                flat2 = None
-                for p_ in head.parameters():
-                    p_.grad = None
-                opt.zero_grad(set_to_none=True)
-                torch.cuda.synchronize()
-                g_fb2, g_up2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                flat2 = kdist.FlatGrads(head.parameters())
-                with torch.cuda.graph(g_fb2):
-                    flat2.zero()
-                    fwd_bwd()
-                with torch.cuda.graph(g_up2, pool=g_fb2.pool()):
-                    update()
-
-                def step_noar():
-                    g_fb2.replay()
-                    g_up2.replay()
-            for _ in range(2):
-                step_noar()
-            ms0, _ = timed(step_noar)
+            for p_ in head.parameters():
+                p_.grad = None
+            step_local = capture('local')
+            ms0, _ = timed(step_local)
             exposed_us = round((ms - ms0) / args.steps * 1e3, 1)
         except Exception as e:
-            log('[bench] no-all-reduce variant failed (%r)' % (e,))
+            log('[bench] collective-free variant failed (%r)' % (e,))
     final_loss = float(loss.item())
     ops.set_precision(args.precision)
     if rank != 0:

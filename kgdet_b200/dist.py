@@ -147,38 +147,44 @@ class FlatGrads(object):
 
 
 class FlatBucketAllReduce(object):
-    """Overlapped all-reduce on a `FlatGrads` buffer: the flat buffer is cut into contiguous buckets of whole
-    parameters (~`bucket_size_mb` each); a post-accumulate-grad hook counts the gradients of a bucket as autograd
-    finishes them and, when the last one arrives, all-reduces that SLICE of the flat buffer in place on a side
-    stream (no flatten / unflatten copies).  `finish()` joins the side stream and divides by the world size: the
-    same result as the reference's one flat all-reduce after backward (mmdet/core/utils/dist_utils.py:14-25), just
-    earlier in time.  Every call is capture-safe (stream waits + NCCL only), so when `start() ... backward ...
-    finish()` runs under `torch.cuda.graph` the collectives become a parallel branch of the captured backward."""
+    """Overlapped gradient averaging into a `FlatGrads` buffer.  The flat buffer is cut into contiguous buckets of
+    whole parameters (~`bucket_size_mb` each).  Backward runs with `p.grad = None` (autograd then simply hands its
+    fresh gradient tensors over: no zero-fill of the flat buffer, no read-modify-write accumulation, no extra add
+    kernel per parameter); a post-accumulate-grad hook counts the gradients of a bucket as autograd finishes them
+    and, when the last one arrives, ON A SIDE STREAM packs them into the bucket's slice of the flat buffer (one
+    `torch.cat(out=slice)`) and all-reduces that slice in place (NCCL: ReduceOp.AVG, so there is no separate
+    divide pass).  `finish()` joins the side stream and re-points every `p.grad` at its view of the flat buffer:
+    the same values as the reference's one flat all-reduce after backward (mmdet/core/utils/dist_utils.py:14-25),
+    just earlier in time.  Every call is capture-safe (stream waits, copies and NCCL only), so when
+    `start() ... backward ... finish()` runs under `torch.cuda.graph` the collectives become a parallel branch of
+    the captured backward."""
 
-    def __init__(self, flat, bucket_size_mb=25):
+    def __init__(self, flat, bucket_size_mb=10):
         self.fg = flat
         self.ws = world_size()
         limit = int(bucket_size_mb * 1024 * 1024)
-        self.buckets = []                # (lo, hi) element ranges of the flat buffer
+        self.buckets = []                # (lo, hi, [params]) element ranges of the flat buffer
         self.where = {}
         lo = off = 0
+        cur = []
         esz = flat.flat.element_size()
         for p in flat.params:
-            if off > lo and (off + p.numel() - lo) * esz > limit:
-                self.buckets.append((lo, off))
-                lo = off
+            if cur and (off + p.numel() - lo) * esz > limit:
+                self.buckets.append((lo, off, cur))
+                lo, cur = off, []
             self.where[id(p)] = len(self.buckets)
+            cur.append(p)
             off += p.numel()
-        self.buckets.append((lo, off))
-        self.count = [0] * len(self.buckets)
-        for p in flat.params:
-            self.count[self.where[id(p)]] += 1
+        self.buckets.append((lo, off, cur))
         self.pending = None
         self.stream = None
+        self.avg = dist.is_initialized() and dist.get_backend() == 'nccl'       # gloo has no ReduceOp.AVG
         self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in flat.params] if self.ws > 1 else []
 
     def start(self):
-        self.pending = list(self.count)
+        for p in self.fg.params:
+            p.grad = None
+        self.pending = [len(b[2]) for b in self.buckets]
         self.launched = [False] * len(self.buckets)
 
     def _hook(self, p):
@@ -193,27 +199,43 @@ class FlatBucketAllReduce(object):
         if self.launched[bi]:
             return
         self.launched[bi] = True
-        lo, hi = self.buckets[bi]
+        lo, hi, params = self.buckets[bi]
         flat = self.fg.flat
+
+        def pack_and_reduce():
+            off = lo
+            pieces = []
+            for p in params:                       # a parameter that received no gradient contributes zeros
+                pieces.append(p.grad.reshape(-1) if p.grad is not None else flat.new_zeros(p.numel()))
+                off += p.numel()
+            torch.cat(pieces, out=flat[lo:hi])
+            if self.avg:
+                dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.AVG)
+            else:
+                dist.all_reduce(flat[lo:hi])
+                flat[lo:hi].div_(self.ws)
         if flat.is_cuda:
             if self.stream is None:
                 self.stream = torch.cuda.Stream(device=flat.device)
             main = torch.cuda.current_stream(flat.device)
             self.stream.wait_event(main.record_event())
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(flat[lo:hi])
+                pack_and_reduce()
         else:
-            dist.all_reduce(flat[lo:hi])
+            pack_and_reduce()
 
     def finish(self):
         if self.ws == 1 or self.pending is None:
             return
-        for bi in range(len(self.buckets)):          # parameters that received no gradient this step
+        for bi in range(len(self.buckets)):          # buckets with parameters that received no gradient this step
             self._launch(bi)
         flat = self.fg.flat
         if flat.is_cuda and self.stream is not None:
             torch.cuda.current_stream(flat.device).wait_event(self.stream.record_event())
-        flat.div_(self.ws)
+        off = 0
+        for p in self.fg.params:                     # the averaged gradients live in the flat buffer
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
         self.pending = None
 
     def remove(self):

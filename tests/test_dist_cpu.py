@@ -75,10 +75,10 @@ def _worker(rank, world, port, q):
     ov = kd.FlatBucketAllReduce(fg4, bucket_size_mb=0.0002)
     out['n_buckets'] = len(ov.buckets)
     for scale in (3.0, 1.0):
-        fg4.zero()
         ov.start()
         net4(x * scale).square().sum().backward()
         ov.finish()
+    out['flat_bucket_views'] = fg4.attached()
     out['avg_flat_buckets'] = [p.grad.clone().tolist() for p in net4.parameters()]
     ov.remove()
     # a detached gradient view is detected (zero_grad(set_to_none=True) drops the aliases)
@@ -125,7 +125,7 @@ def test_two_rank_gloo_host_logic():
             assert torch.allclose(torch.tensor(res[1][key][i]), want, atol=1e-6), key
     assert res[0]['avg3_ok'] and res[1]['avg3_ok']
     assert res[0]['flat_views_kept'] and res[1]['flat_views_kept']
-    assert res[0]['n_buckets'] > 1
+    assert res[0]['n_buckets'] > 1 and res[0]['flat_bucket_views'] and res[1]['flat_bucket_views']
     for r in (0, 1):
         assert res[r]['detached_detected'] and res[r]['detached_raises'] and res[r]['reattached']
 
