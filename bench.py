@@ -444,10 +444,14 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
-        traffic = None
+        traffic, traffic_note = None, None
         try:      # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dcn_traffic.json')))
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r2_dcn_traffic.json')))
             traffic = int(tr['dram_bytes_read']) + int(tr['dram_bytes_write'])
+            traffic_note = ('DRAM read+write bytes of ONE grouped launch (six deformable convolutions of a stage), ncu --set full '
+                            'capture of %s (profiles/r2_dcn_traffic.json); algorithmic bytes of that launch %.1f MB -- the input '
+                            'planes / plans were just written and are L2 hits, half of the output stays in L2 for the 1x1 GEMM'
+                            % (tr['kernel'].split(' ')[0], tr['algorithmic_bytes']['total'] / 1e6))
         except Exception:
             pass
         peak_tf = peaks.get('bf16_tflops_sustained') or 1400.0
@@ -486,8 +490,7 @@ def run_ours(args):
                                    'dcn_umma_stream_kernel (fused bilinear gather + tcgen05 GEMM), 12 launches/step',
                          'bound': 'tensor', 'achieved': round(achieved, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
                          'frac': round(achieved / peak_tf, 4), 'traffic': traffic,
-                         'traffic_note': 'DRAM read+write bytes of one K=49 launch (ncu --set full, profiles/r1_dcn_traffic.json); '
-                                         'algorithmic bytes of that launch 54.4 MB, inputs are L2 hits',
+                         'traffic_note': traffic_note,
                          'peak_source': peak_src,
                          'share_of_step': round(tot_ms / dev_ms, 4), 'per_kernel_size': detail,
                          'timed_in': 'eager pass of the same K steps with CUDA events immediately around each DCN launch on its stream (C-ABI hook); '
@@ -512,17 +515,47 @@ def run_ours(args):
 
 # --------------------------------------------------------------------------------------------
 def _cpu_step_fn(args, n_images):
-    from tests._cpu_head import make_cpu_head
+    """The CPU arm's step and a description of what runs.  Preferred: the UNCHANGED reference head class
+    (RepPointsHeadKp3RepCas1AssignOnce built from the reference's own config by its own builder -- imported from
+    /root/reference where present, else from the untouched archive oracle/_ref/pytree.zip) running forward_single +
+    get_bboxes on the host cores, with mmdet.ops served by the oracles: DeformConv = oracle/dcn_oracle.py (mmdet v1's
+    is CUDA-only, deform_conv.py:44-45), nms = the reference's nms_cpu.cpp compiled unmodified.  Fallback (no
+    reference Python tree): this repo's head mirror with the same oracle operators injected."""
     torch.set_num_threads(os.cpu_count() or 1)
-    head = make_weights(make_cpu_head()).eval()
     x, sc = make_inputs(n_images, seed=100)
+    try:
+        from tests import refshim
+        if not refshim.available():
+            raise RuntimeError('reference python tree not available')
+        refshim.install('oracle')
+        head, cfg = refshim.build_head('kgdet_moment_r50_fpn_1x-deepfashion2.py', device='cpu')
+        make_weights(head)
+        head.eval()
+        tc = refshim.AttrDict(cfg['test_cfg'])
+        metas = [dict(img_shape=IMG_SHAPE + (3,), scale_factor=1.0)] * n_images
+        logit = torch.log(sc.clamp(min=1e-30) / (1 - sc).clamp(min=1e-30))      # sigmoid(logit) == the synthetic scores
+
+        def step():
+            with torch.no_grad():
+                o = head.forward_single(x)
+                return head.get_bboxes([o[0]], [o[1]], [logit], [o[3]], [o[4]], [o[5]], [o[6]], [o[7]], [o[8]], metas, tc,
+                                       rescale=False)
+        what = ('the UNCHANGED reference head class (RepPointsHeadKp3RepCas1AssignOnce.forward_single + get_bboxes, built '
+                'from the reference config by its own builder) on the host cores; mmdet.ops served by the oracles: '
+                'DeformConv = oracle/dcn_oracle.py on all host threads (mmdet v1 DCN is CUDA-only)')
+        return step, what
+    except Exception as e:
+        log('[bench] reference head class unavailable for the CPU arm (%r): using the repo head mirror' % (e,))
+    from tests._cpu_head import make_cpu_head
+    head = make_weights(make_cpu_head()).eval()
     shapes = [IMG_SHAPE] * n_images
 
     def step():
         with torch.no_grad():
             o = head.forward_single(x)
             return head.get_bboxes([o[2]], [o[5]], [o[8]], shapes, 0.05, 0.5, 1000, 100, score_override=[sc])
-    return step
+    return step, ('this repo\'s head mirror (KGDetHead, same data flow as KP3:412-446,770-914) with oracle operators '
+                  'injected: DeformConv = oracle/dcn_oracle.py on all host threads (mmdet v1 DCN is CUDA-only)')
 
 
 def cpu_baseline(args, budget_s=20.0):
@@ -530,7 +563,7 @@ def cpu_baseline(args, budget_s=20.0):
     NMS = the reference's nms_cpu.cpp when oracle/_ref has it).  Bounded sample, reported not targeted."""
     from oracle import build_ref
     n = 1
-    step = _cpu_step_fn(args, n)
+    step, what = _cpu_step_fn(args, n)
     step()                                   # warm-up
     t0 = time.perf_counter()
     reps = 0
@@ -539,9 +572,8 @@ def cpu_baseline(args, budget_s=20.0):
         reps += 1
     dt = time.perf_counter() - t0
     return {'value': round(n * reps / dt, 4), 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': '%d repetition(s) of the same step on %d image (batch 1) instead of %d; DCN via '
-                      'oracle/dcn_oracle.py on all host threads, NMS via %s'
-                      % (reps, n, args.batch, 'reference nms_cpu.cpp (oracle/_ref)'
+            'sample': '%d repetition(s) of the step on %d image per step (batch 1, not %d): %s; NMS = %s'
+                      % (reps, n, args.batch, what, 'reference nms_cpu.cpp compiled unmodified (oracle/_ref)'
                          if build_ref.load('nms_cpu') is not None else 'oracle/nms_oracle.c')}
 
 
@@ -556,7 +588,7 @@ def run_reference(args):
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is one process using all host cores
     torch.set_num_threads(os.cpu_count() or 1)
     n = args.ref_images
-    step = _cpu_step_fn(args, n)
+    step, what = _cpu_step_fn(args, n)
     for _ in range(min(max(args.warmup, 1), 2)):     # CPU arm: at most two untimed warm-up steps
         step()
     t0 = time.perf_counter()
@@ -564,9 +596,9 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     val = round(n * args.steps / dt, 4)
-    sample = ('each step = forward_single + get_bboxes on %d image(s) (bounded sample of the batch-%d workload); '
-              'unchanged head data flow, DCN = oracle/dcn_oracle.py (mmdet v1 DCN is CUDA-only), NMS = %s'
-              % (n, args.batch, 'reference nms_cpu.cpp compiled unmodified (oracle/_ref)'
+    sample = ('each step = forward_single + get_bboxes on %d image(s) per step (bounded sample of the batch-%d workload, '
+              'ONE process on all host cores whatever --gpus says): %s; NMS = %s'
+              % (n, args.batch, what, 'reference nms_cpu.cpp compiled unmodified (oracle/_ref)'
                  if build_ref.load('nms_cpu') is not None else 'oracle/nms_oracle.c'))
     a2 = argparse.Namespace(**vars(args))
     cfg = workload_config(a2, world)

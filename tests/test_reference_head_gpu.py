@@ -157,3 +157,46 @@ def test_unchanged_reference_loss_and_backward_on_the_b200():
     for n, p in head.named_parameters():
         if 'dfmconv' in n:
             assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0, n
+
+
+def test_wire_formats_from_the_batched_gpu_output_match_the_reference_functions():
+    """The detections of the batched, sync-free `KGDetHead.get_bboxes` (padded [B, 100, ...] device tensors)
+    through this package's wire formats (`results.batch_to_results`, `results.kpt2json`) against the UNCHANGED
+    reference functions `bbox2result_kp` (reppoints_detector_kp.py:55-78) and `kpt2json` (coco_utils.py:121-154)
+    fed with the reference head's own `get_bboxes` output for the same inputs -- end to end on the GPU box."""
+    from kgdet_b200 import results as R
+    from kgdet_b200.head import KGDetHead
+    head, cfg, refshim = _reference_head()
+    head.eval()
+    from mmdet.core.evaluation.coco_utils import kpt2json as ref_kpt2json
+    from mmdet.models.detectors.reppoints_detector_kp import RepPointsDetectorKp
+    g = np.load(os.path.join(GOLD, 'get_bboxes.npz'))
+    g7 = np.load(os.path.join(GOLD, 'head_p7.npz'))
+    t = lambda a: torch.from_numpy(a).cuda()
+    tc = refshim.AttrDict(cfg['test_cfg'])
+    metas = [dict(img_shape=(800, 1333, 3), scale_factor=1.0)] * 2
+    dummy = [t(g7['cls_1'])]
+    with torch.no_grad():
+        ref_dets = head.get_bboxes(dummy, dummy, [t(g['logit'])], [t(g7['kpt_1'])], [t(g7['kpt_2'])], [t(g['kpt3'])],
+                                   [t(g7['bbox_1'])], [t(g7['bbox_2'])], [t(g['bbox3'])], metas, tc, rescale=True)
+    ref_res = [RepPointsDetectorKp.bbox2result_kp(None, d, l, k, 14) for d, l, k in ref_dets]
+
+    class DS(object):
+        img_ids = [101, 202]
+        cat_ids = list(range(1, 14))
+
+        def __len__(self):
+            return 2
+    want_bbox, want_kpt = ref_kpt2json(DS(), ref_res)
+    mirror = KGDetHead().cuda().eval()
+    dets, labels, kpts = mirror.get_bboxes([t(g['logit'])], [t(g['kpt3'])], [t(g['bbox3'])], [(800, 1333)] * 2,
+                                           0.05, 0.5, 1000, 100)
+    got_bbox, got_kpt = R.kpt2json(DS.img_ids, DS.cat_ids, R.batch_to_results(dets, labels, kpts, 14))
+    assert len(got_bbox) == len(want_bbox) > 0 and len(got_kpt) == len(want_kpt)
+    key = lambda d: (d['image_id'], d['category_id'], -d['score'])
+    for a, b in zip(sorted(got_bbox, key=key), sorted(want_bbox, key=key)):
+        assert a['image_id'] == b['image_id'] and a['category_id'] == b['category_id']
+        assert abs(a['score'] - b['score']) <= 1e-4 and np.allclose(a['bbox'], b['bbox'], rtol=0, atol=2e-3)
+    for a, b in zip(sorted(got_kpt, key=key), sorted(want_kpt, key=key)):
+        assert a['image_id'] == b['image_id'] and a['category_id'] == b['category_id']
+        assert np.allclose(a['keypoints'], b['keypoints'], rtol=0, atol=2e-3)
