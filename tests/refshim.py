@@ -201,6 +201,23 @@ def patch_point_generator_device(device):
         fn.__defaults__ = tuple(d)
 
 
+def patch_point_assigner_device():
+    """`PointAssigner.assign` builds `torch.arange(num_points)` without a device and indexes it with masks that live
+    on the points' device (mmdet/core/bbox/assigners/point_assigner.py:70-76) -- fine on torch 1.x, an error on
+    torch 2.x when the points are CUDA tensors.  The method body stays the reference's; it merely runs with the
+    points' device as the default device for factory calls."""
+    from mmdet.core.bbox.assigners.point_assigner import PointAssigner
+    if getattr(PointAssigner.assign, '_kgdet_device_patch', False):
+        return
+    orig = PointAssigner.assign
+
+    def assign(self, points, *args, **kwargs):
+        with torch.device(points.device):
+            return orig(self, points, *args, **kwargs)
+    assign._kgdet_device_patch = True
+    PointAssigner.assign = assign
+
+
 def build_head(config_name, device='cpu'):
     """Build the bbox_head of a reference config with the reference's own builder."""
     cfg = load_config(config_name)
