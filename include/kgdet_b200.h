@@ -232,7 +232,8 @@ KGDET_API int kgdet_groupnorm_relu_nhwc_planes(const float* x, const float* gamm
  *   backward  grad_outs[i] (same shapes as outs[i]; NULL = skip) = d(sum_k grad_losses[k] * losses[k]) / d outs[i]. */
 KGDET_API int kgdet_point_assign(const float* gt_boxes, const uint8_t* gt_valid, const float* gt_keypoints, int32_t B,
                        int32_t G, int32_t num_keypoints, int32_t map_h, int32_t map_w, float stride, int32_t pos_num,
-                       int32_t* assigned, float* avg_factor, float* num_visible, void* stream);
+                       int32_t* assigned, float* avg_factor, float* num_visible, int32_t* scratch /* 2 * B ints */,
+                       void* stream);
 KGDET_API int kgdet_point_losses_forward(const float* const* outs, const int32_t* assigned, const float* gt_boxes,
                                const int64_t* gt_labels, const float* gt_keypoints, const float* avg_factor,
                                const float* num_visible, int32_t B, int32_t G, int32_t map_h, int32_t map_w,

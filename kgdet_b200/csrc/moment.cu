@@ -167,6 +167,87 @@ __global__ void moment_bwd_kernel(const float* __restrict__ pts, const float* __
   }
 }
 
+// Backward twin of moment_fwd_split_kernel: a warp covers 32 consecutive positions, G warps split the P points, the
+// values stay in registers (one read of the point tensor), partial sums meet in shared memory in a fixed order.
+// The two moment_transfer partials of a CTA are reduced over the position lanes and leave as one atomic pair.
+template <int G, int MAXK>
+__global__ void __launch_bounds__(32 * G) moment_bwd_split_kernel(const float* __restrict__ pts, const float* __restrict__ mt,
+                                                                  const float* __restrict__ gbox, int N, int P, int S,
+                                                                  int y_first, float moment_mul, float* __restrict__ gpts,
+                                                                  float* __restrict__ gmt) {
+  __shared__ float red[2][2][G][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const bool ok = i < N * S;
+  const int n = ok ? i / S : 0, s = ok ? i - n * S : 0;
+  const int yo = y_first ? 0 : 1, xo = 1 - yo;
+  const float* base = pts + (size_t)n * 2 * P * S + s;
+  float y[MAXK], x[MAXK];
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) {
+    const int k = g + j * G;
+    const bool in = ok && k < P;
+    y[j] = in ? __ldg(base + (size_t)(2 * k + yo) * S) : 0.f;
+    x[j] = in ? __ldg(base + (size_t)(2 * k + xo) * S) : 0.f;
+  }
+  float sy = 0.f, sx = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) { sy += y[j]; sx += x[j]; }
+  red[0][0][g][lane] = sy;
+  red[0][1][g][lane] = sx;
+  __syncthreads();
+  sy = 0.f; sx = 0.f;
+#pragma unroll
+  for (int q = 0; q < G; ++q) { sy += red[0][0][q][lane]; sx += red[0][1][q][lane]; }
+  const float my = sy / (float)P, mx = sx / (float)P;
+  float vy = 0.f, vx = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) {
+    if (g + j * G < P) {
+      const float dy = y[j] - my, dx = x[j] - mx;
+      vy += dy * dy;
+      vx += dx * dx;
+    }
+  }
+  red[1][0][g][lane] = vy;
+  red[1][1][g][lane] = vx;
+  __syncthreads();
+  vy = 0.f; vx = 0.f;
+#pragma unroll
+  for (int q = 0; q < G; ++q) { vy += red[1][0][q][lane]; vx += red[1][1][q][lane]; }
+  const float ew = expf(mt[0]), eh = expf(mt[1]);
+  const float sdy = sqrtf(vy / (float)(P - 1)), sdx = sqrtf(vx / (float)(P - 1));
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  if (ok) {
+    const float* gb = gbox + (size_t)n * 4 * S + s;
+    g0 = gb[0]; g1 = gb[(size_t)S]; g2 = gb[(size_t)2 * S]; g3 = gb[(size_t)3 * S];
+  }
+  const float g_mx = g0 + g2, g_my = g1 + g3, g_hw = g2 - g0, g_hh = g3 - g1;
+  const float g_sdx = g_hw * ew, g_sdy = g_hh * eh;
+  // zero gradient through a collapsed point set, as torch.std's backward (see moment_bwd_kernel)
+  const float cx = sdx == 0.f ? 0.f : g_sdx / ((float)(P - 1) * sdx);
+  const float cy = sdy == 0.f ? 0.f : g_sdy / ((float)(P - 1) * sdy);
+  const float mxP = g_mx / (float)P, myP = g_my / (float)P;
+  float* go = gpts + (size_t)n * 2 * P * S + s;
+#pragma unroll
+  for (int j = 0; j < MAXK; ++j) {
+    const int k = g + j * G;
+    if (ok && k < P) {
+      go[(size_t)(2 * k + yo) * S] = myP + cy * (y[j] - my);
+      go[(size_t)(2 * k + xo) * S] = mxP + cx * (x[j] - mx);
+    }
+  }
+  if (g == 0 && gmt) {
+    float aw = ok ? g_hw * sdx * ew : 0.f, ah = ok ? g_hh * sdy * eh : 0.f;
+    aw = warp_sum(aw);
+    ah = warp_sum(ah);
+    if (lane == 0) {
+      atomicAdd(&gmt[0], aw * moment_mul);
+      atomicAdd(&gmt[1], ah * moment_mul);
+    }
+  }
+}
+
 }  // namespace kgdet
 
 using namespace kgdet;
@@ -211,6 +292,14 @@ extern "C" int kgdet_points2bbox_moment_backward(const float* pts, const float* 
   KG_CHECK_ARG(pts && moment_transfer && grad_bbox && grad_pts,
                "kgdet_points2bbox_moment_backward: NULL pointer");
   KG_CHECK_ARG((long long)N * S < (1ll << 31), "kgdet_points2bbox_moment_backward: N*S overflow");
+  constexpr int G = 8, MAXK = 16;
+  if (S >= 32 && P >= 2 * G && P <= G * MAXK && (long long)N * S < 128ll * 8 * num_sms()) {
+    moment_bwd_split_kernel<G, MAXK><<<ceil_div(N * S, 32), 32 * G, 0, stream>>>(pts, moment_transfer, grad_bbox, N, P, S,
+                                                                                y_first, moment_mul, grad_pts,
+                                                                                grad_moment_transfer);
+    KG_LAUNCH_CHECK("moment_bwd_split_kernel");
+    return KGDET_OK;
+  }
   moment_bwd_kernel<<<moment_grid(N * S), 128, 0, stream>>>(pts, moment_transfer, grad_bbox, N, P,
                                                             S, y_first, moment_mul, grad_pts,
                                                             grad_moment_transfer);

@@ -22,75 +22,77 @@
 
 namespace kgdet {
 
-static constexpr int PA_THREADS = 1024;
+static constexpr int PA_THREADS = 256;
 
-// assigned[b, p] = 0 (background) or g + 1; avg += max(#positives of image b, 1)
+// assigned[b, p] = 0 (background) or g + 1; avg += max(#positives of image b, 1).
+// grid (point blocks of 256, images): every CTA computes the distances of ALL points of its image to the current box
+// (cheap) and ranks only its own 256 points against them (4 distances per shared-memory load); the last CTA of an
+// image to finish (atomic ticket) folds the image's positive count into avg_factor.
 __global__ void __launch_bounds__(PA_THREADS) point_assign_kernel(const float* __restrict__ gt_boxes /*[B,G,4]*/,
                                                                   const unsigned char* __restrict__ gt_valid /*[B,G]*/,
                                                                   const float* __restrict__ gt_kps /*[B,G,K,3]*/,
                                                                   int G, int K, int P, int Wmap, float stride, int pos_num,
                                                                   int* __restrict__ assigned, float* __restrict__ avg,
-                                                                  float* __restrict__ nvis /*[B,G]*/) {
-  extern __shared__ float dist[];                 // [P]
-  __shared__ int npos_sh;
-  const int b = blockIdx.x;
-  if (threadIdx.x == 0) npos_sh = 0;
+                                                                  float* __restrict__ nvis /*[B,G]*/,
+                                                                  int* __restrict__ scratch /*[B][2], zeroed*/) {
+  extern __shared__ __align__(16) float dist[];   // [P rounded up to 4]
+  const int b = blockIdx.y;
+  const int P4 = (P + 3) & ~3;
   // visible keypoints per box (the keypoint-loss weights of a positive row are 4 / (2 * nvis), KP3:639-644)
-  for (int g = threadIdx.x >> 5; g < G; g += blockDim.x >> 5) {
-    const float* gk = gt_kps + ((size_t)b * G + g) * K * 3;
-    float c = 0.f;
-    for (int j = threadIdx.x & 31; j < K; j += 32) c += gk[(size_t)j * 3 + 2] != 0.f ? 1.f : 0.f;
-    c = warp_sum(c);
-    if ((threadIdx.x & 31) == 0) nvis[(size_t)b * G + g] = c;
+  if (blockIdx.x == 0) {
+    for (int g = threadIdx.x >> 5; g < G; g += blockDim.x >> 5) {
+      const float* gk = gt_kps + ((size_t)b * G + g) * K * 3;
+      float c = 0.f;
+      for (int j = threadIdx.x & 31; j < K; j += 32) c += gk[(size_t)j * 3 + 2] != 0.f ? 1.f : 0.f;
+      c = warp_sum(c);
+      if ((threadIdx.x & 31) == 0) nvis[(size_t)b * G + g] = c;
+    }
   }
   const int k = pos_num < P ? pos_num : P;
-  // every thread owns the points p = tid, tid + blockDim, ... (P <= 4 * blockDim)
-  float best[4];
-  int who[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { best[i] = INFINITY; who[i] = 0; }
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;       // this thread's point
+  float best = INFINITY;
+  int who = 0;
   for (int g = 0; g < G; ++g) {
     const bool valid = gt_valid[(size_t)b * G + g] != 0;
+    if (!valid) continue;                                    // uniform over the CTA
     const float* bx = gt_boxes + ((size_t)b * G + g) * 4;
     const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
     const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f), cy = __fmul_rn(__fadd_rn(y1, y2), 0.5f);   // :59 (x / 2)
     const float w = fmaxf(__fsub_rn(x2, x1), 1e-6f), h = fmaxf(__fsub_rn(y2, y1), 1e-6f);           // :60
     __syncthreads();                              // the previous box's ranks have been read
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
-      const float px = (float)(p % Wmap) * stride, py = (float)(p / Wmap) * stride;                 // point_generator.py:14-23
+    for (int q = threadIdx.x; q < P4; q += blockDim.x) {
+      const float px = (float)(q % Wmap) * stride, py = (float)(q / Wmap) * stride;                 // point_generator.py:14-23
       const float dx = __fdiv_rn(__fsub_rn(px, cx), w), dy = __fdiv_rn(__fsub_rn(py, cy), h);       // :84
-      dist[p] = valid ? sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) : INFINITY;
+      dist[q] = q < P ? sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) : INFINITY;
     }
     __syncthreads();
-    if (!valid) continue;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int p = threadIdx.x + i * blockDim.x;
-      if (p >= P) continue;
+    if (p < P) {
       const float mine = dist[p];
       int rank = 0;
-      for (int j = 0; j < P; ++j) {
-        const float o = dist[j];
-        rank += (o < mine || (o == mine && j < p)) ? 1 : 0;
+      for (int j = 0; j < P4; j += 4) {
+        const float4 o = *reinterpret_cast<const float4*>(dist + j);
+        rank += (o.x < mine || (o.x == mine && j < p)) ? 1 : 0;
+        rank += (o.y < mine || (o.y == mine && j + 1 < p)) ? 1 : 0;
+        rank += (o.z < mine || (o.z == mine && j + 2 < p)) ? 1 : 0;
+        rank += (o.w < mine || (o.w == mine && j + 3 < p)) ? 1 : 0;
       }
       // among the k nearest of this box (:90-91) and strictly closer than what an earlier box offered (:98-99)
-      if (rank < k && mine < best[i]) { best[i] = mine; who[i] = g + 1; }
+      if (rank < k && mine < best) { best = mine; who = g + 1; }
     }
   }
-  int mypos = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int p = threadIdx.x + i * blockDim.x;
-    if (p < P) {
-      assigned[(size_t)b * P + p] = who[i];
-      mypos += who[i] > 0 ? 1 : 0;
-    }
-  }
-  __syncthreads();
+  if (p < P) assigned[(size_t)b * P + p] = who;
+  int mypos = (p < P && who > 0) ? 1 : 0;
   mypos = (int)warp_sum((float)mypos);
-  if ((threadIdx.x & 31) == 0 && mypos) atomicAdd(&npos_sh, mypos);
+  if ((threadIdx.x & 31) == 0 && mypos) atomicAdd(&scratch[2 * b], mypos);
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(avg, (float)(npos_sh > 1 ? npos_sh : 1));      // small integers: exact in any order
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(&scratch[2 * b + 1], 1);
+    if (ticket == (int)gridDim.x - 1) {                      // last CTA of this image
+      const int npos = atomicAdd(&scratch[2 * b], 0);
+      atomicAdd(avg, (float)(npos > 1 ? npos : 1));          // small integers: exact in any order
+    }
+  }
 }
 
 struct PointLossParams {
@@ -230,19 +232,21 @@ using namespace kgdet;
 extern "C" int kgdet_point_assign(const float* gt_boxes, const uint8_t* gt_valid, const float* gt_keypoints, int32_t B,
                                   int32_t G, int32_t num_keypoints, int32_t map_h, int32_t map_w, float stride,
                                   int32_t pos_num, int32_t* assigned, float* avg_factor, float* num_visible,
-                                  void* stream_) {
+                                  int32_t* scratch, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   KG_CHECK_ARG(B >= 0 && G >= 0 && map_h > 0 && map_w > 0 && pos_num > 0, "kgdet_point_assign: bad sizes");
   const int P = map_h * map_w;
-  KG_CHECK_ARG(P <= 4 * PA_THREADS, "kgdet_point_assign: at most %d points per level (got %d)", 4 * PA_THREADS, P);
-  KG_CHECK_ARG(assigned && avg_factor && (G == 0 || (gt_boxes && gt_valid && gt_keypoints && num_visible)),
+  KG_CHECK_ARG(P <= 4096, "kgdet_point_assign: at most 4096 points per level (got %d)", P);
+  KG_CHECK_ARG(assigned && avg_factor && scratch && (G == 0 || (gt_boxes && gt_valid && gt_keypoints && num_visible)),
                "kgdet_point_assign: NULL pointer");
+  KG_CHECK_ARG(B <= 65535, "kgdet_point_assign: batch too large");
   KG_CHECK_ARG(num_keypoints >= 0, "kgdet_point_assign: bad keypoint count");
   KG_CUDA(cudaMemsetAsync(avg_factor, 0, sizeof(float), stream));
   if (B == 0) return KGDET_OK;
-  point_assign_kernel<<<B, PA_THREADS, (size_t)P * sizeof(float), stream>>>(gt_boxes, gt_valid, gt_keypoints, G, num_keypoints,
-                                                                          P, map_w, stride, pos_num, assigned, avg_factor,
-                                                                          num_visible);
+  KG_CUDA(cudaMemsetAsync(scratch, 0, (size_t)B * 2 * sizeof(int), stream));
+  point_assign_kernel<<<dim3(ceil_div(P, PA_THREADS), B), PA_THREADS, (size_t)(P + 4) * sizeof(float), stream>>>(
+      gt_boxes, gt_valid, gt_keypoints, G, num_keypoints, P, map_w, stride, pos_num, assigned, avg_factor, num_visible,
+      scratch);
   KG_LAUNCH_CHECK("point_assign_kernel");
   return KGDET_OK;
 }
