@@ -17,6 +17,8 @@
 // tiles; a __syncthreads per tile publishes the next tile index.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "dcn_umma.cuh"
 
 namespace kgdet {
@@ -26,6 +28,15 @@ static constexpr int GP_RPT = 4;                // rows per producer thread
 static constexpr int GP_PWARPS = 8;             // producer warps
 static constexpr int GP_THREADS = (GP_PWARPS + 1) * 32;
 static constexpr int GP_ROW_STEP = 128 / GP_RPT;
+// DEPTH = k-blocks of gathers a producer thread keeps in flight.  With one, every warp waits once per k-block for
+// the slowest of its 64 cache lines (11 % of the sectors miss L1, so there is always one coming back from L2):
+// `long_scoreboard` is the top stall.  Two k-blocks in flight need 64 more registers per producer thread than the
+// 168 that 9 warps can have, so the DEPTH = 2 kernel is launched with 12 warps (three warpgroups) and moves the
+// registers of the third one (control warp + three idle warps) to the producers with setmaxnreg: 224 / 56.
+template <int DEPTH> struct GroupLayout {
+  static constexpr int THREADS = DEPTH == 2 ? 384 : GP_THREADS;
+  static constexpr int SYNC_THREADS = GP_THREADS;        // producers + control warp meet at the tile boundaries
+};
 
 struct GroupProblem {
   const void* in;            // channel-blocked bf16 planes (first pixel of plane 0)
@@ -78,7 +89,8 @@ __device__ __forceinline__ void gp_bulk_s2g(void* gmem_dst, const void* smem_src
                : "memory");
 }
 
-__global__ void __launch_bounds__(GP_THREADS, 1) dcn_umma_group_kernel(const __grid_constant__ GroupParams gp) {
+template <int DEPTH>
+__global__ void __launch_bounds__(GroupLayout<DEPTH>::THREADS, 1) dcn_umma_group_kernel(const __grid_constant__ GroupParams gp) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -115,7 +127,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) dcn_umma_group_kernel(const __g
   int tile = *next_tile;
   int it_base = 0;                              // k-blocks this CTA has pushed through the ring so far
   uint32_t tile_count = 0;
+  // tile-boundary barrier of the 288 working threads (named: the idle warps of the DEPTH = 2 layout have left)
+  auto sync_workers = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(GroupLayout<DEPTH>::SYNC_THREADS) : "memory"); };
 
+  // The tile loop is instantiated once per role and each instance sits in its own top-level branch, directly
+  // after that role's setmaxnreg: ptxas then allocates the producer instance up to the raised register limit.
+  auto tile_loop = [&](auto ctrl_tag) {
+  constexpr bool CTRL = decltype(ctrl_tag)::value;
   while (tile < gp.total_tiles) {
     // ---- which problem, which rows ----
     int pi = 0;
@@ -128,7 +146,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) dcn_umma_group_kernel(const __g
     long long* const tl = (gp.timeline && tile_count < 64) ? gp.timeline + ((size_t)blockIdx.x * 64 + tile_count) * 8 : nullptr;
     if (tl && threadIdx.x == 0) { tl[0] = clock64(); tl[5] = nkb; }
 
-    if (is_control) {
+    if constexpr (CTRL) {
       // =========================== control lane ===========================
       if (lane == 0) {
         auto fetch_b = [&](int kq) {            // weight slab of this tile's k-block kq into its ring stage
@@ -171,8 +189,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) dcn_umma_group_kernel(const __g
       const size_t tap_stride = (size_t)P.rows_padded;
       const int a_off = rbase * 128 + ((chunk ^ (rbase & 7)) << 4);
 
-      uint4 v[GP_RPT][4];
-      uint32_t wy[GP_RPT], wz[GP_RPT];
+      uint4 v[DEPTH][GP_RPT][4];
+      uint32_t wy[DEPTH][GP_RPT], wz[DEPTH][GP_RPT];
       uint4 recn[GP_RPT];
       auto load_recs = [&](int tap) {
 #pragma unroll
@@ -180,42 +198,53 @@ __global__ void __launch_bounds__(GP_THREADS, 1) dcn_umma_group_kernel(const __g
       };
       int tapI = 0, tapR = 0;
       const unsigned char* in_plane = in_base;
-      auto issue = [&](int row, const uint4& rec) {
+      auto issue = [&](int slot, int row, const uint4& rec) {
         const unsigned char* p0 = in_plane + (long long)(int)rec.x * rowb;
-        v[row][0] = __ldg(reinterpret_cast<const uint4*>(p0));
-        v[row][1] = __ldg(reinterpret_cast<const uint4*>(p0 + rowb));
-        v[row][2] = __ldg(reinterpret_cast<const uint4*>(p0 + wrow));
-        v[row][3] = __ldg(reinterpret_cast<const uint4*>(p0 + wrow + rowb));
-        wy[row] = rec.y; wz[row] = rec.z;
+        v[slot][row][0] = __ldg(reinterpret_cast<const uint4*>(p0));
+        v[slot][row][1] = __ldg(reinterpret_cast<const uint4*>(p0 + rowb));
+        v[slot][row][2] = __ldg(reinterpret_cast<const uint4*>(p0 + wrow));
+        v[slot][row][3] = __ldg(reinterpret_cast<const uint4*>(p0 + wrow + rowb));
+        wy[slot][row] = rec.y; wz[slot][row] = rec.z;
       };
       auto advance = [&]() { if (++tapI == K) { tapI = 0; in_plane += P.plane_bytes; } };
 
-      load_recs(0);
+      // prologue: gathers of k-blocks 0 .. DEPTH-1 in flight, records of k-block DEPTH fetched
 #pragma unroll
-      for (int i = 0; i < GP_RPT; ++i) issue(i, recn[i]);
-      advance();
+      for (int d = 0; d < DEPTH; ++d) {
+        if (d < nkb) {
+          load_recs(tapI);
+#pragma unroll
+          for (int i = 0; i < GP_RPT; ++i) issue(d, i, recn[i]);
+          advance();
+        }
+      }
       tapR = tapI;
-      if (1 < nkb) load_recs(tapR);
+      if (DEPTH < nkb) load_recs(tapR);
       if (++tapR == K) tapR = 0;
 
-      for (int kb = 0; kb < nkb; ++kb) {
+      auto body = [&](int kb, int slot) {
         const int G = it_base + kb, s = G % GP_NS;
         unsigned char* a_tile = smem + (size_t)s * stage_bytes;
         gp_spin(&empty_bar[s], ((uint32_t)(G / GP_NS) & 1u) ^ 1u);
-        const bool more = kb + 1 < nkb;
+        const bool more = kb + DEPTH < nkb;
 #pragma unroll
         for (int row = 0; row < GP_RPT; ++row) {
-          gp_combine_store(v[row], wy[row], wz[row], a_tile + a_off + row * (GP_ROW_STEP * 128));
-          if (more) issue(row, recn[row]);
+          gp_combine_store(v[slot][row], wy[slot][row], wz[slot][row], a_tile + a_off + row * (GP_ROW_STEP * 128));
+          if (more) issue(slot, row, recn[row]);                 // re-arm: k-block kb + DEPTH
         }
         if (more) advance();
-        if (kb + 2 < nkb) {
+        if (kb + DEPTH + 1 < nkb) {
           load_recs(tapR);
           if (++tapR == K) tapR = 0;
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[s]);
+      };
+      for (int kb = 0; kb < nkb; kb += DEPTH) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d)
+          if (kb + d < nkb) body(kb + d, d);
       }
 
       // =========================== epilogue ===========================
@@ -307,16 +336,28 @@ __global__ void __launch_bounds__(GP_THREADS, 1) dcn_umma_group_kernel(const __g
 
     // ---- next tile: the ring is drained, every role is done with this tile ----
     if (threadIdx.x == GP_PWARPS * 32) *next_tile = atomicAdd(gp.counter, 1);
-    __syncthreads();
+    sync_workers();
     tc_fence_after();
     tile = *next_tile;
     it_base += nkb;
     ++tile_count;
-    __syncthreads();          // everyone has read next_tile before the control lane overwrites it again
+    sync_workers();           // everyone has read next_tile before the control lane overwrites it again
+  }
+  };
+
+  if (!is_control && warp < GP_PWARPS) {
+    if constexpr (DEPTH == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    tile_loop(std::false_type{});
+  } else {
+    if constexpr (DEPTH == 2) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      if (warp > GP_PWARPS) return;             // the three idle warps of the third warpgroup
+    }
+    tile_loop(std::true_type{});
   }
 
   tc_fence_before();
-  __syncthreads();
+  sync_workers();
   if (is_control) tmem_dealloc(tmem_base, gp.tmem_cols);
 }
 
@@ -330,10 +371,17 @@ int umma_group_forward(GroupParams& gp, cudaStream_t stream) {
     set_error("dcn group: tile does not fit shared memory");
     return KGDET_ERR_UNSUPPORTED;
   }
-  KG_CUDA(cudaFuncSetAttribute(dcn_umma_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int depth = 1;
+  if (const char* e = getenv("KGDET_GROUP_DEPTH")) depth = atoi(e) == 2 ? 2 : 1;
   KG_CUDA(cudaMemsetAsync(gp.counter, 0, sizeof(int), stream));
   const int grid = gp.total_tiles < num_sms() ? gp.total_tiles : num_sms();
-  dcn_umma_group_kernel<<<grid, GP_THREADS, smem, stream>>>(gp);
+  if (depth == 2) {
+    KG_CUDA(cudaFuncSetAttribute(dcn_umma_group_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dcn_umma_group_kernel<2><<<grid, GroupLayout<2>::THREADS, smem, stream>>>(gp);
+  } else {
+    KG_CUDA(cudaFuncSetAttribute(dcn_umma_group_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dcn_umma_group_kernel<1><<<grid, GroupLayout<1>::THREADS, smem, stream>>>(gp);
+  }
   KG_LAUNCH_CHECK("dcn_umma_group_kernel");
   return KGDET_OK;
 }

@@ -623,6 +623,7 @@ class RepPointsKpHead(nn.Module):
             self.cls_convs.append(_ConvGNReLU(chn, feat_channels, num_groups))
             self.reg_convs.append(_ConvGNReLU(chn, feat_channels, num_groups))
         kd, rd, pf = 2 * num_keypts, 2 * num_reppts, point_feat_channels
+        self.grouped_dcn = True             # bf16 inference: the DCNs of all levels in grouped persistent launches
         self.cls_refine_dfmconv = deform_conv_cls(feat_channels, pf, k, 1, self.dcn_pad)
         self.cls_refine_out = nn.Conv2d(pf, self.cls_out_channels, 1, 1, 0)
         self.keypts_init_conv = nn.Conv2d(feat_channels, pf, 3, 1, 1)
@@ -691,8 +692,86 @@ class RepPointsKpHead(nn.Module):
         return cls_out, kpt_init, kpt_ref, rep_init, rep_ref
 
     def forward(self, feats):
+        if (self._fused_inference and self.grouped_dcn and not torch.is_grad_enabled() and feats[0].is_cuda
+                and get_precision(feats[0].dtype) == 'bf16' and feats[0].dtype == torch.float32):
+            return self._forward_grouped(feats)
         outs = [self.forward_single(x) for x in feats]
         return tuple(map(list, zip(*outs)))
+
+    def _forward_grouped(self, feats):
+        """bf16 inference over all levels with the deformable convolutions of EVERY level (3 x 5 parallel, 2 x 5
+        serial) in grouped persistent launches of up to six (kgdet_dcn_forward_prepared_group): one such call is
+        a few tiles on the small levels (P6: 5 tiles per image batch of 8, P7: 1..5) and leaves the machine idle
+        when launched alone; grouped, their tiles fill the SMs the big levels' tails leave free.  Same arithmetic
+        as `forward_single` level by level (bit-identical)."""
+        base = self._dcn_base.to(feats[0].dtype)
+        pf = self.cls_refine_dfmconv.out_channels
+        per_level, jobs = [], []
+        for x in feats:
+            cls_feat = pts_feat = x
+            for m in self.cls_convs:
+                cls_feat = m(cls_feat)
+            for m in self.reg_convs:
+                pts_feat = m(pts_feat)
+            kpt_init = self.keypts_init_out(F.relu(self.keypts_init_conv(pts_feat)))
+            if self.variant == 'parallel':
+                rep_init = self.reppts_init_out(F.relu(self.reppts_init_conv(pts_feat)))     # PAR:314-315
+            else:
+                rep_init = self.reppts_init_out(kpt_init)                                    # SER:314
+            n, c, h, w = cls_feat.shape
+            pts = self.gradient_mul * rep_init + (1 - self.gradient_mul) * rep_init           # PAR:322-325, value-wise
+            plan = prepare_plan(pts - base, (n, c, h, w), pf, self.dcn_kernel, 1, self.dcn_pad, 1, like_dtype=x.dtype)
+            cls_prep = prepare_input(cls_feat, pf)
+            pts_prep = prepare_input(pts_feat, pf)
+            outs = [x.new_empty((n, pf, h, w)) for _ in range(3 if self.variant == 'parallel' else 2)]
+            jobs.append((cls_prep, plan, self.cls_refine_dfmconv.weight, outs[0], 0, True))
+            jobs.append((pts_prep, plan, self.keypts_refine_dfmconv.weight, outs[1], 0, True))
+            if self.variant == 'parallel':
+                jobs.append((pts_prep, plan, self.reppts_refine_dfmconv.weight, outs[2], 0, True))
+            per_level.append((kpt_init, rep_init, outs))
+        jobs.sort(key=lambda j: -j[3].shape[0] * j[3].shape[2] * j[3].shape[3])      # biggest maps first
+        for i in range(0, len(jobs), 6):
+            deform_conv_prepared_group(jobs[i:i + 6])
+        res = []
+        for kpt_init, rep_init, outs in per_level:
+            cls_out = self.cls_refine_out(outs[0])
+            kpt_ref = self.keypts_refine_out(outs[1])
+            rep_ref = self.reppts_refine_out(outs[2]) if self.variant == 'parallel' else self.reppts_refine_out(kpt_ref)
+            res.append((cls_out, kpt_init, kpt_ref + kpt_init, rep_init, rep_ref + rep_init))
+        return tuple(map(list, zip(*res)))
+
+
+class GraphedForward(object):
+    """`head(feats)` of any head of this module captured ONCE into a CUDA graph for fixed input shapes (the forward
+    has static shapes and no host synchronisation).  ``__call__(feats)`` copies the inputs into the static ones and
+    replays; the returned structure holds the graph's static output tensors.  A snapshot of the weights at capture
+    time, like GraphedInference."""
+
+    def __init__(self, head, example_feats, warmup=3):
+        assert all(x.is_cuda for x in example_feats)
+        self.head = head
+        self.static_in = [x.detach().clone() for x in example_feats]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(warmup, 1)):
+                head(self.static_in)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = head(self.static_in)
+        from .ops.pointwise import cache_values
+        self._pinned_buffers = cache_values()
+
+    def __call__(self, feats=None):
+        if feats is not None:
+            for s, x in zip(self.static_in, feats):
+                if x.data_ptr() != s.data_ptr():
+                    s.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
 
 
 class GraphedInference(object):

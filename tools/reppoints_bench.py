@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from kgdet_b200 import ops  # noqa: E402
-from kgdet_b200.head import RepPointsKpHead  # noqa: E402
+from kgdet_b200.head import GraphedForward, RepPointsKpHead  # noqa: E402
 
 LEVELS = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
 
@@ -27,27 +27,31 @@ def main():
         for batch in (1, 8):
             g = torch.Generator().manual_seed(5)
             feats = [torch.randn(batch, 256, h, w, generator=g).cuda() for h, w in LEVELS]
-            with torch.no_grad():
-                for _ in range(3):
-                    head(feats)
-                torch.cuda.synchronize()
-                ts = []
-                for _ in range(10):
-                    flush.fill_(1)
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record()
-                    head(feats)
-                    b.record()
+            for mode in ('eager_per_level', 'eager_grouped', 'graph_grouped'):
+                head.grouped_dcn = mode != 'eager_per_level'
+                fn = GraphedForward(head, feats) if mode == 'graph_grouped' else (lambda f: head(f))
+                with torch.no_grad():
+                    for _ in range(3):
+                        fn(feats)
                     torch.cuda.synchronize()
-                    ts.append(a.elapsed_time(b))
-            ts.sort()
-            ms = ts[len(ts) // 2]
-            positions = sum(h * w for h, w in LEVELS) * batch
-            dcn_gflop = 2.0 * positions * 256 * 256 * 9 * ndcn / 1e9
-            print(json.dumps(dict(variant=variant, batch=batch, levels=LEVELS, ms_per_batch=round(ms, 3),
-                                  images_per_s=round(batch / (ms * 1e-3), 1), dcn_calls_per_level=ndcn,
-                                  dcn_gflop=round(dcn_gflop, 1), launch_mode='eager',
-                                  note='forward of all five levels, L2 flushed before every batch')), flush=True)
+                    ts = []
+                    for _ in range(10):
+                        flush.fill_(1)
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        fn(feats)
+                        b.record()
+                        torch.cuda.synchronize()
+                        ts.append(a.elapsed_time(b))
+                ts.sort()
+                ms = ts[len(ts) // 2]
+                positions = sum(h * w for h, w in LEVELS) * batch
+                dcn_gflop = 2.0 * positions * 256 * 256 * 9 * ndcn / 1e9
+                print(json.dumps(dict(variant=variant, batch=batch, levels=LEVELS, ms_per_batch=round(ms, 3),
+                                      images_per_s=round(batch / (ms * 1e-3), 1), dcn_calls_per_level=ndcn,
+                                      dcn_gflop=round(dcn_gflop, 1), launch_mode=mode,
+                                      note='forward of all five levels, L2 flushed before every batch; towers / 1x1 '
+                                           'convolutions cuDNN (TF32 allowed)')), flush=True)
     ops.set_precision(None)
 
 
