@@ -46,6 +46,7 @@ struct ConvParams {
   int bw, bh, tiles_w, tiles_h, ntiles;       // tile = bh rows x bw columns of one image (bw * bh <= 128)
   int relu;
   uint32_t idesc, tmem_cols;
+  long long* timeline;         // development hook (kgdet_dcn_set_timeline): per CTA 8 clock64() stamps, or NULL
 };
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -75,6 +76,9 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();                 // 0 = the CTA that issues the MMAs
+  // stamps: 0 entry, 1 set-up done, 2 first stage full (MMA issuer), 3 last MMA issued, 4 accumulator ready, 5 epilogue done
+  long long* const tl = prm.timeline ? prm.timeline + (size_t)blockIdx.x * 8 : nullptr;
+  if (tl && tid == 0) tl[0] = clock64();
   const int nkb = prm.ncb * prm.taps;
   // this CTA's tile: image n, rows [y0, y0 + bh), columns [x0, x0 + bw); a padding tile (odd tile count) repeats
   // the last real one and stores nothing
@@ -102,6 +106,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
   cluster_sync_all();                                      // the peer's barriers exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tl && tid == 0) tl[1] = clock64();
 
   if (warp == 0) {
     // =========================== producer ===========================
@@ -139,6 +144,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
         for (int kb = 0; kb < nkb; ++kb) {
           const int s = kb % CV_NS;
           mbar_wait_cluster(&full_bar[s], ((uint32_t)(kb / CV_NS)) & 1u);
+          if (tl && kb == 0) tl[2] = clock64();
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
           const uint64_t a_hi = make_sw128_kmajor_desc(a_addr), a_lo = make_sw128_kmajor_desc(a_addr + CV_A_BYTES);
@@ -153,12 +159,14 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
           tc_commit_pair(&empty_bar[s], (uint16_t)3);      // frees the stage in both CTAs when these MMAs retire
         }
         tc_commit_pair(tmem_full_bar, (uint16_t)3);        // accumulators of both CTAs complete
+        if (tl) tl[3] = clock64();
       }
     }
     __syncwarp();
   } else {
     // =========================== epilogue: TMEM -> NHWC fp32 ===========================
     mbar_wait_cluster(tmem_full_bar, 0);
+    if (tl && tid == 64) tl[4] = clock64();
     tc_fence_after();
     const int q = warp & 3, half = (warp - 2) >> 2;        // TMEM lane quarter (hardware: warp % 4), column half
     const int row = q * 32 + lane;
@@ -187,6 +195,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
       }
     }
   }
+  if (tl && tid == 64) tl[5] = clock64();
   tc_fence_before();
   cluster_sync_all();            // neither CTA may free the shared TMEM allocation while the other still reads
   if (warp == 1) tmem_dealloc_pair(tmem_base, prm.tmem_cols);
@@ -432,6 +441,9 @@ extern "C" int kgdet_conv_forward(const void* planes, const void* weight_packed,
       return KGDET_ERR_CUDA;
     }
   }
+  p.timeline = nullptr;
+  if (g_timeline && g_timeline_entries >= (long long)2 * ceil_div(p.ntiles, 2) * 8) p.timeline = g_timeline;
+  g_timeline = nullptr;
   const int b_half = (Cout / 2) * 128;
   const size_t smem = 1024 + (size_t)CV_NS * (2 * CV_A_BYTES + 2 * b_half) + (2 * CV_NS + 1) * 8 + 16;
   KG_CUDA(cudaFuncSetAttribute(conv_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
