@@ -361,11 +361,283 @@ __global__ void __launch_bounds__(GroupLayout<DEPTH>::THREADS, 1) dcn_umma_group
   if (is_control) tmem_dealloc(tmem_base, gp.tmem_cols);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// 256-row variant: a tile is TWO 128-position halves that share every weight slab.  The loop of the kernel above is
+// bound by the bytes a k-block moves through the SM's L1 / shared-memory array (64 KB of gathers, 16 KB of A stores,
+// 32 KB of weight bulk-writes, 48 KB of MMA operand reads); here a weight slab is written once per TWO half-steps
+// (16 KB per half-step), the pipeline shrinks to 128 KB (A ring 4 x 16 KB, B ring 2 x 32 KB -> the 132 KB carve-out
+// instead of 164 KB: 96 KB of L1 for the gather instead of 64) and there are half as many tiles to fill and drain.
+// Two TMEM accumulators (512 columns), one per half; the arithmetic per output element is unchanged (bit-identical).
+//   step t = 2 * k-block + half:  producers gather + interpolate the A tile of (k-block, half) into the A ring;
+//   the control lane issues MMA(acc[half], A[t], B[k-block]); B(k-block + 1) is fetched when B(k-block - 1) retires.
+static constexpr int G2_NA = 4, G2_NB = 2;
+
+__global__ void __launch_bounds__(GP_THREADS, 1) dcn_umma_group256_kernel(const __grid_constant__ GroupParams gp) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const int BN = gp.Cout;
+  const int b_tile_bytes = BN * 128;
+  unsigned char* const a_ring = smem;
+  unsigned char* const b_ring = smem + (size_t)G2_NA * A_TILE_BYTES;
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(b_ring + (size_t)G2_NB * b_tile_bytes);
+  uint64_t* empty_a = full_a + G2_NA;
+  uint64_t* full_b = empty_a + G2_NA;
+  uint64_t* empty_b = full_b + G2_NB;
+  uint64_t* tmem_full_bar = empty_b + G2_NB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  int* next_tile = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_control = warp == GP_PWARPS;
+  const int tid = threadIdx.x;
+
+  if (is_control) {
+    if (lane == 0) {
+      for (int s = 0; s < G2_NA; ++s) { mbar_init(&full_a[s], GP_PWARPS); mbar_init(&empty_a[s], 1); }
+      for (int s = 0; s < G2_NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+      *next_tile = atomicAdd(gp.counter, 1);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 2 * gp.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  int tile = *next_tile;
+  int step_base = 0, kb_base = 0;                 // half-steps / k-blocks this CTA has pushed through the rings
+  uint32_t tile_count = 0;
+
+  while (tile < gp.total_tiles) {
+    int pi = 0;
+#pragma unroll
+    for (int q = 1; q < KGDET_DCN_GROUP_MAX; ++q)
+      if (q < gp.nprob && tile >= gp.prob[q].tile_begin) pi = q;
+    const GroupProblem& P = gp.prob[pi];
+    const int m0 = (tile - P.tile_begin) * (2 * BM);
+    const int nkb = P.nkb, nsteps = 2 * nkb;
+
+    if (is_control) {
+      if (lane == 0) {
+        auto fetch_b = [&](int kq) {
+          const int sq = (kb_base + kq) % G2_NB;
+          mbar_arrive_expect_tx(&full_b[sq], (uint32_t)b_tile_bytes);
+          bulk_g2s(b_ring + (size_t)sq * b_tile_bytes, P.wp + (size_t)kq * b_tile_bytes, (uint32_t)b_tile_bytes, &full_b[sq]);
+        };
+        fetch_b(0);                               // both rings are drained at a tile boundary
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int KG = kb_base + kb, sb = KG % G2_NB;
+          gp_spin(&full_b[sb], (uint32_t)(KG / G2_NB) & 1u);
+          const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(b_ring + (size_t)sb * b_tile_bytes));
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int T = step_base + 2 * kb + h, sa = T % G2_NA;
+            gp_spin(&full_a[sa], (uint32_t)(T / G2_NA) & 1u);
+            tc_fence_after();
+            const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(a_ring + (size_t)sa * A_TILE_BYTES));
+            const uint32_t acc = tmem_base + (uint32_t)(h * gp.tmem_cols);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(acc, adesc + 2 * k, bdesc + 2 * k, gp.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(&empty_a[sa]);
+            if (h == 0 && kb + 1 < nkb) {
+              // weight slab of the NEXT k-block into the slot of k-block KG - 1: its MMAs were issued two half-steps
+              // ago and have retired by now (this wait ends at once); the slab then has two half-steps to land
+              if (kb >= 1) gp_spin(&empty_b[(KG + 1) % G2_NB], (uint32_t)((KG - 1) / G2_NB) & 1u);
+              fetch_b(kb + 1);
+            }
+          }
+          tc_commit(&empty_b[sb]);
+        }
+        tc_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    } else {
+      // =========================== producers ===========================
+      const int chunk = tid & 7, rbase = tid >> 3;
+      const int K = P.K;
+      constexpr long long rowb = 128;
+      const long long wrow = (long long)P.W * rowb;
+      const unsigned char* in_base = reinterpret_cast<const unsigned char*>(P.in) + chunk * 16;
+      const uint4* plan0 = reinterpret_cast<const uint4*>(P.plan) + (m0 + rbase);
+      const size_t tap_stride = (size_t)P.rows_padded;
+      const int a_off = rbase * 128 + ((chunk ^ (rbase & 7)) << 4);
+
+      uint4 v[GP_RPT][4];
+      uint32_t wy[GP_RPT], wz[GP_RPT];
+      uint4 recn[GP_RPT];
+      auto load_recs = [&](int tap, int half) {
+#pragma unroll
+        for (int i = 0; i < GP_RPT; ++i) recn[i] = __ldg(plan0 + half * BM + (size_t)i * GP_ROW_STEP + tap * tap_stride);
+      };
+      const unsigned char* in_plane = in_base;    // plane of the step whose gathers are issued next
+      auto issue = [&](int row, const uint4& rec) {
+        const unsigned char* p0 = in_plane + (long long)(int)rec.x * rowb;
+        v[row][0] = __ldg(reinterpret_cast<const uint4*>(p0));
+        v[row][1] = __ldg(reinterpret_cast<const uint4*>(p0 + rowb));
+        v[row][2] = __ldg(reinterpret_cast<const uint4*>(p0 + wrow));
+        v[row][3] = __ldg(reinterpret_cast<const uint4*>(p0 + wrow + rowb));
+        wy[row] = rec.y; wz[row] = rec.z;
+      };
+      // tapI: tap of the step whose gathers are issued next; tapR: tap of the step whose records are fetched next
+      int tapI = 0, tapR = 0;
+      load_recs(0, 0);
+#pragma unroll
+      for (int i = 0; i < GP_RPT; ++i) issue(i, recn[i]);     // step 0 = (k-block 0, half 0)
+      load_recs(0, 1);                                        // records of step 1 = (k-block 0, half 1)
+      // after step 1 the issue / record cursors move to k-block 1
+      for (int t = 0; t < nsteps; ++t) {
+        const int T = step_base + t, sa = T % G2_NA;
+        unsigned char* a_tile = a_ring + (size_t)sa * A_TILE_BYTES;
+        gp_spin(&empty_a[sa], ((uint32_t)(T / G2_NA) & 1u) ^ 1u);
+        const bool more = t + 1 < nsteps;
+        if (more && ((t + 1) & 1) == 0) {                     // next step opens a new k-block: advance tap / plane
+          if (++tapI == K) { tapI = 0; in_plane += P.plane_bytes; }
+        }
+#pragma unroll
+        for (int row = 0; row < GP_RPT; ++row) {
+          gp_combine_store(v[row], wy[row], wz[row], a_tile + a_off + row * (GP_ROW_STEP * 128));
+          if (more) issue(row, recn[row]);                    // re-arm: step t + 1
+        }
+        if (t + 2 < nsteps) {
+          if (((t + 2) & 1) == 0) { if (++tapR == K) tapR = 0; }
+          load_recs(tapR, (t + 2) & 1);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[sa]);
+      }
+
+      // =========================== epilogue: the two halves one after the other ===========================
+      gp_spin(tmem_full_bar, tile_count & 1u);
+      tc_fence_after();
+      const int q = warp & 3, cgrp = warp >> 2;
+      const int row = q * 32 + lane;
+      const bool tiled = P.out_layout != KGDET_LAYOUT_NCHW;
+      const bool split = P.out_layout == KGDET_LAYOUT_TILED_SPLIT;
+      const int nslab = BN >> 6;
+      const int m_tiles = (P.M + BM - 1) / BM;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int mh = m0 + h * BM;
+        if ((mh >> 7) >= m_tiles) break;                      // odd number of 128-row tiles: the last half is empty
+        const int m = mh + row;
+        const bool row_ok = m < P.M;
+        const int n = row_ok ? m / P.HoWo : 0;
+        const int pos = row_ok ? m - n * P.HoWo : 0;
+        const uint32_t acc_base = tmem_base + (uint32_t)(h * gp.tmem_cols);
+        for (int col = cgrp * 32; col < BN; col += 32 * (GP_PWARPS / 4)) {
+          uint32_t acc[32];
+          tmem_ld32(acc_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
+          tmem_ld_wait();
+          if (tiled) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float x[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                x[e] = __uint_as_float(acc[j + e]);
+                if (P.bias) x[e] += __ldg(P.bias + col + j + e);
+                if (P.relu) x[e] = fmaxf(x[e], 0.f);
+              }
+              const int c = col + j;
+              unsigned char* dst = smem + (size_t)(c >> 6) * A_TILE_BYTES + row * 128 + ((((c & 63) >> 3) ^ (row & 7)) << 4);
+              uint4 hi4;
+              hi4.x = pack_bf16x2(x[0], x[1]); hi4.y = pack_bf16x2(x[2], x[3]);
+              hi4.z = pack_bf16x2(x[4], x[5]); hi4.w = pack_bf16x2(x[6], x[7]);
+              *reinterpret_cast<uint4*>(dst) = hi4;
+              if (split) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] -= __bfloat162float(__float2bfloat16(x[e]));
+                uint4 lo4;
+                lo4.x = pack_bf16x2(x[0], x[1]); lo4.y = pack_bf16x2(x[2], x[3]);
+                lo4.z = pack_bf16x2(x[4], x[5]); lo4.w = pack_bf16x2(x[6], x[7]);
+                *reinterpret_cast<uint4*>(dst + (size_t)nslab * A_TILE_BYTES) = lo4;
+              }
+            }
+          } else if (row_ok) {
+            if (P.out_dtype == KGDET_F32) {
+              float* obase = reinterpret_cast<float*>(P.out) + ((size_t)n * P.out_ctot + P.out_coff) * P.HoWo + pos;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(acc[j]);
+                if (P.bias) x += __ldg(P.bias + col + j);
+                if (P.relu) x = fmaxf(x, 0.f);
+                obase[(size_t)(col + j) * P.HoWo] = x;
+              }
+            } else {
+              __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(P.out) + ((size_t)n * P.out_ctot + P.out_coff) * P.HoWo + pos;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(acc[j]);
+                if (P.bias) x += __ldg(P.bias + col + j);
+                if (P.relu) x = fmaxf(x, 0.f);
+                obase[(size_t)(col + j) * P.HoWo] = __float2bfloat16(x);
+              }
+            }
+          }
+        }
+        if (tiled) {
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, %0;" ::"n"(GP_PWARPS * 32) : "memory");
+          if (warp == 0 && lane == 0) {
+            const int kblocks = (split ? 2 : 1) * (P.out_ctot >> 6);
+            unsigned char* tbase = reinterpret_cast<unsigned char*>(P.out) + (size_t)(mh >> 7) * kblocks * A_TILE_BYTES +
+                                   (size_t)(P.out_coff >> 6) * A_TILE_BYTES;
+            for (int sl = 0; sl < nslab; ++sl) {
+              gp_bulk_s2g(tbase + (size_t)sl * A_TILE_BYTES, smem + (size_t)sl * A_TILE_BYTES, A_TILE_BYTES);
+              if (split)
+                gp_bulk_s2g(tbase + (size_t)((P.out_ctot >> 6) + sl) * A_TILE_BYTES,
+                            smem + (size_t)(nslab + sl) * A_TILE_BYTES, A_TILE_BYTES);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          // the staging area is rewritten by the second half / refilled by the next tile
+          asm volatile("bar.sync 1, %0;" ::"n"(GP_PWARPS * 32) : "memory");
+        }
+      }
+      tc_fence_before();
+    }
+
+    if (threadIdx.x == GP_PWARPS * 32) *next_tile = atomicAdd(gp.counter, 1);
+    __syncthreads();
+    tc_fence_after();
+    tile = *next_tile;
+    step_base += nsteps;
+    kb_base += nkb;
+    ++tile_count;
+    __syncthreads();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (is_control) tmem_dealloc(tmem_base, 2 * gp.tmem_cols);
+}
+
+static size_t group256_smem_bytes(int Cout) {
+  return 1024 + (size_t)G2_NA * A_TILE_BYTES + (size_t)G2_NB * Cout * 128 + (2 * G2_NA + 2 * G2_NB + 1) * 8 + 32;
+}
+
 static size_t group_smem_bytes(int Cout) {
   return 1024 + (size_t)GP_NS * (A_TILE_BYTES + (size_t)Cout * 128) + (2 * GP_NS + 1) * 8 + 32;
 }
 
-int umma_group_forward(GroupParams& gp, cudaStream_t stream) {
+int umma_group_forward(GroupParams& gp, cudaStream_t stream, bool rows256) {
+  if (rows256) {
+    // staging of one half's tiled split output (hi + lo slabs) must fit the two rings
+    const size_t smem2 = group256_smem_bytes(gp.Cout);
+    KG_CUDA(cudaFuncSetAttribute(dcn_umma_group256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    KG_CUDA(cudaMemsetAsync(gp.counter, 0, sizeof(int), stream));
+    const int grid2 = gp.total_tiles < num_sms() ? gp.total_tiles : num_sms();
+    dcn_umma_group256_kernel<<<grid2, GP_THREADS, smem2, stream>>>(gp);
+    KG_LAUNCH_CHECK("dcn_umma_group256_kernel");
+    return KGDET_OK;
+  }
   const size_t smem = group_smem_bytes(gp.Cout);
   if (smem > 227 * 1024) {
     set_error("dcn group: tile does not fit shared memory");
@@ -414,6 +686,10 @@ extern "C" int kgdet_dcn_forward_prepared_group(const kgdet_dcn_group_item* item
   GroupParams gp;
   gp.nprob = count;
   gp.counter = (int*)workspace;
+  // 256-row tiles (two halves sharing every weight slab) when the group is big enough to keep every SM busy with
+  // them and Cout = 256 (the staging of one half's [hi | lo] output needs the 128 KB of the two rings)
+  bool rows256 = true;
+  if (const char* e = getenv("KGDET_GROUP_ROWS")) rows256 = atoi(e) != 128;
   // longest problems first: the scheduler hands tiles out in global tile order
   int order[KGDET_DCN_GROUP_MAX];
   DcnGeom geoms[KGDET_DCN_GROUP_MAX];
@@ -460,6 +736,14 @@ extern "C" int kgdet_dcn_forward_prepared_group(const kgdet_dcn_group_item* item
     P.tile_begin = tiles;
     tiles += ceil_div(g.M, BM);
   }
+  if (geoms[0].Cout != 256 || ceil_div(tiles, 2) < 2 * num_sms()) rows256 = false;
+  if (rows256) {
+    tiles = 0;
+    for (int k = 0; k < count; ++k) {
+      gp.prob[k].tile_begin = tiles;
+      tiles += ceil_div(geoms[order[k]].M, 2 * BM);
+    }
+  }
   for (int k = count; k < KGDET_DCN_GROUP_MAX; ++k) gp.prob[k] = gp.prob[count - 1];
   gp.total_tiles = tiles;
   gp.Cout = geoms[0].Cout;
@@ -471,7 +755,7 @@ extern "C" int kgdet_dcn_forward_prepared_group(const kgdet_dcn_group_item* item
   cudaEvent_t ev0 = g_group_prof_start, ev1 = g_group_prof_stop;
   g_group_prof_start = g_group_prof_stop = nullptr;
   if (ev0 && ev1) KG_CUDA(cudaEventRecord(ev0, stream));
-  int rc = umma_group_forward(gp, stream);
+  int rc = umma_group_forward(gp, stream, rows256);
   if (rc == KGDET_OK && ev0 && ev1) KG_CUDA(cudaEventRecord(ev1, stream));
   return rc;
 }

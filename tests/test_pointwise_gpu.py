@@ -221,3 +221,65 @@ def test_grouped_dcn_launch_equals_single_launches():
         assert (out_g != -3.0).all()
     finally:
         ops.set_precision(None)
+
+
+def test_grouped_dcn_256_row_tiles_equal_128_row_tiles_full_size(monkeypatch):
+    """The KGDet stage at its full size (batch 16, 25x42, six deformable convolutions, 792 tiles): the grouped kernel's
+    256-row tiles (two halves sharing every weight slab, two TMEM accumulators; the default for big groups) give bit
+    for bit what its 128-row tiles and the single launches give.  M = 16 800 = 65.6 pairs: ragged last pair."""
+    from kgdet_b200 import ops
+    g = torch.Generator().manual_seed(23)
+    N, C, H, W, F = 16, 256, 25, 42, 256
+    xa = torch.randn(N, C, H, W, generator=g).cuda()
+    xb = torch.randn(N, C, H, W, generator=g).cuda()
+    pts = (torch.randn(N, 166, H, W, generator=g) * 2).cuda()
+    ws = {(br, k): (torch.randn(F, C, k, k, generator=g) * (1.0 / (C * k * k) ** 0.5)).cuda()
+          for br in 'ab' for k in (3, 5, 7)}
+    ops.set_precision('bf16')
+    try:
+        pa, pb = ops.prepare_input(xa, F), ops.prepare_input(xb, F)
+        plans, lo = {}, 0
+        for k in (3, 5, 7):
+            plans[k] = ops.prepare_plan_points(pts, lo, (N, C, H, W), F, k, 1, k // 2, 1, gradient_mul=0.1)
+            lo += 2 * k * k
+
+        def run(mode):
+            rows = {br: ops.TiledRows(N * H * W, 3 * F, True, 'cuda') for br in 'ab'}
+            for r in rows.values():
+                r.buf.zero_()
+            jobs = []
+            for i, k in enumerate((3, 5, 7)):
+                jobs.append((pa, plans[k], ws[('a', k)], rows['a'], i * F, True))
+                jobs.append((pb, plans[k], ws[('b', k)], rows['b'], i * F, True))
+            jobs.reverse()
+            if mode == 'single':
+                for j in jobs:
+                    ops.deform_conv_prepared(*j)
+            else:
+                monkeypatch.setenv('KGDET_GROUP_ROWS', mode)
+                ops.deform_conv_prepared_group(jobs)
+            torch.cuda.synchronize()
+            return rows
+        single, g128, g256 = run('single'), run('128'), run('256')
+        for br in 'ab':
+            assert torch.equal(single[br].buf, g128[br].buf)
+            assert torch.equal(single[br].buf, g256[br].buf)
+        # an odd number of 128-row tiles (N = 15: 15 750 positions = 123.05 tiles -> 124, 62 pairs exactly; N = 13: 107 tiles)
+        for n_img in (13,):
+            xs = xa[:n_img].contiguous()
+            pin = ops.prepare_input(xs, F)
+            pl = {k: ops.prepare_plan_points(pts[:n_img].contiguous(), 0 if k == 3 else (18 if k == 5 else 68),
+                                             (n_img, C, H, W), F, k, 1, k // 2, 1) for k in (3, 5, 7)}
+            outs = []
+            for mode in ('128', '256'):
+                monkeypatch.setenv('KGDET_GROUP_ROWS', mode)
+                rows = ops.TiledRows(n_img * H * W, 6 * F, True, 'cuda')
+                rows.buf.zero_()
+                jobs = [(pin, pl[k], ws[(br, k)], rows, (i * 2 + j) * F, True)
+                        for i, k in enumerate((7, 5, 3)) for j, br in enumerate('ab')]
+                ops.deform_conv_prepared_group(jobs)
+                torch.cuda.synchronize()
+                outs.append(rows.buf.clone())
+            assert torch.equal(outs[0], outs[1])
+    finally:
+        ops.set_precision(None)
