@@ -485,7 +485,7 @@ def run_ours(args):
                                  'tiles (+bias+ReLU), 6 sample plans, 2 grouped persistent tcgen05 DCN launches (6 deformable convolutions each), 6 pointwise tcgen05 GEMMs, 3 moment, 3 '
                                  'decode (select / decode / finalize), 1 batched NMS, 1 top-k; no library (cuDNN / cuBLAS) kernel'
                                  % launches_per_step,
-            'roofline': {'kernel': ('dcn_umma_group_kernel (fused bilinear gather + tcgen05 GEMM, persistent: the six deformable '
+            'roofline': {'kernel': ('dcn_umma_group256_kernel (fused bilinear gather + tcgen05 GEMM, persistent, 256-row tiles: the six deformable '
                                     'convolutions of a stage per launch), 2 launches/step') if grouped else
                                    'dcn_umma_stream_kernel (fused bilinear gather + tcgen05 GEMM), 12 launches/step',
                          'bound': 'tensor', 'achieved': round(achieved, 1), 'peak': peak_tf, 'unit': 'TFLOP/s',
