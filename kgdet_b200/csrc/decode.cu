@@ -32,15 +32,18 @@ __device__ __forceinline__ unsigned int rank_key(float v) {
 
 __global__ void __launch_bounds__(256) bbox_select_kernel(const float* __restrict__ scores, int apply_sigmoid, int C,
                                                           int HW, int n, int* __restrict__ order) {
-  extern __shared__ unsigned int skey[];        // [HW] rank keys of the per-position maxima
+  extern __shared__ __align__(16) unsigned int skey[];        // [HW rounded up to 4] rank keys of the per-position maxima
   const int b = blockIdx.y;
   const float* sb = scores + (size_t)b * C * HW;
-  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
-    unsigned int m = 0u;                        // below rank_key(-inf)
-    for (int c = 0; c < C; ++c) {
-      float v = sb[(size_t)c * HW + p];
-      if (apply_sigmoid) v = sigmoid_ref(v);
-      m = max(m, rank_key(v));                  // NaN propagates, like torch.max
+  const int HW4 = (HW + 3) & ~3;
+  for (int p = threadIdx.x; p < HW4; p += blockDim.x) {
+    unsigned int m = 0u;                        // below rank_key(-inf); the padding keys never outrank a real one
+    if (p < HW) {
+      for (int c = 0; c < C; ++c) {
+        float v = sb[(size_t)c * HW + p];
+        if (apply_sigmoid) v = sigmoid_ref(v);
+        m = max(m, rank_key(v));                // NaN propagates, like torch.max
+      }
     }
     skey[p] = m;
   }
@@ -53,9 +56,12 @@ __global__ void __launch_bounds__(256) bbox_select_kernel(const float* __restric
   }
   const unsigned int mine = skey[p];
   int rank = 0;
-  for (int j = 0; j < HW; ++j) {
-    const unsigned int o = skey[j];
-    rank += (o > mine || (o == mine && j < p)) ? 1 : 0;
+  for (int j = 0; j < HW4; j += 4) {            // four keys per shared-memory load
+    const uint4 o = *reinterpret_cast<const uint4*>(skey + j);
+    rank += (o.x > mine || (o.x == mine && j < p)) ? 1 : 0;
+    rank += (o.y > mine || (o.y == mine && j + 1 < p)) ? 1 : 0;
+    rank += (o.z > mine || (o.z == mine && j + 2 < p)) ? 1 : 0;
+    rank += (o.w > mine || (o.w == mine && j + 3 < p)) ? 1 : 0;
   }
   if (rank < n) order[(size_t)b * n + rank] = p;
 }
@@ -209,7 +215,7 @@ extern "C" int kgdet_bbox_select(const float* scores, int apply_sigmoid, int32_t
   KG_CHECK_ARG(B >= 0 && C >= 1 && HW >= 1 && n >= 1 && n <= HW, "kgdet_bbox_select: bad sizes");
   KG_CHECK_ARG(HW <= 16384 && B <= 65535, "kgdet_bbox_select: at most 16384 positions per image and level");
   if (B == 0) return KGDET_OK;
-  const size_t smem = (size_t)HW * sizeof(float);
+  const size_t smem = (size_t)(HW + 4) * sizeof(float);
   KG_CUDA(cudaFuncSetAttribute(bbox_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   bbox_select_kernel<<<dim3(ceil_div(HW, 256), B), 256, smem, (cudaStream_t)stream>>>(scores, apply_sigmoid, C, HW, n,
                                                                                      order);

@@ -443,7 +443,10 @@ extern "C" int kgdet_nms_batched(const float* dets, const int32_t* seg_offsets, 
   size_t smem = small_smem_bytes(P_cap);
   KG_CUDA(cudaFuncSetAttribute(nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
-  nms_small_kernel<<<nseg, kSmallThreads, smem, stream>>>(dets, seg_offsets, seg_offsets ? 0 : max_seg_len,
+  // more segments than SMs (a KGDet batch: 16 images x 13 classes = 208): 512-thread CTAs so that two fit an SM and
+  // the launch is ONE wave (1024-thread CTAs, one per SM, ran two waves for 208 segments)
+  const int threads = (nseg > num_sms() && max_seg_len <= 2048) ? 512 : kSmallThreads;
+  nms_small_kernel<<<nseg, threads, smem, stream>>>(dets, seg_offsets, seg_offsets ? 0 : max_seg_len,
                                                           iou_thr, cmp_mode == KGDET_NMS_GE, score_thr,
                                                           keep_flags, P_cap);
   KG_LAUNCH_CHECK("nms_small_kernel(batched)");
