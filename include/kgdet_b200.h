@@ -172,7 +172,9 @@ KGDET_API int kgdet_topk_flagged(const float* dets, const uint8_t* flags, int32_
  * (core/post_processing/bbox_nms_kp.py:6-75) for ONE head level, batched over images, static shapes:
  *   select   order[b, r] = position of the r-th largest max-over-classes score (topk(nms_pre), KP3:863-874;
  *            ties by ascending position; identity when n == HW).  scores: [B, C, HW] logits
- *            (apply_sigmoid = 1) or probabilities.
+ *            (apply_sigmoid = 1) or probabilities.  HW <= 4096: ranks by counting; larger levels (the FPN
+ *            levels of reppoints_head_kp_parallel.py:703-713; HW <= 40960, n <= 4096): three-pass radix select
+ *            + ranks inside the n selected, one CTA per image -- the same order, bit for bit.
  *   decode   boxes [B, n, 4] = clamp(bbox * stride + centre) (KP3:875-886) and the dense NMS input
  *            dets [B, C, n, 5] for kgdet_nms_batched (one segment per (image, class)).  img_wh: [B, 2].
  *   finalize for top_i [B, k] (= class * n + candidate, from a top-k over the NMS-masked scores, top_s <= 0 =
@@ -216,6 +218,18 @@ KGDET_API int kgdet_conv_forward(const void* planes, const void* weight_packed, 
 KGDET_API int kgdet_groupnorm_relu_nhwc_planes(const float* x, const float* gamma, const float* beta, float eps,
                                      int32_t groups, int fuse_relu, float* y, void* planes, int32_t N, int32_t H,
                                      int32_t W, int32_t C, void* stream);
+
+/* GroupNorm (+ ReLU) of NHWC fp32 maps of ANY size (the resident kernels above need the map in shared memory:
+ * <= 1600 positions): two streaming passes (per-chunk moments merged with Chan's update in chunk order, then
+ * normalise).  y (NHWC fp32) and / or planes may be NULL (not both); planes_hi_only != 0 writes only the hi half
+ * (= the fused deformable convolution's prepared input, kgdet_dcn_prepared_input_bytes).
+ * replaces  ConvModule's norm + activation   mmdet/models/utils/conv_module.py:96-110,156-164 on the FPN levels of
+ *           reppoints_head_kp_parallel.py:115-145 / reppoints_head_kp_serial.py:115-145 */
+KGDET_API size_t kgdet_groupnorm_stream_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t groups);
+KGDET_API int kgdet_groupnorm_relu_nhwc_stream(const float* x, const float* gamma, const float* beta, float eps,
+                                     int32_t groups, int fuse_relu, float* y, void* planes, int planes_hi_only,
+                                     int32_t N, int32_t H, int32_t W, int32_t C, void* workspace,
+                                     size_t workspace_bytes, void* stream);
 
 /* ---- target assignment + the nine training losses of the KGDet head ----------
  * replaces  PointAssigner.assign    mmdet/core/bbox/assigners/point_assigner.py:23-116

@@ -66,6 +66,132 @@ __global__ void __launch_bounds__(256) bbox_select_kernel(const float* __restric
   if (rank < n) order[(size_t)b * n + rank] = p;
 }
 
+// Large levels (FPN P3 / P4 of the RepPoints-Kp heads: 16 800 / 4 200 positions, nms_pre = 1000): counting ranks over
+// all positions is O(HW^2).  One CTA per image instead: (1) keys of the per-position maxima in shared memory,
+// (2) the n-th largest key by a three-pass radix select (11 + 11 + 10 bits, histograms in shared memory),
+// (3) an ordered compaction of the n selected positions (every key above it, then the first positions that equal
+// it -- the same tie rule as above), (4) ranks by counting inside that list, O(n^2).  Same `order` as the kernel
+// above, bit for bit.
+constexpr int kSelThreads = 1024;
+constexpr int kSelMaxHW = 40960;
+constexpr int kSelMaxN = 4096;
+
+__global__ void __launch_bounds__(kSelThreads) bbox_select_radix_kernel(const float* __restrict__ scores,
+                                                                        int apply_sigmoid, int C, int HW, int n,
+                                                                        int* __restrict__ order) {
+  extern __shared__ __align__(16) unsigned int sel_sm[];
+  const int n4 = (n + 3) & ~3;
+  unsigned int* skey = sel_sm;                          // [HW]
+  unsigned int* hist = skey + ((HW + 3) & ~3);          // [2048]
+  unsigned int* lkey = hist + 2048;                     // [n4] keys of the selected positions, ascending position
+  int* lpos = reinterpret_cast<int*>(lkey + n4);        // [n]
+  __shared__ unsigned int s_prefix, s_need;
+  __shared__ int warp_cnt[2][kSelThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* sb = scores + (size_t)b * C * HW;
+  for (int p = tid; p < HW; p += kSelThreads) {
+    unsigned int m = 0u;
+    for (int c = 0; c < C; ++c) {
+      float v = sb[(size_t)c * HW + p];
+      if (apply_sigmoid) v = sigmoid_ref(v);
+      m = max(m, rank_key(v));
+    }
+    skey[p] = m;
+  }
+  for (int i = tid; i < n4; i += kSelThreads) lkey[i] = 0u;     // padding keys never outrank a real one
+  unsigned int prefix = 0u, mask = 0u, need = (unsigned int)n;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0), bits = pass == 2 ? 10 : 11, nb = 1 << bits;
+    for (int i = tid; i < 2048; i += kSelThreads) hist[i] = 0u;
+    __syncthreads();                                  // also: skey complete (first pass)
+    for (int p = tid; p < HW; p += kSelThreads) {
+      const unsigned int k = skey[p];
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & (nb - 1)], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // lane l owns the bins [nb - (l + 1) * per, nb - l * per): lane 0 the largest keys
+      const int per = nb / 32, hi = nb - lane * per;
+      unsigned int sum = 0u;
+      for (int i = 1; i <= per; ++i) sum += hist[hi - i];
+      unsigned int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      unsigned int cum = incl - sum;                  // keys in the bins above mine
+      if (cum < need && need <= incl) {
+        for (int i = 1; i <= per; ++i) {
+          const unsigned int h = hist[hi - i];
+          if (cum + h >= need) {
+            s_prefix = prefix | ((unsigned int)(hi - i) << shift);
+            s_need = need - cum;
+            break;
+          }
+          cum += h;
+        }
+      }
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    need = s_need;
+    mask |= (unsigned int)(nb - 1) << shift;
+  }
+  // prefix = the n-th largest key; `need` positions (>= 1) that equal it are taken, lowest positions first
+  int base_eq = 0, base_sel = 0;
+#pragma unroll 1
+  for (int p0 = 0; p0 < HW; p0 += kSelThreads) {
+    const int p = p0 + tid;
+    const unsigned int k = p < HW ? skey[p] : 0u;
+    const bool gt = p < HW && k > prefix, eq = p < HW && k == prefix;
+    const unsigned int be = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) warp_cnt[0][warp] = __popc(be);
+    __syncthreads();
+    int eq_before = base_eq + __popc(be & ((1u << lane) - 1u)), eq_total = 0;
+    for (int w = 0; w < kSelThreads / 32; ++w) {
+      const int c = warp_cnt[0][w];
+      if (w < warp) eq_before += c;
+      eq_total += c;
+    }
+    const bool take = gt || (eq && eq_before < (int)need);
+    const unsigned int bs = __ballot_sync(0xffffffffu, take);
+    if (lane == 0) warp_cnt[1][warp] = __popc(bs);
+    __syncthreads();
+    int idx = base_sel + __popc(bs & ((1u << lane) - 1u)), sel_total = 0;
+    for (int w = 0; w < kSelThreads / 32; ++w) {
+      const int c = warp_cnt[1][w];
+      if (w < warp) idx += c;
+      sel_total += c;
+    }
+    if (take && idx < n) {
+      lkey[idx] = k;
+      lpos[idx] = p;
+    }
+    base_eq += eq_total;
+    base_sel += sel_total;
+    __syncthreads();                                  // warp_cnt is rewritten by the next chunk
+  }
+  for (int i = tid; i < n; i += kSelThreads) {
+    const unsigned int mine = lkey[i];
+    int rank = 0;
+    for (int j = 0; j < n4; j += 4) {
+      const uint4 o = *reinterpret_cast<const uint4*>(lkey + j);
+      rank += (o.x > mine || (o.x == mine && j < i)) ? 1 : 0;
+      rank += (o.y > mine || (o.y == mine && j + 1 < i)) ? 1 : 0;
+      rank += (o.z > mine || (o.z == mine && j + 2 < i)) ? 1 : 0;
+      rank += (o.w > mine || (o.w == mine && j + 3 < i)) ? 1 : 0;
+    }
+    order[(size_t)b * n + rank] = lpos[i];
+  }
+}
+
+__global__ void iota_rows_kernel(int* __restrict__ order, int HW) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < HW) order[(size_t)blockIdx.y * HW + p] = p;
+}
+
 // ---- 2. decode the candidates: boxes [B, n, 4] and the dense NMS input dets [B, C, n, 5] ---------------------
 __global__ void bbox_decode_kernel(const float* __restrict__ scores, int apply_sigmoid, const float* __restrict__ bbox,
                                    const int* __restrict__ order, const float* __restrict__ lim /*[B,2]: w,h*/,
@@ -213,8 +339,23 @@ extern "C" int kgdet_bbox_select(const float* scores, int apply_sigmoid, int32_t
                                  int32_t n, int32_t* order, void* stream) {
   KG_CHECK_ARG(scores && order, "kgdet_bbox_select: NULL pointer");
   KG_CHECK_ARG(B >= 0 && C >= 1 && HW >= 1 && n >= 1 && n <= HW, "kgdet_bbox_select: bad sizes");
-  KG_CHECK_ARG(HW <= 16384 && B <= 65535, "kgdet_bbox_select: at most 16384 positions per image and level");
+  KG_CHECK_ARG(B <= 65535, "kgdet_bbox_select: batch too large");
   if (B == 0) return KGDET_OK;
+  if (n == HW) {                                 // no top-k in the reference: original order
+    iota_rows_kernel<<<dim3(ceil_div(HW, 256), B), 256, 0, (cudaStream_t)stream>>>(order, HW);
+    KG_LAUNCH_CHECK("iota_rows_kernel");
+    return KGDET_OK;
+  }
+  KG_CHECK_ARG(HW <= 16384 || (HW <= kSelMaxHW && n <= kSelMaxN),
+               "kgdet_bbox_select: at most %d positions per image and level (%d candidates) -- or 16384 positions",
+               kSelMaxHW, kSelMaxN);
+  if (HW > 4096 && n <= kSelMaxN) {
+    const size_t smem = ((size_t)((HW + 3) & ~3) + 2048 + (size_t)((n + 3) & ~3) + (size_t)n) * 4;
+    KG_CUDA(cudaFuncSetAttribute(bbox_select_radix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bbox_select_radix_kernel<<<B, kSelThreads, smem, (cudaStream_t)stream>>>(scores, apply_sigmoid, C, HW, n, order);
+    KG_LAUNCH_CHECK("bbox_select_radix_kernel");
+    return KGDET_OK;
+  }
   const size_t smem = (size_t)(HW + 4) * sizeof(float);
   KG_CUDA(cudaFuncSetAttribute(bbox_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   bbox_select_kernel<<<dim3(ceil_div(HW, 256), B), 256, smem, (cudaStream_t)stream>>>(scores, apply_sigmoid, C, HW, n,

@@ -154,6 +154,168 @@ static int launch_groupnorm_wide(const float* x, const float* gamma, const float
   return KGDET_OK;
 }
 
+// ---- maps that do not fit shared memory (FPN levels P3 / P4 of the RepPoints-Kp heads: 16 800 / 4 200 positions) ----
+// Two streaming passes over chunks of GS_CHUNK positions x all C channels (full 4 C-byte rows, coalesced):
+//   pass 1  per (image, chunk, group): count, mean and sum of squared deviations of the chunk, exactly (the chunk's
+//           values sit in registers: mean first, then deviations), threads merged with Chan's pairwise update;
+//   pass 2  every CTA merges the chunk statistics of its image in chunk order (deterministic), then normalises its
+//           chunk (+ ReLU) into NHWC fp32 and / or split planes.
+// 3 x 4 bytes per value of HBM traffic instead of the 2 x 4 of the resident kernels above.
+constexpr int GS_THREADS = 512;                 // 16 float4 values per thread stay in registers (no spills)
+constexpr int GS_SWEEPS = 16;                     // float4 values per thread per chunk
+
+struct Moments { float n, mean, m2; };
+
+__device__ __forceinline__ Moments merge_moments(Moments a, Moments b) {
+  const float n = a.n + b.n;
+  if (n == 0.f) return a;
+  const float d = b.mean - a.mean, f = b.n / n;
+  Moments r;
+  r.n = n;
+  r.mean = fmaf(d, f, a.mean);
+  r.m2 = a.m2 + b.m2 + d * d * a.n * f;
+  return r;
+}
+
+__global__ void __launch_bounds__(GS_THREADS) groupnorm_stream_stats_kernel(const float* __restrict__ x, int HW, int C,
+                                                                             int cpg, float* __restrict__ partial) {
+  extern __shared__ float red[];                  // [rows][groups][3]
+  const int L = C >> 2, rows = GS_THREADS / L, chunk_px = rows * GS_SWEEPS;
+  const int n = blockIdx.y, chunk = blockIdx.x, groups = C / cpg;
+  const int col = threadIdx.x % L, row = threadIdx.x / L;
+  const int p0 = chunk * chunk_px + row;
+  const float* xg = x + (size_t)n * HW * C + col * 4;
+  float4 v[GS_SWEEPS];
+  int cnt = 0;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < GS_SWEEPS; ++i) {
+    const int p = p0 + i * rows;
+    if (p < HW) {
+      v[i] = *reinterpret_cast<const float4*>(xg + (size_t)p * C);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      ++cnt;
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  Moments m;
+  m.n = 4.f * (float)cnt;
+  m.mean = cnt ? s / m.n : 0.f;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < GS_SWEEPS; ++i) {
+    if (i < cnt) {                                // valid sweeps are the first `cnt` (p grows with i)
+      const float d0 = v[i].x - m.mean, d1 = v[i].y - m.mean, d2 = v[i].z - m.mean, d3 = v[i].w - m.mean;
+      ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
+    }
+  }
+  m.m2 = ss;
+  // lanes of one group are adjacent (cpg / 4 of them, a power of two, inside one warp)
+  for (int o = 1; o < (cpg >> 2); o <<= 1) {
+    Moments b;
+    b.n = __shfl_xor_sync(0xffffffffu, m.n, o);
+    b.mean = __shfl_xor_sync(0xffffffffu, m.mean, o);
+    b.m2 = __shfl_xor_sync(0xffffffffu, m.m2, o);
+    m = (threadIdx.x & o) ? merge_moments(b, m) : merge_moments(m, b);   // same operand order on both lanes
+  }
+  const int g = (col * 4) / cpg;
+  if ((col * 4) % cpg == 0) {
+    float* r = red + ((size_t)row * groups + g) * 3;
+    r[0] = m.n; r[1] = m.mean; r[2] = m.m2;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < groups) {
+    Moments a;
+    a.n = red[threadIdx.x * 3]; a.mean = red[threadIdx.x * 3 + 1]; a.m2 = red[threadIdx.x * 3 + 2];
+    for (int r = 1; r < rows; ++r) {
+      Moments b;
+      const float* q = red + ((size_t)r * groups + threadIdx.x) * 3;
+      b.n = q[0]; b.mean = q[1]; b.m2 = q[2];
+      a = merge_moments(a, b);
+    }
+    float* out = partial + (((size_t)n * gridDim.x + chunk) * groups + threadIdx.x) * 3;
+    out[0] = a.n; out[1] = a.mean; out[2] = a.m2;
+  }
+}
+
+__global__ void __launch_bounds__(GS_THREADS) groupnorm_stream_apply_kernel(
+    const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+    const float* __restrict__ partial, float* __restrict__ y, int HW, int C, int cpg, int relu,
+    unsigned char* __restrict__ hi, unsigned char* __restrict__ lo, size_t plane_bytes) {
+  __shared__ float stat[2][256];                  // mean, rstd per group (C / cpg <= 256)
+  const int L = C >> 2, rows = GS_THREADS / L, chunk_px = rows * GS_SWEEPS;
+  const int n = blockIdx.y, chunk = blockIdx.x, groups = C / cpg;
+  // one warp per group: lane l merges chunks l, l + 32, ... in order, then a fixed xor tree (lower lane first) --
+  // the same order in every CTA, so every CTA of the image normalises with bit-identical statistics
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nchunks = (int)gridDim.x;
+    for (int g = warp; g < groups; g += GS_THREADS / 32) {
+      const float* q = partial + ((size_t)n * nchunks * groups + g) * 3;
+      Moments a;
+      a.n = 0.f; a.mean = 0.f; a.m2 = 0.f;
+      for (int c = lane; c < nchunks; c += 32) {
+        const float* r = q + (size_t)c * groups * 3;
+        Moments b;
+        b.n = r[0]; b.mean = r[1]; b.m2 = r[2];
+        a = merge_moments(a, b);
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        Moments b;
+        b.n = __shfl_xor_sync(0xffffffffu, a.n, o);
+        b.mean = __shfl_xor_sync(0xffffffffu, a.mean, o);
+        b.m2 = __shfl_xor_sync(0xffffffffu, a.m2, o);
+        a = (lane & o) ? merge_moments(b, a) : merge_moments(a, b);
+      }
+      if (lane == 0) {
+        stat[0][g] = a.mean;
+        stat[1][g] = rsqrtf(a.m2 / a.n + eps);
+      }
+    }
+  }
+  __syncthreads();
+  const int col = threadIdx.x % L, row = threadIdx.x / L, c0 = col * 4;
+  const float mean = stat[0][c0 / cpg], rstd = stat[1][c0 / cpg];
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
+  const float* xg = x + (size_t)n * HW * C + c0;
+  float* yg = y ? y + (size_t)n * HW * C + c0 : nullptr;
+  const size_t poff = (size_t)(c0 >> 6) * plane_bytes + (size_t)n * HW * 128 + (size_t)(c0 & 63) * 2;
+#pragma unroll 4
+  for (int i = 0; i < GS_SWEEPS; ++i) {
+    const int p = chunk * chunk_px + row + i * rows;
+    if (p >= HW) break;
+    const float4 v = *reinterpret_cast<const float4*>(xg + (size_t)p * C);
+    float4 o;
+    o.x = (v.x - mean) * rstd * ga.x + be.x;
+    o.y = (v.y - mean) * rstd * ga.y + be.y;
+    o.z = (v.z - mean) * rstd * ga.z + be.z;
+    o.w = (v.w - mean) * rstd * ga.w + be.w;
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (yg) *reinterpret_cast<float4*>(yg + (size_t)p * C) = o;
+    if (hi) {
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - __low2float(h0), o.y - __high2float(h0));
+      const __nv_bfloat162 l1 = __floats2bfloat162_rn(o.z - __low2float(h1), o.w - __high2float(h1));
+      uint2 hv, lv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+      lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(hi + poff + (size_t)p * 128) = hv;
+      if (lo) *reinterpret_cast<uint2*>(lo + poff + (size_t)p * 128) = lv;
+    }
+  }
+}
+
+static bool stream_gn_supported(int C, int groups) {
+  if (C <= 0 || groups <= 0 || C % groups) return false;
+  const int cpg = C / groups, L = C / 4;
+  return (C % 128 == 0) && L <= GS_THREADS && GS_THREADS % L == 0 && cpg % 4 == 0 && cpg <= 128 &&
+         ((cpg / 4) & (cpg / 4 - 1)) == 0 && groups <= 256;
+}
+
+static int stream_gn_chunks(int HW, int C) { return ceil_div(HW, (GS_THREADS / (C / 4)) * GS_SWEEPS); }
+
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&v);
@@ -323,4 +485,51 @@ extern "C" int kgdet_groupnorm_relu_nhwc_planes(const float* x, const float* gam
   }
   set_error("kgdet_groupnorm_relu_nhwc_planes: unsupported channels per group %d", C / groups);
   return KGDET_ERR_UNSUPPORTED;
+}
+
+// GroupNorm (+ ReLU) of NHWC fp32 maps of ANY size, streaming (two passes, see groupnorm_stream_*_kernel): y (NHWC
+// fp32) and / or `planes` (split planes as above; with `planes_hi_only` just the hi half = the DCN prepared input,
+// kgdet_dcn_prepared_input_bytes) may be NULL, not both.  `workspace`: kgdet_groupnorm_stream_workspace_bytes bytes.
+// Reference: torch.nn.GroupNorm inside mmdet ConvModule (conv_module.py:96-110,156-164), as used by the towers of
+// reppoints_head_kp_parallel.py:115-145.
+extern "C" size_t kgdet_groupnorm_stream_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t groups) {
+  if (N <= 0 || HW <= 0 || !stream_gn_supported(C, groups)) return 0;
+  return (size_t)N * stream_gn_chunks(HW, C) * groups * 3 * sizeof(float);
+}
+
+extern "C" int kgdet_groupnorm_relu_nhwc_stream(const float* x, const float* gamma, const float* beta, float eps,
+                                                int32_t groups, int fuse_relu, float* y, void* planes, int planes_hi_only,
+                                                int32_t N, int32_t H, int32_t W, int32_t C, void* workspace,
+                                                size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  KG_CHECK_ARG(x && gamma && beta && (y || planes) && workspace, "kgdet_groupnorm_relu_nhwc_stream: NULL pointer");
+  KG_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && stream_gn_supported(C, groups),
+               "kgdet_groupnorm_relu_nhwc_stream: need C %% 128 == 0, C <= 4096 and a power-of-two multiple of 4 channels per group");
+  const int HW = H * W;
+  KG_CHECK_ARG(workspace_bytes >= kgdet_groupnorm_stream_workspace_bytes(N, HW, C, groups),
+               "kgdet_groupnorm_relu_nhwc_stream: workspace too small");
+  KG_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0 && ((uintptr_t)planes & 255) == 0,
+               "kgdet_groupnorm_relu_nhwc_stream: misaligned pointer");
+  unsigned char *hi = nullptr, *lo = nullptr;
+  size_t plane_bytes = 0;
+  if (planes) {
+    const size_t guard = (size_t)(W + 2) * 128, in_bytes = (size_t)N * HW * 128;
+    plane_bytes = align_up(in_bytes + 2 * guard, 1024);
+    const size_t half = plane_bytes * (C / 64);
+    for (int h = 0; h < (planes_hi_only ? 1 : 2); ++h) {
+      unsigned char* b = (unsigned char*)planes + (size_t)h * half;
+      KG_CUDA(cudaMemset2DAsync(b, plane_bytes, 0, guard, C / 64, stream));
+      KG_CUDA(cudaMemset2DAsync(b + guard + in_bytes, plane_bytes, 0, plane_bytes - guard - in_bytes, C / 64, stream));
+    }
+    hi = (unsigned char*)planes + guard;
+    lo = planes_hi_only ? nullptr : hi + half;
+  }
+  const int cpg = C / groups, chunks = stream_gn_chunks(HW, C), rows = GS_THREADS / (C / 4);
+  const size_t smem = (size_t)rows * groups * 3 * sizeof(float);
+  groupnorm_stream_stats_kernel<<<dim3(chunks, N), GS_THREADS, smem, stream>>>(x, HW, C, cpg, (float*)workspace);
+  KG_LAUNCH_CHECK("groupnorm_stream_stats_kernel");
+  groupnorm_stream_apply_kernel<<<dim3(chunks, N), GS_THREADS, 0, stream>>>(x, gamma, beta, eps, (const float*)workspace, y,
+                                                                           HW, C, cpg, fuse_relu ? 1 : 0, hi, lo, plane_bytes);
+  KG_LAUNCH_CHECK("groupnorm_stream_apply_kernel");
+  return KGDET_OK;
 }

@@ -597,11 +597,14 @@ class RepPointsKpHead(nn.Module):
     def __init__(self, variant='parallel', num_classes=14, in_channels=256, feat_channels=256,
                  point_feat_channels=256, stacked_convs=3, num_reppts=9, num_keypts=294, gradient_mul=0.1,
                  point_strides=(8, 16, 32, 64, 128), moment_mul=0.01, num_groups=32, deform_conv_cls=None,
-                 moment_fn=None):
+                 moment_fn=None, nms_flags_fn=None):
         super().__init__()
         assert variant in ('parallel', 'serial')
         self.variant = variant
         self._fused_inference = deform_conv_cls is None
+        self._fused_decode = True           # get_bboxes: per-level select / decode kernels instead of PyTorch glue
+        self._nms_flags_fn = nms_flags_fn or batched_nms_flags
+        self._lim_cache = {}
         deform_conv_cls = deform_conv_cls or DeformConv
         self._moment_fn = moment_fn or points2bbox_moment
         self.cls_out_channels = num_classes - 1
@@ -624,6 +627,7 @@ class RepPointsKpHead(nn.Module):
             self.reg_convs.append(_ConvGNReLU(chn, feat_channels, num_groups))
         kd, rd, pf = 2 * num_keypts, 2 * num_reppts, point_feat_channels
         self.grouped_dcn = True             # bf16 inference: the DCNs of all levels in grouped persistent launches
+        self.nhwc_towers = True             # ... with position-major towers / 1x1 GEMMs around them (_forward_nhwc)
         self.cls_refine_dfmconv = deform_conv_cls(feat_channels, pf, k, 1, self.dcn_pad)
         self.cls_refine_out = nn.Conv2d(pf, self.cls_out_channels, 1, 1, 0)
         self.keypts_init_conv = nn.Conv2d(feat_channels, pf, 3, 1, 1)
@@ -694,9 +698,114 @@ class RepPointsKpHead(nn.Module):
     def forward(self, feats):
         if (self._fused_inference and self.grouped_dcn and not torch.is_grad_enabled() and feats[0].is_cuda
                 and get_precision(feats[0].dtype) == 'bf16' and feats[0].dtype == torch.float32):
+            if self.nhwc_towers and self._nhwc_supported():
+                return self._forward_nhwc(feats)
             return self._forward_grouped(feats)
         outs = [self.forward_single(x) for x in feats]
         return tuple(map(list, zip(*outs)))
+
+    def _nhwc_supported(self):
+        gns = [m.gn for m in list(self.cls_convs) + list(self.reg_convs)]
+        pf = self.cls_refine_dfmconv.out_channels
+        return (all(g.num_channels % 128 == 0 and g.num_channels // g.num_groups in (4, 8, 16, 32) for g in gns)
+                and pf % 64 == 0 and self.cls_refine_dfmconv.in_channels % 64 == 0)
+
+    def _head_weights(self):
+        """Packed operands of the 1x1 convolutions (cached per parameter version).  Serial variant: the point-set
+        convolutions are linear maps of the keypoint outputs (SER:314,330), composed on the host in fp32 so keypoints
+        and point set come out of one GEMM."""
+        names = ['cls_refine_out', 'keypts_init_out', 'keypts_refine_out', 'reppts_init_out', 'reppts_refine_out']
+        ps = tuple(p for n in names for p in (getattr(self, n).weight, getattr(self, n).bias))
+
+        def build():
+            with torch.no_grad():
+                w = {n: getattr(self, n).weight.detach().float().flatten(1) for n in names}
+                b = {n: getattr(self, n).bias.detach().float() for n in names}
+                out = {'cls': (pack_weight(w['cls_refine_out'], split=True), b['cls_refine_out'].contiguous())}
+                for st in ('init', 'refine'):
+                    wk, bk = w['keypts_%s_out' % st], b['keypts_%s_out' % st]
+                    wr, br = w['reppts_%s_out' % st], b['reppts_%s_out' % st]
+                    if self.variant == 'parallel':
+                        out['kpt_' + st] = (pack_weight(wk, split=True), bk.contiguous())
+                        out['rep_' + st] = (pack_weight(wr, split=True), br.contiguous())
+                    else:
+                        out['kpt_rep_' + st] = (pack_weight(torch.cat([wk, wr @ wk], 0), split=True),
+                                                torch.cat([bk, wr @ bk + br], 0).contiguous())
+                return out
+        return cached(ps, build, tag='reppoints_pointwise')
+
+    def _forward_nhwc(self, feats):
+        """bf16 inference with position-major activations end to end (BASELINE.json configs[3] on the fast path):
+
+        * towers: cuDNN 3x3 convolutions in channels_last (no layout transposes) + this library's GroupNorm + ReLU
+          kernel (resident for maps of <= 1600 positions, two streaming passes for P3 / P4); the last tower layer's
+          normalisation writes the deformable stage's prepared bf16 planes directly;
+        * the init branches' ReLU + bias + re-tiling is one kernel, every 1x1 convolution a tcgen05 GEMM of this
+          library at split ("bf16x3") precision whose epilogue adds the refine stage's residual (PAR:337-338);
+        * one sample plan per level straight from the point tensor (PAR:322-325), the deformable convolutions of ALL
+          levels in grouped persistent launches writing ReLU-ed bf16 rows for those GEMMs.
+        Same values as `forward_single` up to the arithmetic of the 1x1 convolutions (fp32-grade here, cuDNN there)."""
+        pf = self.cls_refine_dfmconv.out_channels
+        kd, rd, nc = 2 * self.num_keypts, 2 * self.num_reppts, self.cls_out_channels
+        W = self._head_weights()
+        par = self.variant == 'parallel'
+        last = len(self.cls_convs) - 1
+        per_level, jobs = [], []
+        for x in feats:
+            n, _, h, w = x.shape
+            dev = x.device
+            cls_feat = pts_feat = to_channels_last(x)
+            cls_prep = pts_prep = None
+            for i, m in enumerate(self.cls_convs):
+                y = _conv3x3_nhwc(cls_feat, m.conv)
+                if i == last:
+                    _, cls_prep = groupnorm_relu_nhwc(y, m.gn, dense=False, prepared_for=pf)
+                else:
+                    cls_feat = groupnorm_relu_nhwc(y, m.gn)
+            for i, m in enumerate(self.reg_convs):
+                y = _conv3x3_nhwc(pts_feat, m.conv)
+                if i == last:
+                    pts_feat, pts_prep = groupnorm_relu_nhwc(y, m.gn, prepared_for=pf)
+                else:
+                    pts_feat = groupnorm_relu_nhwc(y, m.gn)
+            c = pts_feat.shape[1]
+            kpt_init = x.new_empty((n, kd, h, w))
+            rep_init = x.new_empty((n, rd, h, w))
+            kpt_rows = nchw_to_tiled(_conv3x3_nhwc(pts_feat, self.keypts_init_conv, False), relu=True, split=True,
+                                     bias=self.keypts_init_conv.bias)
+            if par:
+                pointwise_conv(kpt_rows, W['kpt_init'][0], W['kpt_init'][1], [(kpt_init, None, 0, kd)], h * w)
+                rep_rows = nchw_to_tiled(_conv3x3_nhwc(pts_feat, self.reppts_init_conv, False), relu=True, split=True,
+                                         bias=self.reppts_init_conv.bias)                    # PAR:314-315
+                pointwise_conv(rep_rows, W['rep_init'][0], W['rep_init'][1], [(rep_init, None, 0, rd)], h * w)
+            else:
+                pointwise_conv(kpt_rows, W['kpt_rep_init'][0], W['kpt_rep_init'][1],
+                               [(kpt_init, None, 0, kd), (rep_init, None, kd, kd + rd)], h * w)   # SER:314
+            plan = prepare_plan_points(rep_init, 0, (n, c, h, w), pf, self.dcn_kernel, 1, self.dcn_pad, 1,
+                                       precision='bf16', gradient_mul=self.gradient_mul)       # PAR:322-325
+            rows = [TiledRows(n * h * w, pf, True, dev) for _ in range(3 if par else 2)]
+            jobs.append((cls_prep, plan, self.cls_refine_dfmconv.weight, rows[0], 0, True))
+            jobs.append((pts_prep, plan, self.keypts_refine_dfmconv.weight, rows[1], 0, True))
+            if par:
+                jobs.append((pts_prep, plan, self.reppts_refine_dfmconv.weight, rows[2], 0, True))
+            per_level.append((n, h, w, kpt_init, rep_init, rows))
+        jobs.sort(key=lambda j: -j[3].M)                                           # biggest maps first
+        for i in range(0, len(jobs), 6):
+            deform_conv_prepared_group(jobs[i:i + 6])
+        res = []
+        for n, h, w, kpt_init, rep_init, rows in per_level:
+            cls_out = kpt_init.new_empty((n, nc, h, w))
+            kpt_ref = torch.empty_like(kpt_init)
+            rep_ref = torch.empty_like(rep_init)
+            pointwise_conv(rows[0], W['cls'][0], W['cls'][1], [(cls_out, None, 0, nc)], h * w)
+            if par:
+                pointwise_conv(rows[1], W['kpt_refine'][0], W['kpt_refine'][1], [(kpt_ref, kpt_init, 0, kd)], h * w)
+                pointwise_conv(rows[2], W['rep_refine'][0], W['rep_refine'][1], [(rep_ref, rep_init, 0, rd)], h * w)
+            else:
+                pointwise_conv(rows[1], W['kpt_rep_refine'][0], W['kpt_rep_refine'][1],
+                               [(kpt_ref, kpt_init, 0, kd), (rep_ref, rep_init, kd, kd + rd)], h * w)  # SER:330
+            res.append((cls_out, kpt_init, kpt_ref, rep_init, rep_ref))
+        return tuple(map(list, zip(*res)))
 
     def _forward_grouped(self, feats):
         """bf16 inference over all levels with the deformable convolutions of EVERY level (3 x 5 parallel, 2 x 5
@@ -739,6 +848,99 @@ class RepPointsKpHead(nn.Module):
             rep_ref = self.reppts_refine_out(outs[2]) if self.variant == 'parallel' else self.reppts_refine_out(kpt_ref)
             res.append((cls_out, kpt_init, kpt_ref + kpt_init, rep_init, rep_ref + rep_init))
         return tuple(map(list, zip(*res)))
+
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def get_bboxes(self, cls_scores, keypts_preds_refine, reppts_preds_refine, img_shapes, score_thr=0.05, iou_thr=0.5,
+                   nms_pre=1000, max_per_img=100, score_override=None):
+        """Batched, sync-free form of get_bboxes + get_bboxes_single of the two baseline heads (PAR:615-752, the
+        same lines of SER) + multiclass_nms_kp (core/post_processing/bbox_nms_kp.py:6-75), over ALL levels.
+
+        cls_scores / keypts_preds_refine / reppts_preds_refine: per-level lists ([B,13,H,W], [B,588,H,W],
+        [B,18,H,W]: outputs 0, 2 and 4 of `forward`).  Per level the `nms_pre` best positions are selected and
+        decoded (kgdet_bbox_select / kgdet_bbox_decode on the GPU), the candidates of all levels form one segment
+        per (image, class) for ONE batched NMS launch, and keypoints are decoded only for the `max_per_img`
+        survivors.  The keypoint clamp is this head's own (PAR:721-722 index the keypoint axis: keypoints 0, 3, 6...
+        are limited to the image width in x AND y, keypoints 1, 4, 7... to the height, the others not at all).
+        Returns dets [B, max_per_img, 5], labels [B, max_per_img] (-1 = empty slot), kpts [B, max_per_img, 294*3]."""
+        bbox_preds = [self.points2bbox(r) for r in reppts_preds_refine]                # PAR:628-631
+        B, dev = cls_scores[0].shape[0], cls_scores[0].device
+        key = (tuple(tuple(s[:2]) for s in img_shapes), str(dev))
+        wh = self._lim_cache.get(key)
+        if wh is None:            # built once per (shapes, device): keeps H2D copies out of graph capture
+            wh = torch.tensor([[s[1], s[0]] for s in img_shapes], dtype=torch.float32, device=dev)
+            self._lim_cache[key] = wh
+        fused = (self._fused_decode and cls_scores[0].is_cuda and self._nms_flags_fn is batched_nms_flags
+                 and all(c.shape[-2] * c.shape[-1] <= 40960 for c in cls_scores) and 0 < nms_pre <= 4096)
+        C = cls_scores[0].shape[1]
+        boxes_l, dets_l, pos_l, lvl_of = [], [], [], []
+        for lvl, (cs, bp) in enumerate(zip(cls_scores, bbox_preds)):
+            stride = self.point_strides[lvl]
+            H, W = cs.shape[-2:]
+            n_l = min(nms_pre, H * W) if nms_pre > 0 else H * W
+            src = (cs if score_override is None else score_override[lvl]).float().contiguous()
+            sig = score_override is None
+            if fused:
+                order = bbox_select(src, sig, n_l)
+                boxes, dets = bbox_decode(src, sig, bp.float().contiguous(), order, wh, stride)
+                order = order.long()
+            else:
+                scores = src.reshape(B, C, H * W)
+                scores = scores.sigmoid() if sig else scores
+                if n_l < H * W:                                                         # PAR:703-713
+                    order = scores.max(dim=1)[0].topk(n_l, dim=1)[1]
+                else:
+                    order = torch.arange(H * W, device=dev)[None].expand(B, -1)
+                ctr = torch.stack([(order % W).float() * stride, (order // W).float() * stride], -1)
+                bbox = bp.float().reshape(B, 4, H * W).gather(2, order[:, None].expand(-1, 4, -1)).transpose(1, 2)
+                boxes = bbox * stride + torch.cat([ctr, ctr], -1)                       # PAR:714-716
+                boxes = torch.min(boxes.clamp(min=0), torch.cat([wh, wh], 1)[:, None])  # PAR:723-727
+                sc = scores.gather(2, order[:, None].expand(-1, C, -1))                # [B, C, n_l]
+                dets = torch.cat([boxes[:, None].expand(B, C, n_l, 4), sc[..., None]], -1)
+            boxes_l.append(boxes)
+            dets_l.append(dets)
+            pos_l.append(order)
+            lvl_of.append(torch.full((n_l,), lvl, dtype=torch.long, device=dev))
+        boxes = torch.cat(boxes_l, 1)                                                   # [B, n, 4]
+        dets = torch.cat(dets_l, 2).contiguous()                                        # [B, C, n, 5]
+        pos = torch.cat(pos_l, 1)                                                       # [B, n] position in its level
+        lvl_of = torch.cat(lvl_of)                                                      # [n]
+        n = boxes.shape[1]
+        flags = self._nms_flags_fn(dets.view(-1, 5), None, n, iou_thr, score_thr=score_thr)
+        masked = torch.where(flags.view(B, C * n).bool(), dets[..., 4].reshape(B, C * n), dets.new_full((), -1.0))
+        k = min(max_per_img, C * n)
+        top_s, top_i = masked.topk(k, dim=1)                                            # bbox_nms_kp.py:64-70
+        valid = top_s > 0
+        cls_i, row_i = top_i // n, top_i % n
+        out_boxes = boxes.gather(1, row_i[..., None].expand(-1, -1, 4))
+        out_dets = torch.cat([out_boxes, top_s[..., None]], -1) * valid[..., None]
+        out_labels = torch.where(valid, cls_i, torch.full_like(cls_i, -1))
+        # keypoints of the survivors only: gathered from their level's map
+        p_i = pos.gather(1, row_i)                                                      # [B, k]
+        l_i = lvl_of[row_i]                                                             # [B, k]
+        P = self.num_keypts
+        kp = top_s.new_zeros((B, k, 2 * P))
+        ctr = top_s.new_zeros((B, k, 2))
+        strd = top_s.new_zeros((B, k))
+        for lvl, kmap in enumerate(keypts_preds_refine):
+            H, W = kmap.shape[-2:]
+            here = l_i == lvl
+            pl = torch.where(here, p_i, torch.zeros_like(p_i))
+            v = kmap.float().reshape(B, 2 * P, H * W).gather(2, pl[:, None].expand(-1, 2 * P, -1)).transpose(1, 2)
+            kp = torch.where(here[..., None], v, kp)
+            c_l = torch.stack([(pl % W).float(), (pl // W).float()], -1) * self.point_strides[lvl]
+            ctr = torch.where(here[..., None], c_l, ctr)
+            strd = torch.where(here, torch.full_like(strd, float(self.point_strides[lvl])), strd)
+        kxy = kp.view(B, k, P, 2).flip(-1)                                              # points2kpt: (y, x) -> (x, y)
+        kxy = kxy * strd[..., None, None] + ctr[:, :, None, :]                          # PAR:717-719
+        idx = torch.arange(P, device=dev) % 3
+        w_, h_ = wh[:, 0].view(B, 1, 1, 1), wh[:, 1].view(B, 1, 1, 1)
+        by_w = torch.min(kxy.clamp(min=0), w_)
+        by_h = torch.min(kxy.clamp(min=0), h_)
+        kxy = torch.where((idx == 0).view(1, 1, P, 1), by_w, torch.where((idx == 1).view(1, 1, P, 1), by_h, kxy))
+        out_kpts = (torch.cat([kxy, torch.ones_like(kxy[..., :1])], -1) * valid[..., None, None]).reshape(B, k, -1)
+        return out_dets, out_labels, out_kpts
 
 
 class GraphedForward(object):

@@ -145,19 +145,55 @@ def to_channels_last(x):
     return y
 
 
-def groupnorm_relu_nhwc(x, gn, relu=True):
-    """GroupNorm (+ ReLU) of a channels_last fp32 activation in one kernel; returns a channels_last tensor.
-    `gn` is the torch.nn.GroupNorm module (same parameters and semantics)."""
+def groupnorm_relu_nhwc(x, gn, relu=True, dense=True, prepared_for=None):
+    """GroupNorm (+ ReLU) of a channels_last fp32 activation; returns a channels_last tensor.
+    `gn` is the torch.nn.GroupNorm module (same parameters and semantics).  Maps of up to 1600 positions are
+    normalised by one resident kernel; larger ones (FPN levels P3 / P4) by the two streaming passes.
+
+    prepared_for: out_channels of a following 3x3 deformable convolution -- the streaming kernel then also writes
+    the fused bf16 DCN's PreparedInput (returned second; with dense=False only that is produced and the first result
+    is None)."""
     lib = _capi.lib()
     _capi.require_cuda(x, 'groupnorm_relu_nhwc')
     assert x.dim() == 4 and x.dtype == torch.float32 and x.is_contiguous(memory_format=torch.channels_last)
     n, c, h, w = x.shape
-    y = torch.empty_like(x, memory_format=torch.channels_last)
-    _capi.check(lib.kgdet_groupnorm_relu_nhwc(x.data_ptr(), gn.weight.detach().float().contiguous().data_ptr(),
-                                              gn.bias.detach().float().contiguous().data_ptr(), float(gn.eps),
-                                              int(gn.num_groups), int(bool(relu)), y.data_ptr(), n, h * w, c,
-                                              _capi.stream_of(x)), 'kgdet_groupnorm_relu_nhwc')
-    return y
+    gamma, beta = gn.weight.detach().float().contiguous(), gn.bias.detach().float().contiguous()
+    resident = h * w <= 1600
+    if resident and prepared_for is None:
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        _capi.check(lib.kgdet_groupnorm_relu_nhwc(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(gn.eps),
+                                                  int(gn.num_groups), int(bool(relu)), y.data_ptr(), n, h * w, c,
+                                                  _capi.stream_of(x)), 'kgdet_groupnorm_relu_nhwc')
+        return y
+    ws_bytes = int(lib.kgdet_groupnorm_stream_workspace_bytes(n, h * w, c, int(gn.num_groups)))
+    if ws_bytes == 0:
+        raise ValueError('groupnorm_relu_nhwc: unsupported shape [%d, %d, %d, %d] with %d groups for the streaming '
+                         'kernel' % (n, c, h, w, gn.num_groups))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    y = torch.empty_like(x, memory_format=torch.channels_last) if dense else None
+    prep = None
+    if prepared_for is not None:
+        from .dcn import PreparedInput, _geom_shape, ctypes_ref
+        shape = _geom_shape(n, c, h, w, int(prepared_for), (3, 3), (1, 1), (1, 1), (1, 1))
+        prep = PreparedInput()
+        prep.shape4 = (n, c, h, w)
+        prep.dtype_code = _capi.F32
+        prep.torch_dtype = torch.float32
+        prep.precision = _capi.PREC_BF16
+        prep.fast = bool(lib.kgdet_dcn_fast_path_supported(ctypes_ref(shape), _capi.PREC_BF16))
+        if not prep.fast:
+            raise ValueError('groupnorm_relu_nhwc: the fused deformable convolution does not support this shape')
+        prep.buf = torch.empty(int(lib.kgdet_dcn_prepared_input_bytes(ctypes_ref(shape), _capi.PREC_BF16)),
+                               dtype=torch.uint8, device=x.device)
+        assert prep.buf.numel() * 2 == int(lib.kgdet_conv_split_planes_bytes(n, c, h, w)), 'plane layouts differ'
+    else:
+        assert dense
+    _capi.check(lib.kgdet_groupnorm_relu_nhwc_stream(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(gn.eps),
+                                                     int(gn.num_groups), int(bool(relu)), _capi.ptr(y),
+                                                     None if prep is None else prep.buf.data_ptr(), 1, n, h, w, c,
+                                                     ws.data_ptr(), ws_bytes, _capi.stream_of(x)),
+                'kgdet_groupnorm_relu_nhwc_stream')
+    return y if prepared_for is None else (y, prep)
 
 
 def pointwise_conv(rows, packed_weight, bias, outputs, hw):

@@ -49,4 +49,4 @@ def make_cpu_head(**kwargs):
 def make_cpu_reppoints_head(variant, **kwargs):
     from kgdet_b200.head import RepPointsKpHead
     return RepPointsKpHead(variant, deform_conv_cls=oracle_ops.DeformConv,
-                           moment_fn=moment_oracle.points2bbox_moment, **kwargs)
+                           moment_fn=moment_oracle.points2bbox_moment, nms_flags_fn=cpu_batched_nms_flags, **kwargs)

@@ -181,3 +181,37 @@ def test_reppoints_kp_mirror_matches_reference_head_golden(variant, n_params):
         for n, o in zip(['cls', 'kpt_init', 'kpt_refine', 'rep_init', 'rep_refine'], outs):
             assert rel_err(o, torch.from_numpy(g['%s%d' % (n, li)])) < 1e-5, (n, li)
         assert rel_err(bbox, torch.from_numpy(g['bbox_refine%d' % li])) < 1e-5
+
+
+def check_reppoints_bboxes(g, variant, dets, labels, kpts):
+    """(dets, labels, kpts) of RepPointsKpHead.get_bboxes against tests/golden/reppoints_bboxes.npz."""
+    for i in range(dets.shape[0]):
+        rd, rl = g['%s_dets_%d' % (variant, i)], g['%s_labels_%d' % (variant, i)]
+        rk, rs = g['%s_kpts_head_%d' % (variant, i)], g['%s_kpts_rowsum_%d' % (variant, i)]
+        nv = int((labels[i] >= 0).sum())
+        assert nv == rd.shape[0]
+        # the reference sorts the concatenated per-class survivors by score (bbox_nms_kp.py:64-70); equal scores
+        # keep class order in both implementations
+        assert np.all(np.diff(rd[:, 4]) <= 0)
+        assert np.allclose(dets[i, :nv].cpu().numpy(), rd, rtol=0, atol=1e-4)
+        assert np.array_equal(labels[i, :nv].cpu().numpy(), rl)
+        kk = kpts[i, :nv].cpu()
+        assert np.allclose(kk[:rk.shape[0]].numpy(), rk, rtol=0, atol=1e-3)
+        assert np.allclose(kk.double().sum(1).numpy(), rs, rtol=0, atol=0.2)      # 882 values of up to ~400 per row
+
+
+@pytest.mark.parametrize('variant', ['parallel', 'serial'])
+def test_reppoints_kp_mirror_get_bboxes_matches_reference_golden(variant):
+    """Multi-level get_bboxes of the RepPoints-Kp heads (PAR/SER:615-752 + multiclass_nms_kp), PyTorch restatement
+    with the reference's nms_cpu, against the UNCHANGED reference class (gen_reppoints_bboxes_golden.py) --
+    including that head's own keypoint clamp."""
+    from tests._cpu_head import make_cpu_reppoints_head
+    from tests.golden.gen_reppoints_bboxes_golden import IMG, NMS_PRE, make_case
+    g = gold('reppoints_bboxes.npz')
+    head = make_cpu_reppoints_head(variant)
+    with torch.no_grad():
+        head.moment_transfer.copy_(torch.tensor([0.25, -0.15]))
+    cls, kpt, rep = make_case()
+    dets, labels, kpts = head.get_bboxes(cls, kpt, rep, [IMG] * 2, float(g[variant + '_score_thr']),
+                                         float(g[variant + '_iou_thr']), NMS_PRE, int(g[variant + '_max_per_img']))
+    check_reppoints_bboxes(g, variant, dets, labels, kpts)

@@ -27,9 +27,10 @@ def main():
         for batch in (1, 8):
             g = torch.Generator().manual_seed(5)
             feats = [torch.randn(batch, 256, h, w, generator=g).cuda() for h, w in LEVELS]
-            for mode in ('eager_per_level', 'eager_grouped', 'graph_grouped'):
+            for mode in ('eager_per_level', 'eager_grouped', 'graph_grouped', 'eager_nhwc', 'graph_nhwc'):
                 head.grouped_dcn = mode != 'eager_per_level'
-                fn = GraphedForward(head, feats) if mode == 'graph_grouped' else (lambda f: head(f))
+                head.nhwc_towers = mode.endswith('nhwc')
+                fn = GraphedForward(head, feats) if mode.startswith('graph') else (lambda f: head(f))
                 with torch.no_grad():
                     for _ in range(3):
                         fn(feats)
@@ -50,8 +51,9 @@ def main():
                 print(json.dumps(dict(variant=variant, batch=batch, levels=LEVELS, ms_per_batch=round(ms, 3),
                                       images_per_s=round(batch / (ms * 1e-3), 1), dcn_calls_per_level=ndcn,
                                       dcn_gflop=round(dcn_gflop, 1), launch_mode=mode,
-                                      note='forward of all five levels, L2 flushed before every batch; towers / 1x1 '
-                                           'convolutions cuDNN (TF32 allowed)')), flush=True)
+                                      note='forward of all five levels, L2 flushed before every batch; 3x3 tower '
+                                           'convolutions cuDNN (TF32 allowed); *_nhwc: position-major towers, own '
+                                           'GroupNorm and 1x1 GEMMs')), flush=True)
     ops.set_precision(None)
 
 
