@@ -188,6 +188,39 @@ def fp32_mode_record(args, head, head_mod, ops, lib, x_dev, sc_dev, shapes, flus
                     'convolutions cuDNN fp32 (TF32 off)' % args.batch}
 
 
+def reppoints_kp_record(args, head_mod, ops, dev, flush):
+    """BASELINE.json configs[3] on the fast path: the RepPoints-Kp parallel / serial baseline heads
+    (reppoints_head_kp_{parallel,serial}.py) on the five FPN levels of an 800x1333 image, batch 8, forward of all
+    levels + the multi-level get_bboxes as ONE CUDA graph, device-resident, L2 flushed between steps."""
+    levels = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
+    batch = 8
+    out = {'levels': levels, 'batch': batch, 'unit': UNIT,
+           'note': 'bf16 DCN mode; 3x3 tower convolutions cuDNN channels_last (TF32), GroupNorm / 1x1 GEMMs / grouped '
+                   'DCNs / candidate selection / decode / batched NMS this library; synthetic scores U^%d as the main '
+                   'record; round-1 forward-only numbers were 789 (parallel) / 880 (serial) images/s' % SCORE_POW}
+    ops.set_precision('bf16')
+    try:
+        for variant in ('parallel', 'serial'):
+            head = head_mod.RepPointsKpHead(variant).to(dev).eval()
+            g = torch.Generator().manual_seed(5)
+            feats = [torch.randn(batch, 256, h, w, generator=g).to(dev) for h, w in levels]
+            scores = [(torch.rand(batch, 13, h, w, generator=g) ** SCORE_POW).to(dev) for h, w in levels]
+            res = {}
+            for what, target in (('forward', head),
+                                 ('forward_get_bboxes', head_mod.RepPointsKpDetect(head, [IMG_SHAPE] * batch,
+                                                                                  score_override=scores))):
+                gf = head_mod.GraphedForward(target, feats)
+                ms = _time_graph_steps(lambda _x, gf=gf: gf(), None, flush, max(args.steps // 2, 5))
+                res[what] = {'ms_per_batch': round(ms, 3), 'value': round(batch / (ms * 1e-3), 1)}
+                del gf
+            out[variant] = res
+            del head, feats, scores
+            torch.cuda.empty_cache()
+    finally:
+        ops.set_precision(args.precision)
+    return out
+
+
 def gpu_incumbent_record(args, dev):
     """The reference's own deform_conv_forward_cuda (mmdet/ops/dcn/src/deform_conv_cuda.cpp:151-258: im2col kernel +
     cuBLAS SGEMM per im2col_step chunk), compiled UNMODIFIED for sm_100a into oracle/_ref, timed on the 12 calls of
@@ -420,7 +453,8 @@ def run_ours(args):
         for name, fn in (('cudnn_tf32_towers', lambda: cudnn_towers_record(args, head, head_mod, x_dev, sc_dev, shapes, flush)),
                          ('fp32_mode', lambda: fp32_mode_record(args, head, head_mod, ops, lib, x_dev, sc_dev, shapes, flush,
                                                                 prof, recording, peaks0.get('bf16_tflops_sustained') or 1400.0)),
-                         ('gpu_incumbent', lambda: gpu_incumbent_record(args, dev))):
+                         ('gpu_incumbent', lambda: gpu_incumbent_record(args, dev)),
+                         ('reppoints_kp', lambda: reppoints_kp_record(args, head_mod, ops, dev, flush))):
             try:
                 sub[name] = fn()
             except Exception as e:

@@ -172,9 +172,11 @@ KGDET_API int kgdet_topk_flagged(const float* dets, const uint8_t* flags, int32_
  * (core/post_processing/bbox_nms_kp.py:6-75) for ONE head level, batched over images, static shapes:
  *   select   order[b, r] = position of the r-th largest max-over-classes score (topk(nms_pre), KP3:863-874;
  *            ties by ascending position; identity when n == HW).  scores: [B, C, HW] logits
- *            (apply_sigmoid = 1) or probabilities.  HW <= 4096: ranks by counting; larger levels (the FPN
- *            levels of reppoints_head_kp_parallel.py:703-713; HW <= 40960, n <= 4096): three-pass radix select
- *            + ranks inside the n selected, one CTA per image -- the same order, bit for bit.
+ *            (apply_sigmoid = 1) or probabilities.  Ranks by counting over all positions (HW <= 16384); with
+ *            kgdet_bbox_select_workspace_bytes(B, HW, n) bytes of scratch (non-zero for HW > 4096, n <= 4096),
+ *            kgdet_bbox_select_ws takes the large-level path (the FPN levels of
+ *            reppoints_head_kp_parallel.py:703-713; HW <= 40960): three-pass radix select of the n-th key +
+ *            ranks inside the n selected -- the same order, bit for bit.
  *   decode   boxes [B, n, 4] = clamp(bbox * stride + centre) (KP3:875-886) and the dense NMS input
  *            dets [B, C, n, 5] for kgdet_nms_batched (one segment per (image, class)).  img_wh: [B, 2].
  *   finalize for top_i [B, k] (= class * n + candidate, from a top-k over the NMS-masked scores, top_s <= 0 =
@@ -182,6 +184,9 @@ KGDET_API int kgdet_topk_flagged(const float* dets, const uint8_t* flags, int32_
  *            = (x, y, 1) decoded from keypts [B, 2 * num_keypts, HW] (y-first pairs) only for the survivors. */
 KGDET_API int kgdet_bbox_select(const float* scores, int apply_sigmoid, int32_t B, int32_t C, int32_t HW, int32_t n,
                       int32_t* order, void* stream);
+KGDET_API size_t kgdet_bbox_select_workspace_bytes(int32_t B, int32_t HW, int32_t n);
+KGDET_API int kgdet_bbox_select_ws(const float* scores, int apply_sigmoid, int32_t B, int32_t C, int32_t HW, int32_t n,
+                         int32_t* order, void* workspace, size_t workspace_bytes, void* stream);
 KGDET_API int kgdet_bbox_decode(const float* scores, int apply_sigmoid, const float* bbox, const int32_t* order,
                       const float* img_wh, float stride, int32_t map_w, int32_t B, int32_t C, int32_t HW,
                       int32_t n, float* boxes, float* dets, void* stream);

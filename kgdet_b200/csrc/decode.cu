@@ -67,38 +67,50 @@ __global__ void __launch_bounds__(256) bbox_select_kernel(const float* __restric
 }
 
 // Large levels (FPN P3 / P4 of the RepPoints-Kp heads: 16 800 / 4 200 positions, nms_pre = 1000): counting ranks over
-// all positions is O(HW^2).  One CTA per image instead: (1) keys of the per-position maxima in shared memory,
-// (2) the n-th largest key by a three-pass radix select (11 + 11 + 10 bits, histograms in shared memory),
-// (3) an ordered compaction of the n selected positions (every key above it, then the first positions that equal
-// it -- the same tie rule as above), (4) ranks by counting inside that list, O(n^2).  Same `order` as the kernel
-// above, bit for bit.
+// all positions is O(HW^2).  Three kernels instead:
+//   keys     the per-position maxima's rank keys, all SMs (one CTA per image cannot hide the latency of the
+//            13 strided score reads per position: 150 us for 8 x 16 800 positions when it was part of `select`);
+//   select   one CTA per image: the n-th largest key by a three-pass radix select (11 + 11 + 10 bits, histograms
+//            in shared memory), then an ordered compaction of the n selected positions (every key above it, then
+//            the first positions that equal it -- the same tie rule as above) into a list in position order;
+//   rank     ranks by counting inside that list, O(n^2) spread over ceil(n / 128) CTAs per image.
+// Same `order` as the kernel above, bit for bit.
 constexpr int kSelThreads = 1024;
 constexpr int kSelMaxHW = 40960;
 constexpr int kSelMaxN = 4096;
 
-__global__ void __launch_bounds__(kSelThreads) bbox_select_radix_kernel(const float* __restrict__ scores,
-                                                                        int apply_sigmoid, int C, int HW, int n,
-                                                                        int* __restrict__ order) {
+__global__ void __launch_bounds__(256) level_keys_kernel(const float* __restrict__ scores, int apply_sigmoid, int C,
+                                                         int HW, unsigned int* __restrict__ keys) {
+  const int b = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const float* sb = scores + (size_t)b * C * HW + p;
+  unsigned int m = 0u;
+  for (int c0 = 0; c0 < C; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (c0 + u < C) ? sb[(size_t)(c0 + u) * HW] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (c0 + u < C) m = max(m, rank_key(apply_sigmoid ? sigmoid_ref(v[u]) : v[u]));
+    }
+  }
+  keys[(size_t)b * HW + p] = m;
+}
+
+__global__ void __launch_bounds__(kSelThreads) bbox_select_radix_kernel(const unsigned int* __restrict__ keys, int HW,
+                                                                        int n, unsigned int* __restrict__ list_key,
+                                                                        int* __restrict__ list_pos) {
   extern __shared__ __align__(16) unsigned int sel_sm[];
-  const int n4 = (n + 3) & ~3;
   unsigned int* skey = sel_sm;                          // [HW]
   unsigned int* hist = skey + ((HW + 3) & ~3);          // [2048]
-  unsigned int* lkey = hist + 2048;                     // [n4] keys of the selected positions, ascending position
-  int* lpos = reinterpret_cast<int*>(lkey + n4);        // [n]
   __shared__ unsigned int s_prefix, s_need;
   __shared__ int warp_cnt[2][kSelThreads / 32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* sb = scores + (size_t)b * C * HW;
-  for (int p = tid; p < HW; p += kSelThreads) {
-    unsigned int m = 0u;
-    for (int c = 0; c < C; ++c) {
-      float v = sb[(size_t)c * HW + p];
-      if (apply_sigmoid) v = sigmoid_ref(v);
-      m = max(m, rank_key(v));
-    }
-    skey[p] = m;
-  }
-  for (int i = tid; i < n4; i += kSelThreads) lkey[i] = 0u;     // padding keys never outrank a real one
+  const int n4 = (n + 3) & ~3;
+  unsigned int* lkey = list_key + (size_t)b * n4;       // keys of the selected positions, ascending position
+  int* lpos = list_pos + (size_t)b * n4;
+  for (int p = tid; p < HW; p += kSelThreads) skey[p] = keys[(size_t)b * HW + p];
+  for (int i = n + tid; i < n4; i += kSelThreads) lkey[i] = 0u;     // padding keys never outrank a real one
   unsigned int prefix = 0u, mask = 0u, need = (unsigned int)n;
 #pragma unroll 1
   for (int pass = 0; pass < 3; ++pass) {
@@ -173,18 +185,28 @@ __global__ void __launch_bounds__(kSelThreads) bbox_select_radix_kernel(const fl
     base_sel += sel_total;
     __syncthreads();                                  // warp_cnt is rewritten by the next chunk
   }
-  for (int i = tid; i < n; i += kSelThreads) {
-    const unsigned int mine = lkey[i];
-    int rank = 0;
-    for (int j = 0; j < n4; j += 4) {
-      const uint4 o = *reinterpret_cast<const uint4*>(lkey + j);
-      rank += (o.x > mine || (o.x == mine && j < i)) ? 1 : 0;
-      rank += (o.y > mine || (o.y == mine && j + 1 < i)) ? 1 : 0;
-      rank += (o.z > mine || (o.z == mine && j + 2 < i)) ? 1 : 0;
-      rank += (o.w > mine || (o.w == mine && j + 3 < i)) ? 1 : 0;
-    }
-    order[(size_t)b * n + rank] = lpos[i];
+}
+
+__global__ void __launch_bounds__(128) bbox_rank_selected_kernel(const unsigned int* __restrict__ list_key,
+                                                                 const int* __restrict__ list_pos, int n,
+                                                                 int* __restrict__ order) {
+  extern __shared__ __align__(16) unsigned int rk_sm[];       // [n4]
+  const int b = blockIdx.y, n4 = (n + 3) & ~3;
+  const unsigned int* lkey = list_key + (size_t)b * n4;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) rk_sm[i] = lkey[i];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned int mine = rk_sm[i];
+  int rank = 0;
+  for (int j = 0; j < n4; j += 4) {
+    const uint4 o = *reinterpret_cast<const uint4*>(rk_sm + j);
+    rank += (o.x > mine || (o.x == mine && j < i)) ? 1 : 0;
+    rank += (o.y > mine || (o.y == mine && j + 1 < i)) ? 1 : 0;
+    rank += (o.z > mine || (o.z == mine && j + 2 < i)) ? 1 : 0;
+    rank += (o.w > mine || (o.w == mine && j + 3 < i)) ? 1 : 0;
   }
+  order[(size_t)b * n + rank] = list_pos[(size_t)b * n4 + i];
 }
 
 __global__ void iota_rows_kernel(int* __restrict__ order, int HW) {
@@ -335,33 +357,57 @@ extern "C" int kgdet_topk_flagged(const float* dets, const uint8_t* flags, int32
   return KGDET_OK;
 }
 
-extern "C" int kgdet_bbox_select(const float* scores, int apply_sigmoid, int32_t B, int32_t C, int32_t HW,
-                                 int32_t n, int32_t* order, void* stream) {
+// scratch of the large-level path of kgdet_bbox_select (0: none needed)
+extern "C" size_t kgdet_bbox_select_workspace_bytes(int32_t B, int32_t HW, int32_t n) {
+  if (B <= 0 || HW <= 4096 || n >= HW || n > kSelMaxN || HW > kSelMaxHW) return 0;
+  return ((size_t)B * HW + 2 * (size_t)B * ((n + 3) & ~3)) * 4;
+}
+
+static int bbox_select_impl(const float* scores, int apply_sigmoid, int32_t B, int32_t C, int32_t HW, int32_t n,
+                            int32_t* order, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
   KG_CHECK_ARG(scores && order, "kgdet_bbox_select: NULL pointer");
   KG_CHECK_ARG(B >= 0 && C >= 1 && HW >= 1 && n >= 1 && n <= HW, "kgdet_bbox_select: bad sizes");
   KG_CHECK_ARG(B <= 65535, "kgdet_bbox_select: batch too large");
   if (B == 0) return KGDET_OK;
   if (n == HW) {                                 // no top-k in the reference: original order
-    iota_rows_kernel<<<dim3(ceil_div(HW, 256), B), 256, 0, (cudaStream_t)stream>>>(order, HW);
+    iota_rows_kernel<<<dim3(ceil_div(HW, 256), B), 256, 0, stream>>>(order, HW);
     KG_LAUNCH_CHECK("iota_rows_kernel");
     return KGDET_OK;
   }
-  KG_CHECK_ARG(HW <= 16384 || (HW <= kSelMaxHW && n <= kSelMaxN),
-               "kgdet_bbox_select: at most %d positions per image and level (%d candidates) -- or 16384 positions",
-               kSelMaxHW, kSelMaxN);
-  if (HW > 4096 && n <= kSelMaxN) {
-    const size_t smem = ((size_t)((HW + 3) & ~3) + 2048 + (size_t)((n + 3) & ~3) + (size_t)n) * 4;
+  const size_t need = kgdet_bbox_select_workspace_bytes(B, HW, n);
+  if (need && workspace && workspace_bytes >= need && ((uintptr_t)workspace & 15) == 0) {
+    const int n4 = (n + 3) & ~3;
+    unsigned int* keys = (unsigned int*)workspace;
+    unsigned int* lkey = keys + (size_t)B * HW;
+    int* lpos = (int*)(lkey + (size_t)B * n4);
+    level_keys_kernel<<<dim3(ceil_div(HW, 256), B), 256, 0, stream>>>(scores, apply_sigmoid, C, HW, keys);
+    KG_LAUNCH_CHECK("level_keys_kernel");
+    const size_t smem = ((size_t)((HW + 3) & ~3) + 2048) * 4;
     KG_CUDA(cudaFuncSetAttribute(bbox_select_radix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bbox_select_radix_kernel<<<B, kSelThreads, smem, (cudaStream_t)stream>>>(scores, apply_sigmoid, C, HW, n, order);
+    bbox_select_radix_kernel<<<B, kSelThreads, smem, stream>>>(keys, HW, n, lkey, lpos);
     KG_LAUNCH_CHECK("bbox_select_radix_kernel");
+    bbox_rank_selected_kernel<<<dim3(ceil_div(n, 128), B), 128, (size_t)n4 * 4, stream>>>(lkey, lpos, n, order);
+    KG_LAUNCH_CHECK("bbox_rank_selected_kernel");
     return KGDET_OK;
   }
+  KG_CHECK_ARG(HW <= 16384, "kgdet_bbox_select: levels of more than 16384 positions need kgdet_bbox_select_ws with "
+               "kgdet_bbox_select_workspace_bytes of scratch (up to %d positions, %d candidates)", kSelMaxHW, kSelMaxN);
   const size_t smem = (size_t)(HW + 4) * sizeof(float);
   KG_CUDA(cudaFuncSetAttribute(bbox_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  bbox_select_kernel<<<dim3(ceil_div(HW, 256), B), 256, smem, (cudaStream_t)stream>>>(scores, apply_sigmoid, C, HW, n,
-                                                                                     order);
+  bbox_select_kernel<<<dim3(ceil_div(HW, 256), B), 256, smem, stream>>>(scores, apply_sigmoid, C, HW, n, order);
   KG_LAUNCH_CHECK("bbox_select_kernel");
   return KGDET_OK;
+}
+
+extern "C" int kgdet_bbox_select(const float* scores, int apply_sigmoid, int32_t B, int32_t C, int32_t HW,
+                                 int32_t n, int32_t* order, void* stream) {
+  return bbox_select_impl(scores, apply_sigmoid, B, C, HW, n, order, nullptr, 0, stream);
+}
+
+extern "C" int kgdet_bbox_select_ws(const float* scores, int apply_sigmoid, int32_t B, int32_t C, int32_t HW,
+                                    int32_t n, int32_t* order, void* workspace, size_t workspace_bytes, void* stream) {
+  return bbox_select_impl(scores, apply_sigmoid, B, C, HW, n, order, workspace, workspace_bytes, stream);
 }
 
 extern "C" int kgdet_bbox_decode(const float* scores, int apply_sigmoid, const float* bbox, const int32_t* order,

@@ -155,14 +155,15 @@ static int launch_groupnorm_wide(const float* x, const float* gamma, const float
 }
 
 // ---- maps that do not fit shared memory (FPN levels P3 / P4 of the RepPoints-Kp heads: 16 800 / 4 200 positions) ----
-// Two streaming passes over chunks of GS_CHUNK positions x all C channels (full 4 C-byte rows, coalesced):
-//   pass 1  per (image, chunk, group): count, mean and sum of squared deviations of the chunk, exactly (the chunk's
-//           values sit in registers: mean first, then deviations), threads merged with Chan's pairwise update;
-//   pass 2  every CTA merges the chunk statistics of its image in chunk order (deterministic), then normalises its
-//           chunk (+ ReLU) into NHWC fp32 and / or split planes.
+// Three streaming kernels over chunks of GS_CHUNK_PX positions x all C channels (full 4 C-byte rows, coalesced):
+//   stats     per (image, chunk, group): count, mean and sum of squared deviations.  Every thread accumulates
+//             sum(x - K) and sum((x - K)^2) around K = its first value (no E[x^2] - mean^2 cancellation: K is a
+//             sample, so (mean - K)^2 is never large against the spread); threads are merged with Chan's update;
+//   finalize  per image, one warp per group: the chunk moments merged in a fixed order -> mean, 1 / std;
+//   apply     normalise (+ ReLU) into NHWC fp32 and / or split planes, pure streaming.
 // 3 x 4 bytes per value of HBM traffic instead of the 2 x 4 of the resident kernels above.
-constexpr int GS_THREADS = 512;                 // 16 float4 values per thread stay in registers (no spills)
-constexpr int GS_SWEEPS = 16;                     // float4 values per thread per chunk
+constexpr int GS_THREADS = 256;
+constexpr int GS_SWEEPS = 16;                     // positions per thread per chunk
 
 struct Moments { float n, mean, m2; };
 
@@ -177,6 +178,14 @@ __device__ __forceinline__ Moments merge_moments(Moments a, Moments b) {
   return r;
 }
 
+__device__ __forceinline__ Moments shfl_xor_moments(Moments m, int o) {
+  Moments b;
+  b.n = __shfl_xor_sync(0xffffffffu, m.n, o);
+  b.mean = __shfl_xor_sync(0xffffffffu, m.mean, o);
+  b.m2 = __shfl_xor_sync(0xffffffffu, m.m2, o);
+  return b;
+}
+
 __global__ void __launch_bounds__(GS_THREADS) groupnorm_stream_stats_kernel(const float* __restrict__ x, int HW, int C,
                                                                              int cpg, float* __restrict__ partial) {
   extern __shared__ float red[];                  // [rows][groups][3]
@@ -185,38 +194,27 @@ __global__ void __launch_bounds__(GS_THREADS) groupnorm_stream_stats_kernel(cons
   const int col = threadIdx.x % L, row = threadIdx.x / L;
   const int p0 = chunk * chunk_px + row;
   const float* xg = x + (size_t)n * HW * C + col * 4;
-  float4 v[GS_SWEEPS];
+  float K = 0.f, s = 0.f, ss = 0.f;
   int cnt = 0;
-  float s = 0.f;
-#pragma unroll
+  if (p0 < HW) K = __ldg(xg + (size_t)p0 * C);
+#pragma unroll 8
   for (int i = 0; i < GS_SWEEPS; ++i) {
     const int p = p0 + i * rows;
     if (p < HW) {
-      v[i] = *reinterpret_cast<const float4*>(xg + (size_t)p * C);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      const float4 v = *reinterpret_cast<const float4*>(xg + (size_t)p * C);
+      const float d0 = v.x - K, d1 = v.y - K, d2 = v.z - K, d3 = v.w - K;
+      s += (d0 + d1) + (d2 + d3);
+      ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
       ++cnt;
-    } else {
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   Moments m;
   m.n = 4.f * (float)cnt;
-  m.mean = cnt ? s / m.n : 0.f;
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < GS_SWEEPS; ++i) {
-    if (i < cnt) {                                // valid sweeps are the first `cnt` (p grows with i)
-      const float d0 = v[i].x - m.mean, d1 = v[i].y - m.mean, d2 = v[i].z - m.mean, d3 = v[i].w - m.mean;
-      ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
-    }
-  }
-  m.m2 = ss;
+  m.mean = cnt ? K + s / m.n : 0.f;
+  m.m2 = cnt ? fmaxf(ss - s * s / m.n, 0.f) : 0.f;
   // lanes of one group are adjacent (cpg / 4 of them, a power of two, inside one warp)
   for (int o = 1; o < (cpg >> 2); o <<= 1) {
-    Moments b;
-    b.n = __shfl_xor_sync(0xffffffffu, m.n, o);
-    b.mean = __shfl_xor_sync(0xffffffffu, m.mean, o);
-    b.m2 = __shfl_xor_sync(0xffffffffu, m.m2, o);
+    const Moments b = shfl_xor_moments(m, o);
     m = (threadIdx.x & o) ? merge_moments(b, m) : merge_moments(m, b);   // same operand order on both lanes
   }
   const int g = (col * 4) / cpg;
@@ -225,84 +223,92 @@ __global__ void __launch_bounds__(GS_THREADS) groupnorm_stream_stats_kernel(cons
     r[0] = m.n; r[1] = m.mean; r[2] = m.m2;
   }
   __syncthreads();
-  if ((int)threadIdx.x < groups) {
+  for (int gi = threadIdx.x; gi < groups; gi += GS_THREADS) {
     Moments a;
-    a.n = red[threadIdx.x * 3]; a.mean = red[threadIdx.x * 3 + 1]; a.m2 = red[threadIdx.x * 3 + 2];
+    a.n = red[gi * 3]; a.mean = red[gi * 3 + 1]; a.m2 = red[gi * 3 + 2];
     for (int r = 1; r < rows; ++r) {
       Moments b;
-      const float* q = red + ((size_t)r * groups + threadIdx.x) * 3;
+      const float* q = red + ((size_t)r * groups + gi) * 3;
       b.n = q[0]; b.mean = q[1]; b.m2 = q[2];
       a = merge_moments(a, b);
     }
-    float* out = partial + (((size_t)n * gridDim.x + chunk) * groups + threadIdx.x) * 3;
+    float* out = partial + (((size_t)n * gridDim.x + chunk) * groups + gi) * 3;
     out[0] = a.n; out[1] = a.mean; out[2] = a.m2;
   }
 }
 
-__global__ void __launch_bounds__(GS_THREADS) groupnorm_stream_apply_kernel(
-    const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-    const float* __restrict__ partial, float* __restrict__ y, int HW, int C, int cpg, int relu,
-    unsigned char* __restrict__ hi, unsigned char* __restrict__ lo, size_t plane_bytes) {
-  __shared__ float stat[2][256];                  // mean, rstd per group (C / cpg <= 256)
-  const int L = C >> 2, rows = GS_THREADS / L, chunk_px = rows * GS_SWEEPS;
-  const int n = blockIdx.y, chunk = blockIdx.x, groups = C / cpg;
-  // one warp per group: lane l merges chunks l, l + 32, ... in order, then a fixed xor tree (lower lane first) --
-  // the same order in every CTA, so every CTA of the image normalises with bit-identical statistics
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nchunks = (int)gridDim.x;
-    for (int g = warp; g < groups; g += GS_THREADS / 32) {
-      const float* q = partial + ((size_t)n * nchunks * groups + g) * 3;
-      Moments a;
-      a.n = 0.f; a.mean = 0.f; a.m2 = 0.f;
-      for (int c = lane; c < nchunks; c += 32) {
-        const float* r = q + (size_t)c * groups * 3;
-        Moments b;
-        b.n = r[0]; b.mean = r[1]; b.m2 = r[2];
-        a = merge_moments(a, b);
+// one CTA per image, one warp per group: lane l merges chunks l, l + 32, ... in order, then a fixed xor tree
+__global__ void __launch_bounds__(1024) groupnorm_stream_finalize_kernel(const float* __restrict__ partial, int nchunks,
+                                                                         int groups, float eps, float* __restrict__ stat) {
+  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int g = warp; g < groups; g += 32) {
+    const float* q = partial + ((size_t)n * nchunks * groups + g) * 3;
+    Moments a;
+    a.n = 0.f; a.mean = 0.f; a.m2 = 0.f;
+    for (int c0 = lane; c0 < nchunks; c0 += 32 * 4) {          // four loads in flight, merged in chunk order
+      Moments b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + 32 * u;
+        const float* r = q + (size_t)(c < nchunks ? c : 0) * groups * 3;
+        b[u].n = c < nchunks ? r[0] : 0.f;                      // an empty set: merging it changes nothing
+        b[u].mean = c < nchunks ? r[1] : 0.f;
+        b[u].m2 = c < nchunks ? r[2] : 0.f;
       }
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        Moments b;
-        b.n = __shfl_xor_sync(0xffffffffu, a.n, o);
-        b.mean = __shfl_xor_sync(0xffffffffu, a.mean, o);
-        b.m2 = __shfl_xor_sync(0xffffffffu, a.m2, o);
-        a = (lane & o) ? merge_moments(b, a) : merge_moments(a, b);
-      }
-      if (lane == 0) {
-        stat[0][g] = a.mean;
-        stat[1][g] = rsqrtf(a.m2 / a.n + eps);
-      }
+      for (int u = 0; u < 4; ++u) a = merge_moments(a, b[u]);
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const Moments b = shfl_xor_moments(a, o);
+      a = (lane & o) ? merge_moments(b, a) : merge_moments(a, b);
+    }
+    if (lane == 0) {
+      stat[((size_t)n * groups + g) * 2] = a.mean;
+      stat[((size_t)n * groups + g) * 2 + 1] = rsqrtf(a.m2 / a.n + eps);
     }
   }
-  __syncthreads();
+}
+
+__global__ void __launch_bounds__(GS_THREADS) groupnorm_stream_apply_kernel(
+    const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ stat, float* __restrict__ y, int HW, int C, int cpg, int relu,
+    unsigned char* __restrict__ hi, unsigned char* __restrict__ lo, size_t plane_bytes) {
+  const int L = C >> 2, rows = GS_THREADS / L, chunk_px = rows * GS_SWEEPS;
+  const int n = blockIdx.y, chunk = blockIdx.x, groups = C / cpg;
   const int col = threadIdx.x % L, row = threadIdx.x / L, c0 = col * 4;
-  const float mean = stat[0][c0 / cpg], rstd = stat[1][c0 / cpg];
+  const float2 st = __ldg(reinterpret_cast<const float2*>(stat) + (size_t)n * groups + c0 / cpg);
+  const float mean = st.x, rstd = st.y;
   const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0));
   const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0));
   const float* xg = x + (size_t)n * HW * C + c0;
   float* yg = y ? y + (size_t)n * HW * C + c0 : nullptr;
   const size_t poff = (size_t)(c0 >> 6) * plane_bytes + (size_t)n * HW * 128 + (size_t)(c0 & 63) * 2;
-#pragma unroll 4
+#pragma unroll 8
   for (int i = 0; i < GS_SWEEPS; ++i) {
     const int p = chunk * chunk_px + row + i * rows;
-    if (p >= HW) break;
-    const float4 v = *reinterpret_cast<const float4*>(xg + (size_t)p * C);
-    float4 o;
-    o.x = (v.x - mean) * rstd * ga.x + be.x;
-    o.y = (v.y - mean) * rstd * ga.y + be.y;
-    o.z = (v.z - mean) * rstd * ga.z + be.z;
-    o.w = (v.w - mean) * rstd * ga.w + be.w;
-    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    if (yg) *reinterpret_cast<float4*>(yg + (size_t)p * C) = o;
-    if (hi) {
-      const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
-      const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - __low2float(h0), o.y - __high2float(h0));
-      const __nv_bfloat162 l1 = __floats2bfloat162_rn(o.z - __low2float(h1), o.w - __high2float(h1));
-      uint2 hv, lv;
-      hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
-      lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
-      *reinterpret_cast<uint2*>(hi + poff + (size_t)p * 128) = hv;
-      if (lo) *reinterpret_cast<uint2*>(lo + poff + (size_t)p * 128) = lv;
+    if (p < HW) {
+      const float4 v = *reinterpret_cast<const float4*>(xg + (size_t)p * C);
+      float4 o;
+      o.x = (v.x - mean) * rstd * ga.x + be.x;
+      o.y = (v.y - mean) * rstd * ga.y + be.y;
+      o.z = (v.z - mean) * rstd * ga.z + be.z;
+      o.w = (v.w - mean) * rstd * ga.w + be.w;
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (yg) *reinterpret_cast<float4*>(yg + (size_t)p * C) = o;
+      if (hi) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+        uint2 hv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(hi + poff + (size_t)p * 128) = hv;
+        if (lo) {
+          const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - __low2float(h0), o.y - __high2float(h0));
+          const __nv_bfloat162 l1 = __floats2bfloat162_rn(o.z - __low2float(h1), o.w - __high2float(h1));
+          uint2 lv;
+          lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+          *reinterpret_cast<uint2*>(lo + poff + (size_t)p * 128) = lv;
+        }
+      }
     }
   }
 }
@@ -494,7 +500,7 @@ extern "C" int kgdet_groupnorm_relu_nhwc_planes(const float* x, const float* gam
 // reppoints_head_kp_parallel.py:115-145.
 extern "C" size_t kgdet_groupnorm_stream_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t groups) {
   if (N <= 0 || HW <= 0 || !stream_gn_supported(C, groups)) return 0;
-  return (size_t)N * stream_gn_chunks(HW, C) * groups * 3 * sizeof(float);
+  return ((((size_t)N * stream_gn_chunks(HW, C) * groups * 3 + 1) & ~(size_t)1) + (size_t)N * groups * 2) * sizeof(float);
 }
 
 extern "C" int kgdet_groupnorm_relu_nhwc_stream(const float* x, const float* gamma, const float* beta, float eps,
@@ -504,12 +510,12 @@ extern "C" int kgdet_groupnorm_relu_nhwc_stream(const float* x, const float* gam
   cudaStream_t stream = (cudaStream_t)stream_;
   KG_CHECK_ARG(x && gamma && beta && (y || planes) && workspace, "kgdet_groupnorm_relu_nhwc_stream: NULL pointer");
   KG_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && stream_gn_supported(C, groups),
-               "kgdet_groupnorm_relu_nhwc_stream: need C %% 128 == 0, C <= 4096 and a power-of-two multiple of 4 channels per group");
+               "kgdet_groupnorm_relu_nhwc_stream: need C %% 128 == 0, C <= 1024 and a power-of-two multiple of 4 channels per group");
   const int HW = H * W;
   KG_CHECK_ARG(workspace_bytes >= kgdet_groupnorm_stream_workspace_bytes(N, HW, C, groups),
                "kgdet_groupnorm_relu_nhwc_stream: workspace too small");
-  KG_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0 && ((uintptr_t)planes & 255) == 0,
-               "kgdet_groupnorm_relu_nhwc_stream: misaligned pointer");
+  KG_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)workspace) & 15) == 0 &&
+                   ((uintptr_t)planes & 255) == 0, "kgdet_groupnorm_relu_nhwc_stream: misaligned pointer");
   unsigned char *hi = nullptr, *lo = nullptr;
   size_t plane_bytes = 0;
   if (planes) {
@@ -526,10 +532,14 @@ extern "C" int kgdet_groupnorm_relu_nhwc_stream(const float* x, const float* gam
   }
   const int cpg = C / groups, chunks = stream_gn_chunks(HW, C), rows = GS_THREADS / (C / 4);
   const size_t smem = (size_t)rows * groups * 3 * sizeof(float);
-  groupnorm_stream_stats_kernel<<<dim3(chunks, N), GS_THREADS, smem, stream>>>(x, HW, C, cpg, (float*)workspace);
+  float* partial = (float*)workspace;
+  float* stat = partial + (((size_t)N * chunks * groups * 3 + 1) & ~(size_t)1);        // 8-byte aligned pairs
+  groupnorm_stream_stats_kernel<<<dim3(chunks, N), GS_THREADS, smem, stream>>>(x, HW, C, cpg, partial);
   KG_LAUNCH_CHECK("groupnorm_stream_stats_kernel");
-  groupnorm_stream_apply_kernel<<<dim3(chunks, N), GS_THREADS, 0, stream>>>(x, gamma, beta, eps, (const float*)workspace, y,
-                                                                           HW, C, cpg, fuse_relu ? 1 : 0, hi, lo, plane_bytes);
+  groupnorm_stream_finalize_kernel<<<N, 1024, 0, stream>>>(partial, chunks, groups, eps, stat);
+  KG_LAUNCH_CHECK("groupnorm_stream_finalize_kernel");
+  groupnorm_stream_apply_kernel<<<dim3(chunks, N), GS_THREADS, 0, stream>>>(x, gamma, beta, stat, y, HW, C, cpg,
+                                                                           fuse_relu ? 1 : 0, hi, lo, plane_bytes);
   KG_LAUNCH_CHECK("groupnorm_stream_apply_kernel");
   return KGDET_OK;
 }

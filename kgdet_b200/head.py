@@ -943,6 +943,24 @@ class RepPointsKpHead(nn.Module):
         return out_dets, out_labels, out_kpts
 
 
+class RepPointsKpDetect(nn.Module):
+    """`head(feats)` + `head.get_bboxes` of a RepPointsKpHead as one callable (simple_test of the reference's
+    detector minus backbone / neck: mmdet/models/detectors/single_stage_kp.py:75-86), e.g. for GraphedForward.
+    score_override: optional per-level sigmoid scores (benchmarks with random-init weights)."""
+
+    def __init__(self, head, img_shapes, score_thr=0.05, iou_thr=0.5, nms_pre=1000, max_per_img=100, score_override=None):
+        super().__init__()
+        self.head = head
+        self.img_shapes = list(img_shapes)
+        self.cfg = (score_thr, iou_thr, nms_pre, max_per_img)
+        self.score_override = score_override
+
+    def forward(self, feats):
+        outs = self.head(feats)
+        return self.head.get_bboxes(outs[0], outs[2], outs[4], self.img_shapes, *self.cfg,
+                                    score_override=self.score_override)
+
+
 class GraphedForward(object):
     """`head(feats)` of any head of this module captured ONCE into a CUDA graph for fixed input shapes (the forward
     has static shapes and no host synchronisation).  ``__call__(feats)`` copies the inputs into the static ones and

@@ -76,6 +76,9 @@ SIGNATURES = {
     'kgdet_dcn_forward_prepared_group': (ctypes.c_int, [c_ptr, c_i32, ctypes.c_int, c_ptr, c_sz, c_ptr]),
     'kgdet_dcn_group_set_profile_events': (None, [c_ptr, c_ptr]),
     'kgdet_bbox_select': (ctypes.c_int, [c_ptr, ctypes.c_int, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
+    'kgdet_bbox_select_workspace_bytes': (ctypes.c_size_t, [c_i32, c_i32, c_i32]),
+    'kgdet_bbox_select_ws': (ctypes.c_int, [c_ptr, ctypes.c_int, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr, ctypes.c_size_t,
+                                            c_ptr]),
     'kgdet_bbox_decode': (ctypes.c_int, [c_ptr, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32,
                                          c_i32, c_ptr, c_ptr, c_ptr]),
     'kgdet_bbox_finalize': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_i32, c_i32, c_i32, c_i32,

@@ -15,6 +15,13 @@ def bbox_select(scores, apply_sigmoid, n):
     assert scores.dtype == torch.float32 and scores.is_contiguous()
     B, C, H, W = scores.shape
     order = torch.empty((B, n), dtype=torch.int32, device=scores.device)
+    ws_bytes = int(lib.kgdet_bbox_select_workspace_bytes(B, H * W, n))
+    if ws_bytes:              # a large level (more than 4096 positions): radix select, needs scratch
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=scores.device)
+        _capi.check(lib.kgdet_bbox_select_ws(scores.data_ptr(), int(bool(apply_sigmoid)), B, C, H * W, n,
+                                             order.data_ptr(), ws.data_ptr(), ws_bytes, _capi.stream_of(scores)),
+                    'kgdet_bbox_select_ws')
+        return order
     _capi.check(lib.kgdet_bbox_select(scores.data_ptr(), int(bool(apply_sigmoid)), B, C, H * W, n, order.data_ptr(),
                                       _capi.stream_of(scores)), 'kgdet_bbox_select')
     return order

@@ -1,7 +1,8 @@
 """BASELINE.json configs[3]: the RepPoints-Kp parallel / serial baseline heads (reppoints_head_kp_parallel.py,
 reppoints_head_kp_serial.py) on the five FPN levels of an 800x1333 image (P3 100x168 ... P7 7x11), forward only,
 random-init weights, bf16 mode.  Prints one JSON line per (variant, batch): device ms per batch and images/s, the
-number of deformable-convolution calls and their algorithmic TFLOP/s share.
+number of deformable-convolution calls and their algorithmic TFLOP/s share.  `graph_nhwc_get_bboxes` adds the
+multi-level get_bboxes (synthetic scores: random-init scores all sit at 0.01) inside the same captured graph.
 
     python tools/reppoints_bench.py > profiles/<name>.jsonl
 """
@@ -13,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from kgdet_b200 import ops  # noqa: E402
-from kgdet_b200.head import GraphedForward, RepPointsKpHead  # noqa: E402
+from kgdet_b200.head import GraphedForward, RepPointsKpDetect, RepPointsKpHead  # noqa: E402
 
 LEVELS = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
 
@@ -27,10 +28,14 @@ def main():
         for batch in (1, 8):
             g = torch.Generator().manual_seed(5)
             feats = [torch.randn(batch, 256, h, w, generator=g).cuda() for h, w in LEVELS]
-            for mode in ('eager_per_level', 'eager_grouped', 'graph_grouped', 'eager_nhwc', 'graph_nhwc'):
+            scores = [(torch.rand(batch, 13, h, w, generator=g) ** 28).cuda() for h, w in LEVELS]   # ~10 % pass 0.05, as bench.py
+            detect = RepPointsKpDetect(head, [(800, 1333)] * batch, score_override=scores)
+            for mode in ('eager_per_level', 'eager_grouped', 'graph_grouped', 'eager_nhwc', 'graph_nhwc',
+                         'graph_nhwc_get_bboxes'):
                 head.grouped_dcn = mode != 'eager_per_level'
-                head.nhwc_towers = mode.endswith('nhwc')
-                fn = GraphedForward(head, feats) if mode.startswith('graph') else (lambda f: head(f))
+                head.nhwc_towers = 'nhwc' in mode
+                target = detect if mode.endswith('get_bboxes') else head
+                fn = GraphedForward(target, feats) if mode.startswith('graph') else (lambda f: head(f))
                 with torch.no_grad():
                     for _ in range(3):
                         fn(feats)
