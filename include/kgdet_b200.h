@@ -249,9 +249,11 @@ KGDET_API int kgdet_groupnorm_relu_nhwc_stream(const float* x, const float* gamm
  *             from the nine head outputs outs[9] = cls_1..3 [B, NC, H, W], kpt_1..3 [B, 2K, H, W] (y-first pairs),
  *             bbox_1..3 [B, 4, H, W], all NCHW fp32, read in place.  loss_weights[9] in the same order as losses.
  *   backward  grad_outs[i] (same shapes as outs[i]; NULL = skip) = d(sum_k grad_losses[k] * losses[k]) / d outs[i]. */
+KGDET_API size_t kgdet_point_assign_scratch_bytes(int32_t B, int32_t map_h, int32_t map_w);
 KGDET_API int kgdet_point_assign(const float* gt_boxes, const uint8_t* gt_valid, const float* gt_keypoints, int32_t B,
                        int32_t G, int32_t num_keypoints, int32_t map_h, int32_t map_w, float stride, int32_t pos_num,
-                       int32_t* assigned, float* avg_factor, float* num_visible, int32_t* scratch /* 2 * B ints */,
+                       int32_t* assigned, float* avg_factor, float* num_visible,
+                       void* scratch /* kgdet_point_assign_scratch_bytes, 16-byte aligned; initialised by the call */,
                        void* stream);
 KGDET_API int kgdet_point_losses_forward(const float* const* outs, const int32_t* assigned, const float* gt_boxes,
                                const int64_t* gt_labels, const float* gt_keypoints, const float* avg_factor,

@@ -116,6 +116,7 @@ SIGNATURES = {
     'kgdet_groupnorm_relu_nhwc_stream': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_f32, c_i32, ctypes.c_int, c_ptr, c_ptr,
                                                         ctypes.c_int, c_i32, c_i32, c_i32, c_i32, c_ptr, ctypes.c_size_t,
                                                         c_ptr]),
+    'kgdet_point_assign_scratch_bytes': (ctypes.c_size_t, [c_i32, c_i32, c_i32]),
     'kgdet_point_assign': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_ptr,
                                           c_ptr, c_ptr, c_ptr, c_ptr]),
     'kgdet_point_losses_forward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32,

@@ -33,7 +33,7 @@ def point_assign(gt_bboxes, gt_valid, gt_keypoints, map_hw, stride, pos_num=25):
     assigned = torch.empty((B, H * W), dtype=torch.int32, device=dev)
     avg = torch.empty(1, dtype=torch.float32, device=dev)
     nvis = torch.empty((B, G), dtype=torch.float32, device=dev)
-    scratch = torch.empty(2 * B, dtype=torch.int32, device=dev)
+    scratch = torch.empty(max(int(lib.kgdet_point_assign_scratch_bytes(B, H, W)), 16), dtype=torch.uint8, device=dev)
     _capi.check(lib.kgdet_point_assign(boxes.data_ptr(), valid.data_ptr(), kps.data_ptr(), B, G, kps.shape[2], H, W,
                                        float(stride), int(pos_num), assigned.data_ptr(), avg.data_ptr(), nvis.data_ptr(),
                                        scratch.data_ptr(), _capi.stream_of(boxes)), 'kgdet_point_assign')
