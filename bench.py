@@ -195,10 +195,12 @@ def reppoints_kp_record(args, head_mod, ops, dev, flush):
     levels = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
     batch = 8
     out = {'levels': levels, 'batch': batch, 'unit': UNIT,
-           'note': 'bf16 DCN mode; 3x3 tower convolutions cuDNN channels_last (TF32), GroupNorm / 1x1 GEMMs / grouped '
+           'note': 'bf16 DCN mode; 3x3 tower convolutions cuDNN channels_last (TF32, cudnn.benchmark), GroupNorm / 1x1 GEMMs / grouped '
                    'DCNs / candidate selection / decode / batched NMS this library; synthetic scores U^%d as the main '
                    'record; round-1 forward-only numbers were 789 (parallel) / 880 (serial) images/s' % SCORE_POW}
     ops.set_precision('bf16')
+    bench_before = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True         # cuDNN picks the tower convolutions' algorithms by measurement
     try:
         for variant in ('parallel', 'serial'):
             head = head_mod.RepPointsKpHead(variant).to(dev).eval()
@@ -218,6 +220,7 @@ def reppoints_kp_record(args, head_mod, ops, dev, flush):
             torch.cuda.empty_cache()
     finally:
         ops.set_precision(args.precision)
+        torch.backends.cudnn.benchmark = bench_before
     return out
 
 
@@ -669,6 +672,10 @@ def train_record(args, rank=None, world=None, local=None):
     ops.set_precision(args.precision)
     B = args.train_batch
     head = make_weights(KGDetHead()).to(dev).train()
+    # cuDNN picks the plain convolutions' fprop / dgrad / wgrad algorithms by measurement instead of by heuristic
+    # (4.36 -> 4.15 ms per step: the heuristic choices wrap every call in NCHW <-> NHWC transposes)
+    cudnn_benchmark_before = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = os.environ.get('KGDET_CUDNN_BENCHMARK', '1') == '1'
     opt = torch.optim.SGD(head.parameters(), lr=1e-6, momentum=0.9)
     g = torch.Generator().manual_seed(200 + rank)
     x = torch.randn(B, C, H, W, generator=g).to(dev)
@@ -821,6 +828,8 @@ def train_record(args, rank=None, world=None, local=None):
             log('[bench] collective-free variant failed (%r)' % (e,))
     final_loss = float(loss.item())
     ops.set_precision(args.precision)
+    cudnn_mode = 'benchmark (measured algorithm choice)' if torch.backends.cudnn.benchmark else 'heuristic'
+    torch.backends.cudnn.benchmark = cudnn_benchmark_before
     if rank != 0:
         return None
     nparam = sum(p.numel() for p in head.parameters())
@@ -832,7 +841,8 @@ def train_record(args, rank=None, world=None, local=None):
                                    'clip + SGD) @800x1333 (map 25x42), batch %d per GPU, synthetic ground truth' % B,
                        'batch_per_gpu': B, 'allreduce': allreduce_kind + (', %.1f MB fp32 gradients' % (nparam * 4 / 1e6)
                                                                            if world > 1 else ''),
-                       'parallelism': 'dp%d' % world, 'l2': 'flushed before every step'},
+                       'parallelism': 'dp%d' % world, 'l2': 'flushed before every step',
+                       'cudnn': 'plain 3x3 / 1x1 convolutions and their gradients on cuDNN, TF32, ' + cudnn_mode},
             'exposed_allreduce_us': exposed_us, 'launch_mode': mode, 'final_loss': final_loss}
 
 

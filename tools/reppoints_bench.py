@@ -20,6 +20,7 @@ LEVELS = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
 
 
 def main():
+    torch.backends.cudnn.benchmark = os.environ.get('KGDET_CUDNN_BENCHMARK', '1') == '1'
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
     ops.set_precision('bf16')
     for variant in ('parallel', 'serial'):
