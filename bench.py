@@ -149,7 +149,7 @@ def cudnn_towers_record(args, head, head_mod, x_dev, sc_dev, shapes, flush):
 
 def fp32_mode_record(args, head, head_mod, ops, lib, x_dev, sc_dev, shapes, flush, prof, recording, peak_tf):
     """The reference's own precision end to end: DCN in the fp32-grade tensor-core mode (tf32x3 with accumulator
-    promotion, rel 1e-5), towers / 1x1 convolutions cuDNN fp32 (TF32 off)."""
+    promotion, rel 1e-5), plain convolutions / 1x1 GEMMs at split precision on this library (fp32-grade)."""
     old = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
     ops.set_precision('tf32x3')
@@ -184,8 +184,9 @@ def fp32_mode_record(args, head, head_mod, ops, lib, x_dev, sc_dev, shapes, flus
                          '(nominal 1.1 vs 2.25 PFLOP/s dense); the 3 MMAs per k-step are NOT counted as useful flops',
             'per_kernel_size': {('k%d' % k): {'launches': len(v), 'avg_us': round(1e3 * sum(v) / len(v), 2)}
                                 for k, v in sorted(per_k.items())},
-            'note': 'forward_single + get_bboxes, batch %d, CUDA-graph replay, device-resident; towers and 1x1 '
-                    'convolutions cuDNN fp32 (TF32 off)' % args.batch}
+            'note': 'forward_single + get_bboxes, batch %d, CUDA-graph replay, device-resident; 3x3 convolutions and '
+                    '1x1 GEMMs on this library at split (bf16x3) precision, no cuDNN kernel in the step '
+                    '(KGDetHead._forward_single_fp32_grade)' % args.batch}
 
 
 def reppoints_kp_record(args, head_mod, ops, dev, flush):

@@ -433,6 +433,11 @@ class KGDetHead(nn.Module):
             for br in branches or ():
                 br.join()
             return cls1, cls2, cls3, kpt1, kpt2, kpt3, bbox1, bbox2, bbox3
+        if (fused and self._tensor_core_heads and self._own_convs and get_precision(x.dtype) == 'tf32x3'
+                and x.dtype == torch.float32 and x.shape[2] * x.shape[3] <= 1600
+                and all(conv_supported(m.conv.in_channels, m.conv.out_channels, 3)
+                        for m in list(self.cls_convs) + list(self.reg_convs))):
+            return self._forward_single_fp32_grade(x)
         cls_feat = pts_feat = x
         for m in self.cls_convs:
             cls_feat = m(cls_feat)
@@ -461,6 +466,54 @@ class KGDetHead(nn.Module):
         kpt3 = kpt3 + kpt2.detach()                                                # KP3:440-441
         rep3 = rep3 + rep2.detach()
         bbox3 = self.points2bbox(rep3)
+        return cls1, cls2, cls3, kpt1, kpt2, kpt3, bbox1, bbox2, bbox3
+
+    def _forward_single_fp32_grade(self, x):
+        """fp32 inference (the reference's precision; DCN mode 'tf32x3', the default for fp32 tensors) with every
+        contraction on this library's tensor-core kernels at fp32-grade accuracy: 3x3 convolutions and 1x1 GEMMs at
+        split precision (bf16x3), GroupNorm fused, deformable convolutions in the tf32x3 mode with accumulator
+        promotion (NCHW fp32 outputs, then one re-tiling pass per branch for the GEMMs).  cuDNN's fp32 path takes
+        1.5 ms per 3x3 convolution at [16, 256, 25, 42] (TF32 off); this path 56 us."""
+        feat = self.kp_rep_block_2.cls_dfmconv_3.out_channels
+        n, _, h, w = x.shape
+        planes = split_planes(x)
+
+        def tower(convs, p):
+            dense = None
+            for i, m in enumerate(convs):
+                y = conv_planes(p, m.conv.weight)
+                if i + 1 < len(convs):
+                    p = groupnorm_relu_planes(y, m.gn)
+                else:
+                    p, dense = groupnorm_relu_planes(y, m.gn, also_dense=True)
+            return p, dense
+
+        for blk in (self.kp_rep_block_1, self.kp_rep_block_2, self.kp_rep_block_3):
+            _pointwise_weights(blk)
+        cls_p, cls_dense = tower(self.cls_convs, planes)
+        pts_p, pts_dense = tower(self.reg_convs, planes)
+        cls1 = self.kp_rep_block_1.forward_planes_cls(cls_p)
+        kpt1, rep1 = self.kp_rep_block_1.forward_planes_kpt(pts_p)
+        bbox1 = self.points2bbox(rep1)
+        cls_prep = prepare_input(cls_dense, feat, precision='tf32x3')
+        pts_prep = prepare_input(pts_dense, feat, precision='tf32x3')
+        outs = [cls1, kpt1, bbox1]
+        rep_prev, kpt_prev = rep1, kpt1
+        for blk in (self.kp_rep_block_2, self.kp_rep_block_3):
+            cls_cat = x.new_empty((n, 3 * feat, h, w))
+            kpt_cat = x.new_empty((n, 3 * feat, h, w))
+            lo = 0
+            for i, k in enumerate(_POINT_SETS):
+                plan = prepare_plan_points(rep_prev, lo, (n, cls_dense.shape[1], h, w), feat, k, 1, (k - 1) // 2, 1,
+                                           precision='tf32x3', gradient_mul=blk.gradient_mul)      # KP3:131-143
+                lo += 2 * k * k
+                deform_conv_prepared(cls_prep, plan, getattr(blk, 'cls_dfmconv_%d' % k).weight, cls_cat, i * feat, True)
+                deform_conv_prepared(pts_prep, plan, getattr(blk, 'keypts_dfmconv_%d' % k).weight, kpt_cat, i * feat, True)
+            cls_k, kpt_k, rep_k = _pointwise_heads(blk, nchw_to_tiled(cls_cat, split=True), nchw_to_tiled(kpt_cat, split=True),
+                                                   n, h, w, kpt_prev, rep_prev)                    # KP3:431-432,440-441
+            outs += [cls_k, kpt_k, self.points2bbox(rep_k)]
+            rep_prev, kpt_prev = rep_k, kpt_k
+        cls1, kpt1, bbox1, cls2, kpt2, bbox2, cls3, kpt3, bbox3 = outs
         return cls1, cls2, cls3, kpt1, kpt2, kpt3, bbox1, bbox2, bbox3
 
     def forward(self, feats):
