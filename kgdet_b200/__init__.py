@@ -13,6 +13,12 @@ from . import ops  # noqa: F401
 __version__ = '0.1.0'
 
 
+def accelerate(ref_head, **inject):
+    """Rebind an UNCHANGED reference head instance to the fused paths of this package (kgdet_b200/adopt.py)."""
+    from .adopt import accelerate as _accelerate
+    return _accelerate(ref_head, **inject)
+
+
 def mount_as_mmdet_ops():
     """Make `import mmdet.ops` (and the sub-modules the reference imports) resolve to kgdet_b200.ops.
 

@@ -546,8 +546,16 @@ class KGDetHead(nn.Module):
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def get_bboxes(self, cls_scores, keypts_preds, bbox_preds, img_shapes, score_thr=0.05, iou_thr=0.5,
-                   nms_pre=1000, max_per_img=100, score_override=None):
+                   nms_pre=1000, max_per_img=100, score_override=None, scale_factors=None, return_kept=False):
         """Batched, sync-free form of KP3:770-914 + multiclass_nms_kp.
+
+        return_kept: also return the number of boxes the NMS kept per image, [B], and the flat (class, candidate)
+        index of every result row, [B, k] (the reference sorts by score only when more than max_per_img boxes were
+        kept, bbox_nms_kp.py:64-70; otherwise its rows stay in class / candidate order -- kgdet_b200.adopt restores
+        that ordering from these two).
+
+        scale_factors: optional per-image floats -- the reference's `rescale=True` (KP3:892-898): boxes and keypoint
+        coordinates are divided by the image's scale factor BEFORE the NMS, as the reference does.
 
         cls_scores / keypts_preds / bbox_preds: per-level lists of the stage-3 outputs
         ([B,13,H,W], [B,588,H,W], [B,4,H,W]).  img_shapes: list of (h, w) per image.
@@ -563,6 +571,13 @@ class KGDetHead(nn.Module):
         if lim is None:       # built once per (shapes, device): keeps H2D copies out of graph capture
             lim = torch.tensor([[s[1], s[0], s[1], s[0]] for s in img_shapes], dtype=torch.float32, device=dev)
             self._lim_cache[key] = lim
+        sf = None
+        if scale_factors is not None:
+            skey = ('scale', tuple(float(f) for f in scale_factors), str(dev))
+            sf = self._lim_cache.get(skey)
+            if sf is None:
+                sf = torch.tensor([float(f) for f in scale_factors], dtype=torch.float32, device=dev)
+                self._lim_cache[skey] = sf
         if (self._fused_decode and len(cls_scores) == 1 and cls_scores[0].is_cuda
                 and self._nms_flags_fn is batched_nms_flags and cls_scores[0].shape[-2] * cls_scores[0].shape[-1] <= 16384):
             # one head level on the GPU: three decode kernels + the batched NMS + one top-k (section 8(f) rank 1)
@@ -576,6 +591,9 @@ class KGDetHead(nn.Module):
             order = bbox_select(src, sig, n)
             boxes, dets = bbox_decode(src, sig, bp.float().contiguous(), order, wh, stride)
             C = dets.shape[1]
+            if sf is not None:                                                          # KP3:892-893
+                boxes = boxes / sf.view(B, 1, 1)
+                dets[..., :4] = dets[..., :4] / sf.view(B, 1, 1, 1)
             flags = self._nms_flags_fn(dets.view(-1, 5), None, n, iou_thr, score_thr=score_thr)
             if C * n <= 16384:
                 # survivors compacted + sorted inside one CTA per image (bbox_nms_kp.py:64-70)
@@ -584,7 +602,11 @@ class KGDetHead(nn.Module):
                 masked = torch.where(flags.view(B, C * n).bool(), dets[..., 4].reshape(B, C * n),
                                      dets.new_full((), -1.0))
                 top_s, top_i = masked.topk(min(max_per_img, C * n), dim=1)
-            return bbox_finalize(boxes, kp.float().contiguous(), order, top_i, top_s, wh, stride, (H, W))
+            res = bbox_finalize(boxes, kp.float().contiguous(), order, top_i, top_s, wh, stride, (H, W))
+            if sf is not None:                                                          # KP3:894-896
+                kv = res[2].view(B, res[2].shape[1], -1, 3)
+                kv[..., :2] = kv[..., :2] / sf.view(B, 1, 1, 1)
+            return res + (flags.view(B, -1).sum(1), top_i) if return_kept else res
         boxes_l, scores_l, kpts_l = [], [], []
         for lvl, (cs, kp, bp) in enumerate(zip(cls_scores, keypts_preds, bbox_preds)):
             stride = self.point_strides[lvl]
@@ -616,6 +638,9 @@ class KGDetHead(nn.Module):
         boxes = torch.cat(boxes_l, 1)
         scores = torch.cat(scores_l, 1)
         kpts = torch.cat(kpts_l, 1)
+        if sf is not None:                                                              # KP3:892-896
+            boxes = boxes / sf.view(B, 1, 1)
+            kpts = kpts / sf.view(B, 1, 1, 1)
         n, C = scores.shape[1], scores.shape[2]
 
         # one dense segment of n rows per (image, class), in the order of the reference's per-class loop
@@ -636,6 +661,8 @@ class KGDetHead(nn.Module):
         out_kpts = kpts.gather(1, row_i[..., None, None].expand(-1, -1, self.num_keypts, 2))
         vis = torch.ones_like(out_kpts[..., :1])
         out_kpts = (torch.cat([out_kpts, vis], -1) * valid[..., None, None]).reshape(B, k, -1)
+        if return_kept:
+            return out_dets, out_labels, out_kpts, flags.view(B, -1).sum(1), top_i
         return out_dets, out_labels, out_kpts
 
 
@@ -906,7 +933,7 @@ class RepPointsKpHead(nn.Module):
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def get_bboxes(self, cls_scores, keypts_preds_refine, reppts_preds_refine, img_shapes, score_thr=0.05, iou_thr=0.5,
-                   nms_pre=1000, max_per_img=100, score_override=None):
+                   nms_pre=1000, max_per_img=100, score_override=None, scale_factors=None, return_kept=False):
         """Batched, sync-free form of get_bboxes + get_bboxes_single of the two baseline heads (PAR:615-752, the
         same lines of SER) + multiclass_nms_kp (core/post_processing/bbox_nms_kp.py:6-75), over ALL levels.
 
@@ -916,6 +943,8 @@ class RepPointsKpHead(nn.Module):
         per (image, class) for ONE batched NMS launch, and keypoints are decoded only for the `max_per_img`
         survivors.  The keypoint clamp is this head's own (PAR:721-722 index the keypoint axis: keypoints 0, 3, 6...
         are limited to the image width in x AND y, keypoints 1, 4, 7... to the height, the others not at all).
+        scale_factors: optional per-image floats = the reference's `rescale=True` (PAR:732-737: boxes and keypoint
+        coordinates divided by the scale factor before the NMS).
         Returns dets [B, max_per_img, 5], labels [B, max_per_img] (-1 = empty slot), kpts [B, max_per_img, 294*3]."""
         bbox_preds = [self.points2bbox(r) for r in reppts_preds_refine]                # PAR:628-631
         B, dev = cls_scores[0].shape[0], cls_scores[0].device
@@ -960,6 +989,15 @@ class RepPointsKpHead(nn.Module):
         pos = torch.cat(pos_l, 1)                                                       # [B, n] position in its level
         lvl_of = torch.cat(lvl_of)                                                      # [n]
         n = boxes.shape[1]
+        sf = None
+        if scale_factors is not None:                                                   # PAR:732-733
+            skey = ('scale', tuple(float(f) for f in scale_factors), str(dev))
+            sf = self._lim_cache.get(skey)
+            if sf is None:
+                sf = torch.tensor([float(f) for f in scale_factors], dtype=torch.float32, device=dev)
+                self._lim_cache[skey] = sf
+            boxes = boxes / sf.view(B, 1, 1)
+            dets[..., :4] = dets[..., :4] / sf.view(B, 1, 1, 1)
         flags = self._nms_flags_fn(dets.view(-1, 5), None, n, iou_thr, score_thr=score_thr)
         masked = torch.where(flags.view(B, C * n).bool(), dets[..., 4].reshape(B, C * n), dets.new_full((), -1.0))
         k = min(max_per_img, C * n)
@@ -992,7 +1030,11 @@ class RepPointsKpHead(nn.Module):
         by_w = torch.min(kxy.clamp(min=0), w_)
         by_h = torch.min(kxy.clamp(min=0), h_)
         kxy = torch.where((idx == 0).view(1, 1, P, 1), by_w, torch.where((idx == 1).view(1, 1, P, 1), by_h, kxy))
+        if sf is not None:                                                              # PAR:734-736
+            kxy = kxy / sf.view(B, 1, 1, 1)
         out_kpts = (torch.cat([kxy, torch.ones_like(kxy[..., :1])], -1) * valid[..., None, None]).reshape(B, k, -1)
+        if return_kept:         # boxes the NMS kept per image (the reference sorts only above max_per_img)
+            return out_dets, out_labels, out_kpts, flags.view(B, -1).sum(1), top_i
         return out_dets, out_labels, out_kpts
 
 

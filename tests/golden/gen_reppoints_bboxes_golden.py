@@ -26,6 +26,7 @@ if ROOT not in sys.path:
 SIZES = [(32, 40), (16, 20), (8, 10), (4, 5), (2, 3)]
 IMG = (256, 320)
 NMS_PRE = 300
+SCALE = 1.6                     # scale_factor of the rescale=True case
 
 
 def make_case(seed=99, batch=2):
@@ -57,13 +58,19 @@ def main():
         with torch.no_grad():
             res = head.get_bboxes([c.clone() for c in cls], [k.clone() for k in kpt], [k.clone() for k in kpt],
                                   [r.clone() for r in rep], [r.clone() for r in rep], metas, tc, rescale=False)
-        for i, (d, l, k) in enumerate(res):
-            out['%s_dets_%d' % (variant, i)] = d.numpy()
-            out['%s_labels_%d' % (variant, i)] = l.numpy()
-            kk = k.reshape(d.shape[0], -1)
-            out['%s_kpts_head_%d' % (variant, i)] = kk[:25].numpy()                 # full rows of the 25 best
-            out['%s_kpts_rowsum_%d' % (variant, i)] = kk.double().sum(1).numpy()     # every row, as a checksum
-            print(variant, i, tuple(d.shape), int(l.min()), int(l.max()), flush=True)
+        # the same call with rescale=True (PAR:732-737: boxes / keypoints divided by the scale factor BEFORE the NMS)
+        metas_rs = [dict(img_shape=IMG + (3,), scale_factor=SCALE)] * cls[0].shape[0]
+        with torch.no_grad():
+            res_rs = head.get_bboxes([c.clone() for c in cls], [k.clone() for k in kpt], [k.clone() for k in kpt],
+                                     [r.clone() for r in rep], [r.clone() for r in rep], metas_rs, tc, rescale=True)
+        for tag, rr in (('', res), ('rs_', res_rs)):
+            for i, (d, l, k) in enumerate(rr):
+                out['%s_%sdets_%d' % (variant, tag, i)] = d.numpy()
+                out['%s_%slabels_%d' % (variant, tag, i)] = l.numpy()
+                kk = k.reshape(d.shape[0], -1)
+                out['%s_%skpts_head_%d' % (variant, tag, i)] = kk[:25].numpy()             # full rows of the 25 best
+                out['%s_%skpts_rowsum_%d' % (variant, tag, i)] = kk.double().sum(1).numpy()  # every row, as a checksum
+                print(variant, tag, i, tuple(d.shape), int(l.min()), int(l.max()), flush=True)
         out['%s_score_thr' % variant] = np.float32(tc['score_thr'])
         out['%s_iou_thr' % variant] = np.float32(tc['nms']['iou_thr'])
         out['%s_max_per_img' % variant] = np.int64(tc['max_per_img'])

@@ -183,8 +183,10 @@ def test_reppoints_kp_mirror_matches_reference_head_golden(variant, n_params):
         assert rel_err(bbox, torch.from_numpy(g['bbox_refine%d' % li])) < 1e-5
 
 
-def check_reppoints_bboxes(g, variant, dets, labels, kpts):
-    """(dets, labels, kpts) of RepPointsKpHead.get_bboxes against tests/golden/reppoints_bboxes.npz."""
+def check_reppoints_bboxes(g, variant, dets, labels, kpts, tag=''):
+    """(dets, labels, kpts) of RepPointsKpHead.get_bboxes against tests/golden/reppoints_bboxes.npz
+    (tag 'rs_': the rescale=True case)."""
+    variant = variant + ('_' + tag if tag else '')
     for i in range(dets.shape[0]):
         rd, rl = g['%s_dets_%d' % (variant, i)], g['%s_labels_%d' % (variant, i)]
         rk, rs = g['%s_kpts_head_%d' % (variant, i)], g['%s_kpts_rowsum_%d' % (variant, i)]
@@ -215,3 +217,31 @@ def test_reppoints_kp_mirror_get_bboxes_matches_reference_golden(variant):
     dets, labels, kpts = head.get_bboxes(cls, kpt, rep, [IMG] * 2, float(g[variant + '_score_thr']),
                                          float(g[variant + '_iou_thr']), NMS_PRE, int(g[variant + '_max_per_img']))
     check_reppoints_bboxes(g, variant, dets, labels, kpts)
+    # rescale=True: boxes / keypoints divided by the scale factor before the NMS (PAR:732-737)
+    from tests.golden.gen_reppoints_bboxes_golden import SCALE
+    dets, labels, kpts = head.get_bboxes(cls, kpt, rep, [IMG] * 2, float(g[variant + '_score_thr']),
+                                         float(g[variant + '_iou_thr']), NMS_PRE, int(g[variant + '_max_per_img']),
+                                         scale_factors=[SCALE] * 2)
+    check_reppoints_bboxes(g, variant, dets, labels, kpts, tag='rs')
+
+
+def check_kgdet_bboxes(g, dets, labels, kpts):
+    for i in range(dets.shape[0]):
+        rd, rl, rk = g['dets_%d' % i], g['labels_%d' % i], g['kpts_%d' % i]
+        nv = int((labels[i] >= 0).sum())
+        assert nv == rd.shape[0]
+        o = np.argsort(-rd[:, 4], kind='stable')
+        assert np.allclose(dets[i, :nv].cpu().numpy(), rd[o], rtol=0, atol=1e-4)
+        assert np.array_equal(labels[i, :nv].cpu().numpy(), rl[o])
+        assert np.allclose(kpts[i, :nv].cpu().numpy(), rk[o], rtol=0, atol=1e-3)
+
+
+def test_head_mirror_get_bboxes_rescale_matches_reference_golden():
+    """rescale=True (KP3:892-898) against the unchanged reference class (gen_kgdet_rescale_golden.py)."""
+    from tests.golden.gen_kgdet_rescale_golden import SCALE
+    g, gr = gold('get_bboxes.npz'), gold('get_bboxes_rescale.npz')
+    head = _cpu_head()
+    dets, labels, kpts = head.get_bboxes([torch.from_numpy(g['logit'])], [torch.from_numpy(g['kpt3'])],
+                                         [torch.from_numpy(g['bbox3'])], [(800, 1333)] * 2, 0.05, 0.5, 1000, 100,
+                                         scale_factors=[SCALE] * 2)
+    check_kgdet_bboxes(gr, dets, labels, kpts)

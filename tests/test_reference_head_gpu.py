@@ -196,3 +196,120 @@ def test_wire_formats_from_the_batched_gpu_output_match_the_reference_functions(
     for a, b in zip(sorted(got_kpt, key=key), sorted(want_kpt, key=key)):
         assert a['image_id'] == b['image_id'] and a['category_id'] == b['category_id']
         assert np.allclose(a['keypoints'], b['keypoints'], rtol=0, atol=2e-3)
+
+
+def _same_lists(a, b, flat):
+    assert len(a) == len(b)
+    for (d1, l1, k1), (d2, l2, k2) in zip(a, b):
+        assert d1.shape == d2.shape and k1.shape == k2.shape and (k1.dim() == 2) == flat
+        assert np.allclose(d1.cpu().numpy(), d2.cpu().numpy(), rtol=0, atol=1e-3)
+        assert np.array_equal(l1.cpu().numpy(), l2.cpu().numpy())
+        assert np.allclose(k1.cpu().numpy(), k2.cpu().numpy(), rtol=0, atol=1e-3)
+
+
+def test_accelerate_rebinds_the_unchanged_kgdet_head_to_the_fused_paths():
+    """`kgdet_b200.accelerate(ref_head)` on the B200: the reference OBJECT (its own parameters, its own method
+    signatures and result formats) now runs forward_single on the fused tensor-core path (bf16 mode: grouped DCN,
+    own convolutions, 1x1 GEMMs; no cuDNN kernel), get_bboxes on the decode kernels + ONE batched NMS launch --
+    rescale=True included, rows in the reference's order -- and loss() on the assignment / loss kernels.  Compared with
+    what the same object returned BEFORE the rebinding (its own methods on top of the mounted ops)."""
+    import kgdet_b200
+    from kgdet_b200 import ops
+    from kgdet_b200.ops import _capi
+    from tests.golden.gen_loss_golden import make_case
+    head, cfg, refshim = _reference_head()
+    refshim.patch_point_assigner_device()
+    head.eval()
+    g = np.load(os.path.join(GOLD, 'get_bboxes.npz'))
+    g7 = np.load(os.path.join(GOLD, 'head_p7.npz'))
+    t = lambda a: torch.from_numpy(a).cuda()                               # noqa: E731
+    x = t(g7['x'])
+    tc = refshim.AttrDict(cfg['test_cfg'])
+    metas = [dict(img_shape=(800, 1333, 3), scale_factor=1.0)] * 2
+    metas_rs = [dict(img_shape=(800, 1333, 3), scale_factor=1.6)] * 2
+    dummy = [t(g7['cls_1'])]
+    bb_args = (dummy, dummy, [t(g['logit'])], [t(g7['kpt_1'])], [t(g7['kpt_2'])], [t(g['kpt3'])], [t(g7['bbox_1'])],
+               [t(g7['bbox_2'])], [t(g['bbox3'])])
+    outs, gt_bboxes, gt_labels, gt_kps, (ih, iw) = make_case()
+    lmetas = [dict(img_shape=(ih, iw, 3), pad_shape=(ih, iw, 3), scale_factor=1.0, flip=False)] * outs[0].shape[0]
+    trc = refshim.AttrDict(uniform=refshim.AttrDict(cfg['train_cfg']['uniform']))
+
+    def run_loss():
+        o = [v.cuda().requires_grad_() for v in outs]
+        losses = head.loss(*[[v] for v in o], [b.clone().cuda() for b in gt_bboxes], [l.cuda() for l in gt_labels],
+                           [k.cuda() for k in gt_kps], lmetas, trc)
+        sum(v[0] for v in losses.values()).backward()
+        return {k: float(v[0]) for k, v in losses.items()}, [v.grad for v in o]
+
+    with _fp32_cudnn(), torch.no_grad():
+        want = head.forward_single(x)
+        ref_plain = head.get_bboxes(*bb_args, metas, tc, rescale=False)
+        ref_rs = head.get_bboxes(*bb_args, metas_rs, tc, rescale=True)
+    ref_losses, ref_grads = run_loss()
+
+    kgdet_b200.accelerate(head)
+    assert all(p is dict(head.named_parameters())[n] for n, p in head.kgdet_mirror.named_parameters())
+    n0 = _capi.lib().kgdet_launch_count()
+    with torch.no_grad():
+        got32 = head.forward_single(x)                    # fp32 tensors: the fp32-grade tensor-core path
+        ops.set_precision('bf16')
+        try:
+            got16 = head.forward_single(x)
+        finally:
+            ops.set_precision(None)
+        plain = head.get_bboxes(*bb_args, metas, tc, rescale=False)
+        rs = head.get_bboxes(*bb_args, metas_rs, tc, rescale=True)
+    assert _capi.lib().kgdet_launch_count() > n0
+    for n, a, b, c in zip(NAMES, got32, got16, want):
+        assert rel_err(a, c) < 2e-3, (n, rel_err(a, c))
+        assert rel_err(b, c) < 3e-2, (n, rel_err(b, c))
+    _same_lists(plain, ref_plain, flat=False)
+    _same_lists(rs, ref_rs, flat=True)
+    losses, grads = run_loss()
+    assert set(losses) == set(ref_losses)
+    for k in losses:
+        assert abs(losses[k] - ref_losses[k]) < 5e-5 * abs(ref_losses[k]), (k, losses[k], ref_losses[k])
+    for a, b in zip(grads, ref_grads):
+        assert (a - b).abs().max().item() <= 2e-5 * b.abs().max().item() + 1e-12
+
+
+@pytest.mark.parametrize('variant', ['parallel', 'serial'])
+def test_accelerate_rebinds_the_unchanged_reppoints_heads(variant):
+    """The RepPoints-Kp baseline head objects: forward over FPN levels on the position-major fused path and the
+    multi-level get_bboxes, against the same object's own methods before the rebinding."""
+    import kgdet_b200
+    from kgdet_b200 import ops
+    from tests import refshim
+    from tests.golden.gen_reppoints_bboxes_golden import IMG, NMS_PRE, SCALE, make_case
+    if not refshim.available():
+        pytest.skip('reference python tree not present')
+    refshim.install('kgdet')
+    head, cfg = refshim.build_head('reppoints_moment_%s_r50_fpn_1x-deepfashion2.py' % variant, device='cuda')
+    head.load_state_dict(fill_state_dict(head.state_dict(), seed=4321), strict=True)
+    head.eval()
+    gen = torch.Generator().manual_seed(12)
+    feats = [torch.randn(2, 256, h, w, generator=gen).cuda() for h, w in [(50, 84), (25, 42), (13, 21), (7, 11), (4, 6)]]
+    cls, kpt, rep = [[v.cuda() for v in vs] for vs in make_case()]
+    tc = refshim.AttrDict(cfg['test_cfg'])
+    tc['nms_pre'] = NMS_PRE
+    metas = [dict(img_shape=IMG + (3,), scale_factor=1.0)] * 2
+    metas_rs = [dict(img_shape=IMG + (3,), scale_factor=SCALE)] * 2
+    call = lambda mt, r: head.get_bboxes([c.clone() for c in cls], [k.clone() for k in kpt], [k.clone() for k in kpt],   # noqa: E731
+                                         [v.clone() for v in rep], [v.clone() for v in rep], mt, tc, rescale=r)
+    with _fp32_cudnn(), torch.no_grad():
+        want = head.forward(feats, None)
+        ref_plain, ref_rs = call(metas, False), call(metas_rs, True)
+    kgdet_b200.accelerate(head)
+    ops.set_precision('bf16')
+    try:
+        with _fp32_cudnn(), torch.no_grad():
+            got = head.forward(feats, None)
+    finally:
+        ops.set_precision(None)
+    assert len(got) == 5 and len(got[0]) == len(feats)
+    for j in range(5):
+        for li in range(len(feats)):
+            assert rel_err(got[j][li], want[j][li]) < 3e-2, (j, li, rel_err(got[j][li], want[j][li]))
+    with torch.no_grad():
+        _same_lists(call(metas, False), ref_plain, flat=False)
+        _same_lists(call(metas_rs, True), ref_rs, flat=True)
