@@ -677,7 +677,7 @@ def train_record(args, rank=None, world=None, local=None):
     # (4.36 -> 4.15 ms per step: the heuristic choices wrap every call in NCHW <-> NHWC transposes)
     cudnn_benchmark_before = torch.backends.cudnn.benchmark
     torch.backends.cudnn.benchmark = os.environ.get('KGDET_CUDNN_BENCHMARK', '1') == '1'
-    opt = torch.optim.SGD(head.parameters(), lr=1e-6, momentum=0.9)
+    opt = torch.optim.SGD(head.parameters(), lr=1e-6, momentum=0.9, fused=os.environ.get('KGDET_FUSED_SGD', '1') == '1')
     g = torch.Generator().manual_seed(200 + rank)
     x = torch.randn(B, C, H, W, generator=g).to(dev)
     # synthetic ground truth as SURVEY.md section 8(d) config 5: per image 1-3 boxes (w, h ~ U(100, 600) inside
@@ -843,7 +843,11 @@ def train_record(args, rank=None, world=None, local=None):
                        'batch_per_gpu': B, 'allreduce': allreduce_kind + (', %.1f MB fp32 gradients' % (nparam * 4 / 1e6)
                                                                            if world > 1 else ''),
                        'parallelism': 'dp%d' % world, 'l2': 'flushed before every step',
-                       'cudnn': 'plain 3x3 / 1x1 convolutions and their gradients on cuDNN, TF32, ' + cudnn_mode},
+                       'cudnn': 'plain 3x3 / 1x1 convolutions and their gradients on cuDNN, TF32, ' + cudnn_mode,
+                       'streams': 'the six deformable convolutions of a stage on six streams and the classification '
+                                  'tower next to the point branch, forward and (through autograd) backward: parallel '
+                                  'branches of the captured graph',
+                       'optimizer': 'SGD momentum 0.9, fused multi-tensor kernel; clip_grad_norm_ 35'},
             'exposed_allreduce_us': exposed_us, 'launch_mode': mode, 'final_loss': final_loss}
 
 

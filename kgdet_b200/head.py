@@ -21,6 +21,7 @@ Tower convolutions / GroupNorm / 1x1 heads are outside the hot path (SURVEY.md s
 and stay PyTorch/cuDNN.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -217,6 +218,7 @@ class _DeformBlock(nn.Module):
         self.gradient_mul = gradient_mul
         self.concurrent_dcn = True          # forward_tc: the six DCNs of the stage on six streams
         self.grouped_dcn = True             # forward_tc: ... or, better, in one persistent grouped launch
+        self.concurrent_training = os.environ.get('KGDET_TRAIN_STREAMS', '1') != '0'   # forward (autograd): six streams
         for k in _POINT_SETS:
             pad = (k - 1) // 2
             setattr(self, 'cls_dfmconv_%d' % k, deform_conv_cls(cin, feat, k, 1, pad))
@@ -314,15 +316,58 @@ class _DeformBlock(nn.Module):
     def forward(self, cls_feat, pts_feat, reppts_offset):
         cls_feats, kpt_feats = [], []
         lo = 0
-        for k in _POINT_SETS:
+        # Training at batch 2 (2 100 positions): every deformable convolution and each kernel of its backward is a
+        # handful of CTAs.  The six calls of a stage are independent, so they are issued on six streams; autograd runs
+        # every backward node on its forward's stream, so the captured training graph gets six parallel branches in
+        # both directions.
+        fork = (self.concurrent_training and cls_feat.is_cuda and torch.is_grad_enabled())
+        if fork:
+            dev = cls_feat.device
+            main = torch.cuda.current_stream(dev)
+            streams = _streams(dev, 6)
+            start = main.record_event()
+        jobs = []
+        for i, k in enumerate(_POINT_SETS):
             n2 = 2 * k * k
             pts = reppts_offset[:, lo:lo + n2]                                     # KP3:131-133
             lo += n2
             # KP3:135-143 -- evaluated in inference too (the identity up to fp32 rounding), exactly as the reference
             pts = self.gradient_mul * pts + (1 - self.gradient_mul) * pts.detach()
             dcn_offset = pts - getattr(self, '_dcn_base_%d' % k).to(pts.dtype)
+            if fork:
+                jobs.append((k, dcn_offset))
+                continue
             cls_feats.append(F.relu(getattr(self, 'cls_dfmconv_%d' % k)(cls_feat, dcn_offset)))
             kpt_feats.append(F.relu(getattr(self, 'keypts_dfmconv_%d' % k)(pts_feat, dcn_offset)))
+        if fork:
+            ready = main.record_event()                 # offsets computed
+            outs = {}
+            for j, (k, dcn_offset) in enumerate(reversed(jobs)):       # longest (49 points) first
+                for b, (name, feat) in enumerate((('cls_dfmconv_%d', cls_feat), ('keypts_dfmconv_%d', pts_feat))):
+                    st = streams[2 * j + b]
+                    st.wait_event(ready)
+                    with torch.cuda.stream(st):
+                        o = F.relu(getattr(self, name % k)(feat, dcn_offset))
+                        done = st.record_event()
+                    o.record_stream(main)
+                    outs[(k, b)] = (o, done)
+            for k in _POINT_SETS:
+                for b, lst in ((0, cls_feats), (1, kpt_feats)):
+                    o, done = outs[(k, b)]
+                    main.wait_event(done)
+                    lst.append(o)
+            del start
+        if fork:
+            st = streams[0]
+            st.wait_event(main.record_event())
+            with torch.cuda.stream(st):
+                cls_out = self.cls_out(torch.cat(cls_feats, dim=1))                # KP3:152-156
+                cls_done = st.record_event()
+            keypts_out = self.keypts_out(torch.cat(kpt_feats, dim=1))              # KP3:164-170
+            rep_out = self.reppts_out(keypts_out)
+            main.wait_event(cls_done)
+            cls_out.record_stream(main)
+            return cls_out, keypts_out, rep_out
         cls_out = self.cls_out(torch.cat(cls_feats, dim=1))                        # KP3:152-156
         keypts_out = self.keypts_out(torch.cat(kpt_feats, dim=1))                  # KP3:164-170
         return cls_out, keypts_out, self.reppts_out(keypts_out)
@@ -439,11 +484,31 @@ class KGDetHead(nn.Module):
                         for m in list(self.cls_convs) + list(self.reg_convs))):
             return self._forward_single_fp32_grade(x)
         cls_feat = pts_feat = x
-        for m in self.cls_convs:
-            cls_feat = m(cls_feat)
-        for m in self.reg_convs:
-            pts_feat = m(pts_feat)
-        cls1, kpt1, rep1 = self.kp_rep_block_1(cls_feat, pts_feat)
+        if x.is_cuda and torch.is_grad_enabled() and self.kp_rep_block_2.concurrent_training:
+            # training: the classification tower + stage-1 classifier run on a side stream next to the point branch
+            # (autograd replays each backward node on its forward's stream: two parallel arms in both directions)
+            main = torch.cuda.current_stream(x.device)
+            side = _streams(x.device, 7)[6]
+            side.wait_event(main.record_event())
+            with torch.cuda.stream(side):
+                for m in self.cls_convs:
+                    cls_feat = m(cls_feat)
+                b1 = self.kp_rep_block_1
+                cls1 = b1.cls_out(F.relu(b1.cls_conv(cls_feat)))
+                cls_done = side.record_event()
+            for m in self.reg_convs:
+                pts_feat = m(pts_feat)
+            kpt1 = b1.keypts_out(F.relu(b1.keypts_conv(pts_feat)))
+            rep1 = b1.reppts_out(kpt1)
+            main.wait_event(cls_done)
+            cls_feat.record_stream(main)
+            cls1.record_stream(main)
+        else:
+            for m in self.cls_convs:
+                cls_feat = m(cls_feat)
+            for m in self.reg_convs:
+                pts_feat = m(pts_feat)
+            cls1, kpt1, rep1 = self.kp_rep_block_1(cls_feat, pts_feat)
         bbox1 = self.points2bbox(rep1)
         if fused:
             feat = self.kp_rep_block_2.cls_dfmconv_3.out_channels
