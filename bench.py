@@ -196,7 +196,7 @@ def reppoints_kp_record(args, head_mod, ops, dev, flush):
     levels = [(100, 168), (50, 84), (25, 42), (13, 21), (7, 11)]
     batch = 8
     out = {'levels': levels, 'batch': batch, 'unit': UNIT,
-           'note': 'bf16 DCN mode; 3x3 tower convolutions cuDNN channels_last (TF32, cudnn.benchmark), GroupNorm / 1x1 GEMMs / grouped '
+           'note': 'bf16 DCN mode; FPN levels as parallel graph branches; 3x3 tower convolutions cuDNN channels_last (TF32, cudnn.benchmark), GroupNorm / 1x1 GEMMs / grouped '
                    'DCNs / candidate selection / decode / batched NMS this library; synthetic scores U^%d as the main '
                    'record; round-1 forward-only numbers were 789 (parallel) / 880 (serial) images/s' % SCORE_POW}
     ops.set_precision('bf16')

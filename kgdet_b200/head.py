@@ -69,6 +69,14 @@ def _streams(device, n):
     return lst[:n]
 
 
+class _null_context(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 def _cl_weight(w):
     """channels_last copy of a convolution weight (cached per parameter version): cuDNN then runs the
     convolution on channels_last activations without inserting layout transposes."""
@@ -773,6 +781,7 @@ class RepPointsKpHead(nn.Module):
         kd, rd, pf = 2 * num_keypts, 2 * num_reppts, point_feat_channels
         self.grouped_dcn = True             # bf16 inference: the DCNs of all levels in grouped persistent launches
         self.nhwc_towers = True             # ... with position-major towers / 1x1 GEMMs around them (_forward_nhwc)
+        self.concurrent_levels = True       # ... and the FPN levels as parallel branches around the grouped launches
         self.cls_refine_dfmconv = deform_conv_cls(feat_channels, pf, k, 1, self.dcn_pad)
         self.cls_refine_out = nn.Conv2d(pf, self.cls_out_channels, 1, 1, 0)
         self.keypts_init_conv = nn.Conv2d(feat_channels, pf, 3, 1, 1)
@@ -896,7 +905,18 @@ class RepPointsKpHead(nn.Module):
         par = self.variant == 'parallel'
         last = len(self.cls_convs) - 1
         per_level, jobs = [], []
-        for x in feats:
+        # levels are independent up to the grouped launches: level i > 0 runs on its own stream (a parallel branch of the
+        # captured graph) next to P3, whose kernels are the only ones that fill the machine
+        dev0 = feats[0].device
+        main = torch.cuda.current_stream(dev0)
+        lvl_streams = [main] + (_streams(dev0, 8 + len(feats))[9:8 + len(feats)] if self.concurrent_levels else
+                                [main] * (len(feats) - 1))
+        start = main.record_event()
+        for li, x in enumerate(feats):
+          st = lvl_streams[li]
+          if st is not main:
+              st.wait_event(start)
+          with torch.cuda.stream(st):                          # (body indented for the `with`)
             n, _, h, w = x.shape
             dev = x.device
             cls_feat = pts_feat = to_channels_last(x)
@@ -934,11 +954,19 @@ class RepPointsKpHead(nn.Module):
             if par:
                 jobs.append((pts_prep, plan, self.reppts_refine_dfmconv.weight, rows[2], 0, True))
             per_level.append((n, h, w, kpt_init, rep_init, rows))
+        for st in lvl_streams[1:]:
+            if st is not main:
+                main.wait_event(st.record_event())
         jobs.sort(key=lambda j: -j[3].M)                                           # biggest maps first
         for i in range(0, len(jobs), 6):
             deform_conv_prepared_group(jobs[i:i + 6])
         res = []
-        for n, h, w, kpt_init, rep_init, rows in per_level:
+        grouped = main.record_event()
+        for li, (n, h, w, kpt_init, rep_init, rows) in enumerate(per_level):
+          st = lvl_streams[li]
+          if st is not main:
+              st.wait_event(grouped)
+          with torch.cuda.stream(st):
             cls_out = kpt_init.new_empty((n, nc, h, w))
             kpt_ref = torch.empty_like(kpt_init)
             rep_ref = torch.empty_like(rep_init)
@@ -950,6 +978,12 @@ class RepPointsKpHead(nn.Module):
                 pointwise_conv(rows[1], W['kpt_rep_refine'][0], W['kpt_rep_refine'][1],
                                [(kpt_ref, kpt_init, 0, kd), (rep_ref, rep_init, kd, kd + rd)], h * w)  # SER:330
             res.append((cls_out, kpt_init, kpt_ref, rep_init, rep_ref))
+        for st in lvl_streams[1:]:
+            if st is not main:
+                main.wait_event(st.record_event())
+        for lvl in res:
+            for t in lvl:
+                t.record_stream(main)
         return tuple(map(list, zip(*res)))
 
     def _forward_grouped(self, feats):
@@ -1011,7 +1045,6 @@ class RepPointsKpHead(nn.Module):
         scale_factors: optional per-image floats = the reference's `rescale=True` (PAR:732-737: boxes and keypoint
         coordinates divided by the scale factor before the NMS).
         Returns dets [B, max_per_img, 5], labels [B, max_per_img] (-1 = empty slot), kpts [B, max_per_img, 294*3]."""
-        bbox_preds = [self.points2bbox(r) for r in reppts_preds_refine]                # PAR:628-631
         B, dev = cls_scores[0].shape[0], cls_scores[0].device
         key = (tuple(tuple(s[:2]) for s in img_shapes), str(dev))
         wh = self._lim_cache.get(key)
@@ -1022,7 +1055,17 @@ class RepPointsKpHead(nn.Module):
                  and all(c.shape[-2] * c.shape[-1] <= 40960 for c in cls_scores) and 0 < nms_pre <= 4096)
         C = cls_scores[0].shape[1]
         boxes_l, dets_l, pos_l, lvl_of = [], [], [], []
-        for lvl, (cs, bp) in enumerate(zip(cls_scores, bbox_preds)):
+        # per-level selection + decode as parallel branches (one CTA per image each: latency, not throughput)
+        par = fused and self.concurrent_levels and len(cls_scores) > 1
+        main = torch.cuda.current_stream(dev) if par else None
+        lvl_streams = ([main] + _streams(dev, 8 + len(cls_scores))[9:8 + len(cls_scores)]) if par else None
+        start = main.record_event() if par else None
+        for lvl, (cs, rp) in enumerate(zip(cls_scores, reppts_preds_refine)):
+          st = lvl_streams[lvl] if par else None
+          if par and st is not main:
+              st.wait_event(start)
+          with (torch.cuda.stream(st) if par else _null_context()):
+            bp = self.points2bbox(rp)                                                   # PAR:628-631
             stride = self.point_strides[lvl]
             H, W = cs.shape[-2:]
             n_l = min(nms_pre, H * W) if nms_pre > 0 else H * W
@@ -1049,6 +1092,9 @@ class RepPointsKpHead(nn.Module):
             dets_l.append(dets)
             pos_l.append(order)
             lvl_of.append(torch.full((n_l,), lvl, dtype=torch.long, device=dev))
+        if par:
+            for st in lvl_streams[1:]:
+                main.wait_event(st.record_event())
         boxes = torch.cat(boxes_l, 1)                                                   # [B, n, 4]
         dets = torch.cat(dets_l, 2).contiguous()                                        # [B, C, n, 5]
         pos = torch.cat(pos_l, 1)                                                       # [B, n] position in its level
@@ -1079,13 +1125,25 @@ class RepPointsKpHead(nn.Module):
         kp = top_s.new_zeros((B, k, 2 * P))
         ctr = top_s.new_zeros((B, k, 2))
         strd = top_s.new_zeros((B, k))
+        picked = []
+        if par:
+            chosen = main.record_event()
         for lvl, kmap in enumerate(keypts_preds_refine):
+          st = lvl_streams[lvl] if par else None
+          if par and st is not main:
+              st.wait_event(chosen)
+          with (torch.cuda.stream(st) if par else _null_context()):
             H, W = kmap.shape[-2:]
             here = l_i == lvl
             pl = torch.where(here, p_i, torch.zeros_like(p_i))
             v = kmap.float().reshape(B, 2 * P, H * W).gather(2, pl[:, None].expand(-1, 2 * P, -1)).transpose(1, 2)
-            kp = torch.where(here[..., None], v, kp)
             c_l = torch.stack([(pl % W).float(), (pl // W).float()], -1) * self.point_strides[lvl]
+            picked.append((here, v, c_l))
+        if par:
+            for st in lvl_streams[1:]:
+                main.wait_event(st.record_event())
+        for lvl, (here, v, c_l) in enumerate(picked):
+            kp = torch.where(here[..., None], v, kp)
             ctr = torch.where(here[..., None], c_l, ctr)
             strd = torch.where(here, torch.full_like(strd, float(self.point_strides[lvl])), strd)
         kxy = kp.view(B, k, P, 2).flip(-1)                                              # points2kpt: (y, x) -> (x, y)
