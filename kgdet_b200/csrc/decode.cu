@@ -39,10 +39,14 @@ __global__ void __launch_bounds__(256) bbox_select_kernel(const float* __restric
   for (int p = threadIdx.x; p < HW4; p += blockDim.x) {
     unsigned int m = 0u;                        // below rank_key(-inf); the padding keys never outrank a real one
     if (p < HW) {
-      for (int c = 0; c < C; ++c) {
-        float v = sb[(size_t)c * HW + p];
-        if (apply_sigmoid) v = sigmoid_ref(v);
-        m = max(m, rank_key(v));                // NaN propagates, like torch.max
+      for (int c0 = 0; c0 < C; c0 += 8) {       // eight classes in flight before the first is used
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (c0 + u < C) ? sb[(size_t)(c0 + u) * HW + p] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (c0 + u < C) m = max(m, rank_key(apply_sigmoid ? sigmoid_ref(v[u]) : v[u]));   // NaN propagates, like torch.max
+        }
       }
     }
     skey[p] = m;

@@ -282,12 +282,22 @@ class _DeformBlock(nn.Module):
         kpt_rows = TiledRows(n * h * w, 3 * feat, True, dev)
         lo = 0
         jobs = []
+        # the three sample plans are independent 8 us kernels: three parallel branches instead of a chain
+        main = torch.cuda.current_stream(dev)
+        plan_streams = [main] + _streams(dev, 2)
+        fork = main.record_event()
         for i, k in enumerate(_POINT_SETS):
-            plan = prepare_plan_points(rep_prev, lo, (n, c, h, w), feat, k, 1, (k - 1) // 2, 1, precision='bf16',
-                                       gradient_mul=self.gradient_mul)
+            st = plan_streams[i]
+            if st is not main:
+                st.wait_event(fork)
+            with torch.cuda.stream(st):
+                plan = prepare_plan_points(rep_prev, lo, (n, c, h, w), feat, k, 1, (k - 1) // 2, 1, precision='bf16',
+                                           gradient_mul=self.gradient_mul)
             lo += 2 * k * k
             jobs.append((cls_prep, plan, getattr(self, 'cls_dfmconv_%d' % k).weight, cls_rows, i * feat))
             jobs.append((pts_prep, plan, getattr(self, 'keypts_dfmconv_%d' % k).weight, kpt_rows, i * feat))
+        for st in plan_streams[1:]:
+            main.wait_event(st.record_event())
         jobs.reverse()                                   # longest first (49, 49, 25, 25, 9, 9 points)
         if self.grouped_dcn:
             # ONE persistent launch for the six DCNs of the stage: 792 tiles handed out longest first to one CTA per
