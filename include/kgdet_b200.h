@@ -224,6 +224,13 @@ KGDET_API int kgdet_groupnorm_relu_nhwc_planes(const float* x, const float* gamm
                                      int32_t groups, int fuse_relu, float* y, void* planes, int32_t N, int32_t H,
                                      int32_t W, int32_t C, void* stream);
 
+/* Backward of kgdet_groupnorm_relu_nhwc for the training step of the towers (maps of at most 1600 positions):
+ * dx (NHWC fp32) and per-image partials dgamma_part / dbeta_part [N, C] (their sum over N is the gradient).
+ * replaces the autograd of torch.nn.GroupNorm + ReLU inside ConvModule (conv_module.py:96-110,156-164). */
+KGDET_API int kgdet_groupnorm_relu_nhwc_backward(const float* x, const float* dy, const float* gamma, const float* beta,
+                                       float eps, int32_t groups, int fuse_relu, float* dx, float* dgamma_part,
+                                       float* dbeta_part, int32_t N, int32_t HW, int32_t C, void* stream);
+
 /* GroupNorm (+ ReLU) of NHWC fp32 maps of ANY size (the resident kernels above need the map in shared memory:
  * <= 1600 positions): two streaming passes (per-chunk moments merged with Chan's update in chunk order, then
  * normalise).  y (NHWC fp32) and / or planes may be NULL (not both); planes_hi_only != 0 writes only the hi half

@@ -322,6 +322,133 @@ static bool stream_gn_supported(int C, int groups) {
 
 static int stream_gn_chunks(int HW, int C) { return ceil_div(HW, (GS_THREADS / (C / 4)) * GS_SWEEPS); }
 
+// Backward of GroupNorm (+ ReLU) on NHWC fp32, same CTA shape as the wide forward kernel (image x 32 channels, the
+// map's x values resident in shared memory; dy is read twice, the second time from L2):
+//   z = (x - mean) * rstd * gamma + beta,  y = relu(z);   dz = dy * [z > 0]
+//   dgamma_c = sum dz * xhat,  dbeta_c = sum dz           (per image here: [N, C] partials, summed by the caller)
+//   dx = rstd * (dz * gamma - (A + xhat * B) / m),   A = sum_group dz * gamma,  B = sum_group dz * gamma * xhat
+// (torch.nn.functional.group_norm's backward, ATen/native/cuda/group_norm_kernel.cu, with the ReLU mask folded in).
+template <int VEC>
+__global__ void __launch_bounds__(1024) groupnorm_relu_bwd_nhwc_wide_kernel(
+    const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float eps, float* __restrict__ dx, float* __restrict__ dgamma_part,
+    float* __restrict__ dbeta_part, int HW, int C, int relu) {
+  constexpr int GPC = 8 / VEC;
+  extern __shared__ float sm[];                 // [HW][32] x values
+  __shared__ float red[32][GPC];
+  __shared__ float cred[32][8][8];              // per warp, per chunk: 4 x (dbeta, dgamma) partials
+  const int n = blockIdx.y, c0 = blockIdx.x * 32;
+  const int chunk = threadIdx.x & 7, gi = chunk / VEC, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t base = (size_t)n * HW * C + c0 + chunk * 4;
+  const float* xg = x + base;
+  const float* dyg = dy + base;
+  float* dxg = dx + base;
+  const int prow = threadIdx.x >> 3, pstep = blockDim.x >> 3;
+  const float inv_total = 1.f / (float)(HW * VEC * 4);
+  auto group_sum = [&](float v) -> float {
+#pragma unroll
+    for (int o = 1; o < VEC; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    __syncthreads();
+    if (lane < 8 && (lane % VEC) == 0) red[warp][gi] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w][gi];
+    return t;
+  };
+  float s = 0.f;
+  for (int p = prow; p < HW; p += pstep) {
+    const float4 v = *reinterpret_cast<const float4*>(xg + (size_t)p * C);
+    *reinterpret_cast<float4*>(sm + (size_t)p * 32 + chunk * 4) = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = group_sum(s) * inv_total;
+  float ss = 0.f;
+  for (int p = prow; p < HW; p += pstep) {
+    const float4 v = *reinterpret_cast<const float4*>(sm + (size_t)p * 32 + chunk * 4);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
+  }
+  const float rstd = rsqrtf(group_sum(ss) * inv_total + eps);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c0 + chunk * 4));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0 + chunk * 4));
+  const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
+  // pass A: per-channel sums of dz and dz * xhat
+  float sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int p = prow; p < HW; p += pstep) {
+    const float4 v4 = *reinterpret_cast<const float4*>(sm + (size_t)p * 32 + chunk * 4);
+    const float4 g4 = *reinterpret_cast<const float4*>(dyg + (size_t)p * C);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xh = (v[k] - mean) * rstd;
+      const float dz = (!relu || xh * gam[k] + bet[k] > 0.f) ? g[k] : 0.f;
+      sb[k] += dz;
+      sg[k] = fmaf(dz, xh, sg[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {                 // lanes chunk, chunk + 8, + 16, + 24 hold the same channels
+    sb[k] += __shfl_xor_sync(0xffffffffu, sb[k], 8);  sb[k] += __shfl_xor_sync(0xffffffffu, sb[k], 16);
+    sg[k] += __shfl_xor_sync(0xffffffffu, sg[k], 8);  sg[k] += __shfl_xor_sync(0xffffffffu, sg[k], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { cred[warp][chunk][k] = sb[k]; cred[warp][chunk][4 + k] = sg[k]; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { sb[k] = 0.f; sg[k] = 0.f; }
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sb[k] += cred[w][chunk][k]; sg[k] += cred[w][chunk][4 + k]; }
+  }
+  if (threadIdx.x < 8) {
+    float* db = dbeta_part + (size_t)n * C + c0 + chunk * 4;
+    float* dg = dgamma_part + (size_t)n * C + c0 + chunk * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { db[k] = sb[k]; dg[k] = sg[k]; }
+  }
+  // group sums A, B from the channel sums (every thread holds the totals of its chunk's four channels)
+  float A = 0.f, B = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { A = fmaf(gam[k], sb[k], A); B = fmaf(gam[k], sg[k], B); }
+#pragma unroll
+  for (int o = 1; o < VEC; o <<= 1) {
+    A += __shfl_xor_sync(0xffffffffu, A, o);
+    B += __shfl_xor_sync(0xffffffffu, B, o);
+  }
+  A *= inv_total; B *= inv_total;
+  // pass B: dx
+  for (int p = prow; p < HW; p += pstep) {
+    const float4 v4 = *reinterpret_cast<const float4*>(sm + (size_t)p * 32 + chunk * 4);
+    const float4 g4 = *reinterpret_cast<const float4*>(dyg + (size_t)p * C);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xh = (v[k] - mean) * rstd;
+      const float dz = (!relu || xh * gam[k] + bet[k] > 0.f) ? g[k] : 0.f;
+      o[k] = rstd * (dz * gam[k] - (A + xh * B));
+    }
+    *reinterpret_cast<float4*>(dxg + (size_t)p * C) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+template <int VEC>
+static int launch_groupnorm_bwd_wide(const float* x, const float* dy, const float* gamma, const float* beta, float eps,
+                                     float* dx, float* dgp, float* dbp, int N, int HW, int C, int relu,
+                                     cudaStream_t stream) {
+  const size_t smem = (size_t)HW * 32 * sizeof(float);
+  KG_CUDA(cudaFuncSetAttribute(groupnorm_relu_bwd_nhwc_wide_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  groupnorm_relu_bwd_nhwc_wide_kernel<VEC><<<dim3(C / 32, N), 1024, smem, stream>>>(x, dy, gamma, beta, eps, dx, dgp, dbp,
+                                                                                    HW, C, relu);
+  KG_LAUNCH_CHECK("groupnorm_relu_bwd_nhwc_wide_kernel");
+  return KGDET_OK;
+}
+
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&v);
@@ -542,4 +669,30 @@ extern "C" int kgdet_groupnorm_relu_nhwc_stream(const float* x, const float* gam
                                                                            fuse_relu ? 1 : 0, hi, lo, plane_bytes);
   KG_LAUNCH_CHECK("groupnorm_stream_apply_kernel");
   return KGDET_OK;
+}
+
+// Backward of kgdet_groupnorm_relu_nhwc (maps of at most 1600 positions): dx (NHWC fp32) and the per-image partials
+// of the affine parameters' gradients, dgamma_part / dbeta_part [N, C] (sum over N = the gradient).
+// replaces torch.nn.GroupNorm's + ReLU's autograd in ConvModule (mmdet/models/utils/conv_module.py:96-110,156-164)
+// for the training step of the towers (KP3:292-313).
+extern "C" int kgdet_groupnorm_relu_nhwc_backward(const float* x, const float* dy, const float* gamma, const float* beta,
+                                                  float eps, int32_t groups, int fuse_relu, float* dx,
+                                                  float* dgamma_part, float* dbeta_part, int32_t N, int32_t HW,
+                                                  int32_t C, void* stream) {
+  KG_CHECK_ARG(x && dy && gamma && beta && dx && dgamma_part && dbeta_part, "kgdet_groupnorm_relu_nhwc_backward: NULL pointer");
+  KG_CHECK_ARG(N > 0 && N <= 65535 && HW > 0 && C > 0 && C % 32 == 0 && groups > 0 && C % groups == 0 &&
+                   32 % (C / groups) == 0 && (C / groups) % 4 == 0 && (size_t)HW * 128 <= 200 * 1024,
+               "kgdet_groupnorm_relu_nhwc_backward: need C %% 32 == 0, 4 | C / groups | 32 and a map of at most 1600 positions");
+  KG_CHECK_ARG((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0,
+               "kgdet_groupnorm_relu_nhwc_backward: misaligned pointer");
+  const int relu = fuse_relu ? 1 : 0;
+  switch ((C / groups) / 4) {
+    case 1: return launch_groupnorm_bwd_wide<1>(x, dy, gamma, beta, eps, dx, dgamma_part, dbeta_part, N, HW, C, relu, (cudaStream_t)stream);
+    case 2: return launch_groupnorm_bwd_wide<2>(x, dy, gamma, beta, eps, dx, dgamma_part, dbeta_part, N, HW, C, relu, (cudaStream_t)stream);
+    case 4: return launch_groupnorm_bwd_wide<4>(x, dy, gamma, beta, eps, dx, dgamma_part, dbeta_part, N, HW, C, relu, (cudaStream_t)stream);
+    case 8: return launch_groupnorm_bwd_wide<8>(x, dy, gamma, beta, eps, dx, dgamma_part, dbeta_part, N, HW, C, relu, (cudaStream_t)stream);
+    default: break;
+  }
+  set_error("kgdet_groupnorm_relu_nhwc_backward: unsupported channels per group %d", C / groups);
+  return KGDET_ERR_UNSUPPORTED;
 }

@@ -33,7 +33,7 @@ from .ops import (DeformConv, TiledRows, batched_nms_flags, deform_conv_prepared
                   prepare_input, prepare_plan, prepare_plan_points)
 from .ops.conv import conv_planes, conv_supported, groupnorm_relu_planes, split_planes
 from .ops.decode import bbox_decode, bbox_finalize, bbox_select, topk_flagged
-from .ops.pointwise import cached, to_channels_last
+from .ops.pointwise import cached, groupnorm_relu_nhwc_autograd, to_channels_last
 
 _POINT_SETS = (3, 5, 7)          # KP3:257: 9 + 25 + 49 points regardless of cfg.num_reppts
 
@@ -405,6 +405,9 @@ class KGDetHead(nn.Module):
         self._fused_decode = True                           # get_bboxes: decode kernels instead of PyTorch glue
         self._own_convs = True                              # bf16 inference: 3x3 convolutions on conv_umma.cu, not cuDNN
         self._fused_loss = True                             # loss(): assignment + losses as CUDA kernels (point_loss.cu)
+        # training towers position-major (cuDNN on channels_last + this library's GroupNorm fwd / bwd kernels): measured
+        # 2.97 -> 2.92 ms per step only -- the towers are not on the critical path of the six-arm graph -- so off by default
+        self._nhwc_training = os.environ.get('KGDET_TRAIN_NHWC', '0') == '1'
         self.concurrent_branches = True                     # bf16 inference: cls / point branches on two streams
         deform_conv_cls = deform_conv_cls or DeformConv
         self._moment_fn = moment_fn or points2bbox_moment
@@ -508,16 +511,34 @@ class KGDetHead(nn.Module):
             main = torch.cuda.current_stream(x.device)
             side = _streams(x.device, 7)[6]
             side.wait_event(main.record_event())
+            nhwc = self._nhwc_training and x.dtype == torch.float32
+            if nhwc:
+                # position-major towers: cuDNN runs fprop / dgrad / wgrad on channels_last tensors without layout
+                # transposes, GroupNorm + ReLU forward and backward are one kernel each of this library
+                cls_feat = pts_feat = x.contiguous(memory_format=torch.channels_last)
+
+            def tower(convs, t):
+                for m in convs:
+                    if nhwc:
+                        wcl = m.conv.weight.contiguous(memory_format=torch.channels_last)
+                        t = groupnorm_relu_nhwc_autograd(F.conv2d(t, wcl, None, 1, 1), m.gn)
+                    else:
+                        t = m(t)
+                return t
+
             with torch.cuda.stream(side):
-                for m in self.cls_convs:
-                    cls_feat = m(cls_feat)
+                cls_feat = tower(self.cls_convs, cls_feat)
                 b1 = self.kp_rep_block_1
                 cls1 = b1.cls_out(F.relu(b1.cls_conv(cls_feat)))
+                if nhwc:
+                    cls_feat = cls_feat.contiguous()          # the deformable stages read NCHW
+                    cls1 = cls1.contiguous()
                 cls_done = side.record_event()
-            for m in self.reg_convs:
-                pts_feat = m(pts_feat)
+            pts_feat = tower(self.reg_convs, pts_feat)
             kpt1 = b1.keypts_out(F.relu(b1.keypts_conv(pts_feat)))
             rep1 = b1.reppts_out(kpt1)
+            if nhwc:
+                pts_feat, kpt1, rep1 = pts_feat.contiguous(), kpt1.contiguous(), rep1.contiguous()
             main.wait_event(cls_done)
             cls_feat.record_stream(main)
             cls1.record_stream(main)

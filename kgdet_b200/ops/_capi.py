@@ -112,6 +112,8 @@ SIGNATURES = {
                                           ctypes.c_int, c_ptr]),
     'kgdet_groupnorm_relu_nhwc_planes': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_f32, c_i32, ctypes.c_int, c_ptr, c_ptr,
                                                         c_i32, c_i32, c_i32, c_i32, c_ptr]),
+    'kgdet_groupnorm_relu_nhwc_backward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_i32, ctypes.c_int, c_ptr, c_ptr,
+                                                          c_ptr, c_i32, c_i32, c_i32, c_ptr]),
     'kgdet_groupnorm_stream_workspace_bytes': (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
     'kgdet_groupnorm_relu_nhwc_stream': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_f32, c_i32, ctypes.c_int, c_ptr, c_ptr,
                                                         ctypes.c_int, c_i32, c_i32, c_i32, c_i32, c_ptr, ctypes.c_size_t,

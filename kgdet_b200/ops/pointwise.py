@@ -196,6 +196,57 @@ def groupnorm_relu_nhwc(x, gn, relu=True, dense=True, prepared_for=None):
     return y if prepared_for is None else (y, prep)
 
 
+class _GroupNormReLUNHWC(torch.autograd.Function):
+    """GroupNorm (+ ReLU) on a channels_last fp32 activation with both directions on this library's kernels
+    (kgdet_groupnorm_relu_nhwc / _backward): the training step of the towers (ConvModule's norm + activation,
+    mmdet/models/utils/conv_module.py:96-110,156-164) without ATen's moments / normalise / clamp kernels forward
+    and its four kernels backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, num_groups, eps, relu):
+        lib = _capi.lib()
+        n, c, h, w = x.shape
+        xd = x.detach()
+        gamma, beta = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        y = torch.empty_like(xd, memory_format=torch.channels_last)
+        _capi.check(lib.kgdet_groupnorm_relu_nhwc(xd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                                  int(num_groups), int(bool(relu)), y.data_ptr(), n, h * w, c,
+                                                  _capi.stream_of(xd)), 'kgdet_groupnorm_relu_nhwc')
+        ctx.save_for_backward(xd, gamma, beta)
+        ctx.cfg = (int(num_groups), float(eps), bool(relu))
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        lib = _capi.lib()
+        x, gamma, beta = ctx.saved_tensors
+        groups, eps, relu = ctx.cfg
+        n, c, h, w = x.shape
+        dy = dy.detach().float().contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        parts = torch.empty((2, n, c), dtype=torch.float32, device=x.device)
+        _capi.check(lib.kgdet_groupnorm_relu_nhwc_backward(x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                           eps, groups, int(relu), dx.data_ptr(), parts[0].data_ptr(),
+                                                           parts[1].data_ptr(), n, h * w, c, _capi.stream_of(x)),
+                    'kgdet_groupnorm_relu_nhwc_backward')
+        sums = parts.sum(1)
+        return dx, sums[0], sums[1], None, None, None
+
+
+def groupnorm_relu_nhwc_autograd(x, gn, relu=True):
+    """Differentiable GroupNorm (+ ReLU) of a channels_last fp32 activation (maps of at most 1600 positions, whole
+    groups inside 32-channel blocks); anything else goes through torch."""
+    n, c, h, w = x.shape
+    cpg = c // gn.num_groups
+    ok = (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous(memory_format=torch.channels_last)
+          and h * w <= 1600 and c % 32 == 0 and cpg in (4, 8, 16, 32) and gn.weight is not None)
+    if not ok:
+        y = torch.nn.functional.group_norm(x, gn.num_groups, gn.weight, gn.bias, gn.eps)
+        return torch.relu(y) if relu else y
+    return _GroupNormReLUNHWC.apply(x, gn.weight, gn.bias, gn.num_groups, gn.eps, relu)
+
+
 def pointwise_conv(rows, packed_weight, bias, outputs, hw):
     """One GEMM over ``rows`` (TiledRows [M, K]) with ``packed_weight`` (from ``pack_weight``, same ``split``).
 

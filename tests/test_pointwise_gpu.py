@@ -283,3 +283,33 @@ def test_grouped_dcn_256_row_tiles_equal_128_row_tiles_full_size(monkeypatch):
             assert torch.equal(outs[0], outs[1])
     finally:
         ops.set_precision(None)
+
+
+@pytest.mark.parametrize('shape,groups,relu', [((2, 256, 25, 42), 32, True), ((3, 64, 13, 21), 16, True),
+                                               ((1, 128, 7, 11), 4, False), ((2, 96, 9, 9), 12, True)])
+def test_groupnorm_relu_nhwc_autograd_matches_torch(shape, groups, relu):
+    """kgdet_groupnorm_relu_nhwc + kgdet_groupnorm_relu_nhwc_backward behind an autograd Function: output and the
+    gradients of the input, gamma and beta against torch's GroupNorm (+ ReLU) evaluated in fp64."""
+    from kgdet_b200.ops.pointwise import groupnorm_relu_nhwc_autograd
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(c + h)
+    gn = torch.nn.GroupNorm(groups, c).cuda()
+    with torch.no_grad():
+        gn.weight.copy_(1 + 0.3 * torch.randn(c, generator=g))
+        gn.bias.copy_(0.3 * torch.randn(c, generator=g))
+    x = (torch.randn(n, c, h, w, generator=g) * 2 + 0.5).cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    up = torch.randn(n, c, h, w, generator=g).cuda()
+    y = groupnorm_relu_nhwc_autograd(x, gn, relu)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    y.backward(up)
+    x64 = x.detach().double().requires_grad_()
+    w64, b64 = gn.weight.detach().double().requires_grad_(), gn.bias.detach().double().requires_grad_()
+    y64 = torch.nn.functional.group_norm(x64, groups, w64, b64, gn.eps)
+    y64 = torch.relu(y64) if relu else y64
+    y64.backward(up.double())
+
+    def close(a, b, tol):
+        return (a.double() - b).abs().max().item() <= tol * b.abs().max().item() + 1e-12
+    assert close(y, y64, 2e-6)
+    assert close(x.grad, x64.grad, 2e-5)
+    assert close(gn.weight.grad, w64.grad, 2e-5) and close(gn.bias.grad, b64.grad, 2e-5)
