@@ -815,6 +815,15 @@ def train_record(args, rank=None, world=None, local=None):
         return kdist.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), dev), out
 
     ms, loss = timed(step)
+    if os.environ.get('KGDET_TRAIN_TRACE') and rank == 0:
+        # kernel timeline of two replayed steps (CUPTI through torch.profiler): tools/train_timeline.py reads it
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof_t:
+            for _ in range(2):
+                flush.fill_(1)
+                step()
+            torch.cuda.synchronize()
+        prof_t.export_chrome_trace(os.environ['KGDET_TRAIN_TRACE'])
     exposed_us = None
     if world > 1 and not args.no_graph:
         # the same step WITHOUT any collective (every rank keeps its local gradients, as at N = 1): the difference
