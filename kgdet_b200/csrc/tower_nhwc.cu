@@ -76,10 +76,26 @@ __global__ void __launch_bounds__(1024) groupnorm_relu_nhwc_wide_kernel(const fl
                                                                         float* __restrict__ y, int HW, int C, int relu,
                                                                         unsigned char* __restrict__ hi,
                                                                         unsigned char* __restrict__ lo,
-                                                                        size_t plane_bytes) {
+                                                                        size_t plane_bytes, int guard_bytes,
+                                                                        int tail_bytes) {
   // y (NHWC fp32) and / or hi + lo ("split planes" of conv_umma.cu: channel-blocked bf16 planes of the values'
   // bf16 hi parts -- the fused DCN kernel's prepared-input layout -- and of the lo parts x - hi) may be NULL
   constexpr int GPC = 8 / VEC;                  // groups per CTA
+  // guard bands of the planes (zero padding the deformable gather reads): written here by the CTAs of image 0 -- the
+  // even 32-channel block of a plane clears the band in front of it, the odd one the band behind it -- instead of by
+  // four memset nodes per call in front of the kernel (5 us each time on the critical path of the captured step)
+  if (hi && guard_bytes > 0 && blockIdx.y == 0) {
+    const int plane = blockIdx.x >> 1;
+    const bool front = (blockIdx.x & 1) == 0;
+    const size_t in_bytes = (size_t)gridDim.y * HW * 128;
+    const size_t off = (size_t)plane * plane_bytes + (front ? 0 : (size_t)guard_bytes + in_bytes);
+    const int nbytes = front ? guard_bytes : tail_bytes;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x * 16; i < nbytes; i += blockDim.x * 16) {
+      *reinterpret_cast<uint4*>(hi - guard_bytes + off + i) = z;
+      if (lo) *reinterpret_cast<uint4*>(lo - guard_bytes + off + i) = z;
+    }
+  }
   extern __shared__ float sm[];                 // [HW][32] values
   __shared__ float red[32][GPC];
   const int n = blockIdx.y, c0 = blockIdx.x * 32;
@@ -144,12 +160,13 @@ __global__ void __launch_bounds__(1024) groupnorm_relu_nhwc_wide_kernel(const fl
 template <int VEC>
 static int launch_groupnorm_wide(const float* x, const float* gamma, const float* beta, float eps, float* y, int N,
                                  int HW, int C, int relu, cudaStream_t stream, unsigned char* hi = nullptr,
-                                 unsigned char* lo = nullptr, size_t plane_bytes = 0) {
+                                 unsigned char* lo = nullptr, size_t plane_bytes = 0, int guard_bytes = 0,
+                                 int tail_bytes = 0) {
   const size_t smem = (size_t)HW * 32 * sizeof(float);
   KG_CUDA(cudaFuncSetAttribute(groupnorm_relu_nhwc_wide_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
   groupnorm_relu_nhwc_wide_kernel<VEC><<<dim3(C / 32, N), 1024, smem, stream>>>(x, gamma, beta, eps, y, HW, C, relu, hi, lo,
-                                                                                plane_bytes);
+                                                                                plane_bytes, guard_bytes, tail_bytes);
   KG_LAUNCH_CHECK("groupnorm_relu_nhwc_wide_kernel");
   return KGDET_OK;
 }
@@ -601,19 +618,15 @@ extern "C" int kgdet_groupnorm_relu_nhwc_planes(const float* x, const float* gam
   // split-plane layout of conv_umma.cu (hi planes in the DCN prepared-input layout, then the lo planes)
   const size_t guard = (size_t)(W + 2) * 128, in_bytes = (size_t)N * HW * 128;
   const size_t plane_bytes = align_up(in_bytes + 2 * guard, 1024), half = plane_bytes * (C / 64);
-  for (int h = 0; h < 2; ++h) {
-    unsigned char* b = (unsigned char*)planes + (size_t)h * half;
-    KG_CUDA(cudaMemset2DAsync(b, plane_bytes, 0, guard, C / 64, stream));
-    KG_CUDA(cudaMemset2DAsync(b + guard + in_bytes, plane_bytes, 0, plane_bytes - guard - in_bytes, C / 64, stream));
-  }
   unsigned char* hi = (unsigned char*)planes + guard;
   unsigned char* lo = hi + half;
   const int relu = fuse_relu ? 1 : 0;
+  const int gb = (int)guard, tb = (int)(plane_bytes - guard - in_bytes);      // zeroed by the kernel (multiples of 16)
   switch ((C / groups) / 4) {
-    case 1: return launch_groupnorm_wide<1>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes);
-    case 2: return launch_groupnorm_wide<2>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes);
-    case 4: return launch_groupnorm_wide<4>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes);
-    case 8: return launch_groupnorm_wide<8>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes);
+    case 1: return launch_groupnorm_wide<1>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes, gb, tb);
+    case 2: return launch_groupnorm_wide<2>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes, gb, tb);
+    case 4: return launch_groupnorm_wide<4>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes, gb, tb);
+    case 8: return launch_groupnorm_wide<8>(x, gamma, beta, eps, y, N, HW, C, relu, stream, hi, lo, plane_bytes, gb, tb);
     default: break;
   }
   set_error("kgdet_groupnorm_relu_nhwc_planes: unsupported channels per group %d", C / groups);
