@@ -218,6 +218,13 @@ KGDET_API int kgdet_conv_pack_weight(const float* weight, void* weight_packed, i
 KGDET_API int kgdet_conv_forward(const void* planes, const void* weight_packed, const float* bias, float* out_nhwc,
                        int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t ksize, int fuse_relu,
                        void* stream);
+/* Two convolutions of the same geometry (different planes, weights, outputs) in ONE launch: the classification and
+ * the point tower's convolution of one layer (KP3:415-420) -- a CTA runs its tile of the first, then of the second
+ * into the other half of TMEM, so the first's epilogue overlaps the second's main loop. */
+KGDET_API int kgdet_conv_forward_pair(const void* planes0, const void* weight_packed0, const float* bias0, float* out0,
+                            const void* planes1, const void* weight_packed1, const float* bias1, float* out1,
+                            int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t ksize, int fuse_relu,
+                            void* stream);
 /* GroupNorm (+ ReLU) of an NHWC fp32 activation (torch.nn.GroupNorm semantics) written as split planes for the next
  * convolution / the deformable stage, and optionally (y != NULL) also as NHWC fp32. */
 KGDET_API int kgdet_groupnorm_relu_nhwc_planes(const float* x, const float* gamma, const float* beta, float eps,

@@ -39,9 +39,13 @@ static constexpr int CV_EPI_WARPS = 8;
 static constexpr int CV_THREADS = (2 + CV_EPI_WARPS) * 32;
 
 struct ConvParams {
-  const unsigned char* wp;     // packed weights: per k-block [hi | lo], Cout rows x 128 B each
-  const float* bias;           // [Cout] or NULL
-  float* out;                  // NHWC fp32 [N, H, W, Cout]
+  // up to two problems of the same geometry (the classification and the point tower's convolution of one layer):
+  // a CTA runs its tile of problem 0, then the same tile of problem 1 into the other half of TMEM -- the epilogue
+  // of the first overlaps the main loop of the second
+  const unsigned char* wp[2];  // packed weights: per k-block [hi | lo], Cout rows x 128 B each
+  const float* bias[2];        // [Cout] or NULL
+  float* out[2];               // NHWC fp32 [N, H, W, Cout]
+  int nprob;
   int N, H, W, Cout, taps, ksz, pad, ncb;     // ncb = C / 64
   int bw, bh, tiles_w, tiles_h, ntiles;       // tile = bh rows x bw columns of one image (bw * bh <= 128)
   int relu;
@@ -63,6 +67,7 @@ __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CV_THREADS, 1)
 conv_umma_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                      const __grid_constant__ CUtensorMap map_hi1, const __grid_constant__ CUtensorMap map_lo1,
                       const ConvParams prm) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
@@ -71,8 +76,8 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
   const int stage_bytes = 2 * CV_A_BYTES + 2 * b_half;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)CV_NS * stage_bytes);
   uint64_t* empty_bar = full_bar + CV_NS;
-  uint64_t* tmem_full_bar = empty_bar + CV_NS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + CV_NS;                 // [2]: one per problem
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();                 // 0 = the CTA that issues the MMAs
@@ -96,11 +101,12 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
         mbar_init(&full_bar[s], rank == 0 ? 2 : 1);
         mbar_init(&empty_bar[s], 1);                       // one tcgen05.commit (multicast to both CTAs)
       }
-      mbar_init(tmem_full_bar, 1);
+      mbar_init(&tmem_full_bar[0], 1);
+      mbar_init(&tmem_full_bar[1], 1);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc_pair(tmem_slot, prm.tmem_cols);
+    tmem_alloc_pair(tmem_slot, prm.tmem_cols * prm.nprob);
   }
   tc_fence_before();
   cluster_sync_all();                                      // the peer's barriers exist before any remote arrive
@@ -114,18 +120,22 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
       const uint32_t a_bytes = (uint32_t)(prm.bw * prm.bh * 128);
       const uint32_t tx = 2u * a_bytes + 2u * (uint32_t)b_half;
       const size_t b_tile = (size_t)prm.Cout * 128;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % CV_NS;
-        mbar_wait(&empty_bar[s], (((uint32_t)(kb / CV_NS)) & 1u) ^ 1u);
-        const int cb = kb / prm.taps, tap = kb - cb * prm.taps;
-        const int i = tap / prm.ksz, j = tap - i * prm.ksz;
-        unsigned char* dst = smem + (size_t)s * stage_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], tx);
-        tma_load_5d(dst, &map_hi, 0, x0 + j - prm.pad, y0 + i - prm.pad, n, cb, &full_bar[s]);
-        tma_load_5d(dst + CV_A_BYTES, &map_lo, 0, x0 + j - prm.pad, y0 + i - prm.pad, n, cb, &full_bar[s]);
-        const unsigned char* w = prm.wp + (size_t)kb * 2 * b_tile + (size_t)rank * b_half;
-        bulk_g2s(dst + 2 * CV_A_BYTES, w, (uint32_t)b_half, &full_bar[s]);
-        bulk_g2s(dst + 2 * CV_A_BYTES + b_half, w + b_tile, (uint32_t)b_half, &full_bar[s]);
+      for (int t = 0; t < prm.nprob; ++t) {
+        const CUtensorMap* mh = t ? &map_hi1 : &map_hi;
+        const CUtensorMap* ml = t ? &map_lo1 : &map_lo;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int g = t * nkb + kb, s = g % CV_NS;          // the stage ring runs on across the two problems
+          mbar_wait(&empty_bar[s], (((uint32_t)(g / CV_NS)) & 1u) ^ 1u);
+          const int cb = kb / prm.taps, tap = kb - cb * prm.taps;
+          const int i = tap / prm.ksz, j = tap - i * prm.ksz;
+          unsigned char* dst = smem + (size_t)s * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], tx);
+          tma_load_5d(dst, mh, 0, x0 + j - prm.pad, y0 + i - prm.pad, n, cb, &full_bar[s]);
+          tma_load_5d(dst + CV_A_BYTES, ml, 0, x0 + j - prm.pad, y0 + i - prm.pad, n, cb, &full_bar[s]);
+          const unsigned char* w = prm.wp[t] + (size_t)kb * 2 * b_tile + (size_t)rank * b_half;
+          bulk_g2s(dst + 2 * CV_A_BYTES, w, (uint32_t)b_half, &full_bar[s]);
+          bulk_g2s(dst + 2 * CV_A_BYTES + b_half, w + b_tile, (uint32_t)b_half, &full_bar[s]);
+        }
       }
     }
     __syncwarp();
@@ -134,63 +144,70 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
       if (rank != 0) {
         // =========================== relay (odd CTA) ===========================
         const uint32_t remote0 = mapa_u32(smem_u32(&full_bar[0]), 0u);
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int s = kb % CV_NS;
-          mbar_wait(&full_bar[s], ((uint32_t)(kb / CV_NS)) & 1u);       // my A tiles and weight half have landed
+        for (int g = 0; g < prm.nprob * nkb; ++g) {
+          const int s = g % CV_NS;
+          mbar_wait(&full_bar[s], ((uint32_t)(g / CV_NS)) & 1u);        // my A tiles and weight half have landed
           mbar_arrive_remote_release(remote0 + (uint32_t)s * 8u);
         }
       } else {
         // =========================== MMA issuer (even CTA) ===========================
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int s = kb % CV_NS;
-          mbar_wait_cluster(&full_bar[s], ((uint32_t)(kb / CV_NS)) & 1u);
-          if (tl && kb == 0) tl[2] = clock64();
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t a_hi = make_sw128_kmajor_desc(a_addr), a_lo = make_sw128_kmajor_desc(a_addr + CV_A_BYTES);
-          const uint64_t b_hi = make_sw128_kmajor_desc(a_addr + 2 * CV_A_BYTES);
-          const uint64_t b_lo = make_sw128_kmajor_desc(a_addr + 2 * CV_A_BYTES + b_half);
+        for (int t = 0; t < prm.nprob; ++t) {
+          const uint32_t acc = tmem_base + (uint32_t)t * prm.tmem_cols;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int g = t * nkb + kb, s = g % CV_NS;
+            mbar_wait_cluster(&full_bar[s], ((uint32_t)(g / CV_NS)) & 1u);
+            if (tl && g == 0) tl[2] = clock64();
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint64_t a_hi = make_sw128_kmajor_desc(a_addr), a_lo = make_sw128_kmajor_desc(a_addr + CV_A_BYTES);
+            const uint64_t b_hi = make_sw128_kmajor_desc(a_addr + 2 * CV_A_BYTES);
+            const uint64_t b_lo = make_sw128_kmajor_desc(a_addr + 2 * CV_A_BYTES + b_half);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_f16_pair(tmem_base, a_lo + 2 * k, b_hi + 2 * k, prm.idesc, (kb > 0 || k > 0) ? 1u : 0u);   // lo . hi
-            umma_f16_pair(tmem_base, a_hi + 2 * k, b_lo + 2 * k, prm.idesc, 1u);                            // hi . lo
-            umma_f16_pair(tmem_base, a_hi + 2 * k, b_hi + 2 * k, prm.idesc, 1u);                            // hi . hi
+            for (int k = 0; k < 4; ++k) {
+              umma_f16_pair(acc, a_lo + 2 * k, b_hi + 2 * k, prm.idesc, (kb > 0 || k > 0) ? 1u : 0u);   // lo . hi
+              umma_f16_pair(acc, a_hi + 2 * k, b_lo + 2 * k, prm.idesc, 1u);                            // hi . lo
+              umma_f16_pair(acc, a_hi + 2 * k, b_hi + 2 * k, prm.idesc, 1u);                            // hi . hi
+            }
+            tc_commit_pair(&empty_bar[s], (uint16_t)3);    // frees the stage in both CTAs when these MMAs retire
           }
-          tc_commit_pair(&empty_bar[s], (uint16_t)3);      // frees the stage in both CTAs when these MMAs retire
+          tc_commit_pair(&tmem_full_bar[t], (uint16_t)3);  // this problem's accumulators of both CTAs complete
         }
-        tc_commit_pair(tmem_full_bar, (uint16_t)3);        // accumulators of both CTAs complete
         if (tl) tl[3] = clock64();
       }
     }
     __syncwarp();
   } else {
     // =========================== epilogue: TMEM -> NHWC fp32 ===========================
-    mbar_wait_cluster(tmem_full_bar, 0);
-    if (tl && tid == 64) tl[4] = clock64();
-    tc_fence_after();
     const int q = warp & 3, half = (warp - 2) >> 2;        // TMEM lane quarter (hardware: warp % 4), column half
     const int row = q * 32 + lane;
     const int hh = row / prm.bw, ww = row - hh * prm.bw;
     const int y = y0 + hh, x = x0 + ww;
     const bool ok = tile_ok && row < prm.bw * prm.bh && y < prm.H && x < prm.W;
-    float* orow = prm.out + (((size_t)n * prm.H + (ok ? y : 0)) * prm.W + (ok ? x : 0)) * prm.Cout;
+    const size_t ooff = (((size_t)n * prm.H + (ok ? y : 0)) * prm.W + (ok ? x : 0)) * prm.Cout;
     const int chalf = prm.Cout / 2;
-    for (int c0 = 0; c0 < chalf; c0 += 32) {
-      const int col = half * chalf + c0;
-      uint32_t acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
-      tmem_ld_wait();
-      if (ok) {
+    for (int t = 0; t < prm.nprob; ++t) {
+      mbar_wait_cluster(&tmem_full_bar[t], 0);
+      if (tl && tid == 64 && t == 0) tl[4] = clock64();
+      tc_fence_after();
+      float* orow = prm.out[t] + ooff;
+      const float* bias = prm.bias[t];
+      for (int c0 = 0; c0 < chalf; c0 += 32) {
+        const int col = half * chalf + c0;
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * prm.tmem_cols + col), acc);
+        tmem_ld_wait();
+        if (ok) {
 #pragma unroll
-        for (int jj = 0; jj < 32; jj += 4) {
-          float4 v = make_float4(__uint_as_float(acc[jj]), __uint_as_float(acc[jj + 1]), __uint_as_float(acc[jj + 2]),
-                                 __uint_as_float(acc[jj + 3]));
-          if (prm.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(prm.bias + col + jj));
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          for (int jj = 0; jj < 32; jj += 4) {
+            float4 v = make_float4(__uint_as_float(acc[jj]), __uint_as_float(acc[jj + 1]), __uint_as_float(acc[jj + 2]),
+                                   __uint_as_float(acc[jj + 3]));
+            if (bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + jj));
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (prm.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            *reinterpret_cast<float4*>(orow + col + jj) = v;
           }
-          if (prm.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          *reinterpret_cast<float4*>(orow + col + jj) = v;
         }
       }
     }
@@ -198,7 +215,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_c
   if (tl && tid == 64) tl[5] = clock64();
   tc_fence_before();
   cluster_sync_all();            // neither CTA may free the shared TMEM allocation while the other still reads
-  if (warp == 1) tmem_dealloc_pair(tmem_base, prm.tmem_cols);
+  if (warp == 1) tmem_dealloc_pair(tmem_base, prm.tmem_cols * prm.nprob);
 }
 
 // ---- weight packing: fp32 [Cout, Cin, k, k] -> per k-block (cb * taps + tap) [hi tile | lo tile] ------------------
@@ -400,24 +417,30 @@ extern "C" int kgdet_conv_supported(int32_t C, int32_t Cout, int32_t ksize) {
   return (C > 0 && C % 64 == 0 && Cout >= 64 && Cout <= 256 && Cout % 64 == 0 && ksize >= 1 && ksize <= 7 && (ksize & 1)) ? 1 : 0;
 }
 
-extern "C" int kgdet_conv_forward(const void* planes, const void* weight_packed, const float* bias, float* out_nhwc,
-                                  int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t ksize,
-                                  int fuse_relu, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  KG_CHECK_ARG(planes && weight_packed && out_nhwc, "kgdet_conv_forward: NULL pointer");
-  KG_CHECK_ARG(N > 0 && H > 0 && W > 0, "kgdet_conv_forward: bad sizes");
-  KG_CHECK_ARG(kgdet_conv_supported(C, Cout, ksize), "kgdet_conv_forward: need C %% 64 == 0, Cout in {64, 128, 192, 256}, odd "
-               "kernel size <= 7 (got C %d, Cout %d, k %d)", C, Cout, ksize);
-  KG_CHECK_ARG(((uintptr_t)planes & 255) == 0 && ((uintptr_t)out_nhwc & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0),
-               "kgdet_conv_forward: planes must be 256-byte aligned, out / bias 16-byte aligned");
+static int conv_launch(const char* what, int nprob, const void* const* planes, const void* const* weight_packed,
+                       const float* const* bias, float* const* out_nhwc, int32_t N, int32_t C, int32_t H, int32_t W,
+                       int32_t Cout, int32_t ksize, int fuse_relu, cudaStream_t stream) {
+  KG_CHECK_ARG(N > 0 && H > 0 && W > 0, "%s: bad sizes", what);
+  KG_CHECK_ARG(kgdet_conv_supported(C, Cout, ksize), "%s: need C %% 64 == 0, Cout in {64, 128, 192, 256}, odd "
+               "kernel size <= 7 (got C %d, Cout %d, k %d)", what, C, Cout, ksize);
+  for (int t = 0; t < nprob; ++t) {
+    KG_CHECK_ARG(planes[t] && weight_packed[t] && out_nhwc[t], "%s: NULL pointer", what);
+    KG_CHECK_ARG(((uintptr_t)planes[t] & 255) == 0 && ((uintptr_t)out_nhwc[t] & 15) == 0 &&
+                     (!bias[t] || ((uintptr_t)bias[t] & 15) == 0),
+                 "%s: planes must be 256-byte aligned, out / bias 16-byte aligned", what);
+  }
   EncodeTiledFn enc = encode_fn();
   if (!enc) {
-    set_error("kgdet_conv_forward: cuTensorMapEncodeTiled is not available from this driver");
+    set_error("%s: cuTensorMapEncodeTiled is not available from this driver", what);
     return KGDET_ERR_UNSUPPORTED;
   }
   const SplitLayout l = split_layout(N, C, H, W);
   ConvParams p;
-  p.wp = (const unsigned char*)weight_packed; p.bias = bias; p.out = out_nhwc;
+  p.nprob = nprob;
+  for (int t = 0; t < 2; ++t) {
+    const int u = t < nprob ? t : 0;
+    p.wp[t] = (const unsigned char*)weight_packed[u]; p.bias[t] = bias[u]; p.out[t] = out_nhwc[u];
+  }
   p.N = N; p.H = H; p.W = W; p.Cout = Cout; p.ksz = ksize; p.taps = ksize * ksize; p.pad = ksize / 2; p.ncb = C / 64;
   pick_tile(H, W, &p.bw, &p.bh);
   p.tiles_w = ceil_div(W, p.bw); p.tiles_h = ceil_div(H, p.bh);
@@ -425,30 +448,56 @@ extern "C" int kgdet_conv_forward(const void* planes, const void* weight_packed,
   p.relu = fuse_relu ? 1 : 0;
   p.idesc = make_idesc(1u, 2 * CV_BM, (uint32_t)Cout);
   p.tmem_cols = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
-  CUtensorMap maps[2];
-  for (int half = 0; half < 2; ++half) {
-    void* base = (unsigned char*)planes + (size_t)half * l.half_bytes + l.guard_bytes;
-    const cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)l.planes};
-    const cuuint64_t strides[4] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128, (cuuint64_t)l.plane_bytes};
-    const cuuint32_t box[5] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1, 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUresult r = enc(&maps[half], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("kgdet_conv_forward: cuTensorMapEncodeTiled failed (%d) for [%d, %d, %d, %d] box %d x %d", (int)r, N, C, H, W,
-                p.bw, p.bh);
-      return KGDET_ERR_CUDA;
+  CUtensorMap maps[4];
+  for (int t = 0; t < 2; ++t) {
+    const int u = t < nprob ? t : 0;
+    for (int half = 0; half < 2; ++half) {
+      void* base = (unsigned char*)planes[u] + (size_t)half * l.half_bytes + l.guard_bytes;
+      const cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)l.planes};
+      const cuuint64_t strides[4] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128, (cuuint64_t)l.plane_bytes};
+      const cuuint32_t box[5] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1, 1};
+      const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      const CUresult r = enc(&maps[2 * t + half], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("%s: cuTensorMapEncodeTiled failed (%d) for [%d, %d, %d, %d] box %d x %d", what, (int)r, N, C, H, W,
+                  p.bw, p.bh);
+        return KGDET_ERR_CUDA;
+      }
     }
   }
   p.timeline = nullptr;
   if (g_timeline && g_timeline_entries >= (long long)2 * ceil_div(p.ntiles, 2) * 8) p.timeline = g_timeline;
   g_timeline = nullptr;
   const int b_half = (Cout / 2) * 128;
-  const size_t smem = 1024 + (size_t)CV_NS * (2 * CV_A_BYTES + 2 * b_half) + (2 * CV_NS + 1) * 8 + 16;
+  const size_t smem = 1024 + (size_t)CV_NS * (2 * CV_A_BYTES + 2 * b_half) + (2 * CV_NS + 2) * 8 + 16;
   KG_CUDA(cudaFuncSetAttribute(conv_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = 2 * ceil_div(p.ntiles, 2);
-  conv_umma_pair_kernel<<<grid, CV_THREADS, smem, stream>>>(maps[0], maps[1], p);
+  conv_umma_pair_kernel<<<grid, CV_THREADS, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
   KG_LAUNCH_CHECK("conv_umma_pair_kernel");
   return KGDET_OK;
+}
+
+extern "C" int kgdet_conv_forward(const void* planes, const void* weight_packed, const float* bias, float* out_nhwc,
+                                  int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t ksize,
+                                  int fuse_relu, void* stream_) {
+  return conv_launch("kgdet_conv_forward", 1, &planes, &weight_packed, &bias, &out_nhwc, N, C, H, W, Cout, ksize, fuse_relu,
+                     (cudaStream_t)stream_);
+}
+
+// Two convolutions of the same geometry in ONE launch (the classification and the point tower's convolution of a
+// layer, KP3:415-420: different inputs, different weights): every CTA runs its tile of the first, then the same
+// tile of the second into the other half of TMEM, so the epilogue of the first (TMEM -> 128 KB of NHWC fp32 per
+// CTA) and the prologue of the second disappear under main loops.  Needs Cout <= 256 twice in TMEM: Cout <= 256.
+extern "C" int kgdet_conv_forward_pair(const void* planes0, const void* weight_packed0, const float* bias0, float* out0,
+                                       const void* planes1, const void* weight_packed1, const float* bias1, float* out1,
+                                       int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t ksize,
+                                       int fuse_relu, void* stream_) {
+  const void* planes[2] = {planes0, planes1};
+  const void* weights[2] = {weight_packed0, weight_packed1};
+  const float* bias[2] = {bias0, bias1};
+  float* outs[2] = {out0, out1};
+  return conv_launch("kgdet_conv_forward_pair", 2, planes, weights, bias, outs, N, C, H, W, Cout, ksize, fuse_relu,
+                     (cudaStream_t)stream_);
 }

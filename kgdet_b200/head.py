@@ -31,7 +31,7 @@ import torch.nn.functional as F
 from .ops import (DeformConv, TiledRows, batched_nms_flags, deform_conv_prepared, deform_conv_prepared_group, get_precision,
                   groupnorm_relu_nhwc, nchw_to_tiled, pack_weight, points2bbox_moment, pointwise_conv,
                   prepare_input, prepare_plan, prepare_plan_points)
-from .ops.conv import conv_planes, conv_supported, groupnorm_relu_planes, split_planes
+from .ops.conv import conv_planes, conv_planes_pair, conv_supported, groupnorm_relu_planes, split_planes
 from .ops.decode import bbox_decode, bbox_finalize, bbox_select, topk_flagged
 from .ops.pointwise import cached, groupnorm_relu_nhwc_autograd, to_channels_last
 
@@ -409,6 +409,10 @@ class KGDetHead(nn.Module):
         # 2.97 -> 2.92 ms per step only -- the towers are not on the critical path of the six-arm graph -- so off by default
         self._nhwc_training = os.environ.get('KGDET_TRAIN_NHWC', '0') == '1'
         self.concurrent_branches = True                     # bf16 inference: cls / point branches on two streams
+        # ... their convolutions of a layer in ONE launch (kgdet_conv_forward_pair): measured neutral (1.648 vs 1.652 ms --
+        # the convolution's main loop is bound by L2 -> SM bytes, 2 100 clk per k-block, not by the prologue / epilogue
+        # the pairing hides), so off by default
+        self.paired_convs = os.environ.get('KGDET_PAIRED_CONVS', '0') == '1'
         deform_conv_cls = deform_conv_cls or DeformConv
         self._moment_fn = moment_fn or points2bbox_moment
         self._nms_flags_fn = nms_flags_fn or batched_nms_flags
@@ -480,7 +484,31 @@ class KGDetHead(nn.Module):
             for blk in (self.kp_rep_block_1, self.kp_rep_block_2, self.kp_rep_block_3):
                 _pointwise_weights(blk)
             branches = [] if self.concurrent_branches else None
-            if self.concurrent_branches:
+            if own and self.paired_convs and self.concurrent_branches:
+                # The two towers' convolutions of a layer in ONE launch (kgdet_conv_forward_pair): on two streams they
+                # only take turns -- 132 one-per-SM CTAs each -- and every CTA pays prologue and epilogue around a
+                # single tile; paired, a CTA runs the classification tile and then the point tile into the other half
+                # of TMEM, the first epilogue under the second main loop.  The two GroupNorms are parallel branches.
+                p_cls = p_pts = cls_feat
+                for mc, mp in zip(self.cls_convs, self.reg_convs):
+                    y_c, y_p = conv_planes_pair(p_cls, mc.conv.weight, p_pts, mp.conv.weight)
+                    with _SideBranch(x.device, 7) as br:
+                        p_cls = groupnorm_relu_planes(y_c, mc.gn)
+                    br.keep(y_c)
+                    p_pts = groupnorm_relu_planes(y_p, mp.gn)
+                    br.join()
+                b1 = self.kp_rep_block_1
+                y_c, y_p = conv_planes_pair(p_cls, b1.cls_conv.weight, p_pts, b1.keypts_conv.weight)
+                n1, _, h1, w1 = p_cls.shape4
+                with _SideBranch(x.device, 7) as br:
+                    cls1 = _pointwise_cls(b1, nchw_to_tiled(y_c, relu=True, split=True, bias=b1.cls_conv.bias), n1, h1, w1)
+                br.keep(y_c)
+                kpt1, rep1 = _pointwise_kpt(b1, nchw_to_tiled(y_p, relu=True, split=True, bias=b1.keypts_conv.bias),
+                                            n1, h1, w1)
+                bbox1 = self.points2bbox(rep1)
+                cls_prep, pts_prep = p_cls.as_prepared_input(feat), p_pts.as_prepared_input(feat)
+                br.join()
+            elif self.concurrent_branches:
                 # The classification and point branches are independent up to the first deformable stage, and a
                 # 3x3 convolution on a 25x42 map is 66 CTAs of cuDNN's 256-row tile -- under half of the SMs:
                 # the two towers run as parallel branches (two streams / two arms of the captured graph).

@@ -110,6 +110,8 @@ SIGNATURES = {
     'kgdet_conv_pack_weight': (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr]),
     'kgdet_conv_forward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
                                           ctypes.c_int, c_ptr]),
+    'kgdet_conv_forward_pair': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32,
+                                               c_i32, c_i32, c_i32, ctypes.c_int, c_ptr]),
     'kgdet_groupnorm_relu_nhwc_planes': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_f32, c_i32, ctypes.c_int, c_ptr, c_ptr,
                                                         c_i32, c_i32, c_i32, c_i32, c_ptr]),
     'kgdet_groupnorm_relu_nhwc_backward': (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_i32, ctypes.c_int, c_ptr, c_ptr,

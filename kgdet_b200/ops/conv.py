@@ -118,6 +118,27 @@ def conv_planes(planes, weight, bias=None, relu=False):
     return out
 
 
+def conv_planes_pair(planes0, weight0, planes1, weight1, bias0=None, bias1=None, relu=False):
+    """Two stride-1 "same" convolutions of the same geometry in one launch (kgdet_conv_forward_pair): the two towers'
+    convolutions of a layer.  Returns the two channels_last fp32 outputs; bit-identical to two `conv_planes` calls."""
+    lib = _capi.lib()
+    n, c, h, w = planes0.shape4
+    assert planes1.shape4 == planes0.shape4 and tuple(weight0.shape) == tuple(weight1.shape)
+    cout, cin, k, _ = weight0.shape
+    assert cin == c, 'weight does not match the planes'
+    p0, p1 = pack_conv_weight(weight0), pack_conv_weight(weight1)
+    dev = planes0.buf.device
+    out0 = torch.empty((n, cout, h, w), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+    out1 = torch.empty((n, cout, h, w), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+    b0 = None if bias0 is None else bias0.detach().float().contiguous()
+    b1 = None if bias1 is None else bias1.detach().float().contiguous()
+    _capi.check(lib.kgdet_conv_forward_pair(planes0.buf.data_ptr(), p0.data_ptr(), _capi.ptr(b0), out0.data_ptr(),
+                                            planes1.buf.data_ptr(), p1.data_ptr(), _capi.ptr(b1), out1.data_ptr(),
+                                            n, c, h, w, cout, k, int(bool(relu)), _capi.stream_of(planes0.buf)),
+                'kgdet_conv_forward_pair')
+    return out0, out1
+
+
 def groupnorm_relu_planes(x, gn, relu=True, also_dense=False):
     """GroupNorm (+ ReLU) of a channels_last fp32 activation, written as SplitPlanes (and, with `also_dense`,
     also returned as a channels_last fp32 tensor).  `gn` is the torch.nn.GroupNorm module."""

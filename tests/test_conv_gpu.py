@@ -91,3 +91,27 @@ def test_groupnorm_relu_planes_matches_torch_and_feeds_the_dcn():
         a = ops.deform_conv_prepared(pin, plan, wd)
         b = ops.deform_conv_prepared(want, plan, wd)
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('shape,cout,k,bias,relu', [((16, 256, 25, 42), 256, 3, False, False),
+                                                    ((2, 64, 13, 21), 128, 3, True, True),
+                                                    ((3, 128, 7, 11), 64, 1, True, False),
+                                                    ((1, 256, 100, 168), 256, 3, False, False)])
+def test_paired_convolutions_equal_two_single_launches(shape, cout, k, bias, relu):
+    """kgdet_conv_forward_pair (two convolutions of one geometry per launch, the second into the other half of
+    TMEM) == two kgdet_conv_forward launches, bit for bit."""
+    from kgdet_b200.ops import conv as kconv
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(c + h + k)
+    xs = [torch.randn(n, c, h, w, generator=g).cuda() for _ in range(2)]
+    ws = [(torch.randn(cout, c, k, k, generator=g) * 0.05).cuda() for _ in range(2)]
+    bs = [torch.randn(cout, generator=g).cuda() if bias else None for _ in range(2)]
+    ps = [kconv.split_planes(x) for x in xs]
+    want = [kconv.conv_planes(p, wt, b, relu) for p, wt, b in zip(ps, ws, bs)]
+    got = kconv.conv_planes_pair(ps[0], ws[0], ps[1], ws[1], bs[0], bs[1], relu)
+    for a, b in zip(got, want):
+        assert a.is_contiguous(memory_format=torch.channels_last) and torch.equal(a, b)
+    # and the same input for both problems (the first tower layer)
+    got2 = kconv.conv_planes_pair(ps[0], ws[0], ps[0], ws[1], bs[0], bs[1], relu)
+    assert torch.equal(got2[0], want[0])
+    assert torch.equal(got2[1], kconv.conv_planes(ps[0], ws[1], bs[1], relu))
