@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(PKG, '_lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libkgdet_b200.so')
 
 SOURCES = ['runtime.cu', 'nms.cu', 'focal_loss.cu', 'point_loss.cu', 'moment.cu', 'dcn_common.cu', 'dcn_simt.cu',
-           'dcn_umma.cu', 'dcn_umma_stream.cu', 'dcn_umma_group.cu', 'gemm_umma.cu', 'pointwise_umma.cu', 'conv_umma.cu', 'tower_nhwc.cu', 'decode.cu', 'dcn_bwd_tc.cu', 'dcn_wgrad_umma.cu', 'dcn_api.cu']
+           'dcn_umma.cu', 'dcn_umma_stream.cu', 'dcn_umma_group.cu', 'gemm_umma.cu', 'pointwise_umma.cu', 'conv_umma.cu', 'tower_nhwc.cu', 'decode.cu', 'dcn_bwd_tc.cu', 'dcn_col2im_own.cu', 'dcn_wgrad_umma.cu', 'dcn_api.cu']
 HEADERS = [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'focal.cuh'), os.path.join(CSRC, 'dcn.cuh'), os.path.join(CSRC, 'dcn_umma.cuh'),
            os.path.join(ROOT, 'include', 'kgdet_b200.h')]
 

@@ -26,6 +26,17 @@ int wgrad_fused(const DcnGeom& g, const void* in_blocked, size_t plane_bytes, co
 int umma_gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, void* C,
               long long ldc, int M, int N, int K, int out_dtype, int splits, float alpha, cudaStream_t stream);
 
+// owned-slice col2im (dcn_col2im_own.cu)
+bool col2im_own_supported(const DcnGeom& g);
+size_t col2im_own_part_bytes(const DcnGeom& g);
+size_t col2im_own_sched_bytes(const DcnGeom& g);
+int col2im_own_schedule(const DcnGeom& g, const SampleRec* plan, const SampleAux* aux, unsigned* sched,
+                        cudaStream_t stream);
+int col2im_own(const DcnGeom& g, const __nv_bfloat16* cg, const __nv_bfloat16* in_nhwc, const SampleRec* plan,
+               const SampleAux* aux, const unsigned* sched, int tap0, int ntaps, float* gin_nhwc, float* gpart,
+               cudaStream_t stream);
+int col2im_own_finish(const DcnGeom& g, const float* gpart, float* goff, float* gmask, cudaStream_t stream);
+
 bool bwd_tc_supported(const DcnGeom& g, int precision) {
   return precision == KGDET_PREC_BF16 && g.groups == 1 && g.dgroups == 1 && g.C % 64 == 0 &&
          g.Cout % 64 == 0;
@@ -150,6 +161,151 @@ col2im_tc_kernel(DcnGeom g, const __nv_bfloat16* __restrict__ cg, const __nv_bfl
       else if (gmask) gmask[((size_t)n * g.K + tap) * HoWo + p] = tot;
     }
   }
+}
+
+// ---- col2im through the bulk-copy engine (default for C = 128 / 256; KGDET_COL2IM_BULK=0 -> col2im_tc_kernel) ----
+// Same mapping as col2im_tc_kernel (one warp per position and group of 5 taps, deterministic offset / mask gradient),
+// but the weighted column-gradient row of a (sample, corner) is staged in shared memory (C floats) and added to the
+// NHWC gradient with ONE cp.reduce.async.bulk .add.f32 of C * 4 bytes issued by lane 0, instead of C / 4
+// red.global.add.v4.f32 issued by the lanes (the SM issues one red per 1.29 clk and lane: 0.86 ms per K = 49 call at
+// batch 16; the bulk engine's reductions reach L2 at 47 % of the SM -> L2 write path instead).  K = 49 call,
+// forward + backward: 1 722 -> 1 422 us; K = 25: 1 002 -> 850; K = 9: 555 -> 494 (profiles/r2_col2im_bulk.txt).
+__device__ __forceinline__ void unpack4b(const uint2& v, float (&f)[4]) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+// Loads run one tap ahead of the staging (the asm statements of the staging are memory barriers for the compiler:
+// without the explicit prefetch every tap's loads waited for the previous tap's bulk issue -- long_scoreboard 8.2
+// stalled warps per issue, 860 -> 760 us only).  NCH = C / 128 (4 channels per lane and chunk).
+template <int NCH, int BULK_SETS>
+__global__ void __launch_bounds__(256, 2)
+col2im_bulk_kernel(DcnGeom g, const __nv_bfloat16* __restrict__ cg, const __nv_bfloat16* __restrict__ in,
+                   const SampleRec* __restrict__ plan, const SampleAux* __restrict__ aux, int tap0, int ntaps,
+                   float* __restrict__ gin, float* __restrict__ goff, float* __restrict__ gmask) {
+  constexpr int TB = COL2IM_TB;
+  constexpr int C = NCH * 128;
+  extern __shared__ __align__(128) float bulk_stage[];          // [8 warps][BULK_SETS][4][C]
+  const int lane = threadIdx.x & 31;
+  float* my = bulk_stage + (size_t)(threadIdx.x >> 5) * (BULK_SETS * 4 * C);
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int HoWo = g.Ho * g.Wo;
+  const int ngroups = (ntaps + TB - 1) / TB;
+  const long long total = (long long)g.M * ngroups;
+  int set = 0;
+  for (long long wi = warp_global; wi < total; wi += nwarps) {
+    const int m = (int)(wi / ngroups), tl0 = (int)(wi - (long long)m * ngroups) * TB;
+    float part[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) part[i] = 0.f;
+    int4 pa[TB];
+    float4 a4[TB];
+#pragma unroll
+    for (int t = 0; t < TB; ++t) {
+      pa[t] = make_int4(0, 0, 0, 0);
+      a4[t] = make_float4(0.f, 0.f, 0.f, 0.f);                    // valid = 0
+      if (tl0 + t < ntaps) {                                      // warp-uniform
+        const size_t ridx = (size_t)m * g.K + tap0 + tl0 + t;
+        pa[t] = __ldg(reinterpret_cast<const int4*>(plan + ridx));
+        a4[t] = __ldg(reinterpret_cast<const float4*>(aux + ridx));
+      }
+    }
+    uint2 gq[2][NCH], vq[2][NCH][4];
+    auto load_tap = [&](int t, int slot) {
+      const int valid = __float_as_int(a4[t].w);
+      const int pix[4] = {pa[t].x, pa[t].y, pa[t].z, pa[t].w};
+      const __nv_bfloat16* cgrow = cg + ((size_t)m * ntaps + tl0 + t) * C;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        gq[slot][ch] = valid ? __ldg(reinterpret_cast<const uint2*>(cgrow + ch * 128 + lane * 4)) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          vq[slot][ch][i] = (valid & (1 << i))
+                                ? __ldg(reinterpret_cast<const uint2*>(in + (size_t)pix[i] * C + ch * 128 + lane * 4))
+                                : make_uint2(0u, 0u);
+      }
+    };
+    load_tap(0, 0);
+#pragma unroll
+    for (int t = 0; t < TB; ++t) {
+      if (t + 1 < TB) load_tap(t + 1, (t + 1) & 1);
+      const int valid = __float_as_int(a4[t].w);
+      if (!valid) continue;                                       // warp-uniform
+      const int pix[4] = {pa[t].x, pa[t].y, pa[t].z, pa[t].w};
+      const float lh = a4[t].x, lw = a4[t].y, mkv = a4[t].z;
+      const float hh = 1.f - lh, hw = 1.f - lw;
+      const float wgt[4] = {hh * hw * mkv, hh * lw * mkv, lh * hw * mkv, lh * lw * mkv};   // as dcn_plan_kernel
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      float* sbuf = my + (size_t)set * 4 * C;
+      // the bulk reductions that last read this set have finished reading it
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(BULK_SETS - 1) : "memory");
+      __syncwarp();
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        float gv[4];
+        unpack4b(gq[t & 1][ch], gv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (valid & (1 << i)) {
+            float v[4];
+            unpack4b(vq[t & 1][ch][i], v);
+            const float wi_ = wgt[i];
+            *reinterpret_cast<float4*>(sbuf + i * C + ch * 128 + lane * 4) =
+                make_float4(gv[0] * wi_, gv[1] * wi_, gv[2] * wi_, gv[3] * wi_);
+            d[i] = fmaf(gv[3], v[3], fmaf(gv[2], v[2], fmaf(gv[1], v[1], fmaf(gv[0], v[0], d[i]))));
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (valid & (1 << i))
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                             gin + (size_t)pix[i] * C),
+                         "r"(smem_u32(sbuf + i * C)), "n"(C * 4)
+                         : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      set = (set + 1 == BULK_SETS) ? 0 : set + 1;
+      part[3 * t + 0] = -hw * d[0] - lw * d[1] + hw * d[2] + lw * d[3];
+      part[3 * t + 1] = -hh * d[0] + hh * d[1] - lh * d[2] + lh * d[3];
+      part[3 * t + 2] = hh * hw * d[0] + hh * lw * d[1] + lh * hw * d[2] + lh * lw * d[3];
+    }
+#pragma unroll
+    for (int lvl = 0; lvl < 4; ++lvl) {
+      const int bit = 16 >> lvl, half = 8 >> lvl;
+      const bool up = (lane & bit) != 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < half) {
+          const float send = up ? part[j] : part[j + half];
+          const float keep = up ? part[j + half] : part[j];
+          part[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+      }
+    }
+    const float tot = part[0] + __shfl_xor_sync(0xffffffffu, part[0], 1);
+    const int idx = lane >> 1;
+    const int t = idx / 3, q = idx - 3 * t;
+    if ((lane & 1) == 0 && idx < 3 * TB && tl0 + t < ntaps) {
+      const int tap = tap0 + tl0 + t;
+      const int n = m / HoWo, p = m - n * HoWo;
+      float mkt = a4[0].z;
+#pragma unroll
+      for (int u = 1; u < TB; ++u) mkt = (t == u) ? a4[u].z : mkt;
+      if (q < 2) goff[((size_t)n * 2 * g.K + 2 * tap + q) * HoWo + p] = tot * mkt;
+      else if (gmask) gmask[((size_t)n * g.K + tap) * HoWo + p] = tot;
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging rows must outlive the copies
+  __syncwarp();
+}
+static bool use_bulk_col2im(const DcnGeom& g) {
+  if (const char* e = getenv("KGDET_COL2IM_BULK"))
+    if (atoi(e) == 0) return false;
+  return g.C == 128 || g.C == 256;
 }
 
 // ---- sampled columns, transposed: colT[(tl*C + c), m] for taps tap0 .. tap0+ntaps-1 ---------------
@@ -293,6 +449,8 @@ __global__ void bias_grad_nchw_kernel(const T* __restrict__ go, int N, int Cout,
 struct TcBwdInWs {
   __nv_bfloat16 *in_nhwc, *go_nhwc, *wd, *cg;
   float* gin_nhwc;
+  float* gpart;               // owned-slice col2im: offset / mask gradient parts per channel block
+  unsigned* sched;            // owned-slice col2im: lane schedule per (image, tap, tile)
   SampleRec* plan;
   SampleAux* aux;
   size_t total;
@@ -306,6 +464,8 @@ static TcBwdInWs carve_tc_in(const DcnGeom& g, void* ws) {
   w.wd = (__nv_bfloat16*)take((size_t)g.K * g.C * g.Cout * 2);
   w.cg = (__nv_bfloat16*)take((size_t)g.M * taps_per_chunk(g, g.M) * g.C * 2);
   w.gin_nhwc = (float*)take((size_t)g.N * g.H * g.W * g.C * 4);
+  w.gpart = (float*)take(col2im_own_part_bytes(g));
+  w.sched = (unsigned*)take(col2im_own_sched_bytes(g));
   w.plan = (SampleRec*)take(plan_bytes(g));
   w.aux = (SampleAux*)take(plan_aux_bytes(g));
   w.total = off;
@@ -384,16 +544,37 @@ int bwd_tc_input(const DcnGeom& g, const void* input, const float* offset, const
   KG_LAUNCH_CHECK("pack_wd_tiled_kernel");
   KG_CUDA(cudaMemsetAsync(w.gin_nhwc, 0, (size_t)g.N * HW * g.C * 4, stream));
   const int tpc = taps_per_chunk(g, g.M);
+  // small maps: a CTA owns its slice of the input gradient in shared memory (dcn_col2im_own.cu)
+  const bool own = col2im_own_supported(g);
+  if (own && (rc = col2im_own_schedule(g, w.plan, w.aux, w.sched, stream)) != KGDET_OK) return rc;
   for (int tap0 = 0; tap0 < g.K; tap0 += tpc) {
     const int nt = (g.K - tap0) < tpc ? (g.K - tap0) : tpc;
     // cg[m, (tl, c)] = go_nhwc[m, :] . Wd[(tap0+tl)*C + c, :]
     if ((rc = umma_gemm(w.go_nhwc, g.Cout, w.wd + (size_t)tap0 * g.C * g.Cout, g.Cout, w.cg, (long long)nt * g.C,
                         g.M, nt * g.C, g.Cout, KGDET_BF16, 1, 1.f, stream)) != KGDET_OK) return rc;
+    if (own) {
+      if ((rc = col2im_own(g, w.cg, w.in_nhwc, w.plan, w.aux, w.sched, tap0, nt, w.gin_nhwc, w.gpart, stream)) != KGDET_OK)
+        return rc;
+      continue;
+    }
     const long long warps = (long long)g.M * ceil_div(nt, COL2IM_TB);
+    if (use_bulk_col2im(g)) {
+      // two staging sets per warp (three measured the same: 1 464 vs 1 479 us for the K = 49 call)
+      const size_t smem = (size_t)8 * 2 * 4 * g.C * 4;
+      auto kern = g.C == 256 ? col2im_bulk_kernel<2, 2> : col2im_bulk_kernel<1, 2>;
+      KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      long long b = (warps * 32 + 255) / 256;
+      const long long cap = (long long)num_sms() * 2;
+      kern<<<(int)(b > cap ? cap : b), 256, smem, stream>>>(g, w.cg, w.in_nhwc, w.plan, w.aux, tap0, nt, w.gin_nhwc,
+                                                           grad_offset, grad_mask);
+      KG_LAUNCH_CHECK("col2im_bulk_kernel");
+      continue;
+    }
     col2im_tc_kernel<<<grid_for(warps * 32, 256), 256, 0, stream>>>(g, w.cg, w.in_nhwc, w.plan, w.aux, tap0, nt,
                                                                     w.gin_nhwc, grad_offset, grad_mask);
     KG_LAUNCH_CHECK("col2im_tc_kernel");
   }
+  if (own && (rc = col2im_own_finish(g, w.gpart, grad_offset, grad_mask, stream)) != KGDET_OK) return rc;
   return launch_transpose(w.gin_nhwc, grad_input, g.N, HW, g.C, KGDET_F32, dtype, stream);
 }
 

@@ -299,6 +299,29 @@ def test_tensor_core_backward_matches_oracle(case):
             assert rel_err(got[k], ref_bw[k]) < TOL['bf16'], (k, rel_err(got[k], ref_bw[k]))
 
 
+@pytest.mark.parametrize('case', [BWD_TC_CASES[1], BWD_TC_CASES[4],
+                                  dict(N=2, C=64, H=25, W=42, Cout=64, k=3, offset_std=0.3)])
+def test_owned_slice_col2im_matches_oracle_and_default_path(case, monkeypatch):
+    """KGDET_COL2IM_OWN=1 (dcn_col2im_own.cu: the CTA owns a 32-channel slice of the input gradient in shared
+    memory, lane schedule precomputed per offset tensor; opt-in because it measured slower): same gradients as the
+    oracle and as the default red.global col2im, grad_offset / grad_mask bitwise reproducible.  The third case has
+    small offsets: neighbouring positions hit the same pixels, the turn-taking path is exercised."""
+    d = dcn_case(**case)
+    ref_out, ref_bw = _oracle(d)
+    default = _ours(d, 'bf16')
+    monkeypatch.setenv('KGDET_COL2IM_OWN', '1')
+    got = _ours(d, 'bf16')
+    again = _ours(d, 'bf16')
+    for k in ('grad_input', 'grad_offset', 'grad_mask'):
+        if k in ref_bw:
+            assert rel_err(got[k], ref_bw[k]) < TOL['bf16'], (k, rel_err(got[k], ref_bw[k]))
+            assert rel_err(got[k], default[k]) < 1e-4, (k, rel_err(got[k], default[k]))
+    assert torch.equal(got['grad_offset'], again['grad_offset'])
+    monkeypatch.setenv('KGDET_COL2IM_OWN_PERMUTE', '0')
+    plain = _ours(d, 'bf16')
+    assert rel_err(plain['grad_input'], default['grad_input']) < 1e-4
+
+
 def test_tensor_core_backward_full_size_vs_exact():
     d = dcn_case(N=16, C=256, H=25, W=42, Cout=256, k=5, seed=11)
     exact = _ours(d, 'fp32')
