@@ -425,8 +425,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_ms = a.elapsed_time(b)
         e2e_evs = [e2e_ms / args.steps]
-        e2e_mode = ('pipelined serve(): two captured instances of the step, H2D of batch i+1 and D2H of batch i-1 overlap '
-                    'replay i; L2 flush inside the timed region')
+        e2e_mode = ('pipelined serve(): two captured instances of the step replayed on two compute streams (batch i+1 '
+                    'starts while batch i is running: the narrow phases of one step run under the wide kernels of the '
+                    'other), H2D of batch i+1 and D2H of batch i-1 on copy streams; L2 flush inside the timed region '
+                    'before every replay')
     else:
         e2e_ms, e2e_evs = e2e_sync_ms, sync_evs
         e2e_mode = 'synchronous per step'

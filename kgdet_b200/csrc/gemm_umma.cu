@@ -14,7 +14,7 @@ namespace kgdet {
 static constexpr int G_BM = 128;
 static constexpr int G_PROD_WARPS = 8;
 static constexpr int G_THREADS = (G_PROD_WARPS + 1) * 32;
-static constexpr int G_NS = 4;
+static constexpr int G_NS = 4;          // pipeline stages of the default instantiations
 
 struct GemmParams {
   const __nv_bfloat16* A;
@@ -47,8 +47,12 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-template <int BN, typename Tout>
-__global__ void __launch_bounds__(G_THREADS, 1) umma_gemm_kernel(const GemmParams prm) {
+// NS pipeline stages, MINB resident CTAs per SM.  <128, bf16, 3, 2>: the column-gradient GEMM of the DCN backward has
+// only K / 64 = 4 k-blocks per tile, so a tile is mostly fill + epilogue (512 clk of MMA in ~5 500); two resident
+// CTAs of 128 x 128 tiles (96 KB of stages, 128 TMEM columns each) let one tile's epilogue run under the other's loads.
+template <int BN, typename Tout, int NS, int MINB>
+__global__ void __launch_bounds__(G_THREADS, MINB) umma_gemm_kernel(const GemmParams prm) {
+  constexpr int G_NS = NS;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) umma_gemm_kernel(const GemmParam
     // proxy (tcgen05.mma reads) and arrives on the stage's full barrier.  The old loop held one k-block in
     // registers and paid a full L2 round trip per k-block (~2 000 clk against a 512-clk MMA).
     const int chunk = tid & 7, rbase = tid >> 3;     // 32 rows per pass
-    constexpr int DEPTH = 3;                         // < G_NS: the stage of kb + DEPTH was freed by MMA(kb + DEPTH - G_NS)
+    constexpr int DEPTH = G_NS - 1;                  // < G_NS: the stage of kb + DEPTH was freed by MMA(kb + DEPTH - G_NS)
     const int off = rbase * 128 + ((chunk ^ (rbase & 7)) << 4);
     auto issue = [&](int kb) {
       const int s = kb % G_NS, it = kb / G_NS;
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) umma_gemm_kernel(const GemmParam
     const int m = m0 + row;
     constexpr int HALF = BN / 2;
     bool staged = false;
-    if constexpr (sizeof(Tout) == 2 && BN == 256) {
+    if constexpr (sizeof(Tout) == 2) {
       // bf16 output, full-width tile: stage the 128 x 256 tile in shared memory (the pipeline buffers are idle
       // once the accumulator is complete) and write whole 512-byte rows, one per warp instruction.  A thread owns
       // an accumulator ROW, so direct stores put 32 different lines (16 bytes each) into every instruction; the
@@ -157,10 +161,19 @@ __global__ void __launch_bounds__(G_THREADS, 1) umma_gemm_kernel(const GemmParam
         }
         asm volatile("bar.sync 1, %0;" ::"n"(G_PROD_WARPS * 32) : "memory");      // the eight epilogue warps only
         __nv_bfloat16* cbase = reinterpret_cast<__nv_bfloat16*>(prm.C) + n0;
-        for (int r = warp; r < G_BM; r += G_PROD_WARPS) {
-          if (m0 + r < prm.M)
-            *reinterpret_cast<uint4*>(cbase + (long long)(m0 + r) * prm.ldc + lane * 8) =
-                *reinterpret_cast<const uint4*>(st + (size_t)r * PITCH + lane * 16);
+        if constexpr (BN == 256) {
+          for (int r = warp; r < G_BM; r += G_PROD_WARPS) {
+            if (m0 + r < prm.M)
+              *reinterpret_cast<uint4*>(cbase + (long long)(m0 + r) * prm.ldc + lane * 8) =
+                  *reinterpret_cast<const uint4*>(st + (size_t)r * PITCH + lane * 16);
+          }
+        } else {                                            // 256-byte rows: two per warp instruction
+          for (int r2 = warp * 2; r2 < G_BM; r2 += 2 * G_PROD_WARPS) {
+            const int r = r2 + (lane >> 4), piece = lane & 15;
+            if (m0 + r < prm.M)
+              *reinterpret_cast<uint4*>(cbase + (long long)(m0 + r) * prm.ldc + piece * 8) =
+                  *reinterpret_cast<const uint4*>(st + (size_t)r * PITCH + piece * 16);
+          }
         }
         staged = true;
       }
@@ -237,11 +250,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) umma_gemm_kernel(const GemmParam
   if (warp == G_PROD_WARPS) tmem_dealloc(tmem_base, prm.tmem_cols);
 }
 
-template <int BN, typename Tout>
+template <int BN, typename Tout, int NS = G_NS, int MINB = 1>
 static int launch_gemm(const GemmParams& p, dim3 grid, cudaStream_t stream) {
-  const size_t smem = 1024 + (size_t)G_NS * (G_BM * 128 + BN * 128) + (2 * G_NS + 1) * 8 + 16;
-  KG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, Tout>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  umma_gemm_kernel<BN, Tout><<<grid, G_THREADS, smem, stream>>>(p);
+  const size_t smem = 1024 + (size_t)NS * (G_BM * 128 + BN * 128) + (2 * NS + 1) * 8 + 16;
+  KG_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<BN, Tout, NS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_gemm_kernel<BN, Tout, NS, MINB><<<grid, G_THREADS, smem, stream>>>(p);
   KG_LAUNCH_CHECK("umma_gemm_kernel");
   return KGDET_OK;
 }
@@ -261,11 +274,15 @@ int umma_gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   splits = ceil_div(p.kblocks_total, p.kblocks_per_split);
   p.atomic = splits > 1 ? 1 : 0;
   p.alpha = alpha;
-  const int BN = N > 128 ? 256 : 128;
+  // few k-blocks, bf16 result (the DCN column gradient): 128-column tiles, two CTAs per SM
+  bool narrow = out_dtype == KGDET_BF16 && splits == 1 && p.kblocks_total <= 8 && N > 128;
+  if (const char* e = getenv("KGDET_GEMM_NARROW")) narrow = narrow && atoi(e) != 0;
+  const int BN = (N > 128 && !narrow) ? 256 : 128;
   p.idesc = make_idesc(1u, G_BM, (uint32_t)BN);
   p.tmem_cols = BN;
   dim3 grid(ceil_div(M, G_BM), ceil_div(N, BN), splits);
   KG_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "umma_gemm: grid too large");
+  if (narrow) return launch_gemm<128, __nv_bfloat16, 3, 2>(p, grid, stream);
   if (BN == 256)
     return out_dtype == KGDET_F32 ? launch_gemm<256, float>(p, grid, stream)
                                   : launch_gemm<256, __nv_bfloat16>(p, grid, stream);

@@ -1348,7 +1348,7 @@ class GraphedInference(object):
             self._twin = twin
         return self._twin
 
-    def serve(self, host_batches, host_outputs=None, before_step=None):
+    def serve(self, host_batches, host_outputs=None, before_step=None, concurrent=None):
         """Throughput path for HOST inputs: a three-stage software pipeline over the batches --
 
             copy-in stream   pinned host batch i+1 -> static input of graph instance (i+1) % 2   (PCIe, host -> device)
@@ -1360,16 +1360,28 @@ class GraphedInference(object):
         `host_batches`: iterable of pinned CPU tensors shaped like the example input.  `host_outputs`: optional list
         (one entry per batch) of pinned (dets, labels, keypoints) triples to fill; allocated when omitted.
         `before_step(i)`: optional callable issued on the compute stream before replay i (bench.py flushes the L2
-        there).  Returns the list of host triples; everything has completed on return."""
+        there).  `concurrent` (default on; environment KGDET_SERVE_CONCURRENT=0 turns it off): the two instances replay on their
+        own compute streams, so batch i + 1 starts while batch i is still running and the narrow phases of one step
+        (towers, stage 1, the point-refinement gap, decode + NMS) overlap the wide kernels of the other; the
+        instances share nothing but read-only weights.  Returns the list of host triples; everything has completed
+        on return."""
         dev = self.static_x.device
         main = torch.cuda.current_stream(dev)
         inst = (self, self._second_instance())
+        if concurrent is None:
+            concurrent = os.environ.get('KGDET_SERVE_CONCURRENT', '1') != '0'
         if not hasattr(self, '_pipe'):
             self._pipe = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
         cin, cout = self._pipe
+        if concurrent and not hasattr(self, '_compute'):
+            self._compute = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        comp = self._compute if concurrent else (main, main)
         start = main.record_event()
         cin.wait_event(start)
         cout.wait_event(start)
+        if concurrent:
+            comp[0].wait_event(start)
+            comp[1].wait_event(start)
         replayed = [None, None]        # instance b has consumed its static input (and rewritten its outputs)
         drained = [None, None]         # copy-out has read instance b's static outputs
         results = []
@@ -1387,13 +1399,15 @@ class GraphedInference(object):
         for i in range(len(batches)):
             b = i % 2
             nxt = copy_in(i + 1) if i + 1 < len(batches) else None     # overlaps replay i
-            main.wait_event(ready)
+            cs = comp[b]
+            cs.wait_event(ready)
             if drained[b] is not None:
-                main.wait_event(drained[b])                            # results of batch i - 2 have left the device
-            if before_step is not None:
-                before_step(i)
-            inst[b].graph.replay()
-            replayed[b] = main.record_event()
+                cs.wait_event(drained[b])                              # results of batch i - 2 have left the device
+            with torch.cuda.stream(cs):
+                if before_step is not None:
+                    before_step(i)
+                inst[b].graph.replay()
+                replayed[b] = cs.record_event()
             host = host_outputs[i] if host_outputs is not None else \
                 tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in self.static_out)
             cout.wait_event(replayed[b])
@@ -1403,6 +1417,9 @@ class GraphedInference(object):
                 drained[b] = cout.record_event()
             results.append(host)
             ready = nxt
+        if concurrent:
+            main.wait_stream(comp[0])
+            main.wait_stream(comp[1])
         main.wait_stream(cout)
         main.wait_stream(cin)
         main.synchronize()

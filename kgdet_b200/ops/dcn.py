@@ -368,7 +368,6 @@ def deform_conv_prepared(pin, plan, weight, out=None, channel_offset=0, relu=Fal
     return out
 
 
-_group_counters = {}
 
 
 def deform_conv_prepared_group(jobs):
@@ -411,11 +410,11 @@ def deform_conv_prepared_group(jobs):
         for job in jobs:
             deform_conv_prepared(*job)
         return
-    dev = ref.device
-    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
-    ctr = _group_counters.get(key)
-    if ctr is None:
-        ctr = _group_counters[key] = torch.zeros(4, dtype=torch.int32, device=dev)
+    # Tile counter of the persistent launch (zeroed by the library on the launch stream).  A fresh stream-ordered
+    # allocation per call: a counter cached per (device, stream) was shared by every CUDA graph captured on torch's
+    # capture stream, and two such graphs replayed at the same time on two streams then handed out each other's
+    # tiles (tools/lockstep_stress.py: 20 of 40 simultaneous replays of two instances returned wrong detections).
+    ctr = _capi.workspace(16, ref)
     _capi.check(lib.kgdet_dcn_forward_prepared_group(ctypes.cast(items, ctypes.c_void_p), len(jobs), _capi.PREC_BF16,
                                                      ctr.data_ptr(), 16, _capi.stream_of(ref)),
                 'kgdet_dcn_forward_prepared_group')
