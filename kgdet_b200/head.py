@@ -1332,23 +1332,35 @@ class GraphedInference(object):
         self.graph.replay()
         return self.static_out
 
+    def _new_instance(self):
+        twin = object.__new__(GraphedInference)
+        twin.head, twin.args, twin.score_override = self.head, self.args, self.score_override
+        twin.static_x = self.static_x.clone()
+        torch.cuda.synchronize()
+        twin.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(twin.graph), torch.no_grad():
+            twin.static_out = twin._run()
+        from .ops.pointwise import cache_values
+        twin._pinned_buffers = cache_values()
+        twin._twin = None
+        return twin
+
     def _second_instance(self):
         """A second capture of the same step with its own static input / outputs (lazy: only `serve` needs it)."""
         if getattr(self, '_twin', None) is None:
-            twin = object.__new__(GraphedInference)
-            twin.head, twin.args, twin.score_override = self.head, self.args, self.score_override
-            twin.static_x = self.static_x.clone()
-            torch.cuda.synchronize()
-            twin.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(twin.graph), torch.no_grad():
-                twin.static_out = twin._run()
-            from .ops.pointwise import cache_values
-            twin._pinned_buffers = cache_values()
-            twin._twin = None
-            self._twin = twin
+            self._twin = self._new_instance()
         return self._twin
 
-    def serve(self, host_batches, host_outputs=None, before_step=None, concurrent=None):
+    def _instances(self, n):
+        """This capture plus n - 1 further captures of the same step (own static input / outputs, own scratch)."""
+        more = getattr(self, '_more', None)
+        if more is None:
+            more = self._more = []
+        while len(more) < n - 2:
+            more.append(self._new_instance())
+        return [self, self._second_instance()][:max(n, 1)] + more[:max(n - 2, 0)]
+
+    def serve(self, host_batches, host_outputs=None, before_step=None, concurrent=None, instances=None):
         """Throughput path for HOST inputs: a three-stage software pipeline over the batches --
 
             copy-in stream   pinned host batch i+1 -> static input of graph instance (i+1) % 2   (PCIe, host -> device)
@@ -1367,28 +1379,34 @@ class GraphedInference(object):
         on return."""
         dev = self.static_x.device
         main = torch.cuda.current_stream(dev)
-        inst = (self, self._second_instance())
         if concurrent is None:
             concurrent = os.environ.get('KGDET_SERVE_CONCURRENT', '1') != '0'
+        if instances is None:
+            instances = int(os.environ.get('KGDET_SERVE_INSTANCES', '2'))
+        ni = max(2, int(instances)) if concurrent else 2
+        inst = self._instances(ni)
         if not hasattr(self, '_pipe'):
             self._pipe = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
         cin, cout = self._pipe
-        if concurrent and not hasattr(self, '_compute'):
-            self._compute = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
-        comp = self._compute if concurrent else (main, main)
+        if concurrent:
+            if len(getattr(self, '_compute', ())) < ni:
+                self._compute = tuple(torch.cuda.Stream(device=dev) for _ in range(ni))
+            comp = self._compute[:ni]
+        else:
+            comp = (main,) * ni
         start = main.record_event()
         cin.wait_event(start)
         cout.wait_event(start)
         if concurrent:
-            comp[0].wait_event(start)
-            comp[1].wait_event(start)
-        replayed = [None, None]        # instance b has consumed its static input (and rewritten its outputs)
-        drained = [None, None]         # copy-out has read instance b's static outputs
+            for c in comp:
+                c.wait_event(start)
+        replayed = [None] * ni         # instance b has consumed its static input (and rewritten its outputs)
+        drained = [None] * ni          # copy-out has read instance b's static outputs
         results = []
         batches = list(host_batches)
 
         def copy_in(i):
-            b = i % 2
+            b = i % ni
             if replayed[b] is not None:
                 cin.wait_event(replayed[b])
             with torch.cuda.stream(cin):
@@ -1397,7 +1415,7 @@ class GraphedInference(object):
 
         ready = copy_in(0) if batches else None
         for i in range(len(batches)):
-            b = i % 2
+            b = i % ni
             nxt = copy_in(i + 1) if i + 1 < len(batches) else None     # overlaps replay i
             cs = comp[b]
             cs.wait_event(ready)
@@ -1418,8 +1436,8 @@ class GraphedInference(object):
             results.append(host)
             ready = nxt
         if concurrent:
-            main.wait_stream(comp[0])
-            main.wait_stream(comp[1])
+            for c in comp:
+                main.wait_stream(c)
         main.wait_stream(cout)
         main.wait_stream(cin)
         main.synchronize()

@@ -28,15 +28,15 @@ hosts = [(x + 0.01 * i).clone().pin_memory() for i in range(3)]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 outs = [tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in g.static_out) for _ in range(steps)]
 ref = None
-for conc in (False, True, False, True):
+for conc in (False, 2, 3, 4, False, 2, 3, 4):
     for fl in (True, False):
         before = (lambda i: flush.fill_(1)) if fl else None
-        g.serve([hosts[i % 3] for i in range(4)], None, before_step=before, concurrent=conc)
+        g.serve([hosts[i % 3] for i in range(6)], None, before_step=before, concurrent=bool(conc), instances=conc or 2)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         a.record()
-        res = g.serve([hosts[i % 3] for i in range(steps)], outs, before_step=before, concurrent=conc)
+        res = g.serve([hosts[i % 3] for i in range(steps)], outs, before_step=before, concurrent=bool(conc), instances=conc or 2)
         b.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
