@@ -177,7 +177,7 @@ __device__ __forceinline__ void unpack4b(const uint2& v, float (&f)[4]) {
 // Loads run one tap ahead of the staging (the asm statements of the staging are memory barriers for the compiler:
 // without the explicit prefetch every tap's loads waited for the previous tap's bulk issue -- long_scoreboard 8.2
 // stalled warps per issue, 860 -> 760 us only).  NCH = C / 128 (4 channels per lane and chunk).
-template <int NCH, int BULK_SETS>
+template <int NCH, int BULK_SETS, bool STREAM_CG>
 __global__ void __launch_bounds__(256, 2)
 col2im_bulk_kernel(DcnGeom g, const __nv_bfloat16* __restrict__ cg, const __nv_bfloat16* __restrict__ in,
                    const SampleRec* __restrict__ plan, const SampleAux* __restrict__ aux, int tap0, int ntaps,
@@ -217,7 +217,9 @@ col2im_bulk_kernel(DcnGeom g, const __nv_bfloat16* __restrict__ cg, const __nv_b
       const __nv_bfloat16* cgrow = cg + ((size_t)m * ntaps + tl0 + t) * C;
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
-        gq[slot][ch] = valid ? __ldg(reinterpret_cast<const uint2*>(cgrow + ch * 128 + lane * 4)) : make_uint2(0u, 0u);
+        gq[slot][ch] = valid ? (STREAM_CG ? __ldcs(reinterpret_cast<const uint2*>(cgrow + ch * 128 + lane * 4))
+                                          : __ldg(reinterpret_cast<const uint2*>(cgrow + ch * 128 + lane * 4)))
+                             : make_uint2(0u, 0u);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           vq[slot][ch][i] = (valid & (1 << i))
@@ -561,7 +563,10 @@ int bwd_tc_input(const DcnGeom& g, const void* input, const float* offset, const
     if (use_bulk_col2im(g)) {
       // two staging sets per warp (three measured the same: 1 464 vs 1 479 us for the K = 49 call)
       const size_t smem = (size_t)8 * 2 * 4 * g.C * 4;
-      auto kern = g.C == 256 ? col2im_bulk_kernel<2, 2> : col2im_bulk_kernel<1, 2>;
+      bool stream_cg = true;
+      if (const char* e = getenv("KGDET_COL2IM_STREAM_CG")) stream_cg = atoi(e) != 0;
+      auto kern = g.C == 256 ? (stream_cg ? col2im_bulk_kernel<2, 2, true> : col2im_bulk_kernel<2, 2, false>)
+                             : (stream_cg ? col2im_bulk_kernel<1, 2, true> : col2im_bulk_kernel<1, 2, false>);
       KG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       long long b = (warps * 32 + 255) / 256;
       const long long cap = (long long)num_sms() * 2;
