@@ -283,6 +283,8 @@ BWD_TC_CASES = [
     dict(N=1, C=256, H=7, W=11, Cout=256, k=5),
     dict(N=1, C=128, H=7, W=11, Cout=192, k=7),
     dict(N=3, C=64, H=25, W=42, Cout=128, k=3, mask=True, bias=True),
+    dict(N=2, C=128, H=9, W=11, Cout=64, k=3, mask=True, bias=True),     # bulk-reduction col2im (C = 128) with a mask
+    dict(N=1, C=256, H=6, W=7, Cout=64, k=5, mask=True, offset_std=5.0),  # ... C = 256, many samples outside the map
 ]
 
 
