@@ -1307,6 +1307,7 @@ class GraphedInference(object):
         from .ops.pointwise import cache_values
         self._pinned_buffers = cache_values()
         self._twin = None
+        self._more = None          # further instances of serve(instances > 2): captured again on demand
 
     def refresh_weights(self):
         """Re-derive every packed weight from the head's CURRENT parameters and capture the step again.  A
