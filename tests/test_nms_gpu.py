@@ -25,9 +25,11 @@ def test_single_cta_path_bit_exact(n, clustered, cmp_mode):
     assert got.dtype == np.int64 and np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize('n', [4097, 10000])
-def test_large_path_bit_exact(n):
-    dets = random_boxes(n, seed=n, clustered=True)
+@pytest.mark.parametrize('n', [4097, 10000, 20011])
+@pytest.mark.parametrize('clustered', [True, False])
+def test_large_path_bit_exact(n, clustered):
+    """mask kernel + pipelined sweep (chain warp + applier warps); 20 011 boxes = 313 blocks, the last one ragged."""
+    dets = random_boxes(n, seed=n, clustered=clustered)
     for cmp_mode in (0, 1):
         assert np.array_equal(_ours_keep(dets, 0.5, cmp_mode), nms_oracle.nms_keep(dets, 0.5, cmp_mode))
 
