@@ -92,22 +92,18 @@ __global__ void focal_sum_bwd_kernel(const T* __restrict__ logits,
 
 // fp32 tensors, four consecutive elements per thread (one 16-byte load / store; the row index is divided out once
 // per four elements), single-precision arithmetic (focal.cuh): HBM-bound instead of bound by fp64 instruction issue.
+// The labels of the (at most two, C >= 4) rows a quad touches are loaded TOGETHER with the quad -- a quad's label
+// load used to be issued when its arithmetic started, a second dependent round trip per iteration.
 template <bool BWD, bool G2>
-__device__ __forceinline__ void focal_quad(const float4& x4, const float4& g4, int i, int C, int M,
-                                           const int64_t* __restrict__ targets, float gamma, float alpha,
-                                           float* __restrict__ out) {
-  int n = i / C, d = i - n * C;
-  int t = (int)__ldg(targets + n);
+__device__ __forceinline__ void focal_quad(const float4& x4, const float4& g4, int i, int d0, int t0, int t1, int C,
+                                           float gamma, float alpha, float* __restrict__ out) {
   const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, gs[4] = {g4.x, g4.y, g4.z, g4.w};
   float r[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
+    const bool next = d0 + e >= C;                       // this element belongs to the following row
+    const int d = next ? d0 + e - C : d0 + e, t = next ? t1 : t0;
     r[e] = BWD ? focal_bwd_fast<G2>(xs[e], t, d, gamma, alpha) * gs[e] : focal_fwd_fast<G2>(xs[e], t, d, gamma, alpha);
-    if (++d == C) {
-      d = 0;
-      ++n;
-      if (n < M) t = (int)__ldg(targets + n);
-    }
   }
   *reinterpret_cast<float4*>(out + i) = make_float4(r[0], r[1], r[2], r[3]);
 }
@@ -117,26 +113,31 @@ __global__ void __launch_bounds__(256) focal_vec4_kernel(const float* __restrict
                                                          const int64_t* __restrict__ targets,
                                                          const float* __restrict__ d_losses, int total, int C, int M,
                                                          float gamma, float alpha, float* __restrict__ out) {
-  // FV_UNROLL quads per thread and iteration, all loads issued before the first use: the kernel is bound by the
-  // bytes in flight per SM, not by arithmetic
+  // FV_UNROLL quads per thread and iteration, all loads (logits, upstream gradient, row labels) issued before the
+  // first use
   constexpr int FV_UNROLL = 4;
   const int quads = total >> 2;
   const int nthreads = blockDim.x * gridDim.x;
   const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
   for (int q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < quads; q0 += nthreads * FV_UNROLL) {
     float4 x4[FV_UNROLL], g4[FV_UNROLL];
+    int d0[FV_UNROLL], t0[FV_UNROLL], t1[FV_UNROLL];
 #pragma unroll
     for (int u = 0; u < FV_UNROLL; ++u) {
       const int q = q0 + u * nthreads;
       if (q < quads) {
         x4[u] = *reinterpret_cast<const float4*>(logits + (size_t)q * 4);
         g4[u] = BWD ? *reinterpret_cast<const float4*>(d_losses + (size_t)q * 4) : one;
+        const int n = (q * 4) / C;
+        d0[u] = q * 4 - n * C;
+        t0[u] = (int)__ldg(targets + n);
+        t1[u] = (int)__ldg(targets + (n + 1 < M ? n + 1 : n));
       }
     }
 #pragma unroll
     for (int u = 0; u < FV_UNROLL; ++u) {
       const int q = q0 + u * nthreads;
-      if (q < quads) focal_quad<BWD, G2>(x4[u], g4[u], q * 4, C, M, targets, gamma, alpha, out);
+      if (q < quads) focal_quad<BWD, G2>(x4[u], g4[u], q * 4, d0[u], t0[u], t1[u], C, gamma, alpha, out);
     }
   }
   // tail (total % 4 elements): one thread
@@ -189,7 +190,7 @@ extern "C" int kgdet_sigmoid_focal_loss_forward(const void* logits, const int64_
   FOCAL_COMMON_CHECKS("kgdet_sigmoid_focal_loss_forward");
   KG_CHECK_ARG(logits && targets && losses, "kgdet_sigmoid_focal_loss_forward: NULL pointer");
   int total = M * C;
-  if (dtype == KGDET_F32 && !focal_exact() && (((uintptr_t)logits | (uintptr_t)losses) & 15) == 0) {
+  if (dtype == KGDET_F32 && C >= 4 && !focal_exact() && (((uintptr_t)logits | (uintptr_t)losses) & 15) == 0) {
     if (gamma == 2.0f)
       focal_vec4_kernel<false, true><<<focal_grid4(total), 256, 0, stream>>>((const float*)logits, targets, nullptr, total, C,
                                                                              M, gamma, alpha, (float*)losses);
@@ -218,7 +219,7 @@ extern "C" int kgdet_sigmoid_focal_loss_backward(const void* logits, const int64
   KG_CHECK_ARG(logits && targets && d_losses && d_logits,
                "kgdet_sigmoid_focal_loss_backward: NULL pointer");
   int total = M * C;
-  if (dtype == KGDET_F32 && !focal_exact() && (((uintptr_t)logits | (uintptr_t)d_losses | (uintptr_t)d_logits) & 15) == 0) {
+  if (dtype == KGDET_F32 && C >= 4 && !focal_exact() && (((uintptr_t)logits | (uintptr_t)d_losses | (uintptr_t)d_logits) & 15) == 0) {
     if (gamma == 2.0f)
       focal_vec4_kernel<true, true><<<focal_grid4(total), 256, 0, stream>>>((const float*)logits, targets,
                                                                             (const float*)d_losses, total, C, M, gamma,
