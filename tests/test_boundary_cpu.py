@@ -51,6 +51,8 @@ def test_built_library_contains_blackwell_instructions():
     if not out:
         pytest.skip('cuobjdump unavailable')
     assert 'UTCHMMA' in out and 'LDTM' in out and 'UBLKCP' in out
+    assert 'UBLKRED' in out                 # cp.reduce.async.bulk: the input gradient's col2im rows
+    assert 'UTMALDG' in out                 # cp.async.bulk.tensor: the 3x3 convolution's tile loads
     assert 'HMMA.16816' not in out          # no mma.sync fallback anywhere
 
 
